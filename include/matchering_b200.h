@@ -1,0 +1,210 @@
+/* matchering_b200 -- C ABI of the B200-native Matchering hot path.
+ *
+ * The reference (sergree/matchering v2.0.6) is pure Python and has no FFI layer; the seam this
+ * library plugs into is the pair of Python call sites
+ *     matchering/core.py:77-86      -> stages.main(target, reference, config, need_*...)
+ *     matchering/stages.py:202      -> limiter.limit(array, config)
+ * Each entry point below cites the reference function(s) it replaces.  The reference-side
+ * binding a maintainer would add (a ctypes stub) is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C, no exceptions: every call returns MGB_OK (0) or a negative mgb_status;
+ *     mgb_last_error_string() describes the last failure on the calling thread.
+ *   - audio is interleaved stereo float32: frame n = (L, R) at x[2n], x[2n+1].
+ *   - all `d_*` pointers are DEVICE pointers owned by the caller and 16-byte aligned; nothing
+ *     here allocates device memory.  Calls are asynchronous on `stream` (a cudaStream_t passed
+ *     as void*); scalar results stay in device memory (mgb_track_state), so no call syncs.
+ *   - Config-only tables (spline factorisations, LOWESS plan, filter coefficients, FFT twiddles)
+ *     live in an mgb_plan that the host builds once per Config (matchering_b200/plan.py) and
+ *     uploads; data-dependent arithmetic never runs on the host.
+ */
+#ifndef MATCHERING_B200_H
+#define MATCHERING_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGB_VERSION 100 /* 0.1.0 */
+
+typedef enum mgb_status {
+    MGB_OK = 0,
+    MGB_ERR_INVALID = -1,     /* bad argument (null / misaligned pointer, size out of range) */
+    MGB_ERR_UNSUPPORTED = -2, /* legal reference Config this build has no kernel for */
+    MGB_ERR_WORKSPACE = -3,   /* workspace too small */
+    MGB_ERR_CUDA = -4         /* CUDA runtime / launch failure */
+} mgb_status;
+
+/* Limiter constants derived from Config (matchering/defaults.py:25-58, limiter/hyrax.py:44-72,
+ * utils.py:50-55).  First-order sections only (the reference defaults); higher Butterworth
+ * orders are rejected with MGB_ERR_UNSUPPORTED by the host before they get here. */
+typedef struct mgb_limiter_params {
+    double threshold;   /* Config.threshold */
+    int32_t reach;      /* make_odd(attack_samples) - 1 : half width of the centred max */
+    int32_t hold;       /* hold_samples : length of the trailing max */
+    int32_t warmup;     /* samples after which attack_c^n < 1e-10 (halo of the attack filter) */
+    int32_t reserved;
+    double attack_c;    /* exp(attack_filter_coefficient / attack_samples) */
+    double hold_b0, hold_b1, hold_a1;       /* butter(1, hold_filter_coefficient, fs) */
+    double release_b0, release_b1, release_a1; /* butter(1, release_filter_coefficient/release, fs) */
+} mgb_limiter_params;
+
+/* Config-only device tables (all double unless noted).  n_lin = fft_size/2+1,
+ * n_log = (fft_size/2)*lin_log_oversampling+1. */
+typedef struct mgb_plan {
+    int32_t sample_rate;
+    int32_t fft_size;          /* F: 1024, 2048, 4096 or 8192 */
+    int32_t n_lin, n_log;
+    int32_t rms_correction_steps;
+    int32_t lowess_k;          /* neighbourhood size int(frac*n_log + 1e-10) */
+    int32_t lowess_nfit;       /* number of regression points */
+    int32_t reserved0;
+    double max_piece_size;     /* samples, as Config stores it (defaults.py:109) */
+    double threshold;
+    double min_value;
+    mgb_limiter_params limiter;
+    /* spline A: knots = linear grid, evaluated on the log grid (match_frequencies.py:60-61) */
+    const double* d_sa_hinv;   /* [n_lin-1] 1/h_i */
+    const double* d_sa_lu;     /* [3][n_lin-2] Thomas factors: sub/denominator, 1/denominator, super' */
+    const double* d_sa_end;    /* [4] not-a-knot closure: M0 = e0*M1 + e1*M2, Mlast = e2*M[n-2] + e3*M[n-3] */
+    const int32_t* d_sa_eval_idx; /* [n_log] interval index */
+    const double* d_sa_eval_w;    /* [n_log][4] weights of (y_i, y_i+1, M_i, M_i+1) */
+    /* spline B: knots = log grid, evaluated on the linear grid (match_frequencies.py:67-70) */
+    const double* d_sb_hinv;   /* [n_log-1] */
+    const double* d_sb_lu;     /* [3][n_log-2] */
+    const double* d_sb_end;    /* [4] */
+    const int32_t* d_sb_eval_idx; /* [n_lin] */
+    const double* d_sb_eval_w;    /* [n_lin][4] */
+    /* LOWESS (dsp.py:103-106, statsmodels semantics, it = 0) */
+    const double* d_lw_x;        /* [n_log] abscissa linspace(0,1,n_log) */
+    const int32_t* d_lw_fit_idx; /* [lowess_nfit] indices with a local regression */
+    const int32_t* d_lw_fit_left;/* [lowess_nfit] left edge of each neighbourhood */
+    const int32_t* d_lw_seg;     /* [n_log] position in fit_idx of the last regression point <= j */
+    /* window (scipy.signal.windows.hann(F), match_frequencies.py:99) */
+    const double* d_hann;        /* [F] */
+    /* FFT twiddles, filled by mgb_plan_fill_twiddles */
+    void* d_tw_f32_F;    /* float2  table of the F-point transform  */
+    void* d_tw_f32_2F;   /* float2  table of the 2F-point transform */
+    void* d_tw_f64_F;    /* double2 table of the F-point transform  */
+    void* d_tw_f64_2F;   /* double2 table of the 2F-point transform */
+} mgb_plan;
+
+/* Per-track scalars, resident in device memory (one struct per track in flight). */
+#define MGB_MAX_CORRECTION_STEPS 16
+typedef struct mgb_track_state {
+    double reference_peak;        /* max|reference|                         dsp.py:97            */
+    double final_amplitude_coef;  /* normalize_reference's coefficient      match_levels.py:29-44 */
+    double target_match_rms;      /* match_levels.py:62-71                                        */
+    double reference_match_rms;   /* of the NORMALISED reference                                   */
+    double rms_coefficient;       /* c0 = ref/max(eps,target)               match_levels.py:106-111 */
+    double gain;                  /* product of the RMS-correction coefficients so far             */
+    double correction[MGB_MAX_CORRECTION_STEPS]; /* stages.py:161-168, one per step                */
+    double result_peak;           /* max|result| after the correction gain                         */
+    double normalize_coef;        /* stages.py:186-191 coefficient of the normalised output        */
+    float conv_peak_bits;         /* max|L|,|R| of the convolution output before correction        */
+    int32_t target_loud_pieces;   /* number of pieces with rms >= average (target)                 */
+    int32_t reference_loud_pieces;
+    int32_t limiter_engaged;      /* 0 when hyrax.py:83-85 takes its early-out                     */
+    int32_t steps_done;
+    int32_t reserved[3];
+} mgb_track_state;
+
+/* Geometry of one mastering job, computed by mgb_track_layout from sizes + plan (host side). */
+typedef struct mgb_track_layout {
+    int64_t target_frames, reference_frames;
+    int64_t target_piece, reference_piece;        /* match_levels.py:47-59 */
+    int32_t target_divisions, reference_divisions;
+    int32_t target_slots, reference_slots;        /* analysis CTAs per piece */
+    int64_t workspace_bytes;                      /* device scratch the stage calls need */
+} mgb_track_layout;
+
+int mgb_version(void);
+const char* mgb_last_error_string(void);
+
+/* Runtime switches for A/B measurements: "tma" (1 = cp.async.bulk frame loads, default; 0 = plain
+ * coalesced loads).  Returns MGB_ERR_INVALID for an unknown name. */
+int mgb_set_option(const char* name, int value);
+
+/* Bytes of the four twiddle tables for `fft_size`, in the order of the mgb_plan fields. */
+int mgb_plan_twiddle_bytes(int32_t fft_size, int64_t bytes_out[4]);
+/* Fill plan->d_tw_* (device buffers of the sizes above) on `stream`. */
+int mgb_plan_fill_twiddles(const mgb_plan* plan, void* stream);
+
+/* match_levels.py:47-59 piece geometry + launch geometry + workspace size. */
+int mgb_track_layout_init(const mgb_plan* plan, int64_t target_frames, int64_t reference_frames,
+                          mgb_track_layout* out);
+
+/* ---- stage 1: stages.__match_levels (stages.py:38-104) --------------------------------------
+ * One pass over each signal: max|x| (dsp.normalize, dsp.py:93-100), mid/side (dsp.lr_to_ms,
+ * dsp.py:57-64), per-piece sum(mid^2) (dsp.batch_rms, dsp.py:80-86) and per-piece sums of
+ * |rfft(frame)| for mid and side (match_frequencies.__average_fft, match_frequencies.py:30-42),
+ * then the loudest-piece masks, match RMS values, c0 and final_amplitude_coefficient
+ * (match_levels.py:62-131) into *d_state. */
+int mgb_match_levels(const mgb_plan* plan, const mgb_track_layout* layout, const float* d_target_lr,
+                     const float* d_reference_lr, void* d_workspace, mgb_track_state* d_state, void* stream);
+
+/* ---- stage 2: stages.__match_frequencies (stages.py:107-135) --------------------------------
+ * FIR design for mid and side (match_frequencies.get_fir, :78-101, incl. __smooth_exponentially
+ * :45-75 and dsp.smooth_lowess) and convolution of the level-matched target with both FIRs
+ * (match_frequencies.convolve :104-119 == scipy fftconvolve 'same'), mid/side -> L/R
+ * (dsp.ms_to_lr, dsp.py:67-68).  Writes the un-corrected result (d_result_lr), its mid channel
+ * (workspace) and the first correction step's per-piece sum(clip(mid)^2).
+ * d_fir_out (optional, may be NULL): [2][F] doubles, the mid and side FIRs, for inspection. */
+int mgb_match_frequencies(const mgb_plan* plan, const mgb_track_layout* layout, const float* d_target_lr,
+                          float* d_result_lr, double* d_fir_out, void* d_workspace, mgb_track_state* d_state,
+                          void* stream);
+
+/* ---- stage 3: stages.__correct_levels (stages.py:138-170) -----------------------------------
+ * rms_correction_steps iterations of clip -> per-piece RMS -> loudest mask -> coefficient.  The
+ * coefficients accumulate in d_state->gain; the samples are scaled once, by the consumer. */
+int mgb_correct_levels(const mgb_plan* plan, const mgb_track_layout* layout, void* d_workspace,
+                       mgb_track_state* d_state, void* stream);
+
+/* ---- stage 4: stages.__finalize (stages.py:173-207) -----------------------------------------
+ * Any of the three outputs may be NULL (the reference's need_* flags, core.py:81-85):
+ *   d_out_limited     = limit(result * gain) * final_amplitude_coefficient   (stages.py:201-203)
+ *   d_out_no_limiter  = result * gain                                       (stages.py:205)
+ *   d_out_normalized  = normalize(result * gain, normalize_clipped=True)    (stages.py:185-191) */
+int mgb_finalize(const mgb_plan* plan, const mgb_track_layout* layout, const float* d_result_lr,
+                 float* d_out_limited, float* d_out_no_limiter, float* d_out_normalized, void* d_workspace,
+                 mgb_track_state* d_state, void* stream);
+
+/* ---- limiter.limit (limiter/hyrax.py:78-99), standalone ---------------------------------------
+ * d_out = limit(d_in) for `frames` stereo frames.  d_engaged (int32, device) receives 0 when the
+ * reference would return its input untouched (hyrax.py:83-85; d_out is then a copy of d_in). */
+int64_t mgb_limiter_workspace_bytes(const mgb_limiter_params* params, int64_t frames);
+int mgb_limit(const mgb_limiter_params* params, const float* d_in_lr, float* d_out_lr, int64_t frames,
+              void* d_workspace, int64_t workspace_bytes, int32_t* d_engaged, void* stream);
+
+/* ---- whole job with HOST buffers (the call the end-to-end benchmark times) --------------------
+ * h_* are host pointers (pinned for full speed).  Copies target and reference to the device,
+ * runs stages 1-4 and copies the requested outputs back; synchronises `stream` before returning.
+ * d_target / d_reference / d_result / d_out are caller-provided device staging buffers of
+ * target_frames (reference_frames) stereo frames each. */
+int mgb_process_host(const mgb_plan* plan, const mgb_track_layout* layout, const float* h_target_lr,
+                     const float* h_reference_lr, float* h_out_limited, float* h_out_no_limiter,
+                     float* h_out_normalized, float* d_target_lr, float* d_reference_lr, float* d_result_lr,
+                     float* d_out_lr, void* d_workspace, mgb_track_state* d_state, mgb_track_state* h_state_out,
+                     void* stream);
+
+/* float64 <-> float32 interleaved conversion on the device (the reference hands float64 arrays
+ * to stages.main; core.py:53-62 / soundfile's default read dtype). */
+int mgb_convert_f64_to_f32(const double* d_in, float* d_out, int64_t count, void* stream);
+int mgb_convert_f32_to_f64(const float* d_in, double* d_out, int64_t count, void* stream);
+
+/* ---- building blocks exported for the parity tests (tests/ only) ------------------------------ */
+/* forward or inverse (dir = +1 / -1) complex FFT of `batch` frames of n points through the same
+ * shared-memory kernel the pipeline uses; is_f64 selects the double variant (n in {F, 2F}). */
+int mgb_test_fft(int32_t n, int32_t is_f64, int32_t dir, const void* d_in, void* d_out, int32_t batch,
+                 const void* d_twiddles, void* stream);
+/* the FIR design alone from given average spectra: d_avg = [4][n_lin] doubles
+ * (target mid, target side, reference mid, reference side), already scaled. d_fir_out [2][F]. */
+int mgb_test_design_fir(const mgb_plan* plan, const double* d_avg, double* d_fir_out, void* d_workspace,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MATCHERING_B200_H */

@@ -1,0 +1,160 @@
+"""ctypes binding of libmatchering_b200.so (include/matchering_b200.h).
+
+The product has exactly one compute path: the nvcc-built CUDA library next to this file.  If it
+is missing or fails to load, importing the GPU entry points raises -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libmatchering_b200.so")
+
+MGB_OK = 0
+MGB_ERR_INVALID = -1
+MGB_ERR_UNSUPPORTED = -2
+MGB_ERR_WORKSPACE = -3
+MGB_ERR_CUDA = -4
+MGB_MAX_CORRECTION_STEPS = 16
+
+
+class LimiterParams(C.Structure):
+    _fields_ = [
+        ("threshold", C.c_double),
+        ("reach", C.c_int32),
+        ("hold", C.c_int32),
+        ("warmup", C.c_int32),
+        ("reserved", C.c_int32),
+        ("attack_c", C.c_double),
+        ("hold_b0", C.c_double), ("hold_b1", C.c_double), ("hold_a1", C.c_double),
+        ("release_b0", C.c_double), ("release_b1", C.c_double), ("release_a1", C.c_double),
+    ]
+
+
+class Plan(C.Structure):
+    _fields_ = [
+        ("sample_rate", C.c_int32),
+        ("fft_size", C.c_int32),
+        ("n_lin", C.c_int32), ("n_log", C.c_int32),
+        ("rms_correction_steps", C.c_int32),
+        ("lowess_k", C.c_int32),
+        ("lowess_nfit", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("max_piece_size", C.c_double),
+        ("threshold", C.c_double),
+        ("min_value", C.c_double),
+        ("limiter", LimiterParams),
+        ("d_sa_hinv", C.c_void_p), ("d_sa_lu", C.c_void_p), ("d_sa_end", C.c_void_p),
+        ("d_sa_eval_idx", C.c_void_p), ("d_sa_eval_w", C.c_void_p),
+        ("d_sb_hinv", C.c_void_p), ("d_sb_lu", C.c_void_p), ("d_sb_end", C.c_void_p),
+        ("d_sb_eval_idx", C.c_void_p), ("d_sb_eval_w", C.c_void_p),
+        ("d_lw_x", C.c_void_p), ("d_lw_fit_idx", C.c_void_p), ("d_lw_fit_left", C.c_void_p),
+        ("d_lw_seg", C.c_void_p),
+        ("d_hann", C.c_void_p),
+        ("d_tw_f32_F", C.c_void_p), ("d_tw_f32_2F", C.c_void_p),
+        ("d_tw_f64_F", C.c_void_p), ("d_tw_f64_2F", C.c_void_p),
+    ]
+
+
+class TrackState(C.Structure):
+    _fields_ = [
+        ("reference_peak", C.c_double),
+        ("final_amplitude_coef", C.c_double),
+        ("target_match_rms", C.c_double),
+        ("reference_match_rms", C.c_double),
+        ("rms_coefficient", C.c_double),
+        ("gain", C.c_double),
+        ("correction", C.c_double * MGB_MAX_CORRECTION_STEPS),
+        ("result_peak", C.c_double),
+        ("normalize_coef", C.c_double),
+        ("conv_peak_bits", C.c_float),
+        ("target_loud_pieces", C.c_int32),
+        ("reference_loud_pieces", C.c_int32),
+        ("limiter_engaged", C.c_int32),
+        ("steps_done", C.c_int32),
+        ("reserved", C.c_int32 * 3),
+    ]
+
+
+class TrackLayout(C.Structure):
+    _fields_ = [
+        ("target_frames", C.c_int64), ("reference_frames", C.c_int64),
+        ("target_piece", C.c_int64), ("reference_piece", C.c_int64),
+        ("target_divisions", C.c_int32), ("reference_divisions", C.c_int32),
+        ("target_slots", C.c_int32), ("reference_slots", C.c_int32),
+        ("workspace_bytes", C.c_int64),
+    ]
+
+
+# name -> (restype, argtypes): every symbol include/matchering_b200.h declares
+PROTOTYPES = {
+    "mgb_version": (C.c_int, []),
+    "mgb_last_error_string": (C.c_char_p, []),
+    "mgb_set_option": (C.c_int, [C.c_char_p, C.c_int]),
+    "mgb_plan_twiddle_bytes": (C.c_int, [C.c_int32, C.POINTER(C.c_int64)]),
+    "mgb_plan_fill_twiddles": (C.c_int, [C.POINTER(Plan), C.c_void_p]),
+    "mgb_track_layout_init": (C.c_int, [C.POINTER(Plan), C.c_int64, C.c_int64, C.POINTER(TrackLayout)]),
+    "mgb_match_levels": (C.c_int, [C.POINTER(Plan), C.POINTER(TrackLayout), C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]),
+    "mgb_match_frequencies": (C.c_int, [C.POINTER(Plan), C.POINTER(TrackLayout), C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mgb_correct_levels": (C.c_int, [C.POINTER(Plan), C.POINTER(TrackLayout), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mgb_finalize": (C.c_int, [C.POINTER(Plan), C.POINTER(TrackLayout), C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mgb_limiter_workspace_bytes": (C.c_int64, [C.POINTER(LimiterParams), C.c_int64]),
+    "mgb_limit": (C.c_int, [C.POINTER(LimiterParams), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                            C.c_void_p, C.c_void_p]),
+    "mgb_process_host": (C.c_int, [C.POINTER(Plan), C.POINTER(TrackLayout), C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mgb_convert_f64_to_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "mgb_convert_f32_to_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "mgb_test_fft": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                               C.c_void_p]),
+    "mgb_test_design_fir": (C.c_int, [C.POINTER(Plan), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+
+
+class NativeError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"matchering_b200 native call failed ({status}): {message}")
+        self.status = status
+
+
+def bind(lib: C.CDLL) -> C.CDLL:
+    """Attach prototypes; raises AttributeError if the library lacks a declared symbol."""
+    for name, (restype, argtypes) in PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    return lib
+
+
+def check(lib: C.CDLL, status: int) -> None:
+    if status != MGB_OK:
+        msg = lib.mgb_last_error_string()
+        text = msg.decode("utf-8", "replace") if msg else ""
+        if status == MGB_ERR_UNSUPPORTED:
+            from .plan import UnsupportedConfig
+            raise UnsupportedConfig(text)
+        if status == MGB_ERR_INVALID:
+            raise ValueError(text)
+        raise NativeError(status, text)
+
+
+_LIB = None
+
+
+def load() -> C.CDLL:
+    """The CUDA library, loaded once.  Fails loudly when it has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m matchering_b200.build` "
+                "(nvcc, sm_100a). matchering_b200 has no CPU fallback.")
+        _LIB = bind(C.CDLL(LIB_PATH))
+        if _LIB.mgb_version() < 100:
+            raise ImportError("libmatchering_b200.so is older than this package")
+    return _LIB

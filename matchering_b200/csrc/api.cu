@@ -1,0 +1,453 @@
+// C ABI of libmatchering_b200 (include/matchering_b200.h): argument checking, workspace carving,
+// stage sequencing.  No kernel lives here except the FFT test harness.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "fft.cuh"
+#include "kernels.cuh"
+
+namespace mgb {
+
+int g_use_tma = 1;
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+#ifdef MGB_EMULATE
+int cuda_status(const char*) { return MGB_OK; }
+int num_sms() { return 8; }
+#else
+int cuda_status(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) return MGB_OK;
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return MGB_ERR_CUDA;
+}
+int num_sms() {
+    static int cached = 0;
+    if (!cached) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            cached = n;
+        else
+            cached = 148;
+    }
+    return cached;
+}
+#endif
+
+static inline int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
+
+Workspace carve_workspace(const mgb_plan& plan, const mgb_track_layout& L, void* base_ptr) {
+    Workspace w;
+    unsigned char* base = reinterpret_cast<unsigned char*>(base_ptr);
+    int64_t off = 0;
+    auto take = [&](int64_t bytes) {
+        unsigned char* p = base ? base + off : nullptr;
+        off += align256(bytes);
+        return p;
+    };
+    const int64_t HB = plan.n_lin, F = plan.fft_size;
+    const int64_t items_t = (int64_t)L.target_divisions * L.target_slots;
+    const int64_t items_r = (int64_t)L.reference_divisions * L.reference_slots;
+    w.spec_part_t = (float*)take(items_t * 2 * HB * 4);
+    w.spec_part_r = (float*)take(items_r * 2 * HB * 4);
+    w.sumsq_part_t = (double*)take(items_t * 8);
+    w.sumsq_part_r = (double*)take(items_r * 8);
+    w.absmax_part_t = (float*)take((items_t + 1) * 4);
+    w.absmax_part_r = (float*)take((items_r + 1) * 4);
+    w.mask_t = take(L.target_divisions);
+    w.mask_r = take(L.reference_divisions);
+    w.design_stride = (design_doubles_per_channel(plan) + 31) / 32 * 32;
+    w.design = (double*)take(2 * w.design_stride * 8);
+    w.h_mid = (float2*)take((F + 1) * 8);
+    w.h_side = (float2*)take((F + 1) * 8);
+    w.mid_plane = (float*)take(L.target_frames * 4);
+    w.zero_begin = base ? base + off : nullptr;
+    w.piece_sums = (double*)take((int64_t)MGB_MAX_CORRECTION_STEPS * L.target_divisions * 8);
+    w.limiter_ticket = (int*)take(16);
+    w.lookback = take(limiter_lookback_bytes(L.target_frames));
+    w.zero_end = base ? base + off : nullptr;
+    w.total_bytes = off;
+    return w;
+}
+
+static int check_plan(const mgb_plan* plan) {
+    MGB_REQUIRE(plan != nullptr, MGB_ERR_INVALID, "plan is NULL");
+    const int F = plan->fft_size;
+    MGB_REQUIRE(F == 1024 || F == 2048 || F == 4096 || F == 8192, MGB_ERR_UNSUPPORTED,
+                "fft_size %d: kernels exist for 1024, 2048, 4096, 8192", F);
+    MGB_REQUIRE(plan->n_lin == F / 2 + 1 && plan->n_log >= 4, MGB_ERR_INVALID, "plan grid sizes inconsistent");
+    MGB_REQUIRE(plan->rms_correction_steps >= 0 && plan->rms_correction_steps <= MGB_MAX_CORRECTION_STEPS,
+                MGB_ERR_UNSUPPORTED, "rms_correction_steps %d > %d", plan->rms_correction_steps, MGB_MAX_CORRECTION_STEPS);
+    MGB_REQUIRE(plan->lowess_k >= 2 && plan->lowess_k <= plan->n_log && plan->lowess_nfit >= 2, MGB_ERR_INVALID,
+                "plan LOWESS sizes inconsistent");
+    return MGB_OK;
+}
+
+static int check_aligned(const void* p, const char* name) {
+    MGB_REQUIRE(p != nullptr, MGB_ERR_INVALID, "%s is NULL", name);
+    MGB_REQUIRE((reinterpret_cast<uintptr_t>(p) & 15) == 0, MGB_ERR_INVALID, "%s is not 16-byte aligned", name);
+    return MGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FFT test harness: one frame per CTA through fft_run, global -> shared -> global
+// ------------------------------------------------------------------------------------------------
+template <int N, int DIR, typename T, int THREADS>
+__global__ void __launch_bounds__(THREADS) test_fft_kernel(const cpx<T>* __restrict__ in, cpx<T>* __restrict__ out,
+                                                           const cpx<T>* __restrict__ tw) {
+    MGB_DYN_SMEM(smem);
+    T* re = reinterpret_cast<T*>(smem);
+    T* im = re + fft_padded_size(N);
+    const cpx<T>* src = in + (long long)blockIdx.x * N;
+    cpx<T>* dst = out + (long long)blockIdx.x * N;
+    auto first = [&](int i) { return src[i]; };
+    auto last = [&](int i, cpx<T> v) { dst[i] = v; };
+    fft_run<N, DIR, THREADS, T>(re, im, tw, first, last, false, false);
+}
+
+template <int N, typename T, int THREADS>
+static int launch_test_fft_t(int dir, const void* in, void* out, int batch, const void* tw, cudaStream_t stream) {
+    const size_t smem = 2 * (size_t)fft_padded_size(N) * sizeof(T);
+    if (dir > 0)
+        return launch("test_fft_kernel", test_fft_kernel<N, +1, T, THREADS>, dim3(batch), dim3(THREADS), smem, stream,
+                      (const cpx<T>*)in, (cpx<T>*)out, (const cpx<T>*)tw);
+    return launch("test_fft_kernel", test_fft_kernel<N, -1, T, THREADS>, dim3(batch), dim3(THREADS), smem, stream,
+                  (const cpx<T>*)in, (cpx<T>*)out, (const cpx<T>*)tw);
+}
+
+int launch_test_fft(int n, int is_f64, int dir, const void* in, void* out, int batch, const void* tw,
+                    cudaStream_t stream) {
+#define MGB_FFT_CASE(NN)                                                                                      \
+    case NN:                                                                                                  \
+        return is_f64 ? launch_test_fft_t<NN, double, 512>(dir, in, out, batch, tw, stream)                   \
+                      : launch_test_fft_t<NN, float, NN / 16>(dir, in, out, batch, tw, stream);
+    switch (n) {
+        MGB_FFT_CASE(1024)
+        MGB_FFT_CASE(2048)
+        MGB_FFT_CASE(4096)
+        MGB_FFT_CASE(8192)
+        case 16384:
+            if (!is_f64) return launch_test_fft_t<16384, float, 1024>(dir, in, out, batch, tw, stream);
+            break;
+        default: break;
+    }
+#undef MGB_FFT_CASE
+    set_error("fft: size %d (%s) has no kernel", n, is_f64 ? "f64" : "f32");
+    return MGB_ERR_UNSUPPORTED;
+}
+
+template <int N>
+static void radices_of(int* npass, int r[4]) {
+    *npass = Radices<N>::n;
+    for (int i = 0; i < 4; ++i) r[i] = Radices<N>::r[i];
+}
+static bool radix_schedule(int n, int* npass, int r[4]) {
+    switch (n) {
+        case 1024: radices_of<1024>(npass, r); return true;
+        case 2048: radices_of<2048>(npass, r); return true;
+        case 4096: radices_of<4096>(npass, r); return true;
+        case 8192: radices_of<8192>(npass, r); return true;
+        case 16384: radices_of<16384>(npass, r); return true;
+        default: return false;
+    }
+}
+int twiddle_count(int n) {
+    int npass, r[4];
+    if (!radix_schedule(n, &npass, r)) return -1;
+    int total = 0, ns = r[0];
+    for (int p = 1; p < npass; ++p) {
+        total += (r[p] - 1) * ns;
+        ns *= r[p];
+    }
+    return total;
+}
+int fill_twiddles(int n, int is_f64, void* table, cudaStream_t stream) {
+    int npass, r[4];
+    MGB_REQUIRE(radix_schedule(n, &npass, r), MGB_ERR_UNSUPPORTED, "fft: size %d has no radix schedule", n);
+    if (is_f64)
+        return launch("fft_twiddle_kernel", fft_twiddle_kernel<double>, dim3(16), dim3(256), 0, stream, (cpx<double>*)table,
+                      npass, r[0], r[1], r[2], r[3]);
+    return launch("fft_twiddle_kernel", fft_twiddle_kernel<float>, dim3(16), dim3(256), 0, stream, (cpx<float>*)table,
+                  npass, r[0], r[1], r[2], r[3]);
+}
+
+}  // namespace mgb
+
+using namespace mgb;
+
+// ================================================================================================
+extern "C" {
+
+int mgb_version(void) { return MGB_VERSION; }
+const char* mgb_last_error_string(void) { return g_error; }
+
+int mgb_set_option(const char* name, int value) {
+    MGB_REQUIRE(name != nullptr, MGB_ERR_INVALID, "option name is NULL");
+    if (strcmp(name, "tma") == 0) {
+        g_use_tma = value ? 1 : 0;
+        return MGB_OK;
+    }
+    set_error("unknown option '%s'", name);
+    return MGB_ERR_INVALID;
+}
+
+int mgb_plan_twiddle_bytes(int32_t fft_size, int64_t bytes_out[4]) {
+    MGB_REQUIRE(bytes_out != nullptr, MGB_ERR_INVALID, "bytes_out is NULL");
+    const int cf = twiddle_count(fft_size), c2 = twiddle_count(2 * fft_size);
+    MGB_REQUIRE(cf > 0 && c2 > 0, MGB_ERR_UNSUPPORTED, "fft_size %d has no kernel", fft_size);
+    bytes_out[0] = (int64_t)cf * 8;
+    bytes_out[1] = (int64_t)c2 * 8;
+    bytes_out[2] = (int64_t)cf * 16;
+    bytes_out[3] = (int64_t)c2 * 16;
+    return MGB_OK;
+}
+
+int mgb_plan_fill_twiddles(const mgb_plan* plan, void* stream) {
+    MGB_TRY(check_plan(plan));
+    cudaStream_t st = (cudaStream_t)stream;
+    MGB_TRY(check_aligned(plan->d_tw_f32_F, "d_tw_f32_F"));
+    MGB_TRY(check_aligned(plan->d_tw_f32_2F, "d_tw_f32_2F"));
+    MGB_TRY(check_aligned(plan->d_tw_f64_F, "d_tw_f64_F"));
+    MGB_TRY(fill_twiddles(plan->fft_size, 0, plan->d_tw_f32_F, st));
+    MGB_TRY(fill_twiddles(2 * plan->fft_size, 0, plan->d_tw_f32_2F, st));
+    MGB_TRY(fill_twiddles(plan->fft_size, 1, plan->d_tw_f64_F, st));
+    if (plan->d_tw_f64_2F && plan->fft_size <= 4096) MGB_TRY(fill_twiddles(2 * plan->fft_size, 1, plan->d_tw_f64_2F, st));
+    return MGB_OK;
+}
+
+int mgb_track_layout_init(const mgb_plan* plan, int64_t target_frames, int64_t reference_frames,
+                          mgb_track_layout* out) {
+    MGB_TRY(check_plan(plan));
+    MGB_REQUIRE(out != nullptr, MGB_ERR_INVALID, "layout is NULL");
+    // core.py:69-74 guarantees both signals are longer than fft_size
+    MGB_REQUIRE(target_frames > plan->fft_size && reference_frames > plan->fft_size, MGB_ERR_INVALID,
+                "target (%lld) and reference (%lld) must be longer than fft_size (%d)", (long long)target_frames,
+                (long long)reference_frames, plan->fft_size);
+    MGB_REQUIRE(plan->max_piece_size > 0, MGB_ERR_INVALID, "max_piece_size must be positive");
+    memset(out, 0, sizeof(*out));
+    out->target_frames = target_frames;
+    out->reference_frames = reference_frames;
+    const int sms = num_sms();
+    for (int sig = 0; sig < 2; ++sig) {
+        const int64_t n = sig == 0 ? target_frames : reference_frames;
+        // match_levels.py:47-59: float division, then int() truncation
+        const double q = (double)n / plan->max_piece_size;
+        MGB_REQUIRE(q < 1.0e6, MGB_ERR_UNSUPPORTED, "more than a million pieces");
+        const int32_t divisions = (int32_t)q + 1;
+        const int64_t piece = (int64_t)((double)n / (double)divisions);
+        MGB_REQUIRE(piece >= plan->fft_size, MGB_ERR_UNSUPPORTED,
+                    "piece of %lld samples is shorter than fft_size %d (the reference's STFT degenerates there)",
+                    (long long)piece, plan->fft_size);
+        const int64_t frames_per_piece = piece / plan->fft_size;
+        int64_t slots = (2LL * sms + divisions - 1) / divisions;
+        if (slots > frames_per_piece) slots = frames_per_piece;
+        if (slots < 1) slots = 1;
+        if (sig == 0) {
+            out->target_divisions = divisions;
+            out->target_piece = piece;
+            out->target_slots = (int32_t)slots;
+        } else {
+            out->reference_divisions = divisions;
+            out->reference_piece = piece;
+            out->reference_slots = (int32_t)slots;
+        }
+    }
+    out->workspace_bytes = carve_workspace(*plan, *out, nullptr).total_bytes;
+    return MGB_OK;
+}
+
+int mgb_match_levels(const mgb_plan* plan, const mgb_track_layout* L, const float* d_target_lr,
+                     const float* d_reference_lr, void* d_workspace, mgb_track_state* d_state, void* stream) {
+    MGB_TRY(check_plan(plan));
+    MGB_REQUIRE(L != nullptr && d_state != nullptr, MGB_ERR_INVALID, "layout/state is NULL");
+    MGB_TRY(check_aligned(d_target_lr, "d_target_lr"));
+    MGB_TRY(check_aligned(d_reference_lr, "d_reference_lr"));
+    MGB_TRY(check_aligned(d_workspace, "d_workspace"));
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace ws = carve_workspace(*plan, *L, d_workspace);
+#ifdef MGB_EMULATE
+    memset(ws.zero_begin, 0, ws.zero_end - ws.zero_begin);
+#else
+    if (cudaMemsetAsync(ws.zero_begin, 0, ws.zero_end - ws.zero_begin, st) != cudaSuccess) return cuda_status("memset");
+#endif
+    MGB_TRY(launch_analyze(*plan, (const float2*)d_target_lr, L->target_frames, L->target_piece, L->target_divisions,
+                           L->target_slots, ws.spec_part_t, ws.sumsq_part_t, ws.absmax_part_t, st));
+    MGB_TRY(launch_analyze(*plan, (const float2*)d_reference_lr, L->reference_frames, L->reference_piece,
+                           L->reference_divisions, L->reference_slots, ws.spec_part_r, ws.sumsq_part_r,
+                           ws.absmax_part_r, st));
+    return launch_levels(*plan, *L, ws, d_state, st);
+}
+
+int mgb_match_frequencies(const mgb_plan* plan, const mgb_track_layout* L, const float* d_target_lr,
+                          float* d_result_lr, double* d_fir_out, void* d_workspace, mgb_track_state* d_state,
+                          void* stream) {
+    MGB_TRY(check_plan(plan));
+    MGB_REQUIRE(L != nullptr && d_state != nullptr, MGB_ERR_INVALID, "layout/state is NULL");
+    MGB_TRY(check_aligned(d_target_lr, "d_target_lr"));
+    MGB_TRY(check_aligned(d_result_lr, "d_result_lr"));
+    MGB_TRY(check_aligned(d_workspace, "d_workspace"));
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace ws = carve_workspace(*plan, *L, d_workspace);
+    MGB_TRY(launch_design(*plan, *L, ws, nullptr, d_fir_out, d_state, st));
+    return launch_convolve(*plan, *L, (const float2*)d_target_lr, (float2*)d_result_lr, ws, d_state, st);
+}
+
+int mgb_correct_levels(const mgb_plan* plan, const mgb_track_layout* L, void* d_workspace, mgb_track_state* d_state,
+                       void* stream) {
+    MGB_TRY(check_plan(plan));
+    MGB_REQUIRE(L != nullptr && d_state != nullptr, MGB_ERR_INVALID, "layout/state is NULL");
+    MGB_TRY(check_aligned(d_workspace, "d_workspace"));
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace ws = carve_workspace(*plan, *L, d_workspace);
+    for (int step = 0; step < plan->rms_correction_steps; ++step) {
+        // step 0's per-piece sums were produced by the convolution's epilogue (gain is still 1)
+        if (step > 0) MGB_TRY(launch_clip_sumsq(*plan, *L, ws, step, d_state, st));
+        MGB_TRY(launch_correction_update(*plan, *L, ws, step, d_state, st));
+    }
+    return launch_finalize_scalars(*plan, d_state, st);
+}
+
+int mgb_finalize(const mgb_plan* plan, const mgb_track_layout* L, const float* d_result_lr, float* d_out_limited,
+                 float* d_out_no_limiter, float* d_out_normalized, void* d_workspace, mgb_track_state* d_state,
+                 void* stream) {
+    MGB_TRY(check_plan(plan));
+    MGB_REQUIRE(L != nullptr && d_state != nullptr, MGB_ERR_INVALID, "layout/state is NULL");
+    MGB_TRY(check_aligned(d_result_lr, "d_result_lr"));
+    MGB_TRY(check_aligned(d_workspace, "d_workspace"));
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace ws = carve_workspace(*plan, *L, d_workspace);
+    const float2* res = (const float2*)d_result_lr;
+    if (d_out_normalized) {
+        MGB_TRY(check_aligned(d_out_normalized, "d_out_normalized"));
+        MGB_TRY(launch_scale(res, (float2*)d_out_normalized, L->target_frames, &d_state->gain, &d_state->normalize_coef, st));
+    }
+    if (d_out_no_limiter) {
+        MGB_TRY(check_aligned(d_out_no_limiter, "d_out_no_limiter"));
+        MGB_TRY(launch_scale(res, (float2*)d_out_no_limiter, L->target_frames, &d_state->gain, nullptr, st));
+    }
+    if (d_out_limited) {
+        MGB_TRY(check_aligned(d_out_limited, "d_out_limited"));
+        MGB_TRY(launch_limiter(plan->limiter, res, (float2*)d_out_limited, L->target_frames, &d_state->gain,
+                               &d_state->final_amplitude_coef, &d_state->limiter_engaged, ws.limiter_ticket,
+                               (LookbackSlot*)ws.lookback, st));
+    }
+    return MGB_OK;
+}
+
+int64_t mgb_limiter_workspace_bytes(const mgb_limiter_params* params, int64_t frames) {
+    (void)params;
+    if (frames <= 0) return 256;
+    return 256 + limiter_lookback_bytes(frames);
+}
+
+int mgb_limit(const mgb_limiter_params* params, const float* d_in_lr, float* d_out_lr, int64_t frames,
+              void* d_workspace, int64_t workspace_bytes, int32_t* d_engaged, void* stream) {
+    MGB_REQUIRE(params != nullptr, MGB_ERR_INVALID, "params is NULL");
+    MGB_TRY(check_aligned(d_in_lr, "d_in_lr"));
+    MGB_TRY(check_aligned(d_out_lr, "d_out_lr"));
+    MGB_TRY(check_aligned(d_workspace, "d_workspace"));
+    MGB_REQUIRE(d_engaged != nullptr, MGB_ERR_INVALID, "d_engaged is NULL");
+    MGB_REQUIRE(frames > 6, MGB_ERR_INVALID, "limit: the input must be longer than filtfilt's padlen (6)");
+    MGB_REQUIRE(workspace_bytes >= mgb_limiter_workspace_bytes(params, frames), MGB_ERR_WORKSPACE,
+                "limit: workspace of %lld bytes, need %lld", (long long)workspace_bytes,
+                (long long)mgb_limiter_workspace_bytes(params, frames));
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* base = (unsigned char*)d_workspace;
+    // [0,4): peak bits  [16,20): ticket  [256, ...): look-back slots
+#ifdef MGB_EMULATE
+    memset(base, 0, 256 + limiter_lookback_bytes(frames));
+#else
+    if (cudaMemsetAsync(base, 0, 256 + limiter_lookback_bytes(frames), st) != cudaSuccess) return cuda_status("memset");
+#endif
+    float* peak = (float*)base;
+    int* ticket = (int*)(base + 16);
+    MGB_TRY(launch_absmax((const float2*)d_in_lr, frames, peak, st));
+    MGB_TRY(launch_limiter_engaged(peak, nullptr, params->threshold, d_engaged, st));
+    return launch_limiter(*params, (const float2*)d_in_lr, (float2*)d_out_lr, frames, nullptr, nullptr, d_engaged, ticket,
+                          (LookbackSlot*)(base + 256), st);
+}
+
+int mgb_process_host(const mgb_plan* plan, const mgb_track_layout* L, const float* h_target_lr,
+                     const float* h_reference_lr, float* h_out_limited, float* h_out_no_limiter,
+                     float* h_out_normalized, float* d_target_lr, float* d_reference_lr, float* d_result_lr,
+                     float* d_out_lr, void* d_workspace, mgb_track_state* d_state, mgb_track_state* h_state_out,
+                     void* stream) {
+    MGB_TRY(check_plan(plan));
+    MGB_REQUIRE(L && h_target_lr && h_reference_lr && d_state, MGB_ERR_INVALID, "NULL argument");
+    MGB_REQUIRE(h_out_limited || h_out_no_limiter || h_out_normalized, MGB_ERR_INVALID, "no output requested");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t tbytes = (size_t)L->target_frames * 8, rbytes = (size_t)L->reference_frames * 8;
+#ifdef MGB_EMULATE
+    memcpy(d_target_lr, h_target_lr, tbytes);
+    memcpy(d_reference_lr, h_reference_lr, rbytes);
+#else
+    if (cudaMemcpyAsync(d_target_lr, h_target_lr, tbytes, cudaMemcpyHostToDevice, st) != cudaSuccess) return cuda_status("H2D target");
+    if (cudaMemcpyAsync(d_reference_lr, h_reference_lr, rbytes, cudaMemcpyHostToDevice, st) != cudaSuccess) return cuda_status("H2D reference");
+#endif
+    MGB_TRY(mgb_match_levels(plan, L, d_target_lr, d_reference_lr, d_workspace, d_state, stream));
+    MGB_TRY(mgb_match_frequencies(plan, L, d_target_lr, d_result_lr, nullptr, d_workspace, d_state, stream));
+    MGB_TRY(mgb_correct_levels(plan, L, d_workspace, d_state, stream));
+    float* outs[3] = {h_out_limited, h_out_no_limiter, h_out_normalized};
+    for (int k = 0; k < 3; ++k) {
+        if (!outs[k]) continue;
+        MGB_TRY(mgb_finalize(plan, L, d_result_lr, k == 0 ? d_out_lr : nullptr, k == 1 ? d_out_lr : nullptr,
+                             k == 2 ? d_out_lr : nullptr, d_workspace, d_state, stream));
+#ifdef MGB_EMULATE
+        memcpy(outs[k], d_out_lr, tbytes);
+#else
+        if (cudaMemcpyAsync(outs[k], d_out_lr, tbytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) return cuda_status("D2H result");
+#endif
+    }
+#ifdef MGB_EMULATE
+    if (h_state_out) memcpy(h_state_out, d_state, sizeof(mgb_track_state));
+#else
+    if (h_state_out && cudaMemcpyAsync(h_state_out, d_state, sizeof(mgb_track_state), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+        return cuda_status("D2H state");
+    if (cudaStreamSynchronize(st) != cudaSuccess) return cuda_status("stream sync");
+#endif
+    return MGB_OK;
+}
+
+int mgb_convert_f64_to_f32(const double* d_in, float* d_out, int64_t count, void* stream) {
+    MGB_REQUIRE(d_in && d_out && count >= 0, MGB_ERR_INVALID, "convert: bad arguments");
+    return launch_convert_f64_f32(d_in, d_out, count, (cudaStream_t)stream);
+}
+int mgb_convert_f32_to_f64(const float* d_in, double* d_out, int64_t count, void* stream) {
+    MGB_REQUIRE(d_in && d_out && count >= 0, MGB_ERR_INVALID, "convert: bad arguments");
+    return launch_convert_f32_f64(d_in, d_out, count, (cudaStream_t)stream);
+}
+
+int mgb_test_fft(int32_t n, int32_t is_f64, int32_t dir, const void* d_in, void* d_out, int32_t batch,
+                 const void* d_twiddles, void* stream) {
+    MGB_REQUIRE(d_in && d_out && d_twiddles && batch > 0, MGB_ERR_INVALID, "test_fft: bad arguments");
+    return launch_test_fft(n, is_f64, dir, d_in, d_out, batch, d_twiddles, (cudaStream_t)stream);
+}
+
+int mgb_test_design_fir(const mgb_plan* plan, const double* d_avg, double* d_fir_out, void* d_workspace, void* stream) {
+    MGB_TRY(check_plan(plan));
+    MGB_REQUIRE(d_avg && d_fir_out, MGB_ERR_INVALID, "test_design_fir: NULL argument");
+    MGB_TRY(check_aligned(d_workspace, "d_workspace"));
+    // workspace: [2][stride] doubles then two (F+1) float2 spectra
+    Workspace ws;
+    memset(&ws, 0, sizeof(ws));
+    ws.design_stride = (design_doubles_per_channel(*plan) + 31) / 32 * 32;
+    ws.design = (double*)d_workspace;
+    ws.h_mid = (float2*)((unsigned char*)d_workspace + align256(2 * ws.design_stride * 8));
+    ws.h_side = ws.h_mid + (plan->fft_size + 1 + 31) / 32 * 32;
+    mgb_track_layout L;
+    memset(&L, 0, sizeof(L));
+    L.target_piece = L.reference_piece = plan->fft_size;
+    return launch_design(*plan, L, ws, d_avg, d_fir_out, nullptr, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,189 @@
+// Shared device helpers for the matchering_b200 kernels (sm_100a).
+//
+// The same sources are also compiled for the host by the test-only emulator
+// (tests/emul/cuda_emul.h, -DMGB_EMULATE); everything PTX-specific therefore lives behind the
+// small wrappers in this file.
+#pragma once
+
+#ifndef MGB_EMULATE
+#include <cuda_runtime.h>
+#endif
+#include <stdint.h>
+
+#include "../../include/matchering_b200.h"
+
+namespace mgb {
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing (no exceptions cross the C ABI)
+// ------------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_status(const char* what);  // 0 or MGB_ERR_CUDA, recording cudaGetLastError()
+
+#define MGB_REQUIRE(cond, code, ...)     \
+    do {                                 \
+        if (!(cond)) {                   \
+            ::mgb::set_error(__VA_ARGS__); \
+            return (code);               \
+        }                                \
+    } while (0)
+
+#define MGB_TRY(expr)                 \
+    do {                              \
+        int mgb_rc_ = (expr);         \
+        if (mgb_rc_ != MGB_OK) return mgb_rc_; \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// launch helper
+// ------------------------------------------------------------------------------------------------
+#ifdef MGB_EMULATE
+#define MGB_DYN_SMEM(name) unsigned char* name = ::emul::dyn_smem()
+template <typename... KA, typename... A>
+inline int launch(const char* what, void (*kernel)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t,
+                  A... args) {
+    (void)what;
+    if (grid.x == 0 || grid.y == 0 || grid.z == 0) return MGB_OK;
+    ::emul::launch(grid, block, smem, [&]() { kernel(static_cast<KA>(args)...); });
+    return MGB_OK;
+}
+#else
+#define MGB_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+template <typename... KA, typename... A>
+inline int launch(const char* what, void (*kernel)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                  A... args) {
+    if (grid.x == 0 || grid.y == 0 || grid.z == 0) return MGB_OK;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("%s: cudaFuncSetAttribute(%zu B smem): %s", what, smem, cudaGetErrorString(e));
+            return MGB_ERR_CUDA;
+        }
+    }
+    kernel<<<grid, block, smem, stream>>>(static_cast<KA>(args)...);
+    return cuda_status(what);
+}
+#endif
+
+int num_sms();
+
+// ------------------------------------------------------------------------------------------------
+// small numeric helpers
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct cpx {
+    T x, y;
+};
+template <typename T>
+__device__ __forceinline__ cpx<T> cmul(cpx<T> a, cpx<T> b) {
+    return cpx<T>{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
+}
+template <typename T>
+__device__ __forceinline__ cpx<T> cadd(cpx<T> a, cpx<T> b) { return cpx<T>{a.x + b.x, a.y + b.y}; }
+template <typename T>
+__device__ __forceinline__ cpx<T> csub(cpx<T> a, cpx<T> b) { return cpx<T>{a.x - b.x, a.y - b.y}; }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-wide sum of a double; result valid in thread 0 (and broadcast through `scratch[0]`
+// after the trailing barrier).  `scratch` holds >= 32 doubles.  All threads must call.
+__device__ __forceinline__ double block_sum(double v, double* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();  // scratch may still be read from a previous call
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        double t = (lane < nwarps) ? scratch[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) scratch[0] = t;
+    }
+    __syncthreads();
+    return scratch[0];
+}
+__device__ __forceinline__ float block_max(float v, float* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        float t = (lane < nwarps) ? scratch[lane] : 0.0f;
+        t = warp_max(t);
+        if (lane == 0) scratch[0] = t;
+    }
+    __syncthreads();
+    return scratch[0];
+}
+
+// Non-negative floats order like their bit patterns: atomic max through the integer unit.
+__device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
+    atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA 1-D bulk copy (cp.async.bulk, SASS UBLKCP) completing on an mbarrier.
+// One thread arms the barrier with the byte count and issues the copy; every consumer waits on
+// the barrier's phase parity.  Sizes and both addresses must be multiples of 16 bytes.
+// ------------------------------------------------------------------------------------------------
+#ifdef MGB_EMULATE
+struct TmaBarrier {
+    volatile unsigned phase_done;  // number of completed phases
+};
+__device__ __forceinline__ void tma_barrier_init(TmaBarrier* b) { b->phase_done = 0; }
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, TmaBarrier* b) {
+    if (bytes) memcpy(smem_dst, gmem_src, bytes);
+    b->phase_done = b->phase_done + 1;
+}
+__device__ __forceinline__ void tma_barrier_wait(TmaBarrier* b, uint32_t phase_index) {
+    while (b->phase_done <= phase_index) ::emul::yield();
+}
+__device__ __forceinline__ void fence_proxy_async() {}
+#else
+struct __align__(8) TmaBarrier {
+    unsigned long long bar;
+};
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void tma_barrier_init(TmaBarrier* b) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&b->bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, TmaBarrier* b) {
+    // bytes == 0 still has to complete the phase: a plain arrive does that.
+    if (bytes == 0) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&b->bar)) : "memory");
+        return;
+    }
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&b->bar)), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(&b->bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_barrier_wait(TmaBarrier* b, uint32_t phase_index) {
+    const uint32_t parity = phase_index & 1u;
+    const uint32_t addr = smem_u32(&b->bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+#endif
+
+}  // namespace mgb

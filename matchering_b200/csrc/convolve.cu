@@ -1,0 +1,214 @@
+// K4 -- overlap-save FFT convolution of the target's mid/side with the two matching FIRs.
+//
+// Replaces (reference file:line):
+//   match_frequencies.convolve        stage_helpers/match_frequencies.py:104-119
+//     = scipy.signal.fftconvolve(x, fir, "same") per channel: full linear convolution sliced at
+//       (F-1)//2 = F/2-1, edges zero-padded (scipy/signal/_signaltools.py fftconvolve/_centered)
+//   dsp.lr_to_ms / dsp.ms_to_lr       dsp.py:57-68   (fused into the load and the store)
+//   dsp.amplify by the RMS coefficient match_levels.py:114-131 (folded into the FIR spectra)
+//   the first RMS-correction step's clip + per-piece sum of squares   stages.py:151-159
+//   the peak that dsp.normalize / the limiter's early-out need        dsp.py:97, hyrax.py:83
+//
+// Framing: the FIR has F taps with fir[0] == 0 (symmetric Hann is zero at index 0), so taps
+// 1..F-1 matter and output sample n needs inputs n-F/2 .. n+F/2-2.  A frame of N = 2F inputs
+// starting at n0 - F/2 therefore yields the F outputs n0 .. n0+F-1 (circular index i = F-1 ..
+// 2F-2), with n0 a multiple of F: every frame start is 16-byte aligned for the TMA bulk copy.
+// mid and side ride one complex transform: z = mid + i*side, Y[k] = Hm[k] M[k] + i Hs[k] S[k]
+// with M, S recovered from Z[k], Z[N-k]; real part of the inverse is the mid output, imaginary
+// part the side output.  The 64 KB landing buffer of the bulk copy is reused in place as the two
+// FFT planes.
+#include "fft.cuh"
+#include "kernels.cuh"
+
+namespace mgb {
+
+namespace {
+
+template <int F>
+struct ConvSmem {
+    static constexpr int N = 2 * F;
+    static constexpr int kPlane = fft_padded_size(N);
+    static constexpr int kBytes = 2 * kPlane * 4 + 16 + 32 * 8 + 32 * 8 + 32 * 4 + 32;
+};
+
+struct ConvFirst {
+    const float2* raw;  // landing buffer, index 0 = sample `origin`
+    long long origin;
+    long long frames;
+    const float2* fixup;
+    int fix_index;
+    __device__ __forceinline__ cpx<float> operator()(int i) const {
+        const long long n = origin + i;
+        float2 v = make_float2(0.0f, 0.0f);
+        if (n >= 0 && n < frames) {
+            v = raw[i];
+            if (i == fix_index) v = *fixup;
+        }
+        const float mid = (v.x + v.y) * 0.5f;  // exact sum rounded once, as (float)((double)L+R)/2
+        return cpx<float>{mid, mid - v.y};
+    }
+};
+
+// Consumes the inverse transform's outputs: circular index i -> output sample n0 + i - (F-1).
+template <int F>
+struct ConvLast {
+    float2* result;
+    float* mid_plane;
+    long long n0, frames, counted;  // counted = piece*divisions: samples that enter the piece RMS
+    long long boundary;             // first sample of the next piece
+    double* sq_a;                   // sum clip(mid)^2 for the frame's first piece / the next one
+    double* sq_b;
+    float* peak;
+    __device__ __forceinline__ void operator()(int i, cpx<float> v) const {
+        if (i < F - 1 || i > 2 * F - 2) return;
+        const long long n = n0 + (i - (F - 1));
+        if (n >= frames) return;
+        const float l = v.x + v.y, r = v.x - v.y;  // dsp.ms_to_lr
+        result[n] = make_float2(l, r);
+        mid_plane[n] = v.x;
+        *peak = fmaxf(*peak, fmaxf(fabsf(l), fabsf(r)));
+        if (n < counted) {
+            const double c = fmin(1.0, fmax(-1.0, (double)v.x));  // dsp.clip
+            if (n < boundary) *sq_a += c * c; else *sq_b += c * c;
+        }
+    }
+};
+
+template <int F>
+__global__ void __launch_bounds__(F / 8)
+convolve_kernel(const float2* __restrict__ x, long long frames, long long piece, int divisions,
+                const cpx<float>* __restrict__ tw, const float2* __restrict__ h_mid,
+                const float2* __restrict__ h_side, float2* __restrict__ result, float* __restrict__ mid_plane,
+                double* __restrict__ piece_sums, mgb_track_state* __restrict__ state, int use_tma) {
+    constexpr int N = 2 * F;
+    constexpr int THREADS = N / 16;
+    using L = ConvSmem<F>;
+    MGB_DYN_SMEM(smem);
+    float* re = reinterpret_cast<float*>(smem);
+    float* im = re + L::kPlane;
+    float2* raw = reinterpret_cast<float2*>(smem);  // aliases the planes until the first pass has gathered
+    unsigned char* tail = reinterpret_cast<unsigned char*>(im + L::kPlane);
+    tail += (16 - (reinterpret_cast<uintptr_t>(tail) & 15)) & 15;
+    TmaBarrier* bar = reinterpret_cast<TmaBarrier*>(tail);
+    double* red_a = reinterpret_cast<double*>(tail + 16);
+    double* red_b = red_a + 32;
+    float* red_f = reinterpret_cast<float*>(red_b + 32);
+
+    const int tid = threadIdx.x;
+    const long long n0 = (long long)blockIdx.x * F;
+    const long long origin = n0 - F / 2;
+
+    // ---- load the frame's 2F input samples (clipped to the signal) -----------------------------
+    const long long lo = origin < 0 ? 0 : origin;
+    const long long hi = (origin + N < frames) ? origin + N : frames;  // exclusive
+    ConvFirst first;
+    first.raw = raw;
+    first.origin = origin;
+    first.frames = frames;
+    first.fixup = nullptr;
+    first.fix_index = -1;
+    if (use_tma) {
+        if (tid == 0) tma_barrier_init(bar);
+        __syncthreads();
+        // lo - origin is 0 or F/2 (multiple of 2): source and destination stay 16-byte aligned
+        long long count = hi - lo;
+        if (count & 1) {  // odd tail: the last sample comes through a plain load
+            first.fix_index = (int)(hi - 1 - origin);
+            first.fixup = x + (hi - 1);
+            count -= 1;
+        }
+        if (tid == 0) tma_load_1d(raw + (lo - origin), x + lo, (uint32_t)(count * 8), bar);
+        tma_barrier_wait(bar, 0);
+    } else {
+        for (long long n = lo + tid; n < hi; n += THREADS) raw[n - origin] = x[n];
+        __syncthreads();
+    }
+
+    // ---- forward transform of z = mid + i*side ---------------------------------------------------
+    fft_first_pass<N, +1, THREADS, float>(re, im, tw, first, /*in_place=*/true);
+    __syncthreads();
+    fft_remaining<N, +1, THREADS, float>(re, im, tw, SmemStore<float>{re, im}, true);
+    __syncthreads();
+
+    // ---- apply both FIR spectra on the pair (k, N-k) ---------------------------------------------
+    for (int k = tid; k <= F; k += THREADS) {
+        const int kn = (N - k) & (N - 1);
+        const int ak = fft_pad(k), an = fft_pad(kn);
+        const float zr = re[ak], zi = im[ak], nr = re[an], ni = im[an];
+        // M = (Z[k] + conj Z[N-k])/2 ; S = (Z[k] - conj Z[N-k])/(2i)
+        const float mr = 0.5f * (zr + nr), mi = 0.5f * (zi - ni);
+        const float sr = 0.5f * (zi + ni), si = 0.5f * (nr - zr);
+        const float2 hm = h_mid[k], hs = h_side[k];
+        const float pmr = hm.x * mr - hm.y * mi, pmi = hm.x * mi + hm.y * mr;
+        const float psr = hs.x * sr - hs.y * si, psi = hs.x * si + hs.y * sr;
+        // Y[k] = Pm + i Ps ; Y[N-k] = conj(Pm) + i conj(Ps)
+        re[ak] = pmr - psi;
+        im[ak] = pmi + psr;
+        if (kn != k) {
+            re[an] = pmr + psi;
+            im[an] = psr - pmi;
+        }
+    }
+    __syncthreads();
+
+    // ---- inverse transform; the last pass writes straight to global memory -----------------------
+    double sq_a = 0.0, sq_b = 0.0;
+    float peak = 0.0f;
+    const long long counted = piece * divisions;
+    const long long pa = n0 / piece;
+    ConvLast<F> last;
+    last.result = result;
+    last.mid_plane = mid_plane;
+    last.n0 = n0;
+    last.frames = frames;
+    last.counted = counted;
+    last.boundary = (pa + 1) * piece;
+    last.sq_a = &sq_a;
+    last.sq_b = &sq_b;
+    last.peak = &peak;
+    fft_first_pass<N, -1, THREADS, float>(re, im, tw, SmemLoad<float>{re, im}, /*in_place=*/true);
+    __syncthreads();
+    fft_remaining<N, -1, THREADS, float>(re, im, tw, last, /*last_in_place=*/false);
+
+    // ---- frame totals -> per-piece sums (correction step 1) and the result's peak -----------------
+    const double ta = block_sum(sq_a, red_a);
+    const double tb = block_sum(sq_b, red_b);
+    const float pk = block_max(peak, red_f);
+    if (tid == 0) {
+        if (pa < divisions && ta != 0.0) atomicAdd(&piece_sums[pa], ta);
+        if (pa + 1 < divisions && tb != 0.0) atomicAdd(&piece_sums[pa + 1], tb);
+        atomic_max_nonneg(&state->conv_peak_bits, pk);
+    }
+}
+
+template <int F>
+int launch_convolve_t(const mgb_plan& plan, const mgb_track_layout& layout, const float2* target, float2* result,
+                      const Workspace& ws, mgb_track_state* state, cudaStream_t stream) {
+    const long long T = layout.target_frames;
+    const unsigned nframes = (unsigned)((T + F - 1) / F);
+    return launch("convolve_kernel", convolve_kernel<F>, dim3(nframes), dim3(F / 8), ConvSmem<F>::kBytes, stream, target, T,
+                  (long long)layout.target_piece, layout.target_divisions, (const cpx<float>*)plan.d_tw_f32_2F,
+                  (const float2*)ws.h_mid, (const float2*)ws.h_side, result, ws.mid_plane, ws.piece_sums, state,
+                  g_use_tma);
+}
+
+}  // namespace
+
+int launch_convolve(const mgb_plan& plan, const mgb_track_layout& layout, const float2* target, float2* result,
+                    const Workspace& ws, mgb_track_state* state, cudaStream_t stream) {
+    if (layout.target_piece < plan.fft_size) {
+        set_error("convolve: piece (%lld) shorter than fft_size", (long long)layout.target_piece);
+        return MGB_ERR_UNSUPPORTED;
+    }
+    switch (plan.fft_size) {
+        case 1024: return launch_convolve_t<1024>(plan, layout, target, result, ws, state, stream);
+        case 2048: return launch_convolve_t<2048>(plan, layout, target, result, ws, state, stream);
+        case 4096: return launch_convolve_t<4096>(plan, layout, target, result, ws, state, stream);
+        case 8192: return launch_convolve_t<8192>(plan, layout, target, result, ws, state, stream);
+        default: break;
+    }
+    set_error("convolve: fft_size %d has no kernel", plan.fft_size);
+    return MGB_ERR_UNSUPPORTED;
+}
+
+}  // namespace mgb

@@ -1,0 +1,184 @@
+// K5 -- RMS correction and the small elementwise kernels of __finalize.
+//
+// Replaces (reference file:line):
+//   stages.__correct_levels                       matchering/stages.py:138-170
+//     dsp.clip                                    matchering/dsp.py:109-110
+//     get_average_rms / get_lpis_and_match_rms    stage_helpers/match_levels.py:62-71,93-103
+//     get_rms_c_and_amplify_pair                  stage_helpers/match_levels.py:114-131
+//   dsp.normalize(..., normalize_clipped=True)    matchering/dsp.py:93-100 (stages.py:186-191)
+//
+// The reference rescales result_mid and result after every step; here the coefficients only
+// accumulate in mgb_track_state::gain (a float64 on the device) and each later pass multiplies by
+// it on the fly, so a step costs one read of the float32 mid plane (4 B/frame, L2-resident for
+// ordinary track lengths) instead of three full-array passes.
+#include "kernels.cuh"
+
+namespace mgb {
+
+namespace {
+
+// sum over a piece of clip(mid * gain)^2 ; grid = (chunks per piece, pieces)
+__global__ void __launch_bounds__(256)
+clip_sumsq_kernel(const float* __restrict__ mid, long long piece, const mgb_track_state* __restrict__ state,
+                  double* __restrict__ sums) {
+    __shared__ double red[32];
+    const double gain = state->gain;
+    const long long p = blockIdx.y;
+    const long long per = (piece + gridDim.x - 1) / gridDim.x;
+    const long long lo = p * piece + (long long)blockIdx.x * per;
+    long long hi = lo + per;
+    if (hi > (p + 1) * piece) hi = (p + 1) * piece;
+    double acc = 0.0;
+    for (long long n = lo + threadIdx.x; n < hi; n += 4 * blockDim.x) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long m = n + (long long)u * blockDim.x;
+            v[u] = m < hi ? mid[m] : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const double c = fmin(1.0, fmax(-1.0, (double)v[u] * gain));
+            acc += c * c;
+        }
+    }
+    const double total = block_sum(acc, red);
+    if (threadIdx.x == 0 && total != 0.0) atomicAdd(&sums[p], total);
+}
+
+// one RMS-correction step's coefficient from the per-piece sums (stages.py:153-168)
+__global__ void __launch_bounds__(256)
+correction_update_kernel(const double* __restrict__ sums, int divisions, long long piece, double eps, int step,
+                         mgb_track_state* __restrict__ state) {
+    __shared__ double red[32];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    double acc = 0.0;
+    for (int p = tid; p < divisions; p += nthr) acc += sums[p] / (double)piece;  // rms^2
+    const double avg = sqrt(block_sum(acc, red) / (double)divisions);
+    double accm = 0.0, cnt = 0.0;
+    for (int p = tid; p < divisions; p += nthr) {
+        const double r = sqrt(sums[p] / (double)piece);
+        if (r >= avg) {
+            accm += r * r;
+            cnt += 1.0;
+        }
+    }
+    const double tm = block_sum(accm, red);
+    const double tc = block_sum(cnt, red);
+    if (tid == 0) {
+        const double match = sqrt(tm / tc);
+        const double c = state->reference_match_rms / fmax(eps, match);
+        state->correction[step] = c;
+        state->gain *= c;
+        state->steps_done = step + 1;
+    }
+}
+
+// result peak after the correction gain, limiter early-out flag, normalisation coefficient
+__global__ void finalize_scalars_kernel(double threshold, double eps, mgb_track_state* __restrict__ state) {
+    const double peak = (double)state->conv_peak_bits * state->gain;
+    state->result_peak = peak;
+    state->normalize_coef = fmax(eps, peak / threshold);  // dsp.py:99 with normalize_clipped=True
+    const double r = fmax(peak, threshold) / threshold;   // dsp.py:117-121 at the loudest frame
+    state->limiter_engaged = (fabs(r - 1.0) <= 1e-8 + 1e-5) ? 0 : 1;  // np.isclose defaults, hyrax.py:83
+}
+
+// out = in * gain / divisor, two frames per thread
+__global__ void __launch_bounds__(256)
+scale_kernel(const float4* __restrict__ in, float4* __restrict__ out, long long pairs, const float2* __restrict__ in_tail,
+             float2* __restrict__ out_tail, const double* __restrict__ gain, const double* __restrict__ divisor) {
+    double g = gain ? *gain : 1.0;
+    if (divisor) g /= *divisor;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += stride) {
+        const float4 v = in[i];
+        out[i] = make_float4((float)((double)v.x * g), (float)((double)v.y * g), (float)((double)v.z * g),
+                             (float)((double)v.w * g));
+    }
+    if (in_tail && blockIdx.x == 0 && threadIdx.x == 0) {
+        const float2 v = *in_tail;
+        *out_tail = make_float2((float)((double)v.x * g), (float)((double)v.y * g));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+absmax_kernel(const float2* __restrict__ in, long long frames, float* __restrict__ out_bits) {
+    __shared__ float red[32];
+    float pk = 0.0f;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < frames; i += stride) {
+        const float2 v = in[i];
+        pk = fmaxf(pk, fmaxf(fabsf(v.x), fabsf(v.y)));
+    }
+    pk = block_max(pk, red);
+    if (threadIdx.x == 0) atomic_max_nonneg(out_bits, pk);
+}
+
+__global__ void convert_f64_f32_kernel(const double* __restrict__ in, float* __restrict__ out, long long count) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) out[i] = (float)in[i];
+}
+__global__ void convert_f32_f64_kernel(const float* __restrict__ in, double* __restrict__ out, long long count) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) out[i] = (double)in[i];
+}
+
+unsigned grid_for(long long items, int per_block) {
+    long long blocks = (items + per_block - 1) / per_block;
+    const long long cap = (long long)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (unsigned)blocks;
+}
+
+}  // namespace
+
+int launch_clip_sumsq(const mgb_plan& plan, const mgb_track_layout& layout, const Workspace& ws, int step,
+                      mgb_track_state* state, cudaStream_t stream) {
+    (void)plan;
+    const int div = layout.target_divisions;
+    long long per_piece = (2LL * num_sms() + div - 1) / div;
+    const long long max_useful = (layout.target_piece + 4095) / 4096;
+    if (per_piece > max_useful) per_piece = max_useful;
+    if (per_piece < 1) per_piece = 1;
+    return launch("clip_sumsq_kernel", clip_sumsq_kernel, dim3((unsigned)per_piece, (unsigned)div), dim3(256), 0, stream,
+                  (const float*)ws.mid_plane, (long long)layout.target_piece, (const mgb_track_state*)state,
+                  ws.piece_sums + (long long)step * div);
+}
+
+int launch_correction_update(const mgb_plan& plan, const mgb_track_layout& layout, const Workspace& ws, int step,
+                             mgb_track_state* state, cudaStream_t stream) {
+    return launch("correction_update_kernel", correction_update_kernel, dim3(1), dim3(256), 0, stream,
+                  (const double*)(ws.piece_sums + (long long)step * layout.target_divisions), layout.target_divisions,
+                  (long long)layout.target_piece, plan.min_value, step, state);
+}
+
+int launch_finalize_scalars(const mgb_plan& plan, mgb_track_state* state, cudaStream_t stream) {
+    return launch("finalize_scalars_kernel", finalize_scalars_kernel, dim3(1), dim3(1), 0, stream, plan.threshold,
+                  plan.min_value, state);
+}
+
+int launch_scale(const float2* in, float2* out, int64_t frames, const double* gain, const double* divisor,
+                 cudaStream_t stream) {
+    const long long pairs = frames / 2;
+    const float2* in_tail = (frames & 1) ? in + (frames - 1) : nullptr;
+    float2* out_tail = (frames & 1) ? out + (frames - 1) : nullptr;
+    return launch("scale_kernel", scale_kernel, dim3(grid_for(pairs, 256)), dim3(256), 0, stream, (const float4*)in,
+                  (float4*)out, pairs, in_tail, out_tail, gain, divisor);
+}
+
+int launch_absmax(const float2* in, int64_t frames, float* out_bits, cudaStream_t stream) {
+    return launch("absmax_kernel", absmax_kernel, dim3(grid_for(frames, 1024)), dim3(256), 0, stream, in,
+                  (long long)frames, out_bits);
+}
+
+int launch_convert_f64_f32(const double* in, float* out, int64_t count, cudaStream_t stream) {
+    return launch("convert_f64_f32_kernel", convert_f64_f32_kernel, dim3(grid_for(count, 1024)), dim3(256), 0, stream, in,
+                  out, (long long)count);
+}
+int launch_convert_f32_f64(const float* in, double* out, int64_t count, cudaStream_t stream) {
+    return launch("convert_f32_f64_kernel", convert_f32_f64_kernel, dim3(grid_for(count, 1024)), dim3(256), 0, stream, in,
+                  out, (long long)count);
+}
+
+}  // namespace mgb

@@ -1,0 +1,403 @@
+// K3 -- level statistics and matching-FIR design: tiny, latency-bound, all float64.
+//
+// levels_kernel replaces (reference file:line)
+//   match_levels.normalize_reference        stage_helpers/match_levels.py:29-44 (dsp.py:93-100)
+//   get_average_rms / get_lpis_and_match_rms stage_helpers/match_levels.py:62-71,93-103
+//   __calculate_rms_coefficient             stage_helpers/match_levels.py:106-111
+// design_kernel replaces
+//   __average_fft's mean over the loudest pieces   stage_helpers/match_frequencies.py:42
+//   get_fir                                        stage_helpers/match_frequencies.py:78-101
+//   __smooth_exponentially                         stage_helpers/match_frequencies.py:45-75
+//   dsp.smooth_lowess (statsmodels lowess, it=0)   dsp.py:103-106
+// and additionally emits the FIR's spectrum on the 2F-point grid of the overlap-save
+// convolution (convolve.cu), with the level-matching gain c0 and the 1/(2F) of the inverse
+// transform folded in.
+//
+// One CTA per channel (mid, side).  The Config-only parts (spline LU factors, evaluation weights,
+// LOWESS neighbourhoods) come from the plan; the substitution sweeps run block-parallel with a
+// warm-up of kWarm rows (the factors decay like 0.27^n, so 48 rows are exact to < 1e-27).
+#include "fft.cuh"
+#include "kernels.cuh"
+
+namespace mgb {
+
+namespace {
+
+constexpr int kDesignThreads = 512;
+constexpr int kWarm = 48;
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+levels_kernel(double* __restrict__ sumsq_t, int div_t, int slots_t, long long piece_t, double* __restrict__ sumsq_r,
+              int div_r, int slots_r, long long piece_r, const float* __restrict__ absmax_r, double threshold,
+              double eps, unsigned char* __restrict__ mask_t, unsigned char* __restrict__ mask_r,
+              mgb_track_state* __restrict__ state) {
+    __shared__ double red_d[32];
+    __shared__ float red_f[32];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+
+    float pk = 0.0f;
+    for (int i = tid; i < div_r * slots_r + 1; i += nthr) pk = fmaxf(pk, absmax_r[i]);
+    pk = block_max(pk, red_f);
+    const double peak = (double)pk;
+    double coef = 1.0;
+    if (peak < threshold) coef = fmax(eps, peak / threshold);  // dsp.py:96-99, normalize_clipped=False
+
+    double match[2];
+    int loud[2];
+    for (int sig = 0; sig < 2; ++sig) {
+        double* part = sig == 0 ? sumsq_t : sumsq_r;
+        const int div = sig == 0 ? div_t : div_r;
+        const int slots = sig == 0 ? slots_t : slots_r;
+        const double piece = (double)(sig == 0 ? piece_t : piece_r);
+        unsigned char* mask = sig == 0 ? mask_t : mask_r;
+        double acc = 0.0;
+        for (int p = tid; p < div; p += nthr) {
+            double s = 0.0;
+            for (int k = 0; k < slots; ++k) s += part[(long long)p * slots + k];
+            const double r = sqrt(s / piece);  // dsp.py:86
+            part[(long long)p * slots] = r;    // slot 0 now holds the piece's RMS
+            acc += r * r;
+        }
+        const double total = block_sum(acc, red_d);
+        const double avg = sqrt(total / (double)div);  // rms(rmses), match_levels.py:101
+        double accm = 0.0, cnt = 0.0;
+        for (int p = tid; p < div; p += nthr) {
+            const double r = part[(long long)p * slots];
+            const bool m = r >= avg;  // match_levels.py:65
+            mask[p] = m ? 1 : 0;
+            if (m) {
+                accm += r * r;
+                cnt += 1.0;
+            }
+        }
+        const double tm = block_sum(accm, red_d);
+        const double tc = block_sum(cnt, red_d);
+        match[sig] = sqrt(tm / tc);
+        loud[sig] = (int)tc;
+    }
+    if (tid == 0) {
+        const double ref_match = match[1] / coef;  // the reference measures the normalised reference
+        state->reference_peak = peak;
+        state->final_amplitude_coef = coef;
+        state->target_match_rms = match[0];
+        state->reference_match_rms = ref_match;
+        state->rms_coefficient = ref_match / fmax(eps, match[0]);
+        state->gain = 1.0;
+        state->result_peak = 0.0;
+        state->normalize_coef = 1.0;
+        state->target_loud_pieces = loud[0];
+        state->reference_loud_pieces = loud[1];
+        state->limiter_engaged = 1;
+        state->conv_peak_bits = 0.0f;
+        state->steps_done = 0;
+        for (int i = 0; i < MGB_MAX_CORRECTION_STEPS; ++i) state->correction[i] = 1.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct SplineTables {
+    const double* hinv;  // [n-1]
+    const double* lu;    // [3][n-2]
+    const double* end;   // [4]
+};
+
+// Second derivatives of the not-a-knot cubic through (knots, y): M[0..n).  z is scratch [n].
+__device__ void spline_moments(const double* __restrict__ y, int n, SplineTables t, double* __restrict__ z,
+                               double* __restrict__ M) {
+    const int m = n - 2;
+    const double* fa = t.lu;
+    const double* invden = t.lu + m;
+    const double* cp = t.lu + 2 * m;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int block = (m + nthr - 1) / nthr;
+    const int lo = tid * block;
+    const int hi = min(m, lo + block);
+    if (lo < m) {
+        double acc = 0.0;
+        for (int i = max(0, lo - kWarm); i < hi; ++i) {
+            // row i of the reduced system is interior knot i+1
+            const double d = 6.0 * ((y[i + 2] - y[i + 1]) * t.hinv[i + 1] - (y[i + 1] - y[i]) * t.hinv[i]);
+            acc = d * invden[i] - fa[i] * acc;
+            if (i >= lo) z[i] = acc;
+        }
+    }
+    __syncthreads();
+    if (lo < m) {
+        double acc = 0.0;
+        for (int i = min(m - 1, hi - 1 + kWarm); i >= lo; --i) {
+            acc = z[i] - cp[i] * acc;
+            if (i < hi) M[i + 1] = acc;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        M[0] = t.end[0] * M[1] + t.end[1] * M[2];
+        M[n - 1] = t.end[2] * M[n - 2] + t.end[3] * M[n - 3];
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ double spline_eval(const double* __restrict__ y, const double* __restrict__ M, int idx,
+                                              const double* __restrict__ w) {
+    return w[0] * y[idx] + w[1] * y[idx + 1] + w[2] * M[idx] + w[3] * M[idx + 1];
+}
+
+struct DesignArgs {
+    // average-spectrum inputs
+    const float* spec_part_t;
+    const float* spec_part_r;
+    const unsigned char* mask_t;
+    const unsigned char* mask_r;
+    int div_t, slots_t, div_r, slots_r;
+    long long frames_per_piece_t, frames_per_piece_r;
+    const double* avg_override;  // [4][n_lin] or null
+    // outputs
+    double* scratch;             // [2][stride]
+    long long stride;
+    double* fir_out;             // [2][F] or null
+    float2* h_mid;
+    float2* h_side;
+    const mgb_track_state* state;  // null with avg_override: c0 = 1, coef = 1
+};
+
+template <int F>
+struct DesignSmem {
+    static constexpr int kPlane = fft_padded_size(F);
+    static constexpr int kBytes = 2 * kPlane * 8 + 64;
+};
+
+template <int F>
+__global__ void __launch_bounds__(kDesignThreads)
+design_kernel(mgb_plan plan, DesignArgs a) {
+    constexpr int HB = F / 2 + 1;
+    MGB_DYN_SMEM(smem);
+    double* re = reinterpret_cast<double*>(smem);
+    double* im = re + DesignSmem<F>::kPlane;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+    const int ch = blockIdx.x;
+    const int NL = plan.n_log;
+    const cpx<double>* tw = (const cpx<double>*)plan.d_tw_f64_F;
+
+    double* base = a.scratch + (long long)ch * a.stride;
+    double* m = base;             // [HB] matching curve
+    double* M1 = m + HB;          // [HB] moments of spline A
+    double* s = M1 + HB;          // [HB] smoothed curve on the linear grid
+    double* mlog = s + HB;        // [NL]
+    double* slog = mlog + NL;     // [NL]
+    double* zz = slog + NL;       // [NL] scratch (sweeps, LOWESS fits)
+    double* M2 = zz + NL;         // [NL]
+    double* fir = M2 + NL;        // [F]
+
+    const double eps = plan.min_value;
+    double c0 = 1.0, coef = 1.0;
+    if (a.state) {
+        c0 = a.state->rms_coefficient;
+        coef = a.state->final_amplitude_coef;
+    }
+
+    // ---- A: matching curve = reference average / max(eps, target average) ---------------------
+    if (a.avg_override) {
+        for (int k = tid; k < HB; k += nthr) {
+            const double at = a.avg_override[(long long)ch * HB + k];
+            const double ar = a.avg_override[(long long)(2 + ch) * HB + k];
+            m[k] = ar / fmax(eps, at);
+        }
+    } else {
+        const double loud_t = (double)a.state->target_loud_pieces;
+        const double loud_r = (double)a.state->reference_loud_pieces;
+        const double norm_t = c0 / (loud_t * (double)a.frames_per_piece_t * (double)F);
+        const double norm_r = 1.0 / (coef * loud_r * (double)a.frames_per_piece_r * (double)F);
+        for (int k = tid; k < HB; k += nthr) {
+            double st = 0.0, sr = 0.0;
+            for (int p = 0; p < a.div_t; ++p) {
+                if (!a.mask_t[p]) continue;
+                for (int q = 0; q < a.slots_t; ++q)
+                    st += (double)a.spec_part_t[(((long long)p * a.slots_t + q) * 2 + ch) * HB + k];
+            }
+            for (int p = 0; p < a.div_r; ++p) {
+                if (!a.mask_r[p]) continue;
+                for (int q = 0; q < a.slots_r; ++q)
+                    sr += (double)a.spec_part_r[(((long long)p * a.slots_r + q) * 2 + ch) * HB + k];
+            }
+            m[k] = (sr * norm_r) / fmax(eps, st * norm_t);  // match_frequencies.py:93-94
+        }
+    }
+    __syncthreads();
+
+    // ---- B/C: cubic spline linear grid -> log grid (match_frequencies.py:60-61) --------------
+    spline_moments(m, HB, SplineTables{plan.d_sa_hinv, plan.d_sa_lu, plan.d_sa_end}, zz, M1);
+    for (int j = tid; j < NL; j += nthr) mlog[j] = spline_eval(m, M1, plan.d_sa_eval_idx[j], plan.d_sa_eval_w + 4LL * j);
+    __syncthreads();
+
+    // ---- D: LOWESS, one warp per local regression (dsp.py:103-106) ---------------------------
+    {
+        const double* x = plan.d_lw_x;
+        const int k = plan.lowess_k;
+        for (int f = warp; f < plan.lowess_nfit; f += nwarps) {
+            const int i = plan.d_lw_fit_idx[f];
+            const int left = plan.d_lw_fit_left[f];
+            const double xi = x[i];
+            const double radius = fmax(fabs(x[left] - xi), fabs(x[left + k - 1] - xi));
+            double sw = 0.0, swx = 0.0, nz = 0.0;
+            for (int j = lane; j < k; j += 32) {
+                const double xj = x[left + j];
+                const double d = fabs(xj - xi);
+                double t = d / radius;
+                double w = 1.0 - t * t * t;
+                w = w * w * w;
+                if (d >= radius) w = 0.0;
+                sw += w;
+                swx += w * xj;
+                nz += (w != 0.0) ? 1.0 : 0.0;
+            }
+            sw = warp_sum(sw);
+            swx = warp_sum(swx);
+            nz = warp_sum(nz);
+            double fit;
+            if (sw <= 0.0 || nz == 1.0) {
+                fit = mlog[i];
+            } else {
+                const double xbar = swx / sw;
+                double sq = 0.0;
+                for (int j = lane; j < k; j += 32) {
+                    const double xj = x[left + j];
+                    const double d = fabs(xj - xi);
+                    double t = d / radius;
+                    double w = 1.0 - t * t * t;
+                    w = w * w * w;
+                    if (d >= radius) w = 0.0;
+                    sq += w * (xj - xbar) * (xj - xbar);
+                }
+                sq = warp_sum(sq) / sw;
+                double acc = 0.0;
+                for (int j = lane; j < k; j += 32) {
+                    const double xj = x[left + j];
+                    const double d = fabs(xj - xi);
+                    double t = d / radius;
+                    double w = 1.0 - t * t * t;
+                    w = w * w * w;
+                    if (d >= radius) w = 0.0;
+                    acc += (w / sw) * (1.0 + (xi - xbar) * (xj - xbar) / sq) * mlog[left + j];
+                }
+                fit = warp_sum(acc);
+            }
+            if (lane == 0) zz[f] = fit;
+        }
+        __syncthreads();
+        for (int j = tid; j < NL; j += nthr) {
+            const int sg = plan.d_lw_seg[j];
+            const int fi = plan.d_lw_fit_idx[sg];
+            if (fi == j) {
+                slog[j] = zz[sg];
+            } else {  // skipped by `delta`: linear interpolation between the bracketing fits
+                const int fn = plan.d_lw_fit_idx[sg + 1];
+                const double al = (x[j] - x[fi]) / (x[fn] - x[fi]);
+                slog[j] = al * zz[sg + 1] + (1.0 - al) * zz[sg];
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- E: cubic spline log grid -> linear grid, then the two overrides (:67-73) -------------
+    spline_moments(slog, NL, SplineTables{plan.d_sb_hinv, plan.d_sb_lu, plan.d_sb_end}, zz, M2);
+    for (int k = tid; k < HB; k += nthr) {
+        double v = spline_eval(slog, M2, plan.d_sb_eval_idx[k], plan.d_sb_eval_w + 4LL * k);
+        if (k == 0) v = 0.0;
+        if (k == 1) v = m[1];
+        s[k] = v;
+    }
+    __syncthreads();
+
+    // ---- F: fir = ifftshift(irfft(s)) * hann (match_frequencies.py:98-99) ---------------------
+    {
+        auto first = [&](int i) { return cpx<double>{s[i <= F / 2 ? i : F - i], 0.0}; };
+        fft_run<F, -1, kDesignThreads, double>(re, im, tw, first, SmemStore<double>{re, im}, false, true);
+        __syncthreads();
+        const double inv = 1.0 / (double)F;
+        for (int i = tid; i < F; i += nthr) {
+            const int src = (i + F / 2) & (F - 1);
+            const double v = re[fft_pad(src)] * inv * plan.d_hann[i];
+            fir[i] = v;
+            if (a.fir_out) a.fir_out[(long long)ch * F + i] = v;
+        }
+        __syncthreads();
+    }
+
+    // ---- G: spectrum of the FIR on the 2F grid, bins 0..F ---------------------------------------
+    // even bins 2j = FFT_F(fir)[j]; odd bins 2j+1 = FFT_F(fir[n] * exp(-i*pi*n/F))[j]
+    {
+        float2* H = ch == 0 ? a.h_mid : a.h_side;
+        const double scale = c0 / (2.0 * (double)F);
+        auto first_even = [&](int i) { return cpx<double>{fir[i], 0.0}; };
+        fft_run<F, +1, kDesignThreads, double>(re, im, tw, first_even, SmemStore<double>{re, im}, false, true);
+        __syncthreads();
+        for (int j = tid; j <= F / 2; j += nthr) {
+            const int jj = j & (F - 1);
+            H[2 * j] = make_float2((float)(re[fft_pad(jj)] * scale), (float)(im[fft_pad(jj)] * scale));
+        }
+        __syncthreads();
+        auto first_odd = [&](int i) {
+            double sn, cs;
+            sincospi(-(double)i / (double)F, &sn, &cs);
+            return cpx<double>{fir[i] * cs, fir[i] * sn};
+        };
+        fft_run<F, +1, kDesignThreads, double>(re, im, tw, first_odd, SmemStore<double>{re, im}, false, true);
+        __syncthreads();
+        for (int j = tid; j < F / 2; j += nthr)
+            H[2 * j + 1] = make_float2((float)(re[fft_pad(j)] * scale), (float)(im[fft_pad(j)] * scale));
+    }
+}
+
+template <int F>
+int launch_design_t(const mgb_plan& plan, const DesignArgs& a, cudaStream_t stream) {
+    return launch("design_kernel", design_kernel<F>, dim3(2), dim3(kDesignThreads), DesignSmem<F>::kBytes, stream, plan, a);
+}
+
+}  // namespace
+
+int64_t design_doubles_per_channel(const mgb_plan& plan) {
+    return 3LL * plan.n_lin + 4LL * plan.n_log + plan.fft_size + 16;
+}
+
+int launch_levels(const mgb_plan& plan, const mgb_track_layout& layout, const Workspace& ws, mgb_track_state* state,
+                  cudaStream_t stream) {
+    return launch("levels_kernel", levels_kernel, dim3(1), dim3(256), 0, stream, ws.sumsq_part_t,
+                  layout.target_divisions, layout.target_slots, (long long)layout.target_piece, ws.sumsq_part_r,
+                  layout.reference_divisions, layout.reference_slots, (long long)layout.reference_piece,
+                  (const float*)ws.absmax_part_r, plan.threshold, plan.min_value, ws.mask_t, ws.mask_r, state);
+}
+
+int launch_design(const mgb_plan& plan, const mgb_track_layout& layout, const Workspace& ws,
+                  const double* avg_override, double* fir_out, mgb_track_state* state, cudaStream_t stream) {
+    DesignArgs a;
+    a.spec_part_t = ws.spec_part_t;
+    a.spec_part_r = ws.spec_part_r;
+    a.mask_t = ws.mask_t;
+    a.mask_r = ws.mask_r;
+    a.div_t = layout.target_divisions;
+    a.slots_t = layout.target_slots;
+    a.div_r = layout.reference_divisions;
+    a.slots_r = layout.reference_slots;
+    a.frames_per_piece_t = layout.target_piece / plan.fft_size;
+    a.frames_per_piece_r = layout.reference_piece / plan.fft_size;
+    a.avg_override = avg_override;
+    a.scratch = ws.design;
+    a.stride = ws.design_stride;
+    a.fir_out = fir_out;
+    a.h_mid = ws.h_mid;
+    a.h_side = ws.h_side;
+    a.state = avg_override ? nullptr : state;
+    switch (plan.fft_size) {
+        case 1024: return launch_design_t<1024>(plan, a, stream);
+        case 2048: return launch_design_t<2048>(plan, a, stream);
+        case 4096: return launch_design_t<4096>(plan, a, stream);
+        case 8192: return launch_design_t<8192>(plan, a, stream);
+        default: break;
+    }
+    set_error("design: fft_size %d has no kernel", plan.fft_size);
+    return MGB_ERR_UNSUPPORTED;
+}
+
+}  // namespace mgb

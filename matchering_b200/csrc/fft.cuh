@@ -1,0 +1,254 @@
+// Fixed-frame mixed-radix FFT in shared memory (Stockham autosort, radix 2/4/8/16 butterflies in
+// registers).  One frame of N complex points lives in two padded shared arrays (re / im); each
+// pass is: every thread gathers the R inputs of its butterflies into registers, barrier, twiddle +
+// radix-R DFT in registers, scatter in place, barrier.  The first pass may read from and the last
+// pass may write to caller-supplied functors (e.g. the TMA landing buffer, a magnitude
+// accumulator), so frames never make an extra trip through shared memory.
+//
+// Twiddles come from a table computed once per FFT size in double precision (fft_twiddle_kernel)
+// and rounded to the working type: table layout is the concatenation over passes of [R-1][NS]
+// entries w = exp(-2*pi*i * r*k / (NS*R)), r = 1..R-1, k = 0..NS-1, so that consecutive lanes read
+// consecutive entries.  The inverse transform conjugates on load.
+#pragma once
+#include "common.cuh"
+
+namespace mgb {
+
+// shared-memory index padding: one extra word per 32 keeps the stride-R scatters of the first
+// pass conflict-free
+__device__ __host__ __forceinline__ constexpr int fft_pad(int i) { return i + (i >> 5); }
+__device__ __host__ constexpr int fft_padded_size(int n) { return n + (n >> 5) + 1; }
+
+// ------------------------------------------------------------------------------------------------
+// compile-time roots of unity for the in-register butterflies (multiples of 2*pi/16)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ constexpr T cos16(int k) {
+    // cos(2*pi*k/16), k = 0..8
+    return k == 0 ? T(1) : k == 1 ? T(0.92387953251128673848) : k == 2 ? T(0.70710678118654752440)
+         : k == 3 ? T(0.38268343236508977173) : k == 4 ? T(0) : k == 5 ? T(-0.38268343236508977173)
+         : k == 6 ? T(-0.70710678118654752440) : k == 7 ? T(-0.92387953251128673848) : T(-1);
+}
+template <typename T>
+__device__ __forceinline__ constexpr T sin16(int k) {
+    // sin(2*pi*k/16), k = 0..8
+    return k == 0 ? T(0) : k == 1 ? T(0.38268343236508977173) : k == 2 ? T(0.70710678118654752440)
+         : k == 3 ? T(0.92387953251128673848) : k == 4 ? T(1) : k == 5 ? T(0.92387953251128673848)
+         : k == 6 ? T(0.70710678118654752440) : k == 7 ? T(0.38268343236508977173) : T(0);
+}
+
+// multiply by exp(DIR * -2*pi*i * q / R), q < R/2, with the trivial cases folded away
+template <int R, int Q, int DIR, typename T>
+__device__ __forceinline__ cpx<T> mul_root(cpx<T> a) {
+    constexpr int K = Q * (16 / R);  // index into the 16th roots, 0..7
+    if constexpr (K == 0) {
+        return a;
+    } else if constexpr (K == 4) {
+        // forward: * (-i) ; inverse: * (+i)
+        return DIR > 0 ? cpx<T>{a.y, -a.x} : cpx<T>{-a.y, a.x};
+    } else if constexpr (K == 2) {
+        constexpr T c = cos16<T>(2);
+        return DIR > 0 ? cpx<T>{c * (a.x + a.y), c * (a.y - a.x)} : cpx<T>{c * (a.x - a.y), c * (a.y + a.x)};
+    } else if constexpr (K == 6) {
+        constexpr T c = cos16<T>(2);
+        return DIR > 0 ? cpx<T>{c * (a.y - a.x), -c * (a.x + a.y)} : cpx<T>{-c * (a.x + a.y), c * (a.x - a.y)};
+    } else {
+        constexpr T wr = cos16<T>(K);
+        constexpr T wi = DIR > 0 ? -sin16<T>(K) : sin16<T>(K);
+        return cpx<T>{a.x * wr - a.y * wi, a.x * wi + a.y * wr};
+    }
+}
+
+// radix-R DFT of v[0..R) in registers, natural order in and out (recursive decimation in time)
+template <int R, int DIR, typename T>
+struct Dft {
+    template <int Q>
+    static __device__ __forceinline__ void combine(cpx<T>* v, const cpx<T>* e, const cpx<T>* o) {
+        if constexpr (Q < R / 2) {
+            cpx<T> t = mul_root<R, Q, DIR, T>(o[Q]);
+            v[Q] = cadd(e[Q], t);
+            v[Q + R / 2] = csub(e[Q], t);
+            combine<Q + 1>(v, e, o);
+        }
+    }
+    static __device__ __forceinline__ void run(cpx<T>* v) {
+        cpx<T> e[R / 2], o[R / 2];
+#pragma unroll
+        for (int i = 0; i < R / 2; ++i) {
+            e[i] = v[2 * i];
+            o[i] = v[2 * i + 1];
+        }
+        Dft<R / 2, DIR, T>::run(e);
+        Dft<R / 2, DIR, T>::run(o);
+        combine<0>(v, e, o);
+    }
+};
+template <int DIR, typename T>
+struct Dft<2, DIR, T> {
+    static __device__ __forceinline__ void run(cpx<T>* v) {
+        cpx<T> a = v[0], b = v[1];
+        v[0] = cadd(a, b);
+        v[1] = csub(a, b);
+    }
+};
+template <int DIR, typename T>
+struct Dft<1, DIR, T> {
+    static __device__ __forceinline__ void run(cpx<T>*) {}
+};
+
+// ------------------------------------------------------------------------------------------------
+// one Stockham pass
+// ------------------------------------------------------------------------------------------------
+template <int N, int R, int NS, int DIR, int THREADS, typename T, typename Load, typename Store>
+__device__ __forceinline__ void fft_pass(const cpx<T>* __restrict__ tw, Load load, Store store, bool barrier_between) {
+    constexpr int NB = N / R;
+    static_assert(NB % THREADS == 0 || NB < THREADS, "butterflies must tile the block");
+    constexpr int PER = (NB >= THREADS) ? NB / THREADS : 1;
+    const int tid = threadIdx.x;
+    const bool active = (NB >= THREADS) || (tid < NB);
+    cpx<T> v[PER][R];
+    if (active) {
+#pragma unroll
+        for (int p = 0; p < PER; ++p) {
+            const int j = tid + p * THREADS;
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[p][r] = load(j + r * NB);
+        }
+    }
+    if (barrier_between) __syncthreads();
+    if (active) {
+#pragma unroll
+        for (int p = 0; p < PER; ++p) {
+            const int j = tid + p * THREADS;
+            const int k = j & (NS - 1);
+            if constexpr (NS > 1) {
+#pragma unroll
+                for (int r = 1; r < R; ++r) {
+                    cpx<T> w = tw[(r - 1) * NS + k];
+                    if constexpr (DIR < 0) w.y = -w.y;
+                    v[p][r] = cmul(v[p][r], w);
+                }
+            }
+            Dft<R, DIR, T>::run(v[p]);
+            const int j0 = (j - k) * R + k;
+#pragma unroll
+            for (int q = 0; q < R; ++q) store(j0 + q * NS, v[p][q]);
+        }
+    }
+}
+
+template <typename T>
+struct SmemLoad {
+    const T* re;
+    const T* im;
+    __device__ __forceinline__ cpx<T> operator()(int i) const {
+        const int a = fft_pad(i);
+        return cpx<T>{re[a], im[a]};
+    }
+};
+template <typename T>
+struct SmemStore {
+    T* re;
+    T* im;
+    __device__ __forceinline__ void operator()(int i, cpx<T> v) const {
+        const int a = fft_pad(i);
+        re[a] = v.x;
+        im[a] = v.y;
+    }
+};
+
+// Radix schedule of an N-point transform.  Sizes outside this list are rejected by the C ABI.
+template <int N> struct Radices;
+template <> struct Radices<256>   { static constexpr int n = 2; static constexpr int r[4] = {16, 16, 1, 1}; };
+template <> struct Radices<512>   { static constexpr int n = 3; static constexpr int r[4] = {8, 8, 8, 1}; };
+template <> struct Radices<1024>  { static constexpr int n = 3; static constexpr int r[4] = {16, 8, 8, 1}; };
+template <> struct Radices<2048>  { static constexpr int n = 3; static constexpr int r[4] = {16, 16, 8, 1}; };
+template <> struct Radices<4096>  { static constexpr int n = 3; static constexpr int r[4] = {16, 16, 16, 1}; };
+template <> struct Radices<8192>  { static constexpr int n = 4; static constexpr int r[4] = {16, 8, 8, 8}; };
+template <> struct Radices<16384> { static constexpr int n = 4; static constexpr int r[4] = {16, 16, 8, 8}; };
+
+template <int N>
+__host__ __device__ constexpr int fft_threads() { return N / 16; }
+
+// First pass of the transform: `first` supplies the input points (logical index -> value), results
+// go to (re, im).  `in_place` says whether `first` reads (re, im) itself (then a barrier separates
+// the gathers from the scatters).  No trailing barrier.
+template <int N, int DIR, int THREADS, typename T, typename First>
+__device__ __forceinline__ void fft_first_pass(T* re, T* im, const cpx<T>* __restrict__ tw, First first,
+                                               bool in_place) {
+    SmemStore<T> ss{re, im};
+    fft_pass<N, Radices<N>::r[0], 1, DIR, THREADS, T>(tw, first, ss, in_place);
+}
+
+// Remaining passes, in place on (re, im); the caller has put a barrier after the first pass.
+// `last` consumes the output points in natural order (`last_in_place`: it writes (re, im)).
+// On return all `last` stores have been ISSUED (no trailing barrier).
+template <int N, int DIR, int THREADS, typename T, typename Last>
+__device__ __forceinline__ void fft_remaining(T* re, T* im, const cpx<T>* __restrict__ tw, Last last,
+                                              bool last_in_place) {
+    using Rd = Radices<N>;
+    constexpr int R0 = Rd::r[0], R1 = Rd::r[1], R2 = Rd::r[2], R3 = Rd::r[3];
+    constexpr int NP = Rd::n;
+    SmemLoad<T> sl{re, im};
+    SmemStore<T> ss{re, im};
+    static_assert(NP >= 2 && NP <= 4, "2..4 passes supported");
+    constexpr int o1 = 0;  // pass 0 has NS = 1: no twiddles stored
+    if constexpr (NP == 2) {
+        fft_pass<N, R1, R0, DIR, THREADS, T>(tw + o1, sl, last, last_in_place);
+    } else {
+        fft_pass<N, R1, R0, DIR, THREADS, T>(tw + o1, sl, ss, true);
+        __syncthreads();
+        constexpr int o2 = o1 + (R1 - 1) * R0;
+        if constexpr (NP == 3) {
+            fft_pass<N, R2, R0 * R1, DIR, THREADS, T>(tw + o2, sl, last, last_in_place);
+        } else {
+            fft_pass<N, R2, R0 * R1, DIR, THREADS, T>(tw + o2, sl, ss, true);
+            __syncthreads();
+            constexpr int o3 = o2 + (R2 - 1) * R0 * R1;
+            fft_pass<N, R3, R0 * R1 * R2, DIR, THREADS, T>(tw + o3, sl, last, last_in_place);
+        }
+    }
+}
+
+// Whole transform: first pass, barrier, remaining passes.
+template <int N, int DIR, int THREADS, typename T, typename First, typename Last>
+__device__ __forceinline__ void fft_run(T* re, T* im, const cpx<T>* __restrict__ tw, First first, Last last,
+                                        bool first_in_place, bool last_in_place) {
+    fft_first_pass<N, DIR, THREADS, T>(re, im, tw, first, first_in_place);
+    __syncthreads();
+    fft_remaining<N, DIR, THREADS, T>(re, im, tw, last, last_in_place);
+}
+
+// number of stored twiddles (pass 0 stores none)
+template <int N>
+__host__ __device__ constexpr int fft_twiddle_stored() {
+    int total = 0, ns = Radices<N>::r[0];
+    for (int p = 1; p < Radices<N>::n; ++p) {
+        total += (Radices<N>::r[p] - 1) * ns;
+        ns *= Radices<N>::r[p];
+    }
+    return total;
+}
+
+// Fill the twiddle table of a transform with the given radix schedule (double-precision sincospi,
+// rounded to T).
+template <typename T>
+__global__ void fft_twiddle_kernel(cpx<T>* __restrict__ tw, int npass, int r0, int r1, int r2, int r3) {
+    const int radix[4] = {r0, r1, r2, r3};
+    int ns = radix[0];
+    int base = 0;
+    for (int p = 1; p < npass; ++p) {
+        const int R = radix[p];
+        const int count = (R - 1) * ns;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+            const int r = i / ns + 1, k = i % ns;
+            double s, c;
+            sincospi(-2.0 * (double)(r * k) / (double)(ns * R), &s, &c);  // exp(-2*pi*i*r*k/(ns*R))
+            tw[base + i] = cpx<T>{(T)c, (T)s};
+        }
+        base += count;
+        ns *= R;
+    }
+}
+
+}  // namespace mgb

@@ -1,0 +1,87 @@
+// Internal interfaces between the translation units of libmatchering_b200.
+#pragma once
+#include "common.cuh"
+
+namespace mgb {
+
+// Device scratch of one track, carved out of the caller's workspace (all 256-byte aligned).
+struct Workspace {
+    float* spec_part_t;     // [Dt][St][2][n_lin]   per-(piece, slot) sums of |rfft| : mid, side
+    float* spec_part_r;     // [Dr][Sr][2][n_lin]
+    double* sumsq_part_t;   // [Dt][St]             per-(piece, slot) sums of mid^2
+    double* sumsq_part_r;   // [Dr][Sr]
+    float* absmax_part_t;   // [Dt*St + 1]
+    float* absmax_part_r;   // [Dr*Sr + 1]
+    unsigned char* mask_t;  // [Dt] loudest-piece mask of the target
+    unsigned char* mask_r;  // [Dr]
+    double* design;         // [2][design_stride] float64 vectors of the FIR design, per channel
+    float2* h_mid;          // [F+1] spectrum of the mid FIR on the 2F grid (bins 0..F), c0/(2F) folded in
+    float2* h_side;         // [F+1]
+    float* mid_plane;       // [T] mid channel of the convolution result
+    // ---- zeroed at the start of every job (one memset) ----
+    unsigned char* zero_begin;
+    double* piece_sums;     // [MGB_MAX_CORRECTION_STEPS][Dt] sums of clip(mid*gain)^2
+    int* limiter_ticket;    // [4] chunk ticket counter (+ padding)
+    unsigned char* lookback;// [nchunks] LookbackSlot
+    unsigned char* zero_end;
+    int64_t design_stride;  // doubles per channel in `design`
+    int64_t total_bytes;
+};
+
+struct LookbackSlot {
+    double hold_agg, hold_inc, rel_agg, rel_inc;
+    int hold_flag, rel_flag;  // 0 = nothing, 1 = aggregate published, 2 = inclusive published
+    int pad[2];
+};
+
+constexpr int kLimiterThreads = 512;
+constexpr int kLimiterCoreEpt = 9;                                   // core samples per thread
+constexpr int kLimiterCore = kLimiterThreads * kLimiterCoreEpt;      // 4608 samples per chunk
+constexpr int kLimiterSpanEptMax = 17;                               // span samples per thread (odd)
+
+Workspace carve_workspace(const mgb_plan& plan, const mgb_track_layout& layout, void* base);
+int64_t limiter_lookback_bytes(int64_t frames);
+
+// analyze.cu ------------------------------------------------------------------------------------
+int launch_analyze(const mgb_plan& plan, const float2* x, int64_t frames, int64_t piece, int divisions, int slots,
+                   float* spec_part, double* sumsq_part, float* absmax_part, cudaStream_t stream);
+
+// design.cu -------------------------------------------------------------------------------------
+int launch_levels(const mgb_plan& plan, const mgb_track_layout& layout, const Workspace& ws, mgb_track_state* state,
+                  cudaStream_t stream);
+int launch_design(const mgb_plan& plan, const mgb_track_layout& layout, const Workspace& ws,
+                  const double* avg_override, double* fir_out, mgb_track_state* state, cudaStream_t stream);
+int64_t design_doubles_per_channel(const mgb_plan& plan);
+
+// convolve.cu -----------------------------------------------------------------------------------
+int launch_convolve(const mgb_plan& plan, const mgb_track_layout& layout, const float2* target, float2* result,
+                    const Workspace& ws, mgb_track_state* state, cudaStream_t stream);
+
+// correct.cu ------------------------------------------------------------------------------------
+int launch_correction_update(const mgb_plan& plan, const mgb_track_layout& layout, const Workspace& ws, int step,
+                             mgb_track_state* state, cudaStream_t stream);
+int launch_clip_sumsq(const mgb_plan& plan, const mgb_track_layout& layout, const Workspace& ws, int step,
+                      mgb_track_state* state, cudaStream_t stream);
+int launch_finalize_scalars(const mgb_plan& plan, mgb_track_state* state, cudaStream_t stream);
+int launch_scale(const float2* in, float2* out, int64_t frames, const double* gain, const double* divisor,
+                 cudaStream_t stream);
+int launch_absmax(const float2* in, int64_t frames, float* out_bits, cudaStream_t stream);
+int launch_convert_f64_f32(const double* in, float* out, int64_t count, cudaStream_t stream);
+int launch_convert_f32_f64(const float* in, double* out, int64_t count, cudaStream_t stream);
+
+// limiter.cu ------------------------------------------------------------------------------------
+int launch_limiter(const mgb_limiter_params& lp, const float2* in, float2* out, int64_t frames, const double* pre_gain,
+                   const double* post_gain, const int* engaged, int* ticket, LookbackSlot* lookback,
+                   cudaStream_t stream);
+int launch_limiter_engaged(const float* peak_bits, const double* pre_gain, double threshold, int* engaged,
+                           cudaStream_t stream);
+
+// fft test entry (api.cu) uses these -------------------------------------------------------------
+int launch_test_fft(int n, int is_f64, int dir, const void* in, void* out, int batch, const void* tw,
+                    cudaStream_t stream);
+int fill_twiddles(int n, int is_f64, void* table, cudaStream_t stream);
+int twiddle_count(int n);
+
+extern int g_use_tma;
+
+}  // namespace mgb
