@@ -1,0 +1,166 @@
+"""Device-side session objects: PyTorch is the memory manager and stream provider, the compute
+is libmatchering_b200 (hand-written sm_100a kernels behind the C ABI).
+
+DevicePlan   Config-only tables on one GPU (cached per device + Config).
+TrackSession the buffers of one mastering job of fixed sizes; calls the four stage entry points
+             that mirror matchering/stages.py's private functions.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native, plan as _plan
+from .log import debug
+
+_PLAN_CACHE: dict = {}
+
+
+def _require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise RuntimeError("matchering_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def _stream_ptr(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class DevicePlan:
+    def __init__(self, config, device: torch.device):
+        self.lib = _native.load()
+        self.device = device
+        self.tables = _plan.build_tables(config)
+        t = self.tables
+        s = _native.Plan()
+        s.sample_rate, s.fft_size, s.n_lin, s.n_log = t.sample_rate, t.fft_size, t.n_lin, t.n_log
+        s.rms_correction_steps, s.lowess_k = t.rms_correction_steps, t.lowess_k
+        s.lowess_nfit = len(t.arrays["lw_fit_idx"])
+        s.max_piece_size, s.threshold, s.min_value = t.max_piece_size, t.threshold, t.min_value
+        s.limiter = limiter_params(t.limiter)
+        self._keep = {}
+        for name, arr in t.arrays.items():
+            dev = torch.from_numpy(arr).to(device)
+            self._keep[name] = dev
+            setattr(s, "d_" + name, dev.data_ptr())
+        sizes = (C.c_int64 * 4)()
+        _native.check(self.lib, self.lib.mgb_plan_twiddle_bytes(t.fft_size, sizes))
+        for name, nbytes in zip(("tw_f32_F", "tw_f32_2F", "tw_f64_F", "tw_f64_2F"), sizes):
+            buf = torch.zeros(int(nbytes), dtype=torch.uint8, device=device)
+            self._keep[name] = buf
+            setattr(s, "d_" + name, buf.data_ptr())
+        self.struct = s
+        with torch.cuda.device(device):
+            _native.check(self.lib, self.lib.mgb_plan_fill_twiddles(C.byref(s), _stream_ptr(device)))
+
+    def layout(self, target_frames: int, reference_frames: int) -> _native.TrackLayout:
+        L = _native.TrackLayout()
+        _native.check(self.lib, self.lib.mgb_track_layout_init(C.byref(self.struct), target_frames,
+                                                              reference_frames, C.byref(L)))
+        return L
+
+
+def limiter_params(lc: _plan.LimiterConstants) -> _native.LimiterParams:
+    p = _native.LimiterParams()
+    p.threshold = lc.threshold
+    p.reach, p.hold, p.warmup = lc.reach, lc.hold, lc.warmup
+    p.attack_c = lc.attack_c
+    p.hold_b0, p.hold_b1, p.hold_a1 = float(lc.hold_b[0]), float(lc.hold_b[1]), float(lc.hold_a[1])
+    p.release_b0, p.release_b1, p.release_a1 = (float(lc.release_b[0]), float(lc.release_b[1]),
+                                                float(lc.release_a[1]))
+    return p
+
+
+def get_plan(config, device=None) -> DevicePlan:
+    _require_cuda()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    key = (device.index, _plan.config_key(config))
+    plan = _PLAN_CACHE.get(key)
+    if plan is None:
+        plan = _PLAN_CACHE[key] = DevicePlan(config, device)
+    return plan
+
+
+def to_device_f32(array, device) -> torch.Tensor:
+    """(N, 2) samples -> contiguous float32 CUDA tensor.  float64 host arrays (what the reference's
+    loader hands to stages.main) are copied as they are and narrowed on the device by the library's
+    own conversion kernel."""
+    if isinstance(array, torch.Tensor):
+        t = array.to(device)
+        if t.dtype == torch.float32:
+            return t.contiguous()
+        t = t.to(torch.float64).contiguous()
+    else:
+        a = np.ascontiguousarray(array)
+        if a.dtype == np.float32:
+            return torch.from_numpy(a).to(device)
+        t = torch.from_numpy(a.astype(np.float64, copy=False)).to(device)
+    out = torch.empty(t.shape, dtype=torch.float32, device=device)
+    lib = _native.load()
+    _native.check(lib, lib.mgb_convert_f64_to_f32(t.data_ptr(), out.data_ptr(), t.numel(), _stream_ptr(device)))
+    return out
+
+
+def to_host_like(t: torch.Tensor, like):
+    """Give a float32 CUDA result back in the caller's currency: torch in -> torch out (float32,
+    on the device); numpy in -> numpy out with the input's dtype (float64 for the reference's)."""
+    if isinstance(like, torch.Tensor):
+        return t
+    want = np.asarray(like).dtype
+    if want == np.float32:
+        return t.cpu().numpy()
+    wide = torch.empty(t.shape, dtype=torch.float64, device=t.device)
+    lib = _native.load()
+    _native.check(lib, lib.mgb_convert_f32_to_f64(t.data_ptr(), wide.data_ptr(), t.numel(), _stream_ptr(t.device)))
+    return wide.cpu().numpy()
+
+
+class TrackSession:
+    """Buffers for one (plan, target length, reference length) and the stage calls over them."""
+
+    def __init__(self, plan: DevicePlan, target_frames: int, reference_frames: int):
+        self.plan = plan
+        self.lib = plan.lib
+        self.device = plan.device
+        self.layout = plan.layout(target_frames, reference_frames)
+        self.workspace = torch.empty(int(self.layout.workspace_bytes), dtype=torch.uint8, device=self.device)
+        self.state = torch.zeros(C.sizeof(_native.TrackState), dtype=torch.uint8, device=self.device)
+        self.result = torch.empty((target_frames, 2), dtype=torch.float32, device=self.device)
+
+    # -- the four stages of matchering/stages.py ------------------------------------------------
+    def _args(self):
+        return C.byref(self.plan.struct), C.byref(self.layout)
+
+    def match_levels(self, target: torch.Tensor, reference: torch.Tensor) -> None:
+        p, l = self._args()
+        _native.check(self.lib, self.lib.mgb_match_levels(p, l, target.data_ptr(), reference.data_ptr(),
+                                                         self.workspace.data_ptr(), self.state.data_ptr(),
+                                                         _stream_ptr(self.device)))
+
+    def match_frequencies(self, target: torch.Tensor, fir_out: torch.Tensor | None = None) -> None:
+        p, l = self._args()
+        _native.check(self.lib, self.lib.mgb_match_frequencies(
+            p, l, target.data_ptr(), self.result.data_ptr(), fir_out.data_ptr() if fir_out is not None else None,
+            self.workspace.data_ptr(), self.state.data_ptr(), _stream_ptr(self.device)))
+
+    def correct_levels(self) -> None:
+        p, l = self._args()
+        _native.check(self.lib, self.lib.mgb_correct_levels(p, l, self.workspace.data_ptr(), self.state.data_ptr(),
+                                                           _stream_ptr(self.device)))
+
+    def finalize(self, need_default: bool, need_no_limiter: bool, need_no_limiter_normalized: bool):
+        p, l = self._args()
+        n = self.layout.target_frames
+        mk = lambda need: torch.empty((n, 2), dtype=torch.float32, device=self.device) if need else None
+        limited, plain, normalized = mk(need_default), mk(need_no_limiter), mk(need_no_limiter_normalized)
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        _native.check(self.lib, self.lib.mgb_finalize(p, l, self.result.data_ptr(), ptr(limited), ptr(plain),
+                                                     ptr(normalized), self.workspace.data_ptr(),
+                                                     self.state.data_ptr(), _stream_ptr(self.device)))
+        return limited, plain, normalized
+
+    def read_state(self) -> _native.TrackState:
+        """One device->host read of the job's scalars (synchronises)."""
+        raw = self.state.cpu().numpy().tobytes()
+        return _native.TrackState.from_buffer_copy(raw)

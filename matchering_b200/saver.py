@@ -1,0 +1,13 @@
+"""Result writer (reference: matchering/saver.py:27-33)."""
+from . import wavio
+from .log import debug
+
+
+def save(file: str, result, sample_rate: int, subtype: str, name: str = "result") -> None:
+    debug(f"Saving the {name.upper()} {sample_rate} Hz Stereo {subtype} to: '{file}'...")
+    try:
+        import soundfile as sf
+        sf.write(file, result, sample_rate, subtype)
+    except ImportError:
+        wavio.write(file, result, sample_rate, subtype)
+    debug(f"'{file}' is saved")

@@ -1,0 +1,145 @@
+"""The CUDA kernel sources, compiled for the host through tests/emul (a CUDA-on-CPU emulator),
+checked against the oracle.  This validates kernel LOGIC in the build container where there is
+no GPU; the same assertions run against the real library in test_gpu_parity.py (-m gpu)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import port
+from emul_harness import EmulPlan, aligned, aligned_copy, emul_lib, limiter_params, ptr, run_pipeline
+from matchering_b200 import _native, plan as plan_mod
+
+TOL = 1e-5  # north-star bound on the sample-wise max-abs error of float32 results
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return emul_lib()
+
+
+@pytest.mark.parametrize("n,f64", [(1024, 0), (4096, 0), (8192, 0), (16384, 0), (2048, 1), (8192, 1)])
+def test_fft_matches_numpy(lib, n, f64):
+    rng = np.random.default_rng(n + f64)
+    dt = np.complex128 if f64 else np.complex64
+    x = (rng.standard_normal((2, n)) + 1j * rng.standard_normal((2, n))).astype(dt)
+    p = _native.Plan()
+    p.fft_size = min(n, 8192) if n <= 8192 else n // 2
+    p.n_lin, p.n_log, p.lowess_k, p.lowess_nfit = p.fft_size // 2 + 1, 10, 2, 2
+    bufs = [aligned((1 << 20,), np.uint8) for _ in range(4)]
+    p.d_tw_f32_F, p.d_tw_f32_2F, p.d_tw_f64_F, p.d_tw_f64_2F = [b.ctypes.data for b in bufs]
+    _native.check(lib, lib.mgb_plan_fill_twiddles(C.byref(p), None))
+    tw = bufs[1] if n > 8192 else (bufs[2] if f64 else bufs[0])
+    xin, out = aligned_copy(x), aligned((2, n), dt)
+    for direction in (1, -1):
+        _native.check(lib, lib.mgb_test_fft(n, f64, direction, ptr(xin), ptr(out), 2, ptr(tw), None))
+        want = np.fft.fft(x.astype(np.complex128), axis=1) if direction == 1 else np.fft.ifft(x.astype(np.complex128), axis=1) * n
+        err = np.abs(out - want).max() / np.abs(want).max()
+        assert err < (1e-14 if f64 else 5e-7)
+
+
+def test_fir_design_matches_oracle(lib):
+    cfg = port.OracleConfig()
+    ep = EmulPlan(cfg)
+    rng = np.random.default_rng(3)
+    k = np.arange(2049)
+    at = 1e-3 * (1 + 0.3 * rng.standard_normal(2049)) ** 2 + 1e-5
+    ar = 3e-3 / np.sqrt(1 + k / 20.0) * (1 + 0.3 * rng.standard_normal(2049)) ** 2 + 1e-6
+    avg = aligned_copy(np.stack([at, 0.5 * at, ar, 0.7 * ar]))
+    fir = aligned((2, 4096), np.float64)
+    ws = aligned((4 << 20,), np.uint8)
+    _native.check(lib, lib.mgb_test_design_fir(C.byref(ep.struct), ptr(avg), ptr(fir), ptr(ws), None))
+    assert np.abs(fir[0] - port.design_fir(at.copy(), ar.copy(), cfg)).max() < 1e-13
+    assert np.abs(fir[1] - port.design_fir(0.5 * at, 0.7 * ar, cfg)).max() < 1e-13
+    assert fir[0][0] == 0.0
+
+
+def _compare(outs, want):
+    for got, ref in zip(outs, want):
+        if got is None:
+            assert ref is None
+            continue
+        assert np.abs(got - ref).max() < TOL
+
+
+@pytest.mark.parametrize("tma", [1, 0])
+def test_pipeline_matches_golden(lib, golden, tma):
+    g = golden("pipeline_small.npz")
+    cfg = port.OracleConfig(max_piece_size=float(g["max_piece_size_s"]))
+    outs, st, fir, _, L = run_pipeline(cfg, g["target"], g["reference"], tma=tma)
+    assert (L.target_divisions, L.target_piece) == (int(g["target_divisions"]), int(g["target_piece"]))
+    assert (L.reference_divisions, L.reference_piece) == (int(g["reference_divisions"]), int(g["reference_piece"]))
+    assert abs(st.rms_coefficient - float(g["rms_coefficient"])) < 1e-9
+    assert abs(st.final_amplitude_coef - float(g["final_amplitude_coefficient"])) < 1e-12
+    assert np.abs(fir[0] - g["fir_mid"]).max() < 1e-7 and np.abs(fir[1] - g["fir_side"]).max() < 1e-7
+    _compare(outs, (g["limited"], g["no_limiter"], g["normalized"]))
+    assert st.limiter_engaged == 1
+
+
+def test_pipeline_quiet_reference_early_out(lib, golden):
+    g = golden("pipeline_quiet_reference.npz")
+    cfg = port.OracleConfig(max_piece_size=float(g["max_piece_size_s"]))
+    outs, st, _, _, _ = run_pipeline(cfg, g["target"], g["reference"], need=(True, True, False))
+    assert st.limiter_engaged == 0 and st.final_amplitude_coef < 1.0
+    _compare(outs, (g["limited"], g["no_limiter"], None))
+
+
+@pytest.mark.parametrize("fft_size,sr", [(1024, 44100), (2048, 22050), (4096, 96000)])
+def test_pipeline_other_configs(lib, fft_size, sr):
+    cfg = port.OracleConfig(internal_sample_rate=sr, fft_size=fft_size, max_piece_size=0.4, rms_correction_steps=2)
+    n = int(sr * 1.1) + 13
+    t, r = port.synth_target(n, 5), port.synth_reference(n - 4001, 6)
+    outs, st, _, _, _ = run_pipeline(cfg, t, r)
+    want = port.main(t.astype(np.float64), r.astype(np.float64), cfg, True, True, True)
+    _compare(outs, want)
+    assert st.steps_done == 2
+
+
+def _limit(lib, x, cfg):
+    params = limiter_params(plan_mod.limiter_constants(cfg))
+    n = len(x)
+    ws_bytes = int(lib.mgb_limiter_workspace_bytes(C.byref(params), n))
+    ws = aligned((ws_bytes,), np.uint8)
+    xin, out = aligned_copy(x, np.float32), aligned((n, 2), np.float32)
+    engaged = aligned((4,), np.int32)
+    _native.check(lib, lib.mgb_limit(C.byref(params), ptr(xin), ptr(out), n, ptr(ws), ws_bytes, ptr(engaged), None))
+    return out, int(engaged[0])
+
+
+def test_limiter_matches_golden_several_chunks(lib, golden):
+    g = golden("limiter.npz")
+    out, engaged = _limit(lib, g["x"], port.OracleConfig())
+    assert engaged == 1
+    assert np.abs(out - g["y_44100"]).max() < 1e-6
+    out96, _ = _limit(lib, g["x"], port.OracleConfig(internal_sample_rate=96000))
+    assert np.abs(out96 - g["y_96000"]).max() < 1e-6
+
+
+@pytest.mark.parametrize("n", [7, 100, 4607, 4608, 4609, 9217])
+def test_limiter_edge_lengths(lib, n):
+    cfg = port.OracleConfig()
+    x = port.synth_limiter_input(max(n, 64), seed=n)[:n]
+    out, engaged = _limit(lib, x, cfg)
+    want = port.limit(x.astype(np.float64), cfg)
+    assert np.abs(out - want).max() < 1e-6
+
+
+def test_limiter_not_engaged_copies_input(lib):
+    x = (0.2 * port.synth_limiter_input(6000, 2)).astype(np.float32)
+    out, engaged = _limit(lib, x, port.OracleConfig())
+    assert engaged == 0 and np.array_equal(out, x)
+
+
+def test_limiter_rejects_too_short_input(lib):
+    with pytest.raises(ValueError):
+        _limit(lib, np.zeros((6, 2), np.float32), port.OracleConfig())
+
+
+def test_unsupported_configs_fail_loudly():
+    with pytest.raises(plan_mod.UnsupportedConfig):
+        plan_mod.build_tables(port.OracleConfig(fft_size=512))
+    with pytest.raises(plan_mod.UnsupportedConfig):
+        plan_mod.build_tables(port.OracleConfig(lowess_it=2))
+    lim = port.OracleLimiterConfig(hold_filter_order=2)
+    with pytest.raises(plan_mod.UnsupportedConfig):
+        plan_mod.build_tables(port.OracleConfig(limiter=lim))

@@ -1,0 +1,250 @@
+"""Parity of the CUDA path (libmatchering_b200.so on a real B200) against the oracle and the
+golden vectors.  Everything goes through the C ABI, either directly or through the reference-shaped
+Python surface (stages.main / limiter.limit).  Tolerance: sample-wise max-abs <= 1e-5 (north star);
+the float64 FIR design is held to 1e-9."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("-m gpu tests need a CUDA device")
+    return torch
+
+
+@pytest.fixture(scope="module")
+def lib(torch_cuda):
+    from matchering_b200 import _native
+    return _native.load()
+
+
+@pytest.fixture(params=[1, 0], ids=["tma", "plain-loads"])
+def tma(request, lib):
+    lib.mgb_set_option(b"tma", request.param)
+    yield request.param
+    lib.mgb_set_option(b"tma", 1)
+
+
+def test_native_library_is_the_cuda_build(lib):
+    import matchering_b200._native as n
+    assert n.LIB_PATH.endswith("libmatchering_b200.so") and lib.mgb_version() >= 100
+
+
+@pytest.mark.parametrize("n,f64", [(1024, 0), (2048, 0), (4096, 0), (8192, 0), (16384, 0), (4096, 1), (8192, 1)])
+def test_fft_matches_numpy(torch_cuda, lib, n, f64):
+    torch = torch_cuda
+    from matchering_b200 import _native
+    rng = np.random.default_rng(n + f64)
+    dt = np.complex128 if f64 else np.complex64
+    x = (rng.standard_normal((5, n)) + 1j * rng.standard_normal((5, n))).astype(dt)
+    p = _native.Plan()
+    p.fft_size = n if n <= 8192 else n // 2
+    p.n_lin, p.n_log, p.lowess_k, p.lowess_nfit = p.fft_size // 2 + 1, 10, 2, 2
+    bufs = [torch.zeros(1 << 20, dtype=torch.uint8, device="cuda") for _ in range(4)]
+    p.d_tw_f32_F, p.d_tw_f32_2F, p.d_tw_f64_F, p.d_tw_f64_2F = [b.data_ptr() for b in bufs]
+    _native.check(lib, lib.mgb_plan_fill_twiddles(C.byref(p), None))
+    tw = bufs[1] if n > 8192 else (bufs[2] if f64 else bufs[0])
+    xin = torch.from_numpy(x).cuda()
+    out = torch.empty_like(xin)
+    for direction in (1, -1):
+        _native.check(lib, lib.mgb_test_fft(n, f64, direction, xin.data_ptr(), out.data_ptr(), 5, tw.data_ptr(), None))
+        torch.cuda.synchronize()
+        want = np.fft.fft(x.astype(np.complex128), axis=1) if direction == 1 else np.fft.ifft(x.astype(np.complex128), axis=1) * n
+        err = np.abs(out.cpu().numpy() - want).max() / np.abs(want).max()
+        assert err < (1e-14 if f64 else 5e-7)
+
+
+def _config(**kw):
+    import matchering_b200 as mg
+    return mg.Config(**kw)
+
+
+def _compare(got, want, tol=TOL):
+    for a, b in zip(got, want):
+        if b is None:
+            assert a is None
+        else:
+            assert a.shape == b.shape and np.abs(a - b).max() < tol
+
+
+def test_pipeline_matches_golden(torch_cuda, tma, golden):
+    from matchering_b200 import stages
+    g = golden("pipeline_small.npz")
+    cfg = _config(max_piece_size=float(g["max_piece_size_s"]))
+    got = stages.main(g["target"].astype(np.float64), g["reference"].astype(np.float64), cfg, True, True, True)
+    assert all(o.dtype == np.float64 for o in got)
+    _compare(got, (g["limited"], g["no_limiter"], g["normalized"]))
+
+
+def test_pipeline_quiet_reference_early_out(torch_cuda, golden):
+    from matchering_b200 import stages
+    g = golden("pipeline_quiet_reference.npz")
+    cfg = _config(max_piece_size=float(g["max_piece_size_s"]))
+    got = stages.main(g["target"], g["reference"], cfg, True, True, False)
+    assert got[0].dtype == np.float32 and got[2] is None
+    _compare(got, (g["limited"], g["no_limiter"], None))
+
+
+def test_fir_and_scalars_match_golden(torch_cuda, golden):
+    torch = torch_cuda
+    from matchering_b200.engine import TrackSession, get_plan, to_device_f32
+    g = golden("pipeline_small.npz")
+    cfg = _config(max_piece_size=float(g["max_piece_size_s"]))
+    plan = get_plan(cfg)
+    t, r = to_device_f32(g["target"], plan.device), to_device_f32(g["reference"], plan.device)
+    s = TrackSession(plan, t.shape[0], r.shape[0])
+    fir = torch.zeros((2, cfg.fft_size), dtype=torch.float64, device=plan.device)
+    s.match_levels(t, r)
+    s.match_frequencies(t, fir)
+    s.correct_levels()
+    st = s.read_state()
+    assert (s.layout.target_divisions, s.layout.target_piece) == (int(g["target_divisions"]), int(g["target_piece"]))
+    assert abs(st.rms_coefficient - float(g["rms_coefficient"])) < 1e-9
+    assert abs(st.final_amplitude_coef - float(g["final_amplitude_coefficient"])) < 1e-12
+    assert abs(st.target_match_rms - float(g["target_match_rms"])) < 1e-9
+    f = fir.cpu().numpy()
+    assert np.abs(f[0] - g["fir_mid"]).max() < 1e-7 and np.abs(f[1] - g["fir_side"]).max() < 1e-7
+    assert st.steps_done == 4 and st.limiter_engaged == 1
+
+
+@pytest.mark.parametrize("fft_size,sr,seconds", [(1024, 44100, 1.5), (2048, 22050, 2.0), (4096, 96000, 1.2), (8192, 44100, 2.5)])
+def test_pipeline_other_configs_against_oracle(torch_cuda, fft_size, sr, seconds):
+    import port
+    from matchering_b200 import stages
+    cfg = _config(internal_sample_rate=sr, fft_size=fft_size, max_piece_size=0.6, rms_correction_steps=3)
+    n = int(sr * seconds) + 13
+    t, r = port.synth_target(n, 5), port.synth_reference(n - 4001, 6)
+    got = stages.main(t, r, cfg, True, True, True)
+    want = port.main(t.astype(np.float64), r.astype(np.float64), cfg, True, True, True)
+    _compare(got, want)
+
+
+def test_pipeline_half_minute_against_oracle(torch_cuda, tma):
+    """30 s at the default Config (3 pieces, ~320 convolution frames, ~290 limiter chunks)."""
+    import port
+    from matchering_b200 import stages
+    cfg = _config()
+    n = 44100 * 30 + 7
+    t, r = port.synth_target(n, 0), port.synth_reference(n + 1001, 1)
+    got = stages.main(t, r, cfg, True, True, True)
+    want = port.main(t.astype(np.float64), r.astype(np.float64), cfg, True, True, True)
+    _compare(got, want)
+    assert abs(np.abs(got[0]).max() - np.abs(want[0]).max()) < 1e-6
+
+
+def test_pipeline_is_reproducible_and_does_not_touch_inputs(torch_cuda):
+    import port
+    from matchering_b200 import stages
+    cfg = _config(max_piece_size=2.0)
+    t, r = port.synth_target(200000, 8), port.synth_reference(190000, 9)
+    t0, r0 = t.copy(), r.copy()
+    a = stages.main(t, r, cfg)[0]
+    b = stages.main(t, r, cfg)[0]
+    assert np.array_equal(t, t0) and np.array_equal(r, r0)
+    assert np.abs(a - b).max() < 1e-6  # float64 atomics may reorder the per-piece sums' last bits
+
+
+def test_limiter_matches_golden(torch_cuda, golden):
+    from matchering_b200.limiter import limit
+    g = golden("limiter.npz")
+    got = limit(g["x"].astype(np.float64), _config())
+    assert got.dtype == np.float64 and np.abs(got - g["y_44100"]).max() < 1e-6
+    got96 = limit(g["x"], _config(internal_sample_rate=96000))
+    assert np.abs(got96 - g["y_96000"]).max() < 1e-6
+
+
+@pytest.mark.parametrize("n", [7, 100, 4607, 4608, 4609, 9217, 200001])
+def test_limiter_edge_lengths(torch_cuda, n):
+    import port
+    from matchering_b200.limiter import limit
+    x = port.synth_limiter_input(max(n, 64), seed=n)[:n]
+    got = limit(x, _config())
+    want = port.limit(x.astype(np.float64), port.OracleConfig())
+    assert np.abs(got - want).max() < 1e-6
+
+
+def test_limiter_early_out_returns_input_object(torch_cuda):
+    import port
+    from matchering_b200.limiter import limit
+    x = (0.2 * port.synth_limiter_input(6000, 2)).astype(np.float64)
+    assert limit(x, _config()) is x
+    with pytest.raises(ValueError):
+        limit(np.zeros((6, 2)), _config())
+
+
+def test_limiter_three_minutes_against_oracle(torch_cuda):
+    """1723 chunks chained by decoupled look-back; the release pole needs float64 carries."""
+    import port
+    from matchering_b200.limiter import limit
+    x = port.synth_limiter_input(44100 * 180, seed=0)
+    got = limit(x, _config())
+    want = port.limit(x.astype(np.float64), port.OracleConfig())
+    assert np.abs(got - want).max() < 1e-6
+    assert abs(np.abs(got).max() - _config().threshold) < 1e-6
+
+
+def test_limiter_one_hour_properties(torch_cuda):
+    """BASELINE config 5 at full size (158.76 M frames; the oracle needs 13.7 GB and a minute for
+    it, so size-independent properties instead): the peak sits at the threshold, the gain never
+    exceeds 1, and -- the limiter being causal up to its short look-ahead -- the first three
+    minutes of the hour equal a three-minute run."""
+    torch = torch_cuda
+    import port
+    from matchering_b200.limiter import limit
+    n3 = 44100 * 180
+    x3 = port.synth_limiter_input(n3, seed=0)
+    reps = 20
+    x = torch.from_numpy(x3).cuda().repeat(reps, 1)
+    y = limit(x, _config())
+    assert y.shape == (n3 * reps, 2)
+    thr = _config().threshold
+    assert abs(float(y.abs().max()) - thr) < 1e-6
+    assert bool((y.abs() <= x.abs() + 1e-7).all())
+    y3 = limit(torch.from_numpy(x3).cuda(), _config())
+    assert float((y[: n3 - 4096] - y3[: n3 - 4096]).abs().max()) < 1e-7
+
+
+def test_full_size_config2_against_oracle(torch_cuda):
+    """BASELINE config 2: 3-minute 44.1 kHz stereo track, full pipeline (oracle: ~9 s of CPU)."""
+    import port
+    from matchering_b200 import stages
+    n = 44100 * 180
+    t, r = port.synth_target(n, 0), port.synth_reference(n, 1)
+    got = stages.main(t, r, _config(), True, True, True)
+    want = port.main(t.astype(np.float64), r.astype(np.float64), port.OracleConfig(), True, True, True)
+    errs = [float(np.abs(a - b).max()) for a, b in zip(got, want)]
+    print("config-2 max-abs errors (limited, no-limiter, normalised):", errs)
+    assert max(errs) < TOL
+
+
+def test_process_files_end_to_end(torch_cuda, tmp_path):
+    """BASELINE config 1 shape: mg.process on WAV files (10 s white target vs pink reference)."""
+    import matchering_b200 as mg
+    import port
+    from matchering_b200 import wavio
+    n = 441000
+    t = port.synth_target(n, 0, kind="white")
+    r = port.synth_reference(n, 1, kind="quiet")
+    wavio.write(str(tmp_path / "t.wav"), t, 44100, "FLOAT")
+    wavio.write(str(tmp_path / "r.wav"), r, 44100, "FLOAT")
+    codes = []
+    mg.log(info_handler=codes.append)
+    try:
+        mg.process(str(tmp_path / "t.wav"), str(tmp_path / "r.wav"),
+                   [mg.pcm16(str(tmp_path / "o16.wav")), mg.Result(str(tmp_path / "of.wav"), "FLOAT", use_limiter=False)])
+    finally:
+        mg.log()
+    assert codes[0] == "Loading and analysis" and codes[-1] == "The task is completed" and "Matching frequencies" in codes
+    want = port.main(t.astype(np.float64), r.astype(np.float64), port.OracleConfig(), True, False, True)
+    got_f, _ = wavio.read(str(tmp_path / "of.wav"))
+    got_16, _ = wavio.read(str(tmp_path / "o16.wav"))
+    assert np.abs(got_f - want[2]).max() < TOL
+    assert np.abs(got_16 - want[0]).max() < 1.0 / 32767 + TOL
