@@ -127,6 +127,14 @@ const char* mgb_last_error_string(void);
  * coalesced loads).  Returns MGB_ERR_INVALID for an unknown name. */
 int mgb_set_option(const char* name, int value);
 
+/* Measurement hooks (bench.py): number of kernel launches made by this library so far; and, while
+ * profiling is enabled, a CUDA-event pair is recorded around every launch on its stream --
+ * mgb_profile_collect synchronises the device, writes up to `capacity` durations (ms) in launch
+ * order with their kernel names ('\n'-separated) and returns how many it wrote. */
+long long mgb_launch_count(void);
+int mgb_profile_enable(int on);
+int mgb_profile_collect(char* names, int names_capacity, float* ms, int capacity);
+
 /* Bytes of the four twiddle tables for `fft_size`, in the order of the mgb_plan fields. */
 int mgb_plan_twiddle_bytes(int32_t fft_size, int64_t bytes_out[4]);
 /* Fill plan->d_tw_* (device buffers of the sizes above) on `stream`. */

@@ -92,6 +92,9 @@ PROTOTYPES = {
     "mgb_version": (C.c_int, []),
     "mgb_last_error_string": (C.c_char_p, []),
     "mgb_set_option": (C.c_int, [C.c_char_p, C.c_int]),
+    "mgb_launch_count": (C.c_longlong, []),
+    "mgb_profile_enable": (C.c_int, [C.c_int]),
+    "mgb_profile_collect": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_float), C.c_int]),
     "mgb_plan_twiddle_bytes": (C.c_int, [C.c_int32, C.POINTER(C.c_int64)]),
     "mgb_plan_fill_twiddles": (C.c_int, [C.POINTER(Plan), C.c_void_p]),
     "mgb_track_layout_init": (C.c_int, [C.POINTER(Plan), C.c_int64, C.c_int64, C.POINTER(TrackLayout)]),

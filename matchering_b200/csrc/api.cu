@@ -4,12 +4,38 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <vector>
+
 #include "fft.cuh"
 #include "kernels.cuh"
 
 namespace mgb {
 
 int g_use_tma = 1;
+
+#ifndef MGB_EMULATE
+long long g_launch_count = 0;
+int g_profile = 0;
+namespace {
+struct ProfileRecord {
+    const char* what;
+    cudaEvent_t start, stop;
+};
+std::vector<ProfileRecord> g_records;
+}  // namespace
+void profile_mark(const char* what, cudaStream_t stream, bool begin) {
+    if (begin) {
+        ProfileRecord r;
+        r.what = what;
+        cudaEventCreate(&r.start);
+        cudaEventCreate(&r.stop);
+        cudaEventRecord(r.start, stream);
+        g_records.push_back(r);
+    } else if (!g_records.empty()) {
+        cudaEventRecord(g_records.back().stop, stream);
+    }
+}
+#endif
 
 static thread_local char g_error[512] = "";
 
@@ -199,6 +225,56 @@ int mgb_set_option(const char* name, int value) {
     }
     set_error("unknown option '%s'", name);
     return MGB_ERR_INVALID;
+}
+
+long long mgb_launch_count(void) {
+#ifdef MGB_EMULATE
+    return 0;
+#else
+    return g_launch_count;
+#endif
+}
+
+int mgb_profile_enable(int on) {
+#ifndef MGB_EMULATE
+    g_profile = on ? 1 : 0;
+#else
+    (void)on;
+#endif
+    return MGB_OK;
+}
+
+int mgb_profile_collect(char* names, int names_capacity, float* ms, int capacity) {
+#ifdef MGB_EMULATE
+    (void)names; (void)names_capacity; (void)ms; (void)capacity;
+    return 0;
+#else
+    cudaDeviceSynchronize();
+    int n = 0;
+    int used = 0;
+    if (names && names_capacity > 0) names[0] = 0;
+    for (auto& r : g_records) {
+        float t = 0.0f;
+        cudaEventElapsedTime(&t, r.start, r.stop);
+        if (n < capacity && ms) {
+            ms[n] = t;
+            if (names) {
+                const int len = (int)strlen(r.what);
+                if (used + len + 2 <= names_capacity) {
+                    memcpy(names + used, r.what, len);
+                    used += len;
+                    names[used++] = '\n';
+                    names[used] = 0;
+                }
+            }
+            ++n;
+        }
+        cudaEventDestroy(r.start);
+        cudaEventDestroy(r.stop);
+    }
+    g_records.clear();
+    return n;
+#endif
 }
 
 int mgb_plan_twiddle_bytes(int32_t fft_size, int64_t bytes_out[4]) {

@@ -49,10 +49,17 @@ inline int launch(const char* what, void (*kernel)(KA...), dim3 grid, dim3 block
 }
 #else
 #define MGB_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+// launch bookkeeping (api.cu): a counter of kernel launches and, when profiling is switched on,
+// a CUDA-event pair around every launch on the launching stream
+extern long long g_launch_count;
+extern int g_profile;
+void profile_mark(const char* what, cudaStream_t stream, bool begin);
+
 template <typename... KA, typename... A>
 inline int launch(const char* what, void (*kernel)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                   A... args) {
     if (grid.x == 0 || grid.y == 0 || grid.z == 0) return MGB_OK;
+    g_launch_count++;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
@@ -60,7 +67,9 @@ inline int launch(const char* what, void (*kernel)(KA...), dim3 grid, dim3 block
             return MGB_ERR_CUDA;
         }
     }
+    if (g_profile) profile_mark(what, stream, true);
     kernel<<<grid, block, smem, stream>>>(static_cast<KA>(args)...);
+    if (g_profile) profile_mark(what, stream, false);
     return cuda_status(what);
 }
 #endif
