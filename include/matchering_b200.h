@@ -77,11 +77,13 @@ typedef struct mgb_plan {
     const double* d_sb_end;    /* [4] */
     const int32_t* d_sb_eval_idx; /* [n_lin] */
     const double* d_sb_eval_w;    /* [n_lin][4] */
-    /* LOWESS (dsp.py:103-106, statsmodels semantics, it = 0) */
-    const double* d_lw_x;        /* [n_log] abscissa linspace(0,1,n_log) */
-    const int32_t* d_lw_fit_idx; /* [lowess_nfit] indices with a local regression */
-    const int32_t* d_lw_fit_left;/* [lowess_nfit] left edge of each neighbourhood */
+    /* LOWESS (dsp.py:103-106, statsmodels semantics, it = 0) as a Config-only linear operator */
+    const int32_t* d_lw_fit_idx; /* [lowess_nfit] abscissae with a local regression */
+    const int32_t* d_lw_fit_left;/* [lowess_nfit] left edge of each neighbourhood [left, left+k) */
     const int32_t* d_lw_seg;     /* [n_log] position in fit_idx of the last regression point <= j */
+    const double* d_lw_alpha;    /* [n_log] weight of the next regression point (delta interpolation) */
+    const double* d_lw_rows;     /* [n_rows][lowess_k] regression coefficients: fit = row . y[left..] */
+    const int32_t* d_lw_row_idx; /* [lowess_nfit] row of each regression point */
     /* window (scipy.signal.windows.hann(F), match_frequencies.py:99) */
     const double* d_hann;        /* [F] */
     /* FFT twiddles, filled by mgb_plan_fill_twiddles */
@@ -89,6 +91,7 @@ typedef struct mgb_plan {
     void* d_tw_f32_2F;   /* float2  table of the 2F-point transform */
     void* d_tw_f64_F;    /* double2 table of the F-point transform  */
     void* d_tw_f64_2F;   /* double2 table of the 2F-point transform */
+    void* d_limiter_tables; /* powers of the limiter's three poles (blocked-scan carries) */
 } mgb_plan;
 
 /* Per-track scalars, resident in device memory (one struct per track in flight). */
@@ -135,9 +138,10 @@ long long mgb_launch_count(void);
 int mgb_profile_enable(int on);
 int mgb_profile_collect(char* names, int names_capacity, float* ms, int capacity);
 
-/* Bytes of the four twiddle tables for `fft_size`, in the order of the mgb_plan fields. */
-int mgb_plan_twiddle_bytes(int32_t fft_size, int64_t bytes_out[4]);
-/* Fill plan->d_tw_* (device buffers of the sizes above) on `stream`. */
+/* Bytes of the four twiddle tables for `fft_size` and of d_limiter_tables, in the order of the
+ * mgb_plan fields. */
+int mgb_plan_twiddle_bytes(int32_t fft_size, int64_t bytes_out[5]);
+/* Fill plan->d_tw_* and plan->d_limiter_tables (device buffers of the sizes above) on `stream`. */
 int mgb_plan_fill_twiddles(const mgb_plan* plan, void* stream);
 
 /* match_levels.py:47-59 piece geometry + launch geometry + workspace size. */

@@ -49,11 +49,12 @@ class Plan(C.Structure):
         ("d_sa_eval_idx", C.c_void_p), ("d_sa_eval_w", C.c_void_p),
         ("d_sb_hinv", C.c_void_p), ("d_sb_lu", C.c_void_p), ("d_sb_end", C.c_void_p),
         ("d_sb_eval_idx", C.c_void_p), ("d_sb_eval_w", C.c_void_p),
-        ("d_lw_x", C.c_void_p), ("d_lw_fit_idx", C.c_void_p), ("d_lw_fit_left", C.c_void_p),
-        ("d_lw_seg", C.c_void_p),
+        ("d_lw_fit_idx", C.c_void_p), ("d_lw_fit_left", C.c_void_p), ("d_lw_seg", C.c_void_p),
+        ("d_lw_alpha", C.c_void_p), ("d_lw_rows", C.c_void_p), ("d_lw_row_idx", C.c_void_p),
         ("d_hann", C.c_void_p),
         ("d_tw_f32_F", C.c_void_p), ("d_tw_f32_2F", C.c_void_p),
         ("d_tw_f64_F", C.c_void_p), ("d_tw_f64_2F", C.c_void_p),
+        ("d_limiter_tables", C.c_void_p),
     ]
 
 

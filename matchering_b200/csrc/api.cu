@@ -277,7 +277,7 @@ int mgb_profile_collect(char* names, int names_capacity, float* ms, int capacity
 #endif
 }
 
-int mgb_plan_twiddle_bytes(int32_t fft_size, int64_t bytes_out[4]) {
+int mgb_plan_twiddle_bytes(int32_t fft_size, int64_t bytes_out[5]) {
     MGB_REQUIRE(bytes_out != nullptr, MGB_ERR_INVALID, "bytes_out is NULL");
     const int cf = twiddle_count(fft_size), c2 = twiddle_count(2 * fft_size);
     MGB_REQUIRE(cf > 0 && c2 > 0, MGB_ERR_UNSUPPORTED, "fft_size %d has no kernel", fft_size);
@@ -285,6 +285,7 @@ int mgb_plan_twiddle_bytes(int32_t fft_size, int64_t bytes_out[4]) {
     bytes_out[1] = (int64_t)c2 * 8;
     bytes_out[2] = (int64_t)cf * 16;
     bytes_out[3] = (int64_t)c2 * 16;
+    bytes_out[4] = (int64_t)align256(3 * sizeof(ScanPow));
     return MGB_OK;
 }
 
@@ -298,7 +299,9 @@ int mgb_plan_fill_twiddles(const mgb_plan* plan, void* stream) {
     MGB_TRY(fill_twiddles(2 * plan->fft_size, 0, plan->d_tw_f32_2F, st));
     MGB_TRY(fill_twiddles(plan->fft_size, 1, plan->d_tw_f64_F, st));
     if (plan->d_tw_f64_2F && plan->fft_size <= 4096) MGB_TRY(fill_twiddles(2 * plan->fft_size, 1, plan->d_tw_f64_2F, st));
-    return MGB_OK;
+    if (!plan->d_limiter_tables) return MGB_OK;  // FFT-only plans (tests); mgb_finalize insists on the tables
+    MGB_TRY(check_aligned(plan->d_limiter_tables, "d_limiter_tables"));
+    return launch_limiter_tables(plan->limiter, (ScanPow*)plan->d_limiter_tables, st);
 }
 
 int mgb_track_layout_init(const mgb_plan* plan, int64_t target_frames, int64_t reference_frames,
@@ -415,15 +418,15 @@ int mgb_finalize(const mgb_plan* plan, const mgb_track_layout* L, const float* d
         MGB_TRY(check_aligned(d_out_limited, "d_out_limited"));
         MGB_TRY(launch_limiter(plan->limiter, res, (float2*)d_out_limited, L->target_frames, &d_state->gain,
                                &d_state->final_amplitude_coef, &d_state->limiter_engaged, ws.limiter_ticket,
-                               (LookbackSlot*)ws.lookback, st));
+                               (LookbackSlot*)ws.lookback, (const ScanPow*)plan->d_limiter_tables, st));
     }
     return MGB_OK;
 }
 
 int64_t mgb_limiter_workspace_bytes(const mgb_limiter_params* params, int64_t frames) {
     (void)params;
-    if (frames <= 0) return 256;
-    return 256 + limiter_lookback_bytes(frames);
+    if (frames <= 0) return 4096;
+    return 4096 + limiter_lookback_bytes(frames);
 }
 
 int mgb_limit(const mgb_limiter_params* params, const float* d_in_lr, float* d_out_lr, int64_t frames,
@@ -439,18 +442,20 @@ int mgb_limit(const mgb_limiter_params* params, const float* d_in_lr, float* d_o
                 (long long)mgb_limiter_workspace_bytes(params, frames));
     cudaStream_t st = (cudaStream_t)stream;
     unsigned char* base = (unsigned char*)d_workspace;
-    // [0,4): peak bits  [16,20): ticket  [256, ...): look-back slots
+    // [0,4): peak bits  [16,20): ticket  [256, 4096): pole tables  [4096, ...): look-back slots
 #ifdef MGB_EMULATE
-    memset(base, 0, 256 + limiter_lookback_bytes(frames));
+    memset(base, 0, 4096 + limiter_lookback_bytes(frames));
 #else
-    if (cudaMemsetAsync(base, 0, 256 + limiter_lookback_bytes(frames), st) != cudaSuccess) return cuda_status("memset");
+    if (cudaMemsetAsync(base, 0, 4096 + limiter_lookback_bytes(frames), st) != cudaSuccess) return cuda_status("memset");
 #endif
+    ScanPow* tables = (ScanPow*)(base + 256);
+    MGB_TRY(launch_limiter_tables(*params, tables, st));
     float* peak = (float*)base;
     int* ticket = (int*)(base + 16);
     MGB_TRY(launch_absmax((const float2*)d_in_lr, frames, peak, st));
     MGB_TRY(launch_limiter_engaged(peak, nullptr, params->threshold, d_engaged, st));
     return launch_limiter(*params, (const float2*)d_in_lr, (float2*)d_out_lr, frames, nullptr, nullptr, d_engaged, ticket,
-                          (LookbackSlot*)(base + 256), st);
+                          (LookbackSlot*)(base + 4096), tables, st);
 }
 
 int mgb_process_host(const mgb_plan* plan, const mgb_track_layout* L, const float* h_target_lr,

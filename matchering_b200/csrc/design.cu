@@ -103,6 +103,9 @@ struct SplineTables {
 };
 
 // Second derivatives of the not-a-knot cubic through (knots, y): M[0..n).  z is scratch [n].
+// The two substitution sweeps are first-order recurrences; each thread runs a block of rows after
+// a kWarm-row warm-up.  Operands are fetched eight rows at a time so that the L2 latency of the
+// factor tables overlaps instead of adding up along the dependent chain.
 __device__ void spline_moments(const double* __restrict__ y, int n, SplineTables t, double* __restrict__ z,
                                double* __restrict__ M) {
     const int m = n - 2;
@@ -110,26 +113,60 @@ __device__ void spline_moments(const double* __restrict__ y, int n, SplineTables
     const double* invden = t.lu + m;
     const double* cp = t.lu + 2 * m;
     const int tid = threadIdx.x, nthr = blockDim.x;
+    // right-hand side scaled by the pivot, all rows in parallel (row i = interior knot i+1)
+    for (int i = tid; i < m; i += nthr)
+        z[i] = 6.0 * ((y[i + 2] - y[i + 1]) * t.hinv[i + 1] - (y[i + 1] - y[i]) * t.hinv[i]) * invden[i];
+    __syncthreads();
     const int block = (m + nthr - 1) / nthr;
     const int lo = tid * block;
     const int hi = min(m, lo + block);
+    // forward sweep: z (scaled right-hand side) -> M (used as scratch for the swept values)
     if (lo < m) {
         double acc = 0.0;
-        for (int i = max(0, lo - kWarm); i < hi; ++i) {
-            // row i of the reduced system is interior knot i+1
-            const double d = 6.0 * ((y[i + 2] - y[i + 1]) * t.hinv[i + 1] - (y[i + 1] - y[i]) * t.hinv[i]);
-            acc = d * invden[i] - fa[i] * acc;
-            if (i >= lo) z[i] = acc;
+        int i = max(0, lo - kWarm);
+        while (i < hi) {
+            double dv[8], fv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int r = min(i + u, m - 1);
+                dv[u] = z[r];
+                fv[u] = fa[r];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (i + u < hi) {
+                    acc = dv[u] - fv[u] * acc;
+                    if (i + u >= lo) M[i + u] = acc;
+                }
+            }
+            i += 8;
         }
     }
     __syncthreads();
+    // backward sweep: M (swept) -> z[i+1] (moment of interior knot i+1)
     if (lo < m) {
         double acc = 0.0;
-        for (int i = min(m - 1, hi - 1 + kWarm); i >= lo; --i) {
-            acc = z[i] - cp[i] * acc;
-            if (i < hi) M[i + 1] = acc;
+        int i = min(m - 1, hi - 1 + kWarm);
+        while (i >= lo) {
+            double zv[8], cv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int r = max(i - u, 0);
+                zv[u] = M[r];
+                cv[u] = cp[r];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (i - u >= lo) {
+                    acc = zv[u] - cv[u] * acc;
+                    if (i - u < hi) z[i - u + 1] = acc;
+                }
+            }
+            i -= 8;
         }
     }
+    __syncthreads();
+    for (int i = 1 + tid; i <= m; i += nthr) M[i] = z[i];
     __syncthreads();
     if (tid == 0) {
         M[0] = t.end[0] * M[1] + t.end[1] * M[2];
@@ -160,6 +197,40 @@ struct DesignArgs {
     float2* h_side;
     const mgb_track_state* state;  // null with avg_override: c0 = 1, coef = 1
 };
+
+// Matching curve m[k] = mean|rfft(reference)| / max(eps, mean|rfft(target)|) from the per-(piece,
+// slot) partial sums of analyze.cu, over the loudest pieces only (match_frequencies.py:42,93-94).
+// grid = (ceil(n_lin/32), 2 channels); block = 32 bins x 8 slices of the (piece, slot) items.
+__global__ void __launch_bounds__(256)
+spectrum_mean_kernel(DesignArgs a, int n_lin, int fft_size, double eps) {
+    __shared__ double part_t[8][33], part_r[8][33];
+    const int bx = threadIdx.x & 31, sy = threadIdx.x >> 5;
+    const int k = blockIdx.x * 32 + bx;
+    const int ch = blockIdx.y;
+    double st = 0.0, sr = 0.0;
+    if (k < n_lin) {
+        const int items_t = a.div_t * a.slots_t, items_r = a.div_r * a.slots_r;
+        for (int it = sy; it < items_t; it += 8)
+            if (a.mask_t[it / a.slots_t]) st += (double)a.spec_part_t[((long long)it * 2 + ch) * n_lin + k];
+        for (int it = sy; it < items_r; it += 8)
+            if (a.mask_r[it / a.slots_r]) sr += (double)a.spec_part_r[((long long)it * 2 + ch) * n_lin + k];
+    }
+    part_t[sy][bx] = st;
+    part_r[sy][bx] = sr;
+    __syncthreads();
+    if (sy == 0 && k < n_lin) {
+        for (int q = 1; q < 8; ++q) {
+            st += part_t[q][bx];
+            sr += part_r[q][bx];
+        }
+        const double c0 = a.state->rms_coefficient, coef = a.state->final_amplitude_coef;
+        // |rfft| is positively homogeneous: the level-matching gain c0 (target) and the reference
+        // normalisation 1/coef are applied to the means instead of to the samples
+        const double norm_t = c0 / ((double)a.state->target_loud_pieces * (double)a.frames_per_piece_t * (double)fft_size);
+        const double norm_r = 1.0 / (coef * (double)a.state->reference_loud_pieces * (double)a.frames_per_piece_r * (double)fft_size);
+        a.scratch[(long long)ch * a.stride + k] = (sr * norm_r) / fmax(eps, st * norm_t);
+    }
+}
 
 template <int F>
 struct DesignSmem {
@@ -204,26 +275,7 @@ design_kernel(mgb_plan plan, DesignArgs a) {
             const double ar = a.avg_override[(long long)(2 + ch) * HB + k];
             m[k] = ar / fmax(eps, at);
         }
-    } else {
-        const double loud_t = (double)a.state->target_loud_pieces;
-        const double loud_r = (double)a.state->reference_loud_pieces;
-        const double norm_t = c0 / (loud_t * (double)a.frames_per_piece_t * (double)F);
-        const double norm_r = 1.0 / (coef * loud_r * (double)a.frames_per_piece_r * (double)F);
-        for (int k = tid; k < HB; k += nthr) {
-            double st = 0.0, sr = 0.0;
-            for (int p = 0; p < a.div_t; ++p) {
-                if (!a.mask_t[p]) continue;
-                for (int q = 0; q < a.slots_t; ++q)
-                    st += (double)a.spec_part_t[(((long long)p * a.slots_t + q) * 2 + ch) * HB + k];
-            }
-            for (int p = 0; p < a.div_r; ++p) {
-                if (!a.mask_r[p]) continue;
-                for (int q = 0; q < a.slots_r; ++q)
-                    sr += (double)a.spec_part_r[(((long long)p * a.slots_r + q) * 2 + ch) * HB + k];
-            }
-            m[k] = (sr * norm_r) / fmax(eps, st * norm_t);  // match_frequencies.py:93-94
-        }
-    }
+    }  // otherwise spectrum_mean_kernel has already written m
     __syncthreads();
 
     // ---- B/C: cubic spline linear grid -> log grid (match_frequencies.py:60-61) --------------
@@ -231,71 +283,23 @@ design_kernel(mgb_plan plan, DesignArgs a) {
     for (int j = tid; j < NL; j += nthr) mlog[j] = spline_eval(m, M1, plan.d_sa_eval_idx[j], plan.d_sa_eval_w + 4LL * j);
     __syncthreads();
 
-    // ---- D: LOWESS, one warp per local regression (dsp.py:103-106) ---------------------------
+    // ---- D: LOWESS (dsp.py:103-106): each regression is a Config-only row of k coefficients ------
     {
-        const double* x = plan.d_lw_x;
         const int k = plan.lowess_k;
         for (int f = warp; f < plan.lowess_nfit; f += nwarps) {
-            const int i = plan.d_lw_fit_idx[f];
-            const int left = plan.d_lw_fit_left[f];
-            const double xi = x[i];
-            const double radius = fmax(fabs(x[left] - xi), fabs(x[left + k - 1] - xi));
-            double sw = 0.0, swx = 0.0, nz = 0.0;
-            for (int j = lane; j < k; j += 32) {
-                const double xj = x[left + j];
-                const double d = fabs(xj - xi);
-                double t = d / radius;
-                double w = 1.0 - t * t * t;
-                w = w * w * w;
-                if (d >= radius) w = 0.0;
-                sw += w;
-                swx += w * xj;
-                nz += (w != 0.0) ? 1.0 : 0.0;
-            }
-            sw = warp_sum(sw);
-            swx = warp_sum(swx);
-            nz = warp_sum(nz);
-            double fit;
-            if (sw <= 0.0 || nz == 1.0) {
-                fit = mlog[i];
-            } else {
-                const double xbar = swx / sw;
-                double sq = 0.0;
-                for (int j = lane; j < k; j += 32) {
-                    const double xj = x[left + j];
-                    const double d = fabs(xj - xi);
-                    double t = d / radius;
-                    double w = 1.0 - t * t * t;
-                    w = w * w * w;
-                    if (d >= radius) w = 0.0;
-                    sq += w * (xj - xbar) * (xj - xbar);
-                }
-                sq = warp_sum(sq) / sw;
-                double acc = 0.0;
-                for (int j = lane; j < k; j += 32) {
-                    const double xj = x[left + j];
-                    const double d = fabs(xj - xi);
-                    double t = d / radius;
-                    double w = 1.0 - t * t * t;
-                    w = w * w * w;
-                    if (d >= radius) w = 0.0;
-                    acc += (w / sw) * (1.0 + (xi - xbar) * (xj - xbar) / sq) * mlog[left + j];
-                }
-                fit = warp_sum(acc);
-            }
-            if (lane == 0) zz[f] = fit;
+            const double* row = plan.d_lw_rows + (long long)plan.d_lw_row_idx[f] * k;
+            const double* yy = mlog + plan.d_lw_fit_left[f];
+            double acc = 0.0;
+            for (int j = lane; j < k; j += 32) acc += row[j] * yy[j];
+            acc = warp_sum(acc);
+            if (lane == 0) zz[f] = acc;
         }
         __syncthreads();
+        const int last = plan.lowess_nfit - 1;
         for (int j = tid; j < NL; j += nthr) {
             const int sg = plan.d_lw_seg[j];
-            const int fi = plan.d_lw_fit_idx[sg];
-            if (fi == j) {
-                slog[j] = zz[sg];
-            } else {  // skipped by `delta`: linear interpolation between the bracketing fits
-                const int fn = plan.d_lw_fit_idx[sg + 1];
-                const double al = (x[j] - x[fi]) / (x[fn] - x[fi]);
-                slog[j] = al * zz[sg + 1] + (1.0 - al) * zz[sg];
-            }
+            const double al = plan.d_lw_alpha[j];  // 0 at a regression point
+            slog[j] = al * zz[min(sg + 1, last)] + (1.0 - al) * zz[sg];
         }
         __syncthreads();
     }
@@ -389,6 +393,9 @@ int launch_design(const mgb_plan& plan, const mgb_track_layout& layout, const Wo
     a.h_mid = ws.h_mid;
     a.h_side = ws.h_side;
     a.state = avg_override ? nullptr : state;
+    if (!avg_override)
+        MGB_TRY(launch("spectrum_mean_kernel", spectrum_mean_kernel, dim3((plan.n_lin + 31) / 32, 2), dim3(256), 0, stream, a,
+                       plan.n_lin, plan.fft_size, plan.min_value));
     switch (plan.fft_size) {
         case 1024: return launch_design_t<1024>(plan, a, stream);
         case 2048: return launch_design_t<2048>(plan, a, stream);

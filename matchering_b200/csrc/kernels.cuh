@@ -34,6 +34,13 @@ struct LookbackSlot {
     int pad[2];
 };
 
+// powers of a pole for a blocked scan with `ept` elements per thread (limiter.cu)
+struct ScanPow {
+    double pe[19];  // p^k, k = 0..18
+    double ql[33];  // q^k, q = p^ept
+    double qw[17];  // Q^k, Q = q^32
+};
+
 constexpr int kLimiterThreads = 512;
 constexpr int kLimiterCoreEpt = 9;                                   // core samples per thread
 constexpr int kLimiterCore = kLimiterThreads * kLimiterCoreEpt;      // 4608 samples per chunk
@@ -72,7 +79,8 @@ int launch_convert_f32_f64(const float* in, double* out, int64_t count, cudaStre
 // limiter.cu ------------------------------------------------------------------------------------
 int launch_limiter(const mgb_limiter_params& lp, const float2* in, float2* out, int64_t frames, const double* pre_gain,
                    const double* post_gain, const int* engaged, int* ticket, LookbackSlot* lookback,
-                   cudaStream_t stream);
+                   const ScanPow* tables, cudaStream_t stream);
+int launch_limiter_tables(const mgb_limiter_params& lp, ScanPow* tables, cudaStream_t stream);
 int launch_limiter_engaged(const float* peak_bits, const double* pre_gain, double threshold, int* engaged,
                            cudaStream_t stream);
 

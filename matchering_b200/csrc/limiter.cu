@@ -31,23 +31,9 @@ constexpr int CORE_EPT = kLimiterCoreEpt;
 constexpr int LC = kLimiterCore;
 constexpr int SPAN_EPT_MAX = kLimiterSpanEptMax;
 
-// powers of a pole for a blocked scan with `ept` elements per thread
-struct ScanPow {
-    double pe[SPAN_EPT_MAX + 2];  // p^k
-    double ql[33];                // q^k, q = p^ept
-    double qw[17];                // Q^k, Q = q^32
-};
-
-__device__ __forceinline__ void scanpow_init(ScanPow* t, double p, int ept) {
-    const int i = threadIdx.x;
-    if (i < SPAN_EPT_MAX + 2) t->pe[i] = pow(p, (double)i);
-    if (i < 33) t->ql[i] = pow(p, (double)(ept * i));
-    if (i < 17) t->qw[i] = pow(p, (double)(ept * 32 * i));
-}
-
 // Exclusive carry of the recurrence y = u + p*y_prev across the block: given each thread's local
-// end value B (zero initial state over its `ept` elements), returns the state just before the
-// thread's first element when the state before the block's first element is c0.
+// end value B (zero initial state over its elements), returns the state just before the thread's
+// first element when the state before the block's first element is c0.
 // scratch: >= 32 doubles.  Contains barriers: every thread of the block must call.
 __device__ __forceinline__ double scan_carry(double B, const ScanPow* t, double c0, double* scratch) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -76,42 +62,6 @@ __device__ __forceinline__ double scan_carry(double B, const ScanPow* t, double 
     return prev + t->ql[lane] * (warp_carry + t->qw[warp] * c0);
 }
 
-// a[i + shift] = max(a[i .. i+win-1]) for every i with the window inside [0, len); other
-// elements end up unspecified.  In place, log2(win) doubling steps.  Contains barriers.
-__device__ __forceinline__ void sliding_max(float* a, int len, int win, int shift, int ept) {
-    const int tid = threadIdx.x;
-    float v[SPAN_EPT_MAX];
-    int pw = 1;
-    while (pw * 2 <= win) {
-#pragma unroll
-        for (int k = 0; k < SPAN_EPT_MAX; ++k) {
-            const int i = tid + k * NT;
-            if (k < ept && i < len) v[k] = (i + pw < len) ? fmaxf(a[i], a[i + pw]) : a[i];
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < SPAN_EPT_MAX; ++k) {
-            const int i = tid + k * NT;
-            if (k < ept && i < len) a[i] = v[k];
-        }
-        __syncthreads();
-        pw *= 2;
-    }
-    const int rem = win - pw;
-#pragma unroll
-    for (int k = 0; k < SPAN_EPT_MAX; ++k) {
-        const int i = tid + k * NT;
-        if (k < ept && i < len) v[k] = (i + rem < len) ? fmaxf(a[i], a[i + rem]) : a[i];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < SPAN_EPT_MAX; ++k) {
-        const int i = tid + k * NT;
-        if (k < ept && i + shift < len) a[i + shift] = v[k];
-    }
-    __syncthreads();
-}
-
 __device__ __forceinline__ void publish(double* value, int* flag, double v, int state) {
     *(volatile double*)value = v;
     __threadfence();
@@ -127,7 +77,7 @@ __device__ __forceinline__ double lookback(LookbackSlot* slots, int chunk, bool 
         LookbackSlot* s = slots + j;
         int* flag = release ? &s->rel_flag : &s->hold_flag;
         int f;
-        while ((f = *(volatile int*)flag) == 0) __nanosleep(40);
+        while ((f = *(volatile int*)flag) == 0) __nanosleep(20);
         __threadfence();
         if (f == 2) {
             carry += mult * *(volatile double*)(release ? &s->rel_inc : &s->hold_inc);
@@ -144,145 +94,150 @@ struct LimiterGeom {
     int reach, hold, warm, left;  // left = max(warm, hold): left halo of the envelope A
     int ept;                      // span elements per thread (odd)
     int span;                     // samples of g the chunk touches
-    int filt;                     // samples the attack filter runs over (LC + left + warm)
+    int filt;                     // samples the attack filter needs to run over (LC + left + warm)
+    int pad;                      // zeroed floats past the span arrays (>= the largest doubling step)
 };
 
-__global__ void __launch_bounds__(NT)
+// powers of the three poles, computed once per parameter set (not per CTA: pow() is slow)
+__global__ void limiter_tables_kernel(mgb_limiter_params lp, int span_ept, ScanPow* tables) {
+    const int i = threadIdx.x;
+    for (int f = 0; f < 3; ++f) {
+        const double p = f == 0 ? lp.attack_c : (f == 1 ? -lp.hold_a1 : -lp.release_a1);
+        const int ept = f == 0 ? span_ept : CORE_EPT;
+        ScanPow* t = tables + f;
+        if (i < SPAN_EPT_MAX + 2) t->pe[i] = pow(p, (double)i);
+        if (i < 33) t->ql[i] = pow(p, (double)(ept * i));
+        if (i < 17) t->qw[i] = pow(p, (double)(ept * 32 * i));
+    }
+}
+
+template <int EPT>
+__global__ void __launch_bounds__(NT, 2)
 limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__ in, float2* __restrict__ out,
                long long frames, const double* __restrict__ pre_gain, const double* __restrict__ post_gain,
-               const int* __restrict__ engaged, int* __restrict__ ticket, LookbackSlot* __restrict__ slots) {
+               const int* __restrict__ engaged, int* __restrict__ ticket, LookbackSlot* __restrict__ slots,
+               const ScanPow* __restrict__ tables) {
+    constexpr int CAP = EPT * NT;
     MGB_DYN_SMEM(smem);
-    const int cap = gm.ept * NT;
-    double* Fd = reinterpret_cast<double*>(smem);                 // [cap] float64 work plane
-    float* G = reinterpret_cast<float*>(smem + (size_t)cap * 8);  // [cap] hard-clip gain, later max(g, g_att)
-    float* A = G + cap;                                           // [cap] envelope, later the hold envelope
-    __shared__ ScanPow pow_att, pow_hold, pow_rel;
+    double* Fd = reinterpret_cast<double*>(smem);                 // [CAP] float64 work plane
+    float* Aenv = reinterpret_cast<float*>(smem) + CAP;           // [CAP] attack envelope, aliases Fd's upper half
+    float* G = reinterpret_cast<float*>(smem + (size_t)CAP * 8);  // [CAP] hard-clip gain, later max(g, g_att)
+    float* Wk = G + CAP;                                          // [CAP + pad] doubling plane, later the hold envelope
+    __shared__ ScanPow pw3[3];
     __shared__ double scratch[32];
     __shared__ double bcast[2];
     __shared__ int chunk_s;
+    const ScanPow* pow_att = &pw3[0];
+    const ScanPow* pow_hold = &pw3[1];
+    const ScanPow* pow_rel = &pw3[2];
 
     const int tid = threadIdx.x;
     const double pre = pre_gain ? *pre_gain : 1.0;
     const double post = post_gain ? *post_gain : 1.0;
 
     if (tid == 0) chunk_s = atomicAdd(ticket, 1);
-    scanpow_init(&pow_att, lp.attack_c, gm.ept);
-    scanpow_init(&pow_hold, -lp.hold_a1, CORE_EPT);
-    scanpow_init(&pow_rel, -lp.release_a1, CORE_EPT);
+    {
+        const double* src = reinterpret_cast<const double*>(tables);
+        double* dst = reinterpret_cast<double*>(pw3);
+        for (int i = tid; i < (int)(3 * sizeof(ScanPow) / sizeof(double)); i += NT) dst[i] = src[i];
+    }
     __syncthreads();
     const int chunk = chunk_s;
     const long long s0 = (long long)chunk * LC;
-    const long long e0 = (s0 + LC < frames) ? s0 + LC : frames;
+    const int core_n = (int)((s0 + LC < frames) ? LC : frames - s0);
 
     if (engaged && *engaged == 0) {  // hyrax.py:83-85: the limiter is not needed
-        for (long long n = s0 + tid; n < e0; n += NT) {
-            const float2 v = in[n];
-            out[n] = make_float2((float)((double)v.x * pre * post), (float)((double)v.y * pre * post));
+        for (int k = tid; k < core_n; k += NT) {
+            const float2 v = in[s0 + k];
+            out[s0 + k] = make_float2((float)((double)v.x * pre * post), (float)((double)v.y * pre * post));
         }
         return;
     }
 
-    const int reach = gm.reach, hold = gm.hold, W = gm.warm, HL = gm.left, ept = gm.ept;
-    const int SP = gm.span, FL = gm.filt;
+    const int reach = gm.reach, hold = gm.hold, HL = gm.left, FL = gm.filt;
     const long long ga = s0 - HL - reach;  // sample at span index 0
     const int cidx = HL + reach;           // span index of the chunk's first sample
+    // span indices that fall inside the signal: [vlo, vhi)
+    const int vlo = ga < 0 ? (int)(-ga) : 0;
+    const int vhi = (frames - ga < (long long)gm.span) ? (int)(frames - ga) : gm.span;
     const double thr = lp.threshold;
 
-    // ---- P0: hard-clip gain g over the span (dsp.rectify + flip, hyrax.py:82-87) ------------------
-    for (int i = tid; i < cap; i += NT) {
-        const long long n = ga + i;
-        float g = 0.0f;
-        if (i < SP && n >= 0 && n < frames) {
-            const float2 v = in[n];
-            const double a = fmax(fabs((double)v.x), fabs((double)v.y)) * pre;
-            const double r = fmax(a, thr) / thr;
-            g = (float)(1.0 - 1.0 / r);
-        }
-        G[i] = g;
-        A[i] = g;
-    }
-    __syncthreads();
-
-    // ---- P1: attack envelope A[n] = max g[n-reach .. n+reach] (hyrax.py:35-37) --------------------
-    sliding_max(A, cap, 2 * reach + 1, reach, ept);
-
-    // ---- P2: g_att = filtfilt one-pole over A (hyrax.py:48-51) ------------------------------------
-    // extended signal of scipy's filtfilt: odd reflection of 6 samples at both ends; constant
-    // beyond, which leaves the steady-state initial condition untouched.
-    const double c = lp.attack_c;
-    auto env = [&](long long n) -> double {  // n inside the signal
-        return (double)A[(int)(n - ga)];
-    };
-    auto ext = [&](long long n) -> double {
-        if (n < 0) {
-            const long long k = (-n < 6) ? -n : 6;
-            return 2.0 * env(0) - env(k);
-        }
-        if (n >= frames) {
-            const long long k = (n - (frames - 1) < 6) ? n - (frames - 1) : 6;
-            return 2.0 * env(frames - 1) - env(frames - 1 - k);
-        }
-        return env(n);
-    };
-    auto clamp_idx = [&](int i) { return i < reach ? reach : (i >= reach + FL ? reach + FL - 1 : i); };
+    // ---- P1: hard-clip gain g = 1 - thr/max(|L|,|R|,thr) over the span (dsp.py:117-121, hyrax.py:87)
     {
-        double y[SPAN_EPT_MAX];
-        double acc = 0.0;
+        const float2* base = in + ga;
 #pragma unroll
-        for (int e = 0; e < SPAN_EPT_MAX; ++e) {
-            if (e < ept) {
-                const int i = clamp_idx(tid * ept + e);
-                acc = (1.0 - c) * ext(ga + i) + c * acc;
-                y[e] = acc;
+        for (int k = 0; k < EPT; ++k) {
+            const int i = tid + k * NT;
+            float g = 0.0f;
+            if (i >= vlo && i < vhi) {
+                const float2 v = base[i];
+                const double a = fmax(fabs((double)v.x), fabs((double)v.y)) * pre;
+                g = (float)(1.0 - thr / fmax(a, thr));
             }
+            G[i] = g;
+            Wk[i] = g;
         }
-        const double c0 = ext(ga + reach);  // state before the first element: steady state
-        const double carry = scan_carry(acc, &pow_att, c0, scratch);
-#pragma unroll
-        for (int e = 0; e < SPAN_EPT_MAX; ++e)
-            if (e < ept) Fd[tid * ept + e] = y[e] + pow_att.pe[e + 1] * carry;
+        for (int i = CAP + tid; i < CAP + gm.pad; i += NT) Wk[i] = 0.0f;
     }
     __syncthreads();
+
+    // ---- P2: both running maxima from one doubling ladder over g ------------------------------------
+    //   A[n] = max g[n-reach .. n+reach]                        (hyrax.py:35-37)
+    //   H[n] = max A[n-hold+1 .. n] = max g[n-hold+1-reach .. n+reach]   (hyrax.py:38-40)
+    // Wk holds m_pw[i] = max g[i .. i+pw-1]; a window of length w is max(m_pw[i], m_pw[i+w-pw]).
     {
-        // backward pass over the forward output; beyond the extension's end (sample frames+5) the
-        // input is held at that last value, which is the reversed filter's steady-state start.
-        const long long last_ext = frames + 5;
-        auto fwd = [&](int i) -> double {
-            i = clamp_idx(i);
-            const long long n = ga + i;
-            if (n > last_ext) i = (int)(last_ext - ga);
-            return Fd[i];
+        const int win_a = 2 * reach + 1, win_h = win_a + hold - 1;
+        float v[EPT];
+        int pw = 1;
+        auto double_step = [&]() {
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) {
+                const int i = tid + k * NT;
+                v[k] = fmaxf(Wk[i], Wk[i + pw]);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) Wk[tid + k * NT] = v[k];
+            __syncthreads();
+            pw *= 2;
         };
-        double y[SPAN_EPT_MAX];
-        double acc = 0.0;
+        while (pw * 2 <= win_a) double_step();
+        {
+            const int rem = win_a - pw;
 #pragma unroll
-        for (int e = 0; e < SPAN_EPT_MAX; ++e) {
-            if (e < ept) {
-                const int i = cap - 1 - (tid * ept + e);
-                acc = (1.0 - c) * fwd(i) + c * acc;
-                y[e] = acc;
+            for (int k = 0; k < EPT; ++k) {
+                const int i = tid + k * NT;
+                const float m = fmaxf(Wk[i], Wk[i + rem]);
+                if (i + reach < CAP) Aenv[i + reach] = m;
+                if (i < reach) Aenv[i] = 0.0f;
             }
         }
-        const double c0 = fwd(cap - 1);
-        const double carry = scan_carry(acc, &pow_att, c0, scratch);
-        // keep max(g, g_att) for the chunk's own samples
+        while (pw * 2 <= win_h) double_step();
+        {
+            const int rem = win_h - pw, shift = reach + hold - 1;
 #pragma unroll
-        for (int e = 0; e < SPAN_EPT_MAX; ++e) {
-            if (e < ept) {
-                const int i = cap - 1 - (tid * ept + e);
-                if (i >= cidx && i < cidx + LC) G[i] = fmaxf(G[i], (float)(y[e] + pow_att.pe[e + 1] * carry));
+            for (int k = 0; k < EPT; ++k) {
+                const int i = tid + k * NT;
+                v[k] = fmaxf(Wk[i], Wk[i + rem]);
             }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) {
+                const int i = tid + k * NT;
+                if (i + shift < CAP) Wk[i + shift] = v[k];
+            }
+            __syncthreads();
         }
     }
-    __syncthreads();
+    if (vlo > 0) {  // lfilter starts from rest: the envelope before the first sample is 0, not a window max
+        for (int i = tid; i < vlo; i += NT) Wk[i] = 0.0f;
+        __syncthreads();
+    }
+    const float* H = Wk;
 
-    // ---- P3: hold envelope H[n] = max A[n-hold+1 .. n], samples before the signal count as 0 -------
-    for (int i = tid; i < cap; i += NT)
-        if (ga + i < 0) A[i] = 0.0f;
-    __syncthreads();
-    sliding_max(A, cap, hold, hold - 1, ept);
-
-    // ---- P4: hold_out = lfilter(butter(1, f_hold), H) (hyrax.py:61-66) ----------------------------
+    // ---- P3: hold_out = lfilter(butter(1, f_hold), H), zero-carry pass (hyrax.py:61-66) -------------
+    // The chunk's aggregate is published now; the carry from the previous chunks is only needed after
+    // the attack filter below, which gives the predecessors time to publish theirs.
     LookbackSlot* slot = slots + chunk;
     double hold_y[CORE_EPT];
     {
@@ -290,74 +245,154 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
 #pragma unroll
         for (int e = 0; e < CORE_EPT; ++e) {
             const int i = cidx + tid * CORE_EPT + e;
-            const double u = lp.hold_b0 * (double)A[i] + lp.hold_b1 * (double)A[i - 1];
+            const double u = lp.hold_b0 * (double)H[i] + lp.hold_b1 * (double)H[i - 1];
             acc = u - lp.hold_a1 * acc;
             hold_y[e] = acc;
         }
-        const double carry = scan_carry(acc, &pow_hold, 0.0, scratch);
+        const double carry = scan_carry(acc, pow_hold, 0.0, scratch);
 #pragma unroll
-        for (int e = 0; e < CORE_EPT; ++e) hold_y[e] += pow_hold.pe[e + 1] * carry;
+        for (int e = 0; e < CORE_EPT; ++e) hold_y[e] += pow_hold->pe[e + 1] * carry;
         if (tid == NT - 1) publish(&slot->hold_agg, &slot->hold_flag, hold_y[CORE_EPT - 1], 1);
-        if (tid == 0) {
-            const double cin = lookback(slots, chunk, false, pow_hold.qw[16]);
-            bcast[0] = cin;
+    }
+
+    // ---- P4: g_att = filtfilt one-pole over A (hyrax.py:48-51) -------------------------------------
+    // scipy's filtfilt runs over the odd extension by 6 samples with the steady-state initial state;
+    // holding the extension's end value constant further out reproduces that state exactly.  Only
+    // chunks that touch an end of the signal see the extension.
+    const double c = lp.attack_c;
+    const bool edge_l = vlo > reach, edge_r = vhi < reach + FL;
+    if (edge_l || edge_r) {
+        const int i0 = vlo, iL = vhi - 1;  // span indices of samples 0 and frames-1
+        float fix[EPT];
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+            const int i = tid + k * NT;
+            fix[k] = Aenv[i];
+            if (i < vlo) {
+                const int d = (vlo - i < 6) ? vlo - i : 6;
+                fix[k] = 2.0f * Aenv[i0] - Aenv[i0 + d];
+            } else if (i >= vhi) {
+                const int d = (i - iL < 6) ? i - iL : 6;
+                fix[k] = 2.0f * Aenv[iL] - Aenv[iL - d];
+            }
         }
         __syncthreads();
-        const double cin = bcast[0];
-        const double lead = pow_hold.ql[tid & 31] * pow_hold.qw[tid >> 5];  // pole^(tid*CORE_EPT)
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) Aenv[tid + k * NT] = fix[k];
+        __syncthreads();
+    }
+    {
+        double y[EPT];
+        double acc = 0.0;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            acc = (1.0 - c) * (double)Aenv[tid * EPT + e] + c * acc;
+            y[e] = acc;
+        }
+        const double c0 = (double)Aenv[0];  // state before the first element: steady state
+        const double carry = scan_carry(acc, pow_att, c0, scratch);  // barriers: Aenv fully read
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) Fd[tid * EPT + e] = y[e] + pow_att->pe[e + 1] * carry;
+    }
+    __syncthreads();
+    if (edge_r) {
+        // past the extension's last sample (frames+5) the backward pass sees that value held
+        const int ilast = (int)(frames + 5 - ga);
+        if (ilast < CAP - 1) {
+            const double held = Fd[ilast];
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) {
+                const int i = tid + k * NT;
+                if (i > ilast) Fd[i] = held;
+            }
+            __syncthreads();
+        }
+    }
+    {
+        double y[EPT];
+        double acc = 0.0;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            acc = (1.0 - c) * Fd[CAP - 1 - (tid * EPT + e)] + c * acc;
+            y[e] = acc;
+        }
+        const double c0 = Fd[CAP - 1];
+        const double carry = scan_carry(acc, pow_att, c0, scratch);
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const int i = CAP - 1 - (tid * EPT + e);
+            if (i >= cidx && i < cidx + LC) G[i] = fmaxf(G[i], (float)(y[e] + pow_att->pe[e + 1] * carry));
+        }
+    }
+
+    // ---- P5: hold carry from the previous chunks (decoupled look-back), finish hold_out -------------
+    if (tid == 0) bcast[0] = lookback(slots, chunk, false, pow_hold->qw[16]);
+    __syncthreads();  // also: every thread is done reading Fd as the attack filter's plane
+    const double hold_cin = bcast[0];
+    {
+        const double lead = pow_hold->ql[tid & 31] * pow_hold->qw[tid >> 5];  // pole^(tid*CORE_EPT)
 #pragma unroll
         for (int e = 0; e < CORE_EPT; ++e) {
-            hold_y[e] += pow_hold.pe[e + 1] * lead * cin;
+            hold_y[e] += pow_hold->pe[e + 1] * lead * hold_cin;
             Fd[tid * CORE_EPT + e] = hold_y[e];
         }
         if (tid == NT - 1) publish(&slot->hold_inc, &slot->hold_flag, hold_y[CORE_EPT - 1], 2);
     }
     __syncthreads();
 
-    // ---- P5: release_out = lfilter(butter(1, f_rel), max(H, hold_out)) (hyrax.py:68-73) -----------
+    // ---- P6: release_out = lfilter(butter(1, f_rel), max(H, hold_out)) (hyrax.py:68-73) -------------
     {
-        const double hold_cin = bcast[0];  // hold_out just before the chunk
         double rel_y[CORE_EPT];
         double acc = 0.0;
         double prev_in;
         {
             const int i = cidx + tid * CORE_EPT - 1;
             const double hprev = tid == 0 ? hold_cin : Fd[tid * CORE_EPT - 1];
-            prev_in = fmax((double)A[i], hprev);
+            prev_in = fmax((double)H[i], hprev);
         }
 #pragma unroll
         for (int e = 0; e < CORE_EPT; ++e) {
             const int i = cidx + tid * CORE_EPT + e;
-            const double cur = fmax((double)A[i], hold_y[e]);
+            const double cur = fmax((double)H[i], hold_y[e]);
             const double u = lp.release_b0 * cur + lp.release_b1 * prev_in;
             prev_in = cur;
             acc = u - lp.release_a1 * acc;
             rel_y[e] = acc;
         }
-        const double carry = scan_carry(acc, &pow_rel, 0.0, scratch);
+        const double carry = scan_carry(acc, pow_rel, 0.0, scratch);
 #pragma unroll
-        for (int e = 0; e < CORE_EPT; ++e) rel_y[e] += pow_rel.pe[e + 1] * carry;
+        for (int e = 0; e < CORE_EPT; ++e) rel_y[e] += pow_rel->pe[e + 1] * carry;
         if (tid == NT - 1) publish(&slot->rel_agg, &slot->rel_flag, rel_y[CORE_EPT - 1], 1);
-        if (tid == 0) bcast[1] = lookback(slots, chunk, true, pow_rel.qw[16]);
+        if (tid == 0) bcast[1] = lookback(slots, chunk, true, pow_rel->qw[16]);
         __syncthreads();
         const double cin = bcast[1];
-        const double lead = pow_rel.ql[tid & 31] * pow_rel.qw[tid >> 5];
+        const double lead = pow_rel->ql[tid & 31] * pow_rel->qw[tid >> 5];
 #pragma unroll
         for (int e = 0; e < CORE_EPT; ++e) {
-            rel_y[e] += pow_rel.pe[e + 1] * lead * cin;
+            rel_y[e] += pow_rel->pe[e + 1] * lead * cin;
             const int i = cidx + tid * CORE_EPT + e;
-            const double g_rel = fmax(hold_y[e], rel_y[e]);          // hyrax.py:75
+            const double g_rel = fmax(hold_y[e], rel_y[e]);            // hyrax.py:75
+#ifdef MGB_LIM_DEBUG
+            Fd[tid * CORE_EPT + e] = hold_y[e];
+            G[i] = (float)rel_y[e];
+#else
             Fd[tid * CORE_EPT + e] = 1.0 - fmax((double)G[i], g_rel);  // hyrax.py:97
+#endif
         }
         if (tid == NT - 1) publish(&slot->rel_inc, &slot->rel_flag, rel_y[CORE_EPT - 1], 2);
     }
     __syncthreads();
 
-    // ---- P6: apply (hyrax.py:99, stages.py:203) ----------------------------------------------------
-    for (int k = tid; k < (int)(e0 - s0); k += NT) {
+    // ---- P7: apply (hyrax.py:99, stages.py:203) -----------------------------------------------------
+    for (int k = tid; k < core_n; k += NT) {
         const float2 v = in[s0 + k];
-        const double gain = Fd[k];
-        out[s0 + k] = make_float2((float)((double)v.x * pre * gain * post), (float)((double)v.y * pre * gain * post));
+        const double gain = Fd[k] * pre * post;
+#ifdef MGB_LIM_DEBUG
+        out[s0 + k] = make_float2((float)Fd[k], G[cidx + k]);
+#else
+        out[s0 + k] = make_float2((float)((double)v.x * gain), (float)((double)v.y * gain));
+#endif
     }
 }
 
@@ -369,14 +404,7 @@ __global__ void limiter_engaged_kernel(const float* peak_bits, const double* pre
     *engaged = (fabs(r - 1.0) <= 1e-8 + 1e-5 * 1.0) ? 0 : 1;
 }
 
-}  // namespace
-
-int64_t limiter_lookback_bytes(int64_t frames) {
-    const int64_t chunks = (frames + LC - 1) / LC;
-    return (chunks * (int64_t)sizeof(LookbackSlot) + 255) / 256 * 256;
-}
-
-static int limiter_geometry(const mgb_limiter_params& lp, LimiterGeom* g) {
+int limiter_geometry(const mgb_limiter_params& lp, LimiterGeom* g) {
     MGB_REQUIRE(lp.reach >= 1 && lp.hold >= 3 && lp.warmup >= 8, MGB_ERR_INVALID, "limiter: bad window sizes");
     MGB_REQUIRE(lp.attack_c > 0.0 && lp.attack_c < 1.0, MGB_ERR_INVALID, "limiter: attack pole out of (0,1)");
     MGB_REQUIRE(lp.threshold > 0.0, MGB_ERR_INVALID, "limiter: threshold must be positive");
@@ -388,22 +416,53 @@ static int limiter_geometry(const mgb_limiter_params& lp, LimiterGeom* g) {
     g->span = g->filt + 2 * g->reach;
     int ept = (g->span + NT - 1) / NT;
     if (!(ept & 1)) ept += 1;  // odd stride: the blocked scans read shared memory conflict-free
+    if (ept < 11) ept = 11;
     g->ept = ept;
+    const int win_h = 2 * lp.reach + lp.hold;
+    int pad = 32;
+    while (pad < win_h) pad *= 2;
+    g->pad = pad;
     MGB_REQUIRE(ept <= SPAN_EPT_MAX, MGB_ERR_UNSUPPORTED,
                 "limiter: halo of %d samples exceeds the kernel's span", g->span - LC);
     return MGB_OK;
 }
 
+}  // namespace
+
+int64_t limiter_lookback_bytes(int64_t frames) {
+    const int64_t chunks = (frames + LC - 1) / LC;
+    return (chunks * (int64_t)sizeof(LookbackSlot) + 255) / 256 * 256;
+}
+
+int launch_limiter_tables(const mgb_limiter_params& lp, ScanPow* tables, cudaStream_t stream) {
+    LimiterGeom g;
+    MGB_TRY(limiter_geometry(lp, &g));
+    return launch("limiter_tables_kernel", limiter_tables_kernel, dim3(1), dim3(64), 0, stream, lp, g.ept, tables);
+}
+
 int launch_limiter(const mgb_limiter_params& lp, const float2* in, float2* out, int64_t frames, const double* pre_gain,
                    const double* post_gain, const int* engaged, int* ticket, LookbackSlot* lookback,
-                   cudaStream_t stream) {
+                   const ScanPow* tables, cudaStream_t stream) {
     LimiterGeom g;
     MGB_TRY(limiter_geometry(lp, &g));
     MGB_REQUIRE(frames > 6, MGB_ERR_INVALID, "limiter: the input must be longer than filtfilt's padlen (6)");
+    MGB_REQUIRE(tables != nullptr, MGB_ERR_INVALID, "limiter: pole tables missing");
     const int64_t chunks = (frames + LC - 1) / LC;
-    const size_t smem = (size_t)g.ept * NT * (8 + 4 + 4);
-    return launch("limiter_kernel", limiter_kernel, dim3((unsigned)chunks), dim3(NT), smem, stream, lp, g, in, out,
-                  (long long)frames, pre_gain, post_gain, engaged, ticket, lookback);
+    const size_t smem = (size_t)g.ept * NT * 16 + (size_t)g.pad * 4;
+#define MGB_LIMITER_CASE(E)                                                                                       \
+    case E:                                                                                                       \
+        return launch("limiter_kernel", limiter_kernel<E>, dim3((unsigned)chunks), dim3(NT), smem, stream, lp, g, in, \
+                      out, (long long)frames, pre_gain, post_gain, engaged, ticket, lookback, tables);
+    switch (g.ept) {
+        MGB_LIMITER_CASE(11)
+        MGB_LIMITER_CASE(13)
+        MGB_LIMITER_CASE(15)
+        MGB_LIMITER_CASE(17)
+        default: break;
+    }
+#undef MGB_LIMITER_CASE
+    set_error("limiter: no kernel for %d span samples per thread", g.ept);
+    return MGB_ERR_UNSUPPORTED;
 }
 
 int launch_limiter_engaged(const float* peak_bits, const double* pre_gain, double threshold, int* engaged,

@@ -44,9 +44,9 @@ class DevicePlan:
             dev = torch.from_numpy(arr).to(device)
             self._keep[name] = dev
             setattr(s, "d_" + name, dev.data_ptr())
-        sizes = (C.c_int64 * 4)()
+        sizes = (C.c_int64 * 5)()
         _native.check(self.lib, self.lib.mgb_plan_twiddle_bytes(t.fft_size, sizes))
-        for name, nbytes in zip(("tw_f32_F", "tw_f32_2F", "tw_f64_F", "tw_f64_2F"), sizes):
+        for name, nbytes in zip(("tw_f32_F", "tw_f32_2F", "tw_f64_F", "tw_f64_2F", "limiter_tables"), sizes):
             buf = torch.zeros(int(nbytes), dtype=torch.uint8, device=device)
             self._keep[name] = buf
             setattr(s, "d_" + name, buf.data_ptr())

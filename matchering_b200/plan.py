@@ -99,9 +99,19 @@ def spline_eval_table(knots: np.ndarray, points: np.ndarray):
 # LOWESS bookkeeping
 # ------------------------------------------------------------------------------------------------
 def lowess_tables(n: int, frac: float, delta: float):
-    """Regression points / neighbourhoods / bracketing table of one LOWESS pass on
-    x = linspace(0, 1, n): the index logic of statsmodels' update_neighborhood and
-    update_indices, which depends on the abscissa only."""
+    """One LOWESS pass (it = 0) on x = linspace(0, 1, n) as a Config-only linear operator.
+
+    With no robustness iterations every fitted value is a fixed linear combination of the k
+    ordinates in its neighbourhood: the tricube weights, the weighted mean and variance of the
+    abscissae (statsmodels calculate_weights / calculate_y_fit) depend on x only.  So the host
+    tabulates, per regression point f (the points statsmodels' update_indices visits):
+        fit_idx[f], fit_left[f]   position and left edge of the neighbourhood [left, left+k)
+        rows[row_idx[f]]          the k coefficients, fit = rows . y[left : left+k]
+    (on the uniform grid all interior rows coincide, so rows are stored once) and, per abscissa j,
+        seg[j]    index of the last regression point <= j
+        alpha[j]  weight of the NEXT regression point in the `delta` interpolation (0 at a
+                  regression point): y_fit[j] = alpha*fit[seg+1] + (1-alpha)*fit[seg].
+    """
     x = np.linspace(0, 1, n)
     k = int(frac * n + 1e-10)
     if not 2 <= k <= n:
@@ -109,12 +119,12 @@ def lowess_tables(n: int, frac: float, delta: float):
     fit_idx, lefts = [], []
     i, left, right = 0, 0, k
     while True:
-        while right < n and (x[i] - x[left]) > (x[right] - x[i]):
+        while right < n and (x[i] - x[left]) > (x[right] - x[i]):  # update_neighborhood
             left += 1
             right += 1
         fit_idx.append(i)
         lefts.append(left)
-        last_fit = i
+        last_fit = i                                               # update_indices
         cut = x[last_fit] + delta
         kk = last_fit
         for kk in range(last_fit + 1, n):
@@ -124,8 +134,39 @@ def lowess_tables(n: int, frac: float, delta: float):
         if last_fit >= n - 1:
             break
     fit_idx = np.asarray(fit_idx, dtype=np.int32)
+    lefts = np.asarray(lefts, dtype=np.int32)
+    rows, row_idx = [], np.zeros(len(fit_idx), dtype=np.int32)
+    for f, (i, left) in enumerate(zip(fit_idx, lefts)):
+        xs = x[left:left + k]
+        dist = np.abs(xs - x[i])
+        radius = max(dist[0], dist[-1])
+        w = dist / radius
+        w = 1.0 - w * w * w
+        w = w * w * w
+        w[dist >= radius] = 0.0
+        sw = w.sum()
+        if sw <= 0.0 or np.count_nonzero(w) == 1:      # regression "not ok": fit = y[i]
+            row = np.zeros(k)
+            row[i - left] = 1.0
+        else:
+            w = w / sw
+            xbar = np.sum(w * xs)
+            sqdev = np.sum(w * (xs - xbar) ** 2)
+            row = w * (1.0 + (x[i] - xbar) * (xs - xbar) / sqdev)
+        if rows and np.abs(row - rows[-1]).max() <= 4e-16 * np.abs(row).max():
+            row_idx[f] = len(rows) - 1                  # same operator as the previous point
+        else:
+            rows.append(row)
+            row_idx[f] = len(rows) - 1
     seg = (np.searchsorted(fit_idx, np.arange(n), side="right") - 1).astype(np.int32)
-    return x, fit_idx, np.asarray(lefts, dtype=np.int32), seg, k
+    alpha = np.zeros(n)
+    for j in range(n):
+        fa = fit_idx[seg[j]]
+        if fa != j:
+            fb = fit_idx[seg[j] + 1]
+            alpha[j] = (x[j] - x[fa]) / (x[fb] - x[fa])
+    return dict(lw_fit_idx=fit_idx, lw_fit_left=lefts, lw_seg=seg, lw_alpha=alpha, lw_rows=np.stack(rows),
+                lw_row_idx=row_idx), k
 
 
 # ------------------------------------------------------------------------------------------------
@@ -163,7 +204,7 @@ def limiter_constants(config) -> LimiterConstants:
     c = math.exp(lim.attack_filter_coefficient / attack)
     if not 0.0 < c < 1.0:
         raise UnsupportedConfig("attack_filter_coefficient must be negative (a decaying one-pole)")
-    warmup = int(math.ceil(math.log(1e-10) / math.log(c)))
+    warmup = int(math.ceil(math.log(1e-8) / math.log(c)))
     warmup = max(32, (warmup + 31) // 32 * 32)
     if 2 * warmup + hold + 2 * reach + 64 > MAX_LIMITER_HALO:
         raise UnsupportedConfig("attack filter decays too slowly for the limiter kernel's halo")
@@ -220,8 +261,8 @@ def build_tables(config) -> PlanTables:
     hinv, lu, end = spline_factor(grid_log)
     idx, w = spline_eval_table(grid_log, grid_lin)
     arrays.update(sb_hinv=hinv, sb_lu=lu, sb_end=end, sb_eval_idx=idx, sb_eval_w=w)
-    x, fit_idx, fit_left, seg, k = lowess_tables(n_log, config.lowess_frac, config.lowess_delta)
-    arrays.update(lw_x=x, lw_fit_idx=fit_idx, lw_fit_left=fit_left, lw_seg=seg)
+    lw, k = lowess_tables(n_log, config.lowess_frac, config.lowess_delta)
+    arrays.update(lw)
     arrays["hann"] = _signal.windows.hann(F)
     for name, arr in arrays.items():
         want = np.int32 if arr.dtype.kind == "i" else np.float64

@@ -43,31 +43,11 @@ def spline_eval(y, M, idx, w):
     return w[:, 0] * y[idx] + w[:, 1] * y[idx + 1] + w[:, 2] * M[idx] + w[:, 3] * M[idx + 1]
 
 
-def lowess_fit(y, x, fit_idx, fit_left, seg, k):
-    fits = np.empty(len(fit_idx))
-    for f, (i, left) in enumerate(zip(fit_idx, fit_left)):
-        xs = x[left:left + k]
-        dist = np.abs(xs - x[i])
-        radius = max(dist[0], dist[-1])
-        t = dist / radius
-        w = (1 - t ** 3) ** 3
-        w[dist >= radius] = 0.0
-        sw = w.sum()
-        if sw <= 0 or np.count_nonzero(w) == 1:
-            fits[f] = y[i]
-            continue
-        xbar = (w * xs).sum() / sw
-        sq = (w * (xs - xbar) ** 2).sum() / sw
-        fits[f] = ((w / sw) * (1 + (x[i] - xbar) * (xs - xbar) / sq) * y[left:left + k]).sum()
-    out = np.empty(len(x))
-    for j in range(len(x)):
-        s = seg[j]
-        if fit_idx[s] == j:
-            out[j] = fits[s]
-        else:
-            a = (x[j] - x[fit_idx[s]]) / (x[fit_idx[s + 1]] - x[fit_idx[s]])
-            out[j] = a * fits[s + 1] + (1 - a) * fits[s]
-    return out
+def lowess_fit(y, a, k):
+    fits = np.array([a["lw_rows"][r] @ y[l:l + k] for r, l in zip(a["lw_row_idx"], a["lw_fit_left"])])
+    seg, al = a["lw_seg"], a["lw_alpha"]
+    nxt = np.minimum(seg + 1, len(fits) - 1)
+    return al * fits[nxt] + (1.0 - al) * fits[seg]
 
 
 def design_fir(avg_t, avg_r, tables):
@@ -76,7 +56,7 @@ def design_fir(avg_t, avg_r, tables):
     m = avg_r / np.maximum(tables.min_value, avg_t)
     M1 = spline_moments(m, a["sa_hinv"], a["sa_lu"], a["sa_end"])
     m_log = spline_eval(m, M1, a["sa_eval_idx"], a["sa_eval_w"])
-    s_log = lowess_fit(m_log, a["lw_x"], a["lw_fit_idx"], a["lw_fit_left"], a["lw_seg"], tables.lowess_k)
+    s_log = lowess_fit(m_log, a, tables.lowess_k)
     M2 = spline_moments(s_log, a["sb_hinv"], a["sb_lu"], a["sb_end"])
     s = spline_eval(s_log, M2, a["sb_eval_idx"], a["sb_eval_w"])
     s[0] = 0.0

@@ -70,9 +70,9 @@ class EmulPlan:
             buf = aligned_copy(arr)
             self.keep[name] = buf
             setattr(s, "d_" + name, buf.ctypes.data)
-        sizes = (C.c_int64 * 4)()
+        sizes = (C.c_int64 * 5)()
         _native.check(self.lib, self.lib.mgb_plan_twiddle_bytes(t.fft_size, sizes))
-        for name, nbytes in zip(("tw_f32_F", "tw_f32_2F", "tw_f64_F", "tw_f64_2F"), sizes):
+        for name, nbytes in zip(("tw_f32_F", "tw_f32_2F", "tw_f64_F", "tw_f64_2F", "limiter_tables"), sizes):
             buf = aligned((nbytes,), np.uint8)
             self.keep[name] = buf
             setattr(s, "d_" + name, buf.ctypes.data)
