@@ -60,7 +60,7 @@ typedef struct mgb_plan {
     int32_t rms_correction_steps;
     int32_t lowess_k;          /* neighbourhood size int(frac*n_log + 1e-10) */
     int32_t lowess_nfit;       /* number of regression points */
-    int32_t reserved0;
+    int32_t lowess_nrows;      /* distinct coefficient rows in d_lw_rows */
     double max_piece_size;     /* samples, as Config stores it (defaults.py:109) */
     double threshold;
     double min_value;

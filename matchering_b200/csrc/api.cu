@@ -328,7 +328,9 @@ int mgb_track_layout_init(const mgb_plan* plan, int64_t target_frames, int64_t r
                     "piece of %lld samples is shorter than fft_size %d (the reference's STFT degenerates there)",
                     (long long)piece, plan->fft_size);
         const int64_t frames_per_piece = piece / plan->fft_size;
-        int64_t slots = (2LL * sms + divisions - 1) / divisions;
+        // analysis work items: one wave of three resident CTAs per SM (register/shared-memory limit of
+        // analyze_kernel), never more items than that so that no tail wave forms
+        int64_t slots = (3LL * sms) / divisions;
         if (slots > frames_per_piece) slots = frames_per_piece;
         if (slots < 1) slots = 1;
         if (sig == 0) {

@@ -17,7 +17,14 @@ namespace mgb {
 
 namespace {
 
-// sum over a piece of clip(mid * gain)^2 ; grid = (chunks per piece, pieces)
+// sum over a piece of clip(mid * gain)^2 ; grid = (chunks per piece, pieces).  Pieces start at
+// arbitrary offsets of the float plane, so a chunk is a scalar head, an aligned float4 body and a
+// scalar tail.
+__device__ __forceinline__ double clip_sq(float v, double gain) {
+    const double c = fmin(1.0, fmax(-1.0, (double)v * gain));  // dsp.clip
+    return c * c;
+}
+
 __global__ void __launch_bounds__(256)
 clip_sumsq_kernel(const float* __restrict__ mid, long long piece, const mgb_track_state* __restrict__ state,
                   double* __restrict__ sums) {
@@ -29,17 +36,21 @@ clip_sumsq_kernel(const float* __restrict__ mid, long long piece, const mgb_trac
     long long hi = lo + per;
     if (hi > (p + 1) * piece) hi = (p + 1) * piece;
     double acc = 0.0;
-    for (long long n = lo + threadIdx.x; n < hi; n += 4 * blockDim.x) {
-        float v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const long long m = n + (long long)u * blockDim.x;
-            v[u] = m < hi ? mid[m] : 0.0f;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const double c = fmin(1.0, fmax(-1.0, (double)v[u] * gain));
-            acc += c * c;
+    if (lo < hi) {
+        long long body_lo = (lo + 3) & ~3LL;
+        if (body_lo > hi) body_lo = hi;
+        long long body_hi = hi & ~3LL;
+        if (body_hi < body_lo) body_hi = body_lo;
+        if ((long long)threadIdx.x < body_lo - lo) acc += clip_sq(mid[lo + threadIdx.x], gain);       // head (< 4)
+        if ((long long)threadIdx.x < hi - body_hi) acc += clip_sq(mid[body_hi + threadIdx.x], gain);  // tail (< 4)
+        const float4* body = reinterpret_cast<const float4*>(mid + body_lo);
+        const long long nvec = (body_hi - body_lo) >> 2;
+        for (long long i = threadIdx.x; i < nvec; i += 2 * blockDim.x) {
+            const float4 a = body[i];
+            const long long i2 = i + blockDim.x;
+            const float4 b = i2 < nvec ? body[i2] : make_float4(0.f, 0.f, 0.f, 0.f);
+            acc += clip_sq(a.x, gain) + clip_sq(a.y, gain) + clip_sq(a.z, gain) + clip_sq(a.w, gain);
+            acc += clip_sq(b.x, gain) + clip_sq(b.y, gain) + clip_sq(b.z, gain) + clip_sq(b.w, gain);
         }
     }
     const double total = block_sum(acc, red);
@@ -137,8 +148,8 @@ int launch_clip_sumsq(const mgb_plan& plan, const mgb_track_layout& layout, cons
                       mgb_track_state* state, cudaStream_t stream) {
     (void)plan;
     const int div = layout.target_divisions;
-    long long per_piece = (2LL * num_sms() + div - 1) / div;
-    const long long max_useful = (layout.target_piece + 4095) / 4096;
+    long long per_piece = (8LL * num_sms() + div - 1) / div;
+    const long long max_useful = (layout.target_piece + 8191) / 8192;
     if (per_piece > max_useful) per_piece = max_useful;
     if (per_piece < 1) per_piece = 1;
     return launch("clip_sumsq_kernel", clip_sumsq_kernel, dim3((unsigned)per_piece, (unsigned)div), dim3(256), 0, stream,

@@ -25,6 +25,7 @@ namespace {
 
 constexpr int kDesignThreads = 512;
 constexpr int kWarm = 48;
+constexpr int kBatch = 16;  // rows fetched together in the substitution sweeps
 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -104,7 +105,7 @@ struct SplineTables {
 
 // Second derivatives of the not-a-knot cubic through (knots, y): M[0..n).  z is scratch [n].
 // The two substitution sweeps are first-order recurrences; each thread runs a block of rows after
-// a kWarm-row warm-up.  Operands are fetched eight rows at a time so that the L2 latency of the
+// a kWarm-row warm-up.  Operands are fetched kBatch rows at a time so that the L2 latency of the
 // factor tables overlaps instead of adding up along the dependent chain.
 __device__ void spline_moments(const double* __restrict__ y, int n, SplineTables t, double* __restrict__ z,
                                double* __restrict__ M) {
@@ -125,21 +126,21 @@ __device__ void spline_moments(const double* __restrict__ y, int n, SplineTables
         double acc = 0.0;
         int i = max(0, lo - kWarm);
         while (i < hi) {
-            double dv[8], fv[8];
+            double dv[kBatch], fv[kBatch];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < kBatch; ++u) {
                 const int r = min(i + u, m - 1);
                 dv[u] = z[r];
                 fv[u] = fa[r];
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < kBatch; ++u) {
                 if (i + u < hi) {
                     acc = dv[u] - fv[u] * acc;
                     if (i + u >= lo) M[i + u] = acc;
                 }
             }
-            i += 8;
+            i += kBatch;
         }
     }
     __syncthreads();
@@ -148,21 +149,21 @@ __device__ void spline_moments(const double* __restrict__ y, int n, SplineTables
         double acc = 0.0;
         int i = min(m - 1, hi - 1 + kWarm);
         while (i >= lo) {
-            double zv[8], cv[8];
+            double zv[kBatch], cv[kBatch];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < kBatch; ++u) {
                 const int r = max(i - u, 0);
                 zv[u] = M[r];
                 cv[u] = cp[r];
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < kBatch; ++u) {
                 if (i - u >= lo) {
                     acc = zv[u] - cv[u] * acc;
                     if (i - u < hi) z[i - u + 1] = acc;
                 }
             }
-            i -= 8;
+            i -= kBatch;
         }
     }
     __syncthreads();
@@ -201,9 +202,33 @@ struct DesignArgs {
 // Matching curve m[k] = mean|rfft(reference)| / max(eps, mean|rfft(target)|) from the per-(piece,
 // slot) partial sums of analyze.cu, over the loudest pieces only (match_frequencies.py:42,93-94).
 // grid = (ceil(n_lin/32), 2 channels); block = 32 bins x 8 slices of the (piece, slot) items.
+struct PrefetchList {
+    const void* ptr[14];
+    long long bytes[14];
+    int count;
+};
+
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+#ifndef MGB_EMULATE
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 __global__ void __launch_bounds__(256)
-spectrum_mean_kernel(DesignArgs a, int n_lin, int fft_size, double eps) {
+spectrum_mean_kernel(DesignArgs a, int n_lin, int fft_size, double eps, PrefetchList pf) {
     __shared__ double part_t[8][33], part_r[8][33];
+    // The design kernel that follows is two latency-bound CTAs walking Config-only tables that the
+    // streaming kernels in between have pushed out of L2: pull them back in from here, where
+    // there are CTAs to spare.
+    {
+        const long long gtid = ((long long)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+        const long long gsize = (long long)gridDim.x * gridDim.y * blockDim.x;
+        for (int t = 0; t < pf.count; ++t)
+            for (long long off = gtid * 128; off < pf.bytes[t]; off += gsize * 128)
+                prefetch_l2(reinterpret_cast<const char*>(pf.ptr[t]) + off);
+    }
     const int bx = threadIdx.x & 31, sy = threadIdx.x >> 5;
     const int k = blockIdx.x * 32 + bx;
     const int ch = blockIdx.y;
@@ -286,13 +311,24 @@ design_kernel(mgb_plan plan, DesignArgs a) {
     // ---- D: LOWESS (dsp.py:103-106): each regression is a Config-only row of k coefficients ------
     {
         const int k = plan.lowess_k;
-        for (int f = warp; f < plan.lowess_nfit; f += nwarps) {
-            const double* row = plan.d_lw_rows + (long long)plan.d_lw_row_idx[f] * k;
-            const double* yy = mlog + plan.d_lw_fit_left[f];
-            double acc = 0.0;
-            for (int j = lane; j < k; j += 32) acc += row[j] * yy[j];
-            acc = warp_sum(acc);
-            if (lane == 0) zz[f] = acc;
+        const int nfit = plan.lowess_nfit;
+        for (int f = warp; f < nfit; f += 2 * nwarps) {  // two regressions per pass: twice the loads in flight
+            const int f2 = min(f + nwarps, nfit - 1);
+            const double* row_a = plan.d_lw_rows + (long long)plan.d_lw_row_idx[f] * k;
+            const double* row_b = plan.d_lw_rows + (long long)plan.d_lw_row_idx[f2] * k;
+            const double* ya = mlog + plan.d_lw_fit_left[f];
+            const double* yb = mlog + plan.d_lw_fit_left[f2];
+            double acc_a = 0.0, acc_b = 0.0;
+            for (int j = lane; j < k; j += 32) {
+                acc_a += row_a[j] * ya[j];
+                acc_b += row_b[j] * yb[j];
+            }
+            acc_a = warp_sum(acc_a);
+            acc_b = warp_sum(acc_b);
+            if (lane == 0) {
+                zz[f] = acc_a;
+                zz[f2] = acc_b;
+            }
         }
         __syncthreads();
         const int last = plan.lowess_nfit - 1;
@@ -393,9 +429,34 @@ int launch_design(const mgb_plan& plan, const mgb_track_layout& layout, const Wo
     a.h_mid = ws.h_mid;
     a.h_side = ws.h_side;
     a.state = avg_override ? nullptr : state;
-    if (!avg_override)
+    if (!avg_override) {
+        PrefetchList pf;
+        pf.count = 0;
+        auto add = [&](const void* p, long long bytes) {
+            if (p && pf.count < 14) {
+                pf.ptr[pf.count] = p;
+                pf.bytes[pf.count] = bytes;
+                pf.count++;
+            }
+        };
+        const long long nl = plan.n_lin, ng = plan.n_log, F = plan.fft_size;
+        add(plan.d_sa_hinv, (nl - 1) * 8);
+        add(plan.d_sa_lu, 3 * (nl - 2) * 8);
+        add(plan.d_sa_eval_idx, ng * 4);
+        add(plan.d_sa_eval_w, ng * 32);
+        add(plan.d_sb_hinv, (ng - 1) * 8);
+        add(plan.d_sb_lu, 3 * (ng - 2) * 8);
+        add(plan.d_sb_eval_idx, nl * 4);
+        add(plan.d_sb_eval_w, nl * 32);
+        add(plan.d_lw_fit_left, (long long)plan.lowess_nfit * 4);
+        add(plan.d_lw_row_idx, (long long)plan.lowess_nfit * 4);
+        add(plan.d_lw_seg, ng * 4);
+        add(plan.d_lw_alpha, ng * 8);
+        add(plan.d_lw_rows, (long long)plan.lowess_nrows * plan.lowess_k * 8);
+        add(plan.d_hann, F * 8);
         MGB_TRY(launch("spectrum_mean_kernel", spectrum_mean_kernel, dim3((plan.n_lin + 31) / 32, 2), dim3(256), 0, stream, a,
-                       plan.n_lin, plan.fft_size, plan.min_value));
+                       plan.n_lin, plan.fft_size, plan.min_value, pf));
+    }
     switch (plan.fft_size) {
         case 1024: return launch_design_t<1024>(plan, a, stream);
         case 2048: return launch_design_t<2048>(plan, a, stream);

@@ -39,6 +39,7 @@ struct ScanPow {
     double pe[19];  // p^k, k = 0..18
     double ql[33];  // q^k, q = p^ept
     double qw[17];  // Q^k, Q = q^32
+    double pc[33];  // P^k, P = p^kLimiterCore: weight of a chunk k chunks back (look-back)
 };
 
 constexpr int kLimiterThreads = 512;

@@ -68,24 +68,34 @@ __device__ __forceinline__ void publish(double* value, int* flag, double v, int 
     *(volatile int*)flag = state;
 }
 
-// Carry into chunk `chunk` of a first-order recurrence whose per-chunk multiplier is `pchunk`:
-// walk back over the predecessors' published values until one is inclusive (or the weight of
-// anything older is below double precision).  Called by one thread.
-__device__ __forceinline__ double lookback(LookbackSlot* slots, int chunk, bool release, double pchunk) {
+// Carry into chunk `chunk` of a first-order recurrence whose per-chunk multiplier is P = pc[1]
+// (decoupled look-back).  One warp inspects 32 predecessors at a time: every lane reads one
+// predecessor's published value, the window is cut at the nearest predecessor whose INCLUSIVE
+// state is known, and the lanes' values are combined with weights P^lane by a warp reduction.
+// The walk stops when whatever lies further back weighs less than 1e-13 (all values are <= 1).
+// Called by all 32 lanes of one warp.
+__device__ __forceinline__ double lookback(LookbackSlot* slots, int chunk, bool release, const double* pc) {
+    const int lane = threadIdx.x & 31;
     double carry = 0.0, mult = 1.0;
-    for (int j = chunk - 1; j >= 0; --j) {
-        LookbackSlot* s = slots + j;
-        int* flag = release ? &s->rel_flag : &s->hold_flag;
-        int f;
-        while ((f = *(volatile int*)flag) == 0) __nanosleep(20);
-        __threadfence();
-        if (f == 2) {
-            carry += mult * *(volatile double*)(release ? &s->rel_inc : &s->hold_inc);
-            break;
+    for (int base = chunk - 1; base >= 0 && mult > 1e-13; base -= 32) {
+        const int j = base - lane;
+        int f = 2;         // before the first chunk: inclusive state 0 (lfilter starts from rest)
+        double val = 0.0;
+        if (j >= 0) {
+            LookbackSlot* s = slots + j;
+            int* flag = release ? &s->rel_flag : &s->hold_flag;
+            while ((f = *(volatile int*)flag) == 0) __nanosleep(20);
+            __threadfence();
+            val = (f == 2) ? *(volatile double*)(release ? &s->rel_inc : &s->hold_inc)
+                           : *(volatile double*)(release ? &s->rel_agg : &s->hold_agg);
         }
-        carry += mult * *(volatile double*)(release ? &s->rel_agg : &s->hold_agg);
-        mult *= pchunk;
-        if (mult < 1e-20) break;
+        const unsigned inclusive = __ballot_sync(0xffffffffu, f == 2);
+        const int first = inclusive ? __ffs((int)inclusive) - 1 : 32;
+        double part = lane <= first ? pc[lane] * val : 0.0;
+        part = warp_sum(part);
+        carry += mult * part;
+        if (inclusive) break;
+        mult *= pc[32];
     }
     return carry;
 }
@@ -108,6 +118,7 @@ __global__ void limiter_tables_kernel(mgb_limiter_params lp, int span_ept, ScanP
         if (i < SPAN_EPT_MAX + 2) t->pe[i] = pow(p, (double)i);
         if (i < 33) t->ql[i] = pow(p, (double)(ept * i));
         if (i < 17) t->qw[i] = pow(p, (double)(ept * 32 * i));
+        if (i < 33) t->pc[i] = pow(p, (double)LC * (double)i);
     }
 }
 
@@ -327,7 +338,10 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
     }
 
     // ---- P5: hold carry from the previous chunks (decoupled look-back), finish hold_out -------------
-    if (tid == 0) bcast[0] = lookback(slots, chunk, false, pow_hold->qw[16]);
+    if (tid < 32) {
+        const double cin = lookback(slots, chunk, false, pow_hold->pc);
+        if (tid == 0) bcast[0] = cin;
+    }
     __syncthreads();  // also: every thread is done reading Fd as the attack filter's plane
     const double hold_cin = bcast[0];
     {
@@ -364,7 +378,10 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
 #pragma unroll
         for (int e = 0; e < CORE_EPT; ++e) rel_y[e] += pow_rel->pe[e + 1] * carry;
         if (tid == NT - 1) publish(&slot->rel_agg, &slot->rel_flag, rel_y[CORE_EPT - 1], 1);
-        if (tid == 0) bcast[1] = lookback(slots, chunk, true, pow_rel->qw[16]);
+        if (tid < 32) {
+            const double cr = lookback(slots, chunk, true, pow_rel->pc);
+            if (tid == 0) bcast[1] = cr;
+        }
         __syncthreads();
         const double cin = bcast[1];
         const double lead = pow_rel->ql[tid & 31] * pow_rel->qw[tid >> 5];
