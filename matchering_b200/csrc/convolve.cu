@@ -33,49 +33,22 @@ struct ConvSmem {
 
 struct ConvFirst {
     const float2* raw;  // landing buffer, index 0 = sample `origin`
-    long long origin;
-    long long frames;
+    int lo, hi;         // indices of the buffer that lie inside the signal: [lo, hi)
     const float2* fixup;
     int fix_index;
     __device__ __forceinline__ cpx<float> operator()(int i) const {
-        const long long n = origin + i;
         float2 v = make_float2(0.0f, 0.0f);
-        if (n >= 0 && n < frames) {
+        if (i >= lo && i < hi) {
             v = raw[i];
             if (i == fix_index) v = *fixup;
         }
-        const float mid = (v.x + v.y) * 0.5f;  // exact sum rounded once, as (float)((double)L+R)/2
+        const float mid = (v.x + v.y) * 0.5f;  // exact sum rounded once, as (float)(((double)L+R)/2)
         return cpx<float>{mid, mid - v.y};
     }
 };
 
-// Consumes the inverse transform's outputs: circular index i -> output sample n0 + i - (F-1).
 template <int F>
-struct ConvLast {
-    float2* result;
-    float* mid_plane;
-    long long n0, frames, counted;  // counted = piece*divisions: samples that enter the piece RMS
-    long long boundary;             // first sample of the next piece
-    double* sq_a;                   // sum clip(mid)^2 for the frame's first piece / the next one
-    double* sq_b;
-    float* peak;
-    __device__ __forceinline__ void operator()(int i, cpx<float> v) const {
-        if (i < F - 1 || i > 2 * F - 2) return;
-        const long long n = n0 + (i - (F - 1));
-        if (n >= frames) return;
-        const float l = v.x + v.y, r = v.x - v.y;  // dsp.ms_to_lr
-        result[n] = make_float2(l, r);
-        mid_plane[n] = v.x;
-        *peak = fmaxf(*peak, fmaxf(fabsf(l), fabsf(r)));
-        if (n < counted) {
-            const double c = fmin(1.0, fmax(-1.0, (double)v.x));  // dsp.clip
-            if (n < boundary) *sq_a += c * c; else *sq_b += c * c;
-        }
-    }
-};
-
-template <int F>
-__global__ void __launch_bounds__(F / 8)
+__global__ void __launch_bounds__(F / 8, (F <= 4096 ? 2 : 1))
 convolve_kernel(const float2* __restrict__ x, long long frames, long long piece, int divisions,
                 const cpx<float>* __restrict__ tw, const float2* __restrict__ h_mid,
                 const float2* __restrict__ h_side, float2* __restrict__ result, float* __restrict__ mid_plane,
@@ -103,8 +76,8 @@ convolve_kernel(const float2* __restrict__ x, long long frames, long long piece,
     const long long hi = (origin + N < frames) ? origin + N : frames;  // exclusive
     ConvFirst first;
     first.raw = raw;
-    first.origin = origin;
-    first.frames = frames;
+    first.lo = (int)(lo - origin);
+    first.hi = (int)(hi - origin);
     first.fixup = nullptr;
     first.fix_index = -1;
     if (use_tma) {
@@ -151,26 +124,40 @@ convolve_kernel(const float2* __restrict__ x, long long frames, long long piece,
     }
     __syncthreads();
 
-    // ---- inverse transform; the last pass writes straight to global memory -----------------------
-    double sq_a = 0.0, sq_b = 0.0;
-    float peak = 0.0f;
-    const long long counted = piece * divisions;
-    const long long pa = n0 / piece;
-    ConvLast<F> last;
-    last.result = result;
-    last.mid_plane = mid_plane;
-    last.n0 = n0;
-    last.frames = frames;
-    last.counted = counted;
-    last.boundary = (pa + 1) * piece;
-    last.sq_a = &sq_a;
-    last.sq_b = &sq_b;
-    last.peak = &peak;
+    // ---- inverse transform, in place ------------------------------------------------------------------
     fft_first_pass<N, -1, THREADS, float>(re, im, tw, SmemLoad<float>{re, im}, /*in_place=*/true);
     __syncthreads();
-    fft_remaining<N, -1, THREADS, float>(re, im, tw, last, /*last_in_place=*/false);
+    fft_remaining<N, -1, THREADS, float>(re, im, tw, SmemStore<float>{re, im}, /*last_in_place=*/true);
+    __syncthreads();
 
-    // ---- frame totals -> per-piece sums (correction step 1) and the result's peak -----------------
+    // ---- epilogue: circular index F-1+o is output sample n0+o; coalesced stores, mid/side -> L/R
+    // (dsp.ms_to_lr), the first RMS-correction step's sum of clip(mid)^2 per piece, the peak ---------
+    const int valid = (int)((frames - n0 < F) ? frames - n0 : F);
+    const long long counted = piece * divisions;  // samples that enter the piece RMS (dsp.unfold)
+    const long long pa = n0 / piece;
+    const long long brel = (pa + 1) * piece - n0;  // first output of the next piece
+    const int boundary = (int)(brel < F ? brel : F);
+    const int count_to = (int)((counted - n0 < 0) ? 0 : (counted - n0 < F ? counted - n0 : F));
+    double sq_a = 0.0, sq_b = 0.0;
+    float peak = 0.0f;
+    float2* res = result + n0;
+    float* midp = mid_plane + n0;
+#pragma unroll
+    for (int k = 0; k < F / THREADS; ++k) {
+        const int o = tid + k * THREADS;
+        if (o < valid) {
+            const int a = fft_pad(F - 1 + o);
+            const float m = re[a], sd = im[a];
+            const float l = m + sd, r = m - sd;
+            res[o] = make_float2(l, r);
+            midp[o] = m;
+            peak = fmaxf(peak, fmaxf(fabsf(l), fabsf(r)));
+            if (o < count_to) {
+                const double c = fmin(1.0, fmax(-1.0, (double)m));  // dsp.clip
+                if (o < boundary) sq_a += c * c; else sq_b += c * c;
+            }
+        }
+    }
     const double ta = block_sum(sq_a, red_a);
     const double tb = block_sum(sq_b, red_b);
     const float pk = block_max(peak, red_f);

@@ -99,6 +99,43 @@ struct Dft<1, DIR, T> {
 // ------------------------------------------------------------------------------------------------
 // one Stockham pass
 // ------------------------------------------------------------------------------------------------
+// Twiddles of one butterfly, w[r] = w1^r for r = 1..R-1.  The float kernels fetch only w1 (and w4
+// for radix 16) from the table and build the other powers in registers (products at most four
+// deep, ~2e-7 relative): a radix-16 butterfly then costs 2 table reads instead of 15, which
+// matters because the table does not fit in what is left of L1 next to the frame.  The double
+// kernels (FIR design) read every power from the table.
+template <int R, int NS, int DIR, bool CHAIN, typename T>
+__device__ __forceinline__ void load_twiddles(const cpx<T>* __restrict__ tw, int k, cpx<T>* w) {
+    if constexpr (!CHAIN || R == 2) {
+#pragma unroll
+        for (int r = 1; r < R; ++r) {
+            w[r] = tw[(r - 1) * NS + k];
+            if constexpr (DIR < 0) w[r].y = -w[r].y;
+        }
+    } else {
+        w[1] = tw[k];
+        if constexpr (DIR < 0) w[1].y = -w[1].y;
+        w[2] = cmul(w[1], w[1]);
+        w[3] = cmul(w[1], w[2]);
+        if constexpr (R >= 8) {
+            if constexpr (R == 16) {
+                w[4] = tw[3 * NS + k];
+                if constexpr (DIR < 0) w[4].y = -w[4].y;
+            } else {
+                w[4] = cmul(w[2], w[2]);
+            }
+            w[5] = cmul(w[4], w[1]);
+            w[6] = cmul(w[4], w[2]);
+            w[7] = cmul(w[4], w[3]);
+        }
+        if constexpr (R == 16) {
+            w[8] = cmul(w[4], w[4]);
+#pragma unroll
+            for (int r = 9; r < 16; ++r) w[r] = cmul(w[8], w[r - 8]);
+        }
+    }
+}
+
 template <int N, int R, int NS, int DIR, int THREADS, typename T, typename Load, typename Store>
 __device__ __forceinline__ void fft_pass(const cpx<T>* __restrict__ tw, Load load, Store store, bool barrier_between) {
     constexpr int NB = N / R;
@@ -122,12 +159,10 @@ __device__ __forceinline__ void fft_pass(const cpx<T>* __restrict__ tw, Load loa
             const int j = tid + p * THREADS;
             const int k = j & (NS - 1);
             if constexpr (NS > 1) {
+                cpx<T> w[R];
+                load_twiddles<R, NS, DIR, sizeof(T) == 4, T>(tw, k, w);
 #pragma unroll
-                for (int r = 1; r < R; ++r) {
-                    cpx<T> w = tw[(r - 1) * NS + k];
-                    if constexpr (DIR < 0) w.y = -w.y;
-                    v[p][r] = cmul(v[p][r], w);
-                }
+                for (int r = 1; r < R; ++r) v[p][r] = cmul(v[p][r], w[r]);
             }
             Dft<R, DIR, T>::run(v[p]);
             const int j0 = (j - k) * R + k;
