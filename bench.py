@@ -40,6 +40,7 @@ def parse_args():
     ap.add_argument("--seconds", type=float, default=180.0, help="track length (config 2: 180)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--reference-sample-seconds", type=float, default=30.0)
+    ap.add_argument("--opt", action="append", default=[], help="library switch name=value (A/B measurements)")
     return ap.parse_args()
 
 
@@ -198,6 +199,9 @@ def run_b200(args) -> dict:
     cfg = mg.Config()
     plan = get_plan(cfg, device)
     lib = plan.lib
+    for item in args.opt:
+        name, value = item.split("=")
+        _native.check(lib, lib.mgb_set_option(name.encode(), int(value)))
     n = int(SAMPLE_RATE * args.seconds)
     stream = torch.cuda.current_stream(device)
     sptr = C.c_void_p(stream.cuda_stream)

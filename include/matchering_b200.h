@@ -92,6 +92,10 @@ typedef struct mgb_plan {
     void* d_tw_f64_F;    /* double2 table of the F-point transform  */
     void* d_tw_f64_2F;   /* double2 table of the 2F-point transform */
     void* d_limiter_tables; /* powers of the limiter's three poles (blocked-scan carries) */
+    /* optional: the whole smoothing chain (spline, LOWESS, spline, overrides) as one matrix,
+     * s = S m, S row-major [n_lin][n_lin], built on the device by mgb_plan_build_operator.  NULL =
+     * run the chain directly per track (slower: two latency-bound CTAs). */
+    const double* d_smooth_op;
 } mgb_plan;
 
 /* Per-track scalars, resident in device memory (one struct per track in flight). */
@@ -143,6 +147,12 @@ int mgb_profile_collect(char* names, int names_capacity, float* ms, int capacity
 int mgb_plan_twiddle_bytes(int32_t fft_size, int64_t bytes_out[5]);
 /* Fill plan->d_tw_* and plan->d_limiter_tables (device buffers of the sizes above) on `stream`. */
 int mgb_plan_fill_twiddles(const mgb_plan* plan, void* stream);
+
+/* Build the smoothing operator of `plan` (plan->d_smooth_op may be NULL in the plan passed here)
+ * into d_operator_out [n_lin*n_lin doubles] using d_workspace of mgb_plan_operator_workspace_bytes. */
+int64_t mgb_plan_operator_workspace_bytes(const mgb_plan* plan);
+int mgb_plan_build_operator(const mgb_plan* plan, double* d_operator_out, void* d_workspace, int64_t workspace_bytes,
+                            void* stream);
 
 /* match_levels.py:47-59 piece geometry + launch geometry + workspace size. */
 int mgb_track_layout_init(const mgb_plan* plan, int64_t target_frames, int64_t reference_frames,

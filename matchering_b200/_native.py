@@ -55,6 +55,7 @@ class Plan(C.Structure):
         ("d_tw_f32_F", C.c_void_p), ("d_tw_f32_2F", C.c_void_p),
         ("d_tw_f64_F", C.c_void_p), ("d_tw_f64_2F", C.c_void_p),
         ("d_limiter_tables", C.c_void_p),
+        ("d_smooth_op", C.c_void_p),
     ]
 
 
@@ -98,6 +99,8 @@ PROTOTYPES = {
     "mgb_profile_collect": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_float), C.c_int]),
     "mgb_plan_twiddle_bytes": (C.c_int, [C.c_int32, C.POINTER(C.c_int64)]),
     "mgb_plan_fill_twiddles": (C.c_int, [C.POINTER(Plan), C.c_void_p]),
+    "mgb_plan_operator_workspace_bytes": (C.c_int64, [C.POINTER(Plan)]),
+    "mgb_plan_build_operator": (C.c_int, [C.POINTER(Plan), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "mgb_track_layout_init": (C.c_int, [C.POINTER(Plan), C.c_int64, C.c_int64, C.POINTER(TrackLayout)]),
     "mgb_match_levels": (C.c_int, [C.POINTER(Plan), C.POINTER(TrackLayout), C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),

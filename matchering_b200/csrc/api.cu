@@ -8,10 +8,12 @@
 
 #include "fft.cuh"
 #include "kernels.cuh"
+#include "tail.cuh"
 
 namespace mgb {
 
 int g_use_tma = 1;
+int g_twiddle_chain = 1;
 
 #ifndef MGB_EMULATE
 long long g_launch_count = 0;
@@ -99,7 +101,7 @@ Workspace carve_workspace(const mgb_plan& plan, const mgb_track_layout& L, void*
     w.mid_plane = (float*)take(L.target_frames * 4);
     w.zero_begin = base ? base + off : nullptr;
     w.piece_sums = (double*)take((int64_t)MGB_MAX_CORRECTION_STEPS * L.target_divisions * 8);
-    w.limiter_ticket = (int*)take(16);
+    w.tickets = (int*)take(256);
     w.lookback = take(limiter_lookback_bytes(L.target_frames));
     w.zero_end = base ? base + off : nullptr;
     w.total_bytes = off;
@@ -223,6 +225,14 @@ int mgb_set_option(const char* name, int value) {
         g_use_tma = value ? 1 : 0;
         return MGB_OK;
     }
+    if (strcmp(name, "twiddle_chain") == 0) {
+        g_twiddle_chain = value ? 1 : 0;
+        return MGB_OK;
+    }
+    if (strcmp(name, "design_direct") == 0) {
+        g_design_direct = value ? 1 : 0;
+        return MGB_OK;
+    }
     set_error("unknown option '%s'", name);
     return MGB_ERR_INVALID;
 }
@@ -304,6 +314,20 @@ int mgb_plan_fill_twiddles(const mgb_plan* plan, void* stream) {
     return launch_limiter_tables(plan->limiter, (ScanPow*)plan->d_limiter_tables, st);
 }
 
+int64_t mgb_plan_operator_workspace_bytes(const mgb_plan* plan) {
+    if (check_plan(plan) != MGB_OK) return -1;
+    return operator_workspace_bytes(*plan);
+}
+
+int mgb_plan_build_operator(const mgb_plan* plan, double* d_operator_out, void* d_workspace, int64_t workspace_bytes,
+                            void* stream) {
+    MGB_TRY(check_plan(plan));
+    MGB_TRY(check_aligned(d_operator_out, "d_operator_out"));
+    MGB_TRY(check_aligned(d_workspace, "d_workspace"));
+    MGB_REQUIRE(workspace_bytes >= operator_workspace_bytes(*plan), MGB_ERR_WORKSPACE, "operator workspace too small");
+    return build_operator(*plan, d_operator_out, d_workspace, (cudaStream_t)stream);
+}
+
 int mgb_track_layout_init(const mgb_plan* plan, int64_t target_frames, int64_t reference_frames,
                           mgb_track_layout* out) {
     MGB_TRY(check_plan(plan));
@@ -361,12 +385,28 @@ int mgb_match_levels(const mgb_plan* plan, const mgb_track_layout* L, const floa
 #else
     if (cudaMemsetAsync(ws.zero_begin, 0, ws.zero_end - ws.zero_begin, st) != cudaSuccess) return cuda_status("memset");
 #endif
+    LevelsArgs lv;
+    memset(&lv, 0, sizeof(lv));
     MGB_TRY(launch_analyze(*plan, (const float2*)d_target_lr, L->target_frames, L->target_piece, L->target_divisions,
-                           L->target_slots, ws.spec_part_t, ws.sumsq_part_t, ws.absmax_part_t, st));
-    MGB_TRY(launch_analyze(*plan, (const float2*)d_reference_lr, L->reference_frames, L->reference_piece,
-                           L->reference_divisions, L->reference_slots, ws.spec_part_r, ws.sumsq_part_r,
-                           ws.absmax_part_r, st));
-    return launch_levels(*plan, *L, ws, d_state, st);
+                           L->target_slots, ws.spec_part_t, ws.sumsq_part_t, ws.absmax_part_t, ws.tickets + 1, lv, st));
+    lv.sumsq_t = ws.sumsq_part_t;
+    lv.sumsq_r = ws.sumsq_part_r;
+    lv.absmax_r = ws.absmax_part_r;
+    lv.mask_t = ws.mask_t;
+    lv.mask_r = ws.mask_r;
+    lv.state = d_state;
+    lv.piece_t = L->target_piece;
+    lv.piece_r = L->reference_piece;
+    lv.div_t = L->target_divisions;
+    lv.slots_t = L->target_slots;
+    lv.div_r = L->reference_divisions;
+    lv.slots_r = L->reference_slots;
+    lv.threshold = plan->threshold;
+    lv.eps = plan->min_value;
+    lv.enabled = 1;
+    return launch_analyze(*plan, (const float2*)d_reference_lr, L->reference_frames, L->reference_piece,
+                          L->reference_divisions, L->reference_slots, ws.spec_part_r, ws.sumsq_part_r, ws.absmax_part_r,
+                          ws.tickets + 1, lv, st);
 }
 
 int mgb_match_frequencies(const mgb_plan* plan, const mgb_track_layout* L, const float* d_target_lr,
@@ -390,12 +430,11 @@ int mgb_correct_levels(const mgb_plan* plan, const mgb_track_layout* L, void* d_
     MGB_TRY(check_aligned(d_workspace, "d_workspace"));
     cudaStream_t st = (cudaStream_t)stream;
     Workspace ws = carve_workspace(*plan, *L, d_workspace);
-    for (int step = 0; step < plan->rms_correction_steps; ++step) {
-        // step 0's per-piece sums were produced by the convolution's epilogue (gain is still 1)
-        if (step > 0) MGB_TRY(launch_clip_sumsq(*plan, *L, ws, step, d_state, st));
-        MGB_TRY(launch_correction_update(*plan, *L, ws, step, d_state, st));
-    }
-    return launch_finalize_scalars(*plan, d_state, st);
+    // step 0's per-piece sums and coefficient come out of the convolution kernel's epilogue and tail
+    // (gain is still 1 there); each later step is one pass over the mid plane whose last CTA updates
+    // the gain, and the last step's tail also writes the final scalars.
+    for (int step = 1; step < plan->rms_correction_steps; ++step) MGB_TRY(launch_clip_sumsq(*plan, *L, ws, step, d_state, st));
+    return MGB_OK;
 }
 
 int mgb_finalize(const mgb_plan* plan, const mgb_track_layout* L, const float* d_result_lr, float* d_out_limited,
@@ -419,7 +458,7 @@ int mgb_finalize(const mgb_plan* plan, const mgb_track_layout* L, const float* d
     if (d_out_limited) {
         MGB_TRY(check_aligned(d_out_limited, "d_out_limited"));
         MGB_TRY(launch_limiter(plan->limiter, res, (float2*)d_out_limited, L->target_frames, &d_state->gain,
-                               &d_state->final_amplitude_coef, &d_state->limiter_engaged, ws.limiter_ticket,
+                               &d_state->final_amplitude_coef, &d_state->limiter_engaged, ws.tickets,
                                (LookbackSlot*)ws.lookback, (const ScanPow*)plan->d_limiter_tables, st));
     }
     return MGB_OK;

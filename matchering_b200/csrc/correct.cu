@@ -12,6 +12,7 @@
 // it on the fly, so a step costs one read of the float32 mid plane (4 B/frame, L2-resident for
 // ordinary track lengths) instead of three full-array passes.
 #include "kernels.cuh"
+#include "tail.cuh"
 
 namespace mgb {
 
@@ -27,7 +28,7 @@ __device__ __forceinline__ double clip_sq(float v, double gain) {
 
 __global__ void __launch_bounds__(256)
 clip_sumsq_kernel(const float* __restrict__ mid, long long piece, const mgb_track_state* __restrict__ state,
-                  double* __restrict__ sums) {
+                  double* __restrict__ sums, int* __restrict__ ticket, CorrectionArgs ca) {
     __shared__ double red[32];
     const double gain = state->gain;
     const long long p = blockIdx.y;
@@ -55,43 +56,8 @@ clip_sumsq_kernel(const float* __restrict__ mid, long long piece, const mgb_trac
     }
     const double total = block_sum(acc, red);
     if (threadIdx.x == 0 && total != 0.0) atomicAdd(&sums[p], total);
-}
-
-// one RMS-correction step's coefficient from the per-piece sums (stages.py:153-168)
-__global__ void __launch_bounds__(256)
-correction_update_kernel(const double* __restrict__ sums, int divisions, long long piece, double eps, int step,
-                         mgb_track_state* __restrict__ state) {
-    __shared__ double red[32];
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    double acc = 0.0;
-    for (int p = tid; p < divisions; p += nthr) acc += sums[p] / (double)piece;  // rms^2
-    const double avg = sqrt(block_sum(acc, red) / (double)divisions);
-    double accm = 0.0, cnt = 0.0;
-    for (int p = tid; p < divisions; p += nthr) {
-        const double r = sqrt(sums[p] / (double)piece);
-        if (r >= avg) {
-            accm += r * r;
-            cnt += 1.0;
-        }
-    }
-    const double tm = block_sum(accm, red);
-    const double tc = block_sum(cnt, red);
-    if (tid == 0) {
-        const double match = sqrt(tm / tc);
-        const double c = state->reference_match_rms / fmax(eps, match);
-        state->correction[step] = c;
-        state->gain *= c;
-        state->steps_done = step + 1;
-    }
-}
-
-// result peak after the correction gain, limiter early-out flag, normalisation coefficient
-__global__ void finalize_scalars_kernel(double threshold, double eps, mgb_track_state* __restrict__ state) {
-    const double peak = (double)state->conv_peak_bits * state->gain;
-    state->result_peak = peak;
-    state->normalize_coef = fmax(eps, peak / threshold);  // dsp.py:99 with normalize_clipped=True
-    const double r = fmax(peak, threshold) / threshold;   // dsp.py:117-121 at the loudest frame
-    state->limiter_engaged = (fabs(r - 1.0) <= 1e-8 + 1e-5) ? 0 : 1;  // np.isclose defaults, hyrax.py:83
+    __shared__ int last_flag;
+    if (block_is_last(ticket, (int)(gridDim.x * gridDim.y), &last_flag)) correction_block(ca, red);
 }
 
 // out = in * gain / divisor, two frames per thread
@@ -146,27 +112,24 @@ unsigned grid_for(long long items, int per_block) {
 
 int launch_clip_sumsq(const mgb_plan& plan, const mgb_track_layout& layout, const Workspace& ws, int step,
                       mgb_track_state* state, cudaStream_t stream) {
-    (void)plan;
     const int div = layout.target_divisions;
     long long per_piece = (8LL * num_sms() + div - 1) / div;
     const long long max_useful = (layout.target_piece + 8191) / 8192;
     if (per_piece > max_useful) per_piece = max_useful;
     if (per_piece < 1) per_piece = 1;
+    CorrectionArgs ca;
+    ca.sums = ws.piece_sums + (long long)step * div;
+    ca.state = state;
+    ca.piece = layout.target_piece;
+    ca.divisions = div;
+    ca.step = step;
+    ca.update = 1;
+    ca.finalize = step == plan.rms_correction_steps - 1;
+    ca.eps = plan.min_value;
+    ca.threshold = plan.threshold;
     return launch("clip_sumsq_kernel", clip_sumsq_kernel, dim3((unsigned)per_piece, (unsigned)div), dim3(256), 0, stream,
                   (const float*)ws.mid_plane, (long long)layout.target_piece, (const mgb_track_state*)state,
-                  ws.piece_sums + (long long)step * div);
-}
-
-int launch_correction_update(const mgb_plan& plan, const mgb_track_layout& layout, const Workspace& ws, int step,
-                             mgb_track_state* state, cudaStream_t stream) {
-    return launch("correction_update_kernel", correction_update_kernel, dim3(1), dim3(256), 0, stream,
-                  (const double*)(ws.piece_sums + (long long)step * layout.target_divisions), layout.target_divisions,
-                  (long long)layout.target_piece, plan.min_value, step, state);
-}
-
-int launch_finalize_scalars(const mgb_plan& plan, mgb_track_state* state, cudaStream_t stream) {
-    return launch("finalize_scalars_kernel", finalize_scalars_kernel, dim3(1), dim3(1), 0, stream, plan.threshold,
-                  plan.min_value, state);
+                  ws.piece_sums + (long long)step * div, ws.tickets + 3 + step, ca);
 }
 
 int launch_scale(const float2* in, float2* out, int64_t frames, const double* gain, const double* divisor,

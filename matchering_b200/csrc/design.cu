@@ -1,10 +1,8 @@
 // K3 -- level statistics and matching-FIR design: tiny, latency-bound, all float64.
 //
-// levels_kernel replaces (reference file:line)
-//   match_levels.normalize_reference        stage_helpers/match_levels.py:29-44 (dsp.py:93-100)
-//   get_average_rms / get_lpis_and_match_rms stage_helpers/match_levels.py:62-71,93-103
-//   __calculate_rms_coefficient             stage_helpers/match_levels.py:106-111
-// design_kernel replaces
+// (the level statistics -- normalize_reference, loudest-piece masks, match RMS, c0 -- live in
+//  tail.cuh and run in the last CTA of the reference's analysis pass)
+// These kernels replace
 //   __average_fft's mean over the loudest pieces   stage_helpers/match_frequencies.py:42
 //   get_fir                                        stage_helpers/match_frequencies.py:78-101
 //   __smooth_exponentially                         stage_helpers/match_frequencies.py:45-75
@@ -26,75 +24,6 @@ namespace {
 constexpr int kDesignThreads = 512;
 constexpr int kWarm = 48;
 constexpr int kBatch = 16;  // rows fetched together in the substitution sweeps
-
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-levels_kernel(double* __restrict__ sumsq_t, int div_t, int slots_t, long long piece_t, double* __restrict__ sumsq_r,
-              int div_r, int slots_r, long long piece_r, const float* __restrict__ absmax_r, double threshold,
-              double eps, unsigned char* __restrict__ mask_t, unsigned char* __restrict__ mask_r,
-              mgb_track_state* __restrict__ state) {
-    __shared__ double red_d[32];
-    __shared__ float red_f[32];
-    const int tid = threadIdx.x, nthr = blockDim.x;
-
-    float pk = 0.0f;
-    for (int i = tid; i < div_r * slots_r + 1; i += nthr) pk = fmaxf(pk, absmax_r[i]);
-    pk = block_max(pk, red_f);
-    const double peak = (double)pk;
-    double coef = 1.0;
-    if (peak < threshold) coef = fmax(eps, peak / threshold);  // dsp.py:96-99, normalize_clipped=False
-
-    double match[2];
-    int loud[2];
-    for (int sig = 0; sig < 2; ++sig) {
-        double* part = sig == 0 ? sumsq_t : sumsq_r;
-        const int div = sig == 0 ? div_t : div_r;
-        const int slots = sig == 0 ? slots_t : slots_r;
-        const double piece = (double)(sig == 0 ? piece_t : piece_r);
-        unsigned char* mask = sig == 0 ? mask_t : mask_r;
-        double acc = 0.0;
-        for (int p = tid; p < div; p += nthr) {
-            double s = 0.0;
-            for (int k = 0; k < slots; ++k) s += part[(long long)p * slots + k];
-            const double r = sqrt(s / piece);  // dsp.py:86
-            part[(long long)p * slots] = r;    // slot 0 now holds the piece's RMS
-            acc += r * r;
-        }
-        const double total = block_sum(acc, red_d);
-        const double avg = sqrt(total / (double)div);  // rms(rmses), match_levels.py:101
-        double accm = 0.0, cnt = 0.0;
-        for (int p = tid; p < div; p += nthr) {
-            const double r = part[(long long)p * slots];
-            const bool m = r >= avg;  // match_levels.py:65
-            mask[p] = m ? 1 : 0;
-            if (m) {
-                accm += r * r;
-                cnt += 1.0;
-            }
-        }
-        const double tm = block_sum(accm, red_d);
-        const double tc = block_sum(cnt, red_d);
-        match[sig] = sqrt(tm / tc);
-        loud[sig] = (int)tc;
-    }
-    if (tid == 0) {
-        const double ref_match = match[1] / coef;  // the reference measures the normalised reference
-        state->reference_peak = peak;
-        state->final_amplitude_coef = coef;
-        state->target_match_rms = match[0];
-        state->reference_match_rms = ref_match;
-        state->rms_coefficient = ref_match / fmax(eps, match[0]);
-        state->gain = 1.0;
-        state->result_peak = 0.0;
-        state->normalize_coef = 1.0;
-        state->target_loud_pieces = loud[0];
-        state->reference_loud_pieces = loud[1];
-        state->limiter_engaged = 1;
-        state->conv_peak_bits = 0.0f;
-        state->steps_done = 0;
-        for (int i = 0; i < MGB_MAX_CORRECTION_STEPS; ++i) state->correction[i] = 1.0;
-    }
-}
 
 // ------------------------------------------------------------------------------------------------
 struct SplineTables {
@@ -181,6 +110,72 @@ __device__ __forceinline__ double spline_eval(const double* __restrict__ y, cons
     return w[0] * y[idx] + w[1] * y[idx + 1] + w[2] * M[idx] + w[3] * M[idx + 1];
 }
 
+// Scratch layout of one channel's design vectors (doubles): m, M1, s [n_lin each], then
+// mlog, slog, zz, M2 [n_log each], then fir [F].
+// smooth_curve: m -> s, match_frequencies.__smooth_exponentially (:45-75): cubic spline to the
+// log grid, LOWESS, cubic spline back, then out[0] = 0 and out[1] = m[1].  Every step is linear in
+// m (lowess_it == 0), which is what operator_columns_kernel exploits.  Contains barriers.
+__device__ void smooth_curve(const mgb_plan& plan, double* __restrict__ base) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+    const int HB = plan.n_lin, NL = plan.n_log;
+    double* m = base;
+    double* M1 = m + HB;
+    double* s = M1 + HB;
+    double* mlog = s + HB;
+    double* slog = mlog + NL;
+    double* zz = slog + NL;
+    double* M2 = zz + NL;
+
+    // ---- B/C: cubic spline linear grid -> log grid (match_frequencies.py:60-61) --------------
+    spline_moments(m, HB, SplineTables{plan.d_sa_hinv, plan.d_sa_lu, plan.d_sa_end}, zz, M1);
+    for (int j = tid; j < NL; j += nthr) mlog[j] = spline_eval(m, M1, plan.d_sa_eval_idx[j], plan.d_sa_eval_w + 4LL * j);
+    __syncthreads();
+
+    // ---- D: LOWESS (dsp.py:103-106): each regression is a Config-only row of k coefficients ------
+    {
+        const int k = plan.lowess_k;
+        const int nfit = plan.lowess_nfit;
+        for (int f = warp; f < nfit; f += 2 * nwarps) {  // two regressions per pass: twice the loads in flight
+            const int f2 = min(f + nwarps, nfit - 1);
+            const double* row_a = plan.d_lw_rows + (long long)plan.d_lw_row_idx[f] * k;
+            const double* row_b = plan.d_lw_rows + (long long)plan.d_lw_row_idx[f2] * k;
+            const double* ya = mlog + plan.d_lw_fit_left[f];
+            const double* yb = mlog + plan.d_lw_fit_left[f2];
+            double acc_a = 0.0, acc_b = 0.0;
+            for (int j = lane; j < k; j += 32) {
+                acc_a += row_a[j] * ya[j];
+                acc_b += row_b[j] * yb[j];
+            }
+            acc_a = warp_sum(acc_a);
+            acc_b = warp_sum(acc_b);
+            if (lane == 0) {
+                zz[f] = acc_a;
+                zz[f2] = acc_b;
+            }
+        }
+        __syncthreads();
+        const int last = plan.lowess_nfit - 1;
+        for (int j = tid; j < NL; j += nthr) {
+            const int sg = plan.d_lw_seg[j];
+            const double al = plan.d_lw_alpha[j];  // 0 at a regression point
+            slog[j] = al * zz[min(sg + 1, last)] + (1.0 - al) * zz[sg];
+        }
+        __syncthreads();
+    }
+
+    // ---- E: cubic spline log grid -> linear grid, then the two overrides (:67-73) -------------
+    spline_moments(slog, NL, SplineTables{plan.d_sb_hinv, plan.d_sb_lu, plan.d_sb_end}, zz, M2);
+    for (int k = tid; k < HB; k += nthr) {
+        double v = spline_eval(slog, M2, plan.d_sb_eval_idx[k], plan.d_sb_eval_w + 4LL * k);
+        if (k == 0) v = 0.0;
+        if (k == 1) v = m[1];
+        s[k] = v;
+    }
+    __syncthreads();
+
+}
+
 struct DesignArgs {
     // average-spectrum inputs
     const float* spec_part_t;
@@ -197,6 +192,7 @@ struct DesignArgs {
     float2* h_mid;
     float2* h_side;
     const mgb_track_state* state;  // null with avg_override: c0 = 1, coef = 1
+    int s_ready;                   // the smoothed curve is already in the scratch (operator path)
 };
 
 // Matching curve m[k] = mean|rfft(reference)| / max(eps, mean|rfft(target)|) from the per-(piece,
@@ -271,20 +267,14 @@ design_kernel(mgb_plan plan, DesignArgs a) {
     double* re = reinterpret_cast<double*>(smem);
     double* im = re + DesignSmem<F>::kPlane;
     const int tid = threadIdx.x, nthr = blockDim.x;
-    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
     const int ch = blockIdx.x;
     const int NL = plan.n_log;
     const cpx<double>* tw = (const cpx<double>*)plan.d_tw_f64_F;
 
     double* base = a.scratch + (long long)ch * a.stride;
-    double* m = base;             // [HB] matching curve
-    double* M1 = m + HB;          // [HB] moments of spline A
-    double* s = M1 + HB;          // [HB] smoothed curve on the linear grid
-    double* mlog = s + HB;        // [NL]
-    double* slog = mlog + NL;     // [NL]
-    double* zz = slog + NL;       // [NL] scratch (sweeps, LOWESS fits)
-    double* M2 = zz + NL;         // [NL]
-    double* fir = M2 + NL;        // [F]
+    double* m = base;                    // [HB] matching curve
+    double* s = base + 2 * HB;           // [HB] smoothed curve on the linear grid
+    double* fir = base + 3 * HB + 4 * NL;  // [F]
 
     const double eps = plan.min_value;
     double c0 = 1.0, coef = 1.0;
@@ -303,52 +293,8 @@ design_kernel(mgb_plan plan, DesignArgs a) {
     }  // otherwise spectrum_mean_kernel has already written m
     __syncthreads();
 
-    // ---- B/C: cubic spline linear grid -> log grid (match_frequencies.py:60-61) --------------
-    spline_moments(m, HB, SplineTables{plan.d_sa_hinv, plan.d_sa_lu, plan.d_sa_end}, zz, M1);
-    for (int j = tid; j < NL; j += nthr) mlog[j] = spline_eval(m, M1, plan.d_sa_eval_idx[j], plan.d_sa_eval_w + 4LL * j);
-    __syncthreads();
-
-    // ---- D: LOWESS (dsp.py:103-106): each regression is a Config-only row of k coefficients ------
-    {
-        const int k = plan.lowess_k;
-        const int nfit = plan.lowess_nfit;
-        for (int f = warp; f < nfit; f += 2 * nwarps) {  // two regressions per pass: twice the loads in flight
-            const int f2 = min(f + nwarps, nfit - 1);
-            const double* row_a = plan.d_lw_rows + (long long)plan.d_lw_row_idx[f] * k;
-            const double* row_b = plan.d_lw_rows + (long long)plan.d_lw_row_idx[f2] * k;
-            const double* ya = mlog + plan.d_lw_fit_left[f];
-            const double* yb = mlog + plan.d_lw_fit_left[f2];
-            double acc_a = 0.0, acc_b = 0.0;
-            for (int j = lane; j < k; j += 32) {
-                acc_a += row_a[j] * ya[j];
-                acc_b += row_b[j] * yb[j];
-            }
-            acc_a = warp_sum(acc_a);
-            acc_b = warp_sum(acc_b);
-            if (lane == 0) {
-                zz[f] = acc_a;
-                zz[f2] = acc_b;
-            }
-        }
-        __syncthreads();
-        const int last = plan.lowess_nfit - 1;
-        for (int j = tid; j < NL; j += nthr) {
-            const int sg = plan.d_lw_seg[j];
-            const double al = plan.d_lw_alpha[j];  // 0 at a regression point
-            slog[j] = al * zz[min(sg + 1, last)] + (1.0 - al) * zz[sg];
-        }
-        __syncthreads();
-    }
-
-    // ---- E: cubic spline log grid -> linear grid, then the two overrides (:67-73) -------------
-    spline_moments(slog, NL, SplineTables{plan.d_sb_hinv, plan.d_sb_lu, plan.d_sb_end}, zz, M2);
-    for (int k = tid; k < HB; k += nthr) {
-        double v = spline_eval(slog, M2, plan.d_sb_eval_idx[k], plan.d_sb_eval_w + 4LL * k);
-        if (k == 0) v = 0.0;
-        if (k == 1) v = m[1];
-        s[k] = v;
-    }
-    __syncthreads();
+    // ---- B-E: smoothing on the log-frequency grid, unless the operator kernel already produced s ---
+    if (!a.s_ready) smooth_curve(plan, base);
 
     // ---- F: fir = ifftshift(irfft(s)) * hann (match_frequencies.py:98-99) ---------------------
     {
@@ -390,6 +336,73 @@ design_kernel(mgb_plan plan, DesignArgs a) {
     }
 }
 
+__global__ void ratio_kernel(const double* __restrict__ avg, double* __restrict__ scratch, long long stride, int n_lin,
+                             double eps) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x, ch = blockIdx.y;
+    if (k < n_lin) scratch[(long long)ch * stride + k] = avg[(long long)(2 + ch) * n_lin + k] / fmax(eps, avg[(long long)ch * n_lin + k]);
+}
+
+// ---- the smoothing as a Config-only matrix ------------------------------------------------------
+// s = S m with S [n_lin][n_lin]: column c of S is smooth_curve applied to the unit vector e_c.
+// Built once per plan by running the direct algorithm on every unit vector (persistent CTAs, one
+// scratch block each); per track the whole spline/LOWESS/spline chain is then one GEMV spread over
+// the GPU instead of two latency-bound CTAs.
+__global__ void __launch_bounds__(256)
+operator_columns_kernel(mgb_plan plan, double* scratch, long long stride, double* st /*[n_lin][n_lin], column-major S*/) {
+    const int HB = plan.n_lin;
+    double* base = scratch + (long long)blockIdx.x * stride;
+    for (int c = blockIdx.x; c < HB; c += gridDim.x) {
+        for (int k = threadIdx.x; k < HB; k += blockDim.x) base[k] = (k == c) ? 1.0 : 0.0;
+        __syncthreads();
+        smooth_curve(plan, base);
+        const double* s = base + 2 * HB;
+        for (int k = threadIdx.x; k < HB; k += blockDim.x) st[(long long)c * HB + k] = s[k];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+transpose_kernel(const double* __restrict__ in, double* __restrict__ out, int n) {
+    __shared__ double tile[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int r = ty; r < 32; r += 8)
+        if (by + r < n && bx + tx < n) tile[r][tx] = in[(long long)(by + r) * n + bx + tx];
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8)
+        if (bx + r < n && by + tx < n) out[(long long)(bx + r) * n + by + tx] = tile[tx][r];
+}
+
+// s[ch] = S m[ch] for both channels; one warp per row, grid = ceil(n_lin / 8).
+__global__ void __launch_bounds__(256)
+smooth_operator_kernel(const double* __restrict__ S, double* __restrict__ scratch, long long stride, int n_lin) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r = blockIdx.x * 8 + warp;
+    if (r >= n_lin) return;
+    const double* row = S + (long long)r * n_lin;
+    const double* m0 = scratch;
+    const double* m1 = scratch + stride;
+    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+    int c = lane;
+    for (; c + 32 < n_lin; c += 64) {
+        const double w0 = row[c], w1 = row[c + 32];
+        a0 += w0 * m0[c];
+        a1 += w1 * m0[c + 32];
+        b0 += w0 * m1[c];
+        b1 += w1 * m1[c + 32];
+    }
+    if (c < n_lin) {
+        const double w0 = row[c];
+        a0 += w0 * m0[c];
+        b0 += w0 * m1[c];
+    }
+    const double sa = warp_sum(a0 + a1), sb = warp_sum(b0 + b1);
+    if (lane == 0) {
+        scratch[2LL * n_lin + r] = sa;
+        scratch[stride + 2LL * n_lin + r] = sb;
+    }
+}
+
 template <int F>
 int launch_design_t(const mgb_plan& plan, const DesignArgs& a, cudaStream_t stream) {
     return launch("design_kernel", design_kernel<F>, dim3(2), dim3(kDesignThreads), DesignSmem<F>::kBytes, stream, plan, a);
@@ -401,12 +414,24 @@ int64_t design_doubles_per_channel(const mgb_plan& plan) {
     return 3LL * plan.n_lin + 4LL * plan.n_log + plan.fft_size + 16;
 }
 
-int launch_levels(const mgb_plan& plan, const mgb_track_layout& layout, const Workspace& ws, mgb_track_state* state,
-                  cudaStream_t stream) {
-    return launch("levels_kernel", levels_kernel, dim3(1), dim3(256), 0, stream, ws.sumsq_part_t,
-                  layout.target_divisions, layout.target_slots, (long long)layout.target_piece, ws.sumsq_part_r,
-                  layout.reference_divisions, layout.reference_slots, (long long)layout.reference_piece,
-                  (const float*)ws.absmax_part_r, plan.threshold, plan.min_value, ws.mask_t, ws.mask_r, state);
+int g_design_direct = 0;
+
+int64_t operator_workspace_bytes(const mgb_plan& plan) {
+    const int64_t ctas = plan.n_lin < 2 * num_sms() ? plan.n_lin : 2 * num_sms();
+    const int64_t stride = (design_doubles_per_channel(plan) + 31) / 32 * 32;
+    return ctas * stride * 8 + (int64_t)plan.n_lin * plan.n_lin * 8 + 512;
+}
+
+int build_operator(const mgb_plan& plan, double* op_out, void* workspace, cudaStream_t stream) {
+    const int ctas = plan.n_lin < 2 * num_sms() ? plan.n_lin : 2 * num_sms();
+    const int64_t stride = (design_doubles_per_channel(plan) + 31) / 32 * 32;
+    double* scratch = (double*)workspace;
+    double* st = scratch + ctas * stride;
+    MGB_TRY(launch("operator_columns_kernel", operator_columns_kernel, dim3(ctas), dim3(256), 0, stream, plan, scratch,
+                   (long long)stride, st));
+    const unsigned tiles = (plan.n_lin + 31) / 32;
+    return launch("transpose_kernel", transpose_kernel, dim3(tiles, tiles), dim3(256), 0, stream, (const double*)st, op_out,
+                  plan.n_lin);
 }
 
 int launch_design(const mgb_plan& plan, const mgb_track_layout& layout, const Workspace& ws,
@@ -429,6 +454,7 @@ int launch_design(const mgb_plan& plan, const mgb_track_layout& layout, const Wo
     a.h_mid = ws.h_mid;
     a.h_side = ws.h_side;
     a.state = avg_override ? nullptr : state;
+    a.s_ready = 0;
     if (!avg_override) {
         PrefetchList pf;
         pf.count = 0;
@@ -456,6 +482,17 @@ int launch_design(const mgb_plan& plan, const mgb_track_layout& layout, const Wo
         add(plan.d_hann, F * 8);
         MGB_TRY(launch("spectrum_mean_kernel", spectrum_mean_kernel, dim3((plan.n_lin + 31) / 32, 2), dim3(256), 0, stream, a,
                        plan.n_lin, plan.fft_size, plan.min_value, pf));
+    }
+    if (plan.d_smooth_op && !(avg_override && g_design_direct)) {
+        if (avg_override) {
+            // test entry: the matching curve has to exist before the GEMV
+            MGB_TRY(launch("ratio_kernel", ratio_kernel, dim3((plan.n_lin + 255) / 256, 2), dim3(256), 0, stream, avg_override,
+                           a.scratch, a.stride, plan.n_lin, plan.min_value));
+            a.avg_override = nullptr;
+        }
+        MGB_TRY(launch("smooth_operator_kernel", smooth_operator_kernel, dim3((plan.n_lin + 7) / 8), dim3(256), 0, stream,
+                       plan.d_smooth_op, a.scratch, a.stride, plan.n_lin));
+        a.s_ready = 1;
     }
     switch (plan.fft_size) {
         case 1024: return launch_design_t<1024>(plan, a, stream);

@@ -136,7 +136,7 @@ __device__ __forceinline__ void load_twiddles(const cpx<T>* __restrict__ tw, int
     }
 }
 
-template <int N, int R, int NS, int DIR, int THREADS, typename T, typename Load, typename Store>
+template <int N, int R, int NS, int DIR, int THREADS, typename T, bool CHAIN, typename Load, typename Store>
 __device__ __forceinline__ void fft_pass(const cpx<T>* __restrict__ tw, Load load, Store store, bool barrier_between) {
     constexpr int NB = N / R;
     static_assert(NB % THREADS == 0 || NB < THREADS, "butterflies must tile the block");
@@ -160,7 +160,7 @@ __device__ __forceinline__ void fft_pass(const cpx<T>* __restrict__ tw, Load loa
             const int k = j & (NS - 1);
             if constexpr (NS > 1) {
                 cpx<T> w[R];
-                load_twiddles<R, NS, DIR, sizeof(T) == 4, T>(tw, k, w);
+                load_twiddles<R, NS, DIR, CHAIN, T>(tw, k, w);
 #pragma unroll
                 for (int r = 1; r < R; ++r) v[p][r] = cmul(v[p][r], w[r]);
             }
@@ -212,13 +212,13 @@ template <int N, int DIR, int THREADS, typename T, typename First>
 __device__ __forceinline__ void fft_first_pass(T* re, T* im, const cpx<T>* __restrict__ tw, First first,
                                                bool in_place) {
     SmemStore<T> ss{re, im};
-    fft_pass<N, Radices<N>::r[0], 1, DIR, THREADS, T>(tw, first, ss, in_place);
+    fft_pass<N, Radices<N>::r[0], 1, DIR, THREADS, T, false>(tw, first, ss, in_place);  // NS = 1: no twiddles
 }
 
 // Remaining passes, in place on (re, im); the caller has put a barrier after the first pass.
 // `last` consumes the output points in natural order (`last_in_place`: it writes (re, im)).
 // On return all `last` stores have been ISSUED (no trailing barrier).
-template <int N, int DIR, int THREADS, typename T, typename Last>
+template <int N, int DIR, int THREADS, typename T, bool CHAIN = false, typename Last>
 __device__ __forceinline__ void fft_remaining(T* re, T* im, const cpx<T>* __restrict__ tw, Last last,
                                               bool last_in_place) {
     using Rd = Radices<N>;
@@ -229,29 +229,29 @@ __device__ __forceinline__ void fft_remaining(T* re, T* im, const cpx<T>* __rest
     static_assert(NP >= 2 && NP <= 4, "2..4 passes supported");
     constexpr int o1 = 0;  // pass 0 has NS = 1: no twiddles stored
     if constexpr (NP == 2) {
-        fft_pass<N, R1, R0, DIR, THREADS, T>(tw + o1, sl, last, last_in_place);
+        fft_pass<N, R1, R0, DIR, THREADS, T, CHAIN>(tw + o1, sl, last, last_in_place);
     } else {
-        fft_pass<N, R1, R0, DIR, THREADS, T>(tw + o1, sl, ss, true);
+        fft_pass<N, R1, R0, DIR, THREADS, T, CHAIN>(tw + o1, sl, ss, true);
         __syncthreads();
         constexpr int o2 = o1 + (R1 - 1) * R0;
         if constexpr (NP == 3) {
-            fft_pass<N, R2, R0 * R1, DIR, THREADS, T>(tw + o2, sl, last, last_in_place);
+            fft_pass<N, R2, R0 * R1, DIR, THREADS, T, CHAIN>(tw + o2, sl, last, last_in_place);
         } else {
-            fft_pass<N, R2, R0 * R1, DIR, THREADS, T>(tw + o2, sl, ss, true);
+            fft_pass<N, R2, R0 * R1, DIR, THREADS, T, CHAIN>(tw + o2, sl, ss, true);
             __syncthreads();
             constexpr int o3 = o2 + (R2 - 1) * R0 * R1;
-            fft_pass<N, R3, R0 * R1 * R2, DIR, THREADS, T>(tw + o3, sl, last, last_in_place);
+            fft_pass<N, R3, R0 * R1 * R2, DIR, THREADS, T, CHAIN>(tw + o3, sl, last, last_in_place);
         }
     }
 }
 
 // Whole transform: first pass, barrier, remaining passes.
-template <int N, int DIR, int THREADS, typename T, typename First, typename Last>
+template <int N, int DIR, int THREADS, typename T, bool CHAIN = false, typename First, typename Last>
 __device__ __forceinline__ void fft_run(T* re, T* im, const cpx<T>* __restrict__ tw, First first, Last last,
                                         bool first_in_place, bool last_in_place) {
     fft_first_pass<N, DIR, THREADS, T>(re, im, tw, first, first_in_place);
     __syncthreads();
-    fft_remaining<N, DIR, THREADS, T>(re, im, tw, last, last_in_place);
+    fft_remaining<N, DIR, THREADS, T, CHAIN>(re, im, tw, last, last_in_place);
 }
 
 // number of stored twiddles (pass 0 stores none)

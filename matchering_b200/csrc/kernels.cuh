@@ -21,7 +21,7 @@ struct Workspace {
     // ---- zeroed at the start of every job (one memset) ----
     unsigned char* zero_begin;
     double* piece_sums;     // [MGB_MAX_CORRECTION_STEPS][Dt] sums of clip(mid*gain)^2
-    int* limiter_ticket;    // [4] chunk ticket counter (+ padding)
+    int* tickets;           // [64] zeroed counters: 0 limiter chunks, 1 analysis tail, 2 convolution tail, 3+step clip tails
     unsigned char* lookback;// [nchunks] LookbackSlot
     unsigned char* zero_end;
     int64_t design_stride;  // doubles per channel in `design`
@@ -51,26 +51,26 @@ Workspace carve_workspace(const mgb_plan& plan, const mgb_track_layout& layout, 
 int64_t limiter_lookback_bytes(int64_t frames);
 
 // analyze.cu ------------------------------------------------------------------------------------
+struct LevelsArgs;
 int launch_analyze(const mgb_plan& plan, const float2* x, int64_t frames, int64_t piece, int divisions, int slots,
-                   float* spec_part, double* sumsq_part, float* absmax_part, cudaStream_t stream);
+                   float* spec_part, double* sumsq_part, float* absmax_part, int* ticket, const LevelsArgs& lv,
+                   cudaStream_t stream);
 
 // design.cu -------------------------------------------------------------------------------------
-int launch_levels(const mgb_plan& plan, const mgb_track_layout& layout, const Workspace& ws, mgb_track_state* state,
-                  cudaStream_t stream);
 int launch_design(const mgb_plan& plan, const mgb_track_layout& layout, const Workspace& ws,
                   const double* avg_override, double* fir_out, mgb_track_state* state, cudaStream_t stream);
 int64_t design_doubles_per_channel(const mgb_plan& plan);
+int64_t operator_workspace_bytes(const mgb_plan& plan);
+int build_operator(const mgb_plan& plan, double* op_out, void* workspace, cudaStream_t stream);
+extern int g_design_direct;  // tests: force the direct (non-operator) smoothing in mgb_test_design_fir
 
 // convolve.cu -----------------------------------------------------------------------------------
 int launch_convolve(const mgb_plan& plan, const mgb_track_layout& layout, const float2* target, float2* result,
                     const Workspace& ws, mgb_track_state* state, cudaStream_t stream);
 
 // correct.cu ------------------------------------------------------------------------------------
-int launch_correction_update(const mgb_plan& plan, const mgb_track_layout& layout, const Workspace& ws, int step,
-                             mgb_track_state* state, cudaStream_t stream);
 int launch_clip_sumsq(const mgb_plan& plan, const mgb_track_layout& layout, const Workspace& ws, int step,
                       mgb_track_state* state, cudaStream_t stream);
-int launch_finalize_scalars(const mgb_plan& plan, mgb_track_state* state, cudaStream_t stream);
 int launch_scale(const float2* in, float2* out, int64_t frames, const double* gain, const double* divisor,
                  cudaStream_t stream);
 int launch_absmax(const float2* in, int64_t frames, float* out_bits, cudaStream_t stream);
@@ -92,5 +92,6 @@ int fill_twiddles(int n, int is_f64, void* table, cudaStream_t stream);
 int twiddle_count(int n);
 
 extern int g_use_tma;
+extern int g_twiddle_chain;  // convolution FFTs: build twiddle powers in registers (1) or read them all (0)
 
 }  // namespace mgb

@@ -54,6 +54,16 @@ class DevicePlan:
         self.struct = s
         with torch.cuda.device(device):
             _native.check(self.lib, self.lib.mgb_plan_fill_twiddles(C.byref(s), _stream_ptr(device)))
+            # the smoothing chain as one Config-only matrix, built on the device from the direct kernels
+            ws_bytes = int(self.lib.mgb_plan_operator_workspace_bytes(C.byref(s)))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+            op = torch.empty((t.n_lin, t.n_lin), dtype=torch.float64, device=device)
+            _native.check(self.lib, self.lib.mgb_plan_build_operator(C.byref(s), op.data_ptr(), ws.data_ptr(), ws_bytes,
+                                                                    _stream_ptr(device)))
+            torch.cuda.current_stream(device).synchronize()
+            del ws
+            self._keep["smooth_op"] = op
+            s.d_smooth_op = op.data_ptr()
 
     def layout(self, target_frames: int, reference_frames: int) -> _native.TrackLayout:
         L = _native.TrackLayout()

@@ -55,7 +55,7 @@ def limiter_params(lc: plan_mod.LimiterConstants) -> _native.LimiterParams:
 class EmulPlan:
     """mgb_plan over numpy memory (device pointers == host pointers in the emulator)."""
 
-    def __init__(self, config):
+    def __init__(self, config, operator=False):
         self.lib = emul_lib()
         self.tables = plan_mod.build_tables(config)
         t = self.tables
@@ -79,6 +79,13 @@ class EmulPlan:
             setattr(s, "d_" + name, buf.ctypes.data)
         self.struct = s
         _native.check(self.lib, self.lib.mgb_plan_fill_twiddles(C.byref(s), None))
+        if operator:
+            ws_bytes = int(self.lib.mgb_plan_operator_workspace_bytes(C.byref(s)))
+            ws = aligned((ws_bytes,), np.uint8)
+            op = aligned((t.n_lin, t.n_lin), np.float64)
+            _native.check(self.lib, self.lib.mgb_plan_build_operator(C.byref(s), ptr(op), ptr(ws), ws_bytes, None))
+            self.keep["smooth_op"] = op
+            s.d_smooth_op = op.ctypes.data
 
     def layout(self, target_frames, reference_frames):
         L = _native.TrackLayout()
@@ -87,11 +94,21 @@ class EmulPlan:
         return L
 
 
-def run_pipeline(config, target_f32, reference_f32, need=(True, True, True), tma=1):
+_PLANS = {}
+
+
+def get_emul_plan(config, operator=False):
+    key = (plan_mod.config_key(config), operator)
+    if key not in _PLANS:
+        _PLANS[key] = EmulPlan(config, operator)
+    return _PLANS[key]
+
+
+def run_pipeline(config, target_f32, reference_f32, need=(True, True, True), tma=1, operator=False):
     """All four stages through the emulator; returns (outputs, state, fir[2,F])."""
     lib = emul_lib()
     lib.mgb_set_option(b"tma", tma)
-    ep = EmulPlan(config)
+    ep = get_emul_plan(config, operator)
     T, R = len(target_f32), len(reference_f32)
     L = ep.layout(T, R)
     ws = aligned((L.workspace_bytes,), np.uint8)

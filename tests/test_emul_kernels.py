@@ -54,6 +54,34 @@ def test_fir_design_matches_oracle(lib):
     assert fir[0][0] == 0.0
 
 
+def test_smoothing_operator_matches_direct_path_and_oracle(lib):
+    """The Config-only smoothing matrix (built on the device from the direct kernels) against the
+    direct chain and the oracle; a small grid keeps the emulated build of the matrix short."""
+    cfg = port.OracleConfig(fft_size=1024, lin_log_oversampling=1, lowess_frac=0.06)
+    ep = EmulPlan(cfg, operator=True)
+    n = cfg.fft_size // 2 + 1
+    rng = np.random.default_rng(8)
+    at = 1e-3 * (1 + 0.3 * rng.standard_normal(n)) ** 2 + 1e-5
+    ar = 2e-3 * (1 + 0.3 * rng.standard_normal(n)) ** 2 + 1e-6
+    avg = aligned_copy(np.stack([at, 0.5 * at, ar, 0.7 * ar]))
+    ws = aligned((4 << 20,), np.uint8)
+    want = port.design_fir(at.copy(), ar.copy(), cfg)
+    got = {}
+    for direct in (0, 1):
+        lib.mgb_set_option(b"design_direct", direct)
+        fir = aligned((2, cfg.fft_size), np.float64)
+        _native.check(lib, lib.mgb_test_design_fir(C.byref(ep.struct), ptr(avg), ptr(fir), ptr(ws), None))
+        got[direct] = fir.copy()
+    lib.mgb_set_option(b"design_direct", 0)
+    assert np.abs(got[0][0] - want).max() < 1e-13 and np.abs(got[1][0] - want).max() < 1e-13
+    assert np.abs(got[0] - got[1]).max() < 1e-13
+    # and through the whole pipeline
+    t, r = port.synth_target(30000, 1), port.synth_reference(28000, 2)
+    cfg2 = port.OracleConfig(fft_size=1024, lin_log_oversampling=1, lowess_frac=0.06, max_piece_size=0.2)
+    outs, _, _, _, _ = run_pipeline(cfg2, t, r, operator=True)
+    _compare(outs, port.main(t.astype(np.float64), r.astype(np.float64), cfg2, True, True, True))
+
+
 def _compare(outs, want):
     for got, ref in zip(outs, want):
         if got is None:
