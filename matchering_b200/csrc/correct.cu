@@ -27,10 +27,18 @@ __device__ __forceinline__ double clip_sq(float v, double gain) {
 }
 
 __global__ void __launch_bounds__(256)
-clip_sumsq_kernel(const float* __restrict__ mid, long long piece, const mgb_track_state* __restrict__ state,
-                  double* __restrict__ sums, int* __restrict__ ticket, CorrectionArgs ca) {
+clip_sumsq_kernel(const float* __restrict__ mid, long long piece, int divisions, int step, double eps,
+                  mgb_track_state* __restrict__ state, const double* __restrict__ prev_sums, double* __restrict__ sums) {
     __shared__ double red[32];
-    const double gain = state->gain;
+    // prologue, identical in every CTA: the previous step's coefficient from its per-piece sums, and
+    // the gain accumulated so far (stages.py:161-168 applied lazily)
+    const double c_prev = correction_coefficient(prev_sums, divisions, piece, eps, state->reference_match_rms, red);
+    double gain = c_prev;
+    for (int j = 0; j < step - 1; ++j) gain *= state->correction[j];
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+        state->correction[step - 1] = c_prev;  // no CTA of this launch reads this slot
+        state->steps_done = step;
+    }
     const long long p = blockIdx.y;
     const long long per = (piece + gridDim.x - 1) / gridDim.x;
     const long long lo = p * piece + (long long)blockIdx.x * per;
@@ -56,8 +64,30 @@ clip_sumsq_kernel(const float* __restrict__ mid, long long piece, const mgb_trac
     }
     const double total = block_sum(acc, red);
     if (threadIdx.x == 0 && total != 0.0) atomicAdd(&sums[p], total);
-    __shared__ int last_flag;
-    if (block_is_last(ticket, (int)(gridDim.x * gridDim.y), &last_flag)) correction_block(ca, red);
+}
+
+// after the last step: its coefficient, the total gain, the result's peak, the limiter's early-out
+// flag (hyrax.py:83-85) and the normalisation coefficient (stages.py:186-191); one CTA
+__global__ void __launch_bounds__(256)
+correction_final_kernel(const double* __restrict__ last_sums, int divisions, long long piece, int steps, double eps,
+                        double threshold, mgb_track_state* __restrict__ state) {
+    __shared__ double red[32];
+    double gain = 1.0;
+    if (steps > 0) {
+        const double c_last = correction_coefficient(last_sums, divisions, piece, eps, state->reference_match_rms, red);
+        gain = c_last;
+        for (int j = 0; j < steps - 1; ++j) gain *= state->correction[j];
+        if (threadIdx.x == 0) state->correction[steps - 1] = c_last;
+    }
+    if (threadIdx.x == 0) {
+        state->steps_done = steps;
+        state->gain = gain;
+        const double peak = (double)state->conv_peak_bits * gain;
+        state->result_peak = peak;
+        state->normalize_coef = fmax(eps, peak / threshold);  // dsp.py:99 with normalize_clipped=True
+        const double r = fmax(peak, threshold) / threshold;   // dsp.py:117-121 at the loudest frame
+        state->limiter_engaged = (fabs(r - 1.0) <= 1e-8 + 1e-5) ? 0 : 1;  // np.isclose defaults, hyrax.py:83
+    }
 }
 
 // out = in * gain / divisor, two frames per thread
@@ -113,23 +143,21 @@ unsigned grid_for(long long items, int per_block) {
 int launch_clip_sumsq(const mgb_plan& plan, const mgb_track_layout& layout, const Workspace& ws, int step,
                       mgb_track_state* state, cudaStream_t stream) {
     const int div = layout.target_divisions;
-    long long per_piece = (8LL * num_sms() + div - 1) / div;
+    long long per_piece = (3LL * num_sms() + div - 1) / div;
     const long long max_useful = (layout.target_piece + 8191) / 8192;
     if (per_piece > max_useful) per_piece = max_useful;
     if (per_piece < 1) per_piece = 1;
-    CorrectionArgs ca;
-    ca.sums = ws.piece_sums + (long long)step * div;
-    ca.state = state;
-    ca.piece = layout.target_piece;
-    ca.divisions = div;
-    ca.step = step;
-    ca.update = 1;
-    ca.finalize = step == plan.rms_correction_steps - 1;
-    ca.eps = plan.min_value;
-    ca.threshold = plan.threshold;
     return launch("clip_sumsq_kernel", clip_sumsq_kernel, dim3((unsigned)per_piece, (unsigned)div), dim3(256), 0, stream,
-                  (const float*)ws.mid_plane, (long long)layout.target_piece, (const mgb_track_state*)state,
-                  ws.piece_sums + (long long)step * div, ws.tickets + 3 + step, ca);
+                  (const float*)ws.mid_plane, (long long)layout.target_piece, div, step, plan.min_value, state,
+                  (const double*)(ws.piece_sums + (long long)(step - 1) * div), ws.piece_sums + (long long)step * div);
+}
+
+int launch_correction_final(const mgb_plan& plan, const mgb_track_layout& layout, const Workspace& ws,
+                            mgb_track_state* state, cudaStream_t stream) {
+    const int steps = plan.rms_correction_steps, div = layout.target_divisions;
+    const double* last = ws.piece_sums + (long long)(steps > 0 ? steps - 1 : 0) * div;
+    return launch("correction_final_kernel", correction_final_kernel, dim3(1), dim3(256), 0, stream, last, div,
+                  (long long)layout.target_piece, steps, plan.min_value, plan.threshold, state);
 }
 
 int launch_scale(const float2* in, float2* out, int64_t frames, const double* gain, const double* divisor,

@@ -16,6 +16,7 @@
 // warm-up of kWarm rows (the factors decay like 0.27^n, so 48 rows are exact to < 1e-27).
 #include "fft.cuh"
 #include "kernels.cuh"
+#include "tail.cuh"
 
 namespace mgb {
 
@@ -180,8 +181,9 @@ struct DesignArgs {
     // average-spectrum inputs
     const float* spec_part_t;
     const float* spec_part_r;
-    const unsigned char* mask_t;
-    const unsigned char* mask_r;
+    unsigned char* mask_t;  // global copies of the loudest-piece masks (written for inspection)
+    unsigned char* mask_r;
+    LevelsArgs levels;
     int div_t, slots_t, div_r, slots_r;
     long long frames_per_piece_t, frames_per_piece_r;
     const double* avg_override;  // [4][n_lin] or null
@@ -191,7 +193,7 @@ struct DesignArgs {
     double* fir_out;             // [2][F] or null
     float2* h_mid;
     float2* h_side;
-    const mgb_track_state* state;  // null with avg_override: c0 = 1, coef = 1
+    mgb_track_state* state;        // null with avg_override: c0 = 1, coef = 1
     int s_ready;                   // the smoothed curve is already in the scratch (operator path)
 };
 
@@ -215,15 +217,31 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 __global__ void __launch_bounds__(256)
 spectrum_mean_kernel(DesignArgs a, int n_lin, int fft_size, double eps, PrefetchList pf) {
     __shared__ double part_t[8][33], part_r[8][33];
-    // The design kernel that follows is two latency-bound CTAs walking Config-only tables that the
-    // streaming kernels in between have pushed out of L2: pull them back in from here, where
-    // there are CTAs to spare.
+    __shared__ double red_d[32];
+    __shared__ float red_f[32];
+    MGB_DYN_SMEM(smem);  // loudest-piece masks: [div_t] then [div_r] bytes
+    unsigned char* mask_t = smem;
+    unsigned char* mask_r = smem + a.div_t;
+    // The design kernels that follow walk Config-only tables that the streaming kernels in between
+    // have pushed out of L2: pull them back in from here, where there are CTAs to spare.
     {
         const long long gtid = ((long long)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
         const long long gsize = (long long)gridDim.x * gridDim.y * blockDim.x;
         for (int t = 0; t < pf.count; ++t)
             for (long long off = gtid * 128; off < pf.bytes[t]; off += gsize * 128)
                 prefetch_l2(reinterpret_cast<const char*>(pf.ptr[t]) + off);
+    }
+    // Level statistics (match_levels.py:29-131), recomputed identically by every CTA from the
+    // analysis pass's partial sums; CTA (0,0) records them in the track state.
+    const LevelsResult lv = levels_compute(a.levels, mask_t, mask_r, red_d, red_f);
+    __syncthreads();
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
+        if (threadIdx.x == 0) {
+            levels_store(lv, a.state);
+            a.state->conv_peak_bits = 0.0f;
+        }
+        for (int p = threadIdx.x; p < a.div_t; p += blockDim.x) a.mask_t[p] = mask_t[p];
+        for (int p = threadIdx.x; p < a.div_r; p += blockDim.x) a.mask_r[p] = mask_r[p];
     }
     const int bx = threadIdx.x & 31, sy = threadIdx.x >> 5;
     const int k = blockIdx.x * 32 + bx;
@@ -232,9 +250,9 @@ spectrum_mean_kernel(DesignArgs a, int n_lin, int fft_size, double eps, Prefetch
     if (k < n_lin) {
         const int items_t = a.div_t * a.slots_t, items_r = a.div_r * a.slots_r;
         for (int it = sy; it < items_t; it += 8)
-            if (a.mask_t[it / a.slots_t]) st += (double)a.spec_part_t[((long long)it * 2 + ch) * n_lin + k];
+            if (mask_t[it / a.slots_t]) st += (double)a.spec_part_t[((long long)it * 2 + ch) * n_lin + k];
         for (int it = sy; it < items_r; it += 8)
-            if (a.mask_r[it / a.slots_r]) sr += (double)a.spec_part_r[((long long)it * 2 + ch) * n_lin + k];
+            if (mask_r[it / a.slots_r]) sr += (double)a.spec_part_r[((long long)it * 2 + ch) * n_lin + k];
     }
     part_t[sy][bx] = st;
     part_r[sy][bx] = sr;
@@ -244,11 +262,10 @@ spectrum_mean_kernel(DesignArgs a, int n_lin, int fft_size, double eps, Prefetch
             st += part_t[q][bx];
             sr += part_r[q][bx];
         }
-        const double c0 = a.state->rms_coefficient, coef = a.state->final_amplitude_coef;
         // |rfft| is positively homogeneous: the level-matching gain c0 (target) and the reference
         // normalisation 1/coef are applied to the means instead of to the samples
-        const double norm_t = c0 / ((double)a.state->target_loud_pieces * (double)a.frames_per_piece_t * (double)fft_size);
-        const double norm_r = 1.0 / (coef * (double)a.state->reference_loud_pieces * (double)a.frames_per_piece_r * (double)fft_size);
+        const double norm_t = lv.c0 / ((double)lv.loud_t * (double)a.frames_per_piece_t * (double)fft_size);
+        const double norm_r = 1.0 / (lv.coef * (double)lv.loud_r * (double)a.frames_per_piece_r * (double)fft_size);
         a.scratch[(long long)ch * a.stride + k] = (sr * norm_r) / fmax(eps, st * norm_t);
     }
 }
@@ -441,6 +458,17 @@ int launch_design(const mgb_plan& plan, const mgb_track_layout& layout, const Wo
     a.spec_part_r = ws.spec_part_r;
     a.mask_t = ws.mask_t;
     a.mask_r = ws.mask_r;
+    a.levels.sumsq_t = ws.sumsq_part_t;
+    a.levels.sumsq_r = ws.sumsq_part_r;
+    a.levels.absmax_r = ws.absmax_part_r;
+    a.levels.piece_t = layout.target_piece;
+    a.levels.piece_r = layout.reference_piece;
+    a.levels.div_t = layout.target_divisions;
+    a.levels.slots_t = layout.target_slots;
+    a.levels.div_r = layout.reference_divisions;
+    a.levels.slots_r = layout.reference_slots;
+    a.levels.threshold = plan.threshold;
+    a.levels.eps = plan.min_value;
     a.div_t = layout.target_divisions;
     a.slots_t = layout.target_slots;
     a.div_r = layout.reference_divisions;
@@ -480,8 +508,9 @@ int launch_design(const mgb_plan& plan, const mgb_track_layout& layout, const Wo
         add(plan.d_lw_alpha, ng * 8);
         add(plan.d_lw_rows, (long long)plan.lowess_nrows * plan.lowess_k * 8);
         add(plan.d_hann, F * 8);
-        MGB_TRY(launch("spectrum_mean_kernel", spectrum_mean_kernel, dim3((plan.n_lin + 31) / 32, 2), dim3(256), 0, stream, a,
-                       plan.n_lin, plan.fft_size, plan.min_value, pf));
+        MGB_TRY(launch("spectrum_mean_kernel", spectrum_mean_kernel, dim3((plan.n_lin + 31) / 32, 2), dim3(256),
+                       (size_t)(layout.target_divisions + layout.reference_divisions + 16), stream, a, plan.n_lin,
+                       plan.fft_size, plan.min_value, pf));
     }
     if (plan.d_smooth_op && !(avg_override && g_design_direct)) {
         if (avg_override) {

@@ -159,10 +159,19 @@ __device__ __forceinline__ void fft_pass(const cpx<T>* __restrict__ tw, Load loa
             const int j = tid + p * THREADS;
             const int k = j & (NS - 1);
             if constexpr (NS > 1) {
-                cpx<T> w[R];
-                load_twiddles<R, NS, DIR, CHAIN, T>(tw, k, w);
+                if constexpr (CHAIN && R > 2) {
+                    cpx<T> w[R];
+                    load_twiddles<R, NS, DIR, true, T>(tw, k, w);
 #pragma unroll
-                for (int r = 1; r < R; ++r) v[p][r] = cmul(v[p][r], w[r]);
+                    for (int r = 1; r < R; ++r) v[p][r] = cmul(v[p][r], w[r]);
+                } else {
+#pragma unroll
+                    for (int r = 1; r < R; ++r) {
+                        cpx<T> w = tw[(r - 1) * NS + k];
+                        if constexpr (DIR < 0) w.y = -w.y;
+                        v[p][r] = cmul(v[p][r], w);
+                    }
+                }
             }
             Dft<R, DIR, T>::run(v[p]);
             const int j0 = (j - k) * R + k;

@@ -21,7 +21,7 @@ struct Workspace {
     // ---- zeroed at the start of every job (one memset) ----
     unsigned char* zero_begin;
     double* piece_sums;     // [MGB_MAX_CORRECTION_STEPS][Dt] sums of clip(mid*gain)^2
-    int* tickets;           // [64] zeroed counters: 0 limiter chunks, 1 analysis tail, 2 convolution tail, 3+step clip tails
+    int* tickets;           // [64] zeroed counters: 0 = limiter chunk ticket
     unsigned char* lookback;// [nchunks] LookbackSlot
     unsigned char* zero_end;
     int64_t design_stride;  // doubles per channel in `design`
@@ -51,10 +51,8 @@ Workspace carve_workspace(const mgb_plan& plan, const mgb_track_layout& layout, 
 int64_t limiter_lookback_bytes(int64_t frames);
 
 // analyze.cu ------------------------------------------------------------------------------------
-struct LevelsArgs;
 int launch_analyze(const mgb_plan& plan, const float2* x, int64_t frames, int64_t piece, int divisions, int slots,
-                   float* spec_part, double* sumsq_part, float* absmax_part, int* ticket, const LevelsArgs& lv,
-                   cudaStream_t stream);
+                   float* spec_part, double* sumsq_part, float* absmax_part, cudaStream_t stream);
 
 // design.cu -------------------------------------------------------------------------------------
 int launch_design(const mgb_plan& plan, const mgb_track_layout& layout, const Workspace& ws,
@@ -69,6 +67,8 @@ int launch_convolve(const mgb_plan& plan, const mgb_track_layout& layout, const 
                     const Workspace& ws, mgb_track_state* state, cudaStream_t stream);
 
 // correct.cu ------------------------------------------------------------------------------------
+int launch_correction_final(const mgb_plan& plan, const mgb_track_layout& layout, const Workspace& ws,
+                            mgb_track_state* state, cudaStream_t stream);
 int launch_clip_sumsq(const mgb_plan& plan, const mgb_track_layout& layout, const Workspace& ws, int step,
                       mgb_track_state* state, cudaStream_t stream);
 int launch_scale(const float2* in, float2* out, int64_t frames, const double* gain, const double* divisor,

@@ -4,15 +4,15 @@ import subprocess
 
 from . import wavio
 from .log import Code, ModuleError, debug, info, warning
+from .results import real_soundfile
 from .utils import random_file
 
 
 def _read(file: str):
-    try:
-        import soundfile as sf
+    sf = real_soundfile()
+    if sf is not None:
         return sf.read(file, always_2d=True)
-    except ImportError:
-        return wavio.read(file)
+    return wavio.read(file)
 
 
 def load(file: str, file_type: str, temp_folder: str):

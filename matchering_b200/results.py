@@ -8,14 +8,22 @@ WAV_SUBTYPES = ("PCM_16", "PCM_24", "PCM_32", "FLOAT", "DOUBLE")
 _FORMATS = {"WAV": WAV_SUBTYPES}
 
 
-def _check_format(ext: str, subtype: str = None) -> bool:
+def real_soundfile():
+    """libsndfile's binding when it is really installed (not a test stand-in), else None."""
     try:
-        import soundfile as sf  # used when present, so FLAC/AIFF/... keep working
-        return bool(sf.check_format(ext, subtype))
+        import soundfile as sf
     except ImportError:
-        if ext not in _FORMATS:
-            return False
-        return subtype is None or subtype in _FORMATS[ext]
+        return None
+    return sf if getattr(sf, "__libsndfile_version__", None) else None
+
+
+def _check_format(ext: str, subtype: str = None) -> bool:
+    sf = real_soundfile()  # used when present, so FLAC/AIFF/... keep working
+    if sf is not None:
+        return bool(sf.check_format(ext, subtype))
+    if ext not in _FORMATS:
+        return False
+    return subtype is None or subtype in _FORMATS[ext]
 
 
 class Result:
