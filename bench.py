@@ -257,20 +257,44 @@ def run_b200(args) -> dict:
         ms = e0.elapsed_time(e1)
         return ms, lib.mgb_launch_count() - launches0
 
+    # end to end, batch entry: three tracks in flight per GPU (mgb_pipeline_*), host buffers in and out
+    from matchering_b200.batch import MasteringPipeline
+    depth = 3
+    pipe = MasteringPipeline(cfg, n, n, depth, device)
+    outs_host = [torch.empty((n, 2), dtype=torch.float32).pin_memory() for _ in range(depth)]
+    s_h2d, _, s_d2h = (torch.cuda.ExternalStream(p, device=device) for p in pipe.streams())
+
+    def timed_pipeline(steps, warmup):
+        for k in range(warmup):
+            pipe.submit(host_t[k % n_sets], host_r[k % n_sets], outs_host[k % depth])
+        pipe.wait_all()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s_h2d)
+        for k in range(steps):
+            pipe.submit(host_t[(warmup + k) % n_sets], host_r[(warmup + k) % n_sets], outs_host[k % depth])
+        pipe.wait_all()
+        e1.record(s_d2h)
+        barrier()
+        return e0.elapsed_time(e1)
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     dev_ms, launches = timed(step_device, args.steps, args.warmup)
-    e2e_ms, _ = timed(step_host, args.steps, max(3, args.warmup))
+    e2e_single_ms, _ = timed(step_host, args.steps, max(3, args.warmup))
+    e2e_ms = timed_pipeline(args.steps, max(3, args.warmup))
     clocks = sampler.stop() if rank == 0 else None
+    pipe.close()
 
     # max over ranks of the device times
     if world > 1:
-        tms = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=device)
+        tms = torch.tensor([dev_ms, e2e_ms, e2e_single_ms], dtype=torch.float64, device=device)
         gathered = [torch.zeros_like(tms) for _ in range(world)]
         dist.all_gather(gathered, tms)
         dev_ms = max(float(g[0]) for g in gathered)
         e2e_ms = max(float(g[1]) for g in gathered)
+        e2e_single_ms = max(float(g[2]) for g in gathered)
     frames_total = world * args.steps * n
     value = frames_total / (dev_ms * 1e-3) / SAMPLE_RATE
     e2e_value = frames_total / (e2e_ms * 1e-3) / SAMPLE_RATE
@@ -337,7 +361,11 @@ def run_b200(args) -> dict:
                        "precision": "float32 I/O and FFTs, float64 reductions / FIR design / IIR state"},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": 2 * n * 8, "d2h_bytes_per_step": n * 8,
-                    "api": "mgb_process_host (pinned float32 host buffers in and out)"},
+                    "api": "mgb_pipeline_submit/wait (batch entry, 3 tracks in flight per GPU; pinned float32 host "
+                           "buffers in and out; every step's H2D and D2H copies are inside the timed region)",
+                    "single_call": {"value": frames_total / (e2e_single_ms * 1e-3) / SAMPLE_RATE,
+                                    "ms_per_step": e2e_single_ms / args.steps,
+                                    "api": "mgb_process_host (one track per call, copies and kernels back to back)"}},
             "gpu_launches": int(launches),
             "roofline": roofline, "kernels": summary, "cpu_baseline": cpu_baseline, "clocks": clocks,
         }

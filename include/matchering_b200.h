@@ -211,6 +211,22 @@ int mgb_process_host(const mgb_plan* plan, const mgb_track_layout* layout, const
                      float* d_out_lr, void* d_workspace, mgb_track_state* d_state, mgb_track_state* h_state_out,
                      void* stream);
 
+/* ---- batches of tracks with HOST buffers: `depth` tracks in flight ------------------------------
+ * mgb_process_host serialises copies and kernels of one track; tracks are independent, so a
+ * pipeline overlaps track k+1's host->device copy, track k's kernels and track k-1's device->host
+ * copy on three streams.  The pipeline object owns its device staging buffers (the one place in
+ * this library that calls cudaMalloc).  Host buffers should be pinned and must stay valid until
+ * mgb_pipeline_wait returns for their slot.  submit blocks only when the slot it is about to reuse
+ * still holds an uncollected result. */
+typedef struct mgb_pipeline mgb_pipeline;
+int mgb_pipeline_create(const mgb_plan* plan, int64_t max_target_frames, int64_t max_reference_frames, int32_t depth,
+                        mgb_pipeline** out);
+int mgb_pipeline_submit(mgb_pipeline* p, const float* h_target_lr, int64_t target_frames, const float* h_reference_lr,
+                        int64_t reference_frames, float* h_out_limited, int32_t* slot_out);
+int mgb_pipeline_wait(mgb_pipeline* p, int32_t slot, mgb_track_state* state_out);
+int mgb_pipeline_streams(mgb_pipeline* p, void** h2d, void** compute, void** d2h);
+int mgb_pipeline_destroy(mgb_pipeline* p);
+
 /* float64 <-> float32 interleaved conversion on the device (the reference hands float64 arrays
  * to stages.main; core.py:53-62 / soundfile's default read dtype). */
 int mgb_convert_f64_to_f32(const double* d_in, float* d_out, int64_t count, void* stream);

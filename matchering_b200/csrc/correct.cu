@@ -21,9 +21,16 @@ namespace {
 // sum over a piece of clip(mid * gain)^2 ; grid = (chunks per piece, pieces).  Pieces start at
 // arbitrary offsets of the float plane, so a chunk is a scalar head, an aligned float4 body and a
 // scalar tail.
-__device__ __forceinline__ double clip_sq(float v, double gain) {
-    const double c = fmin(1.0, fmax(-1.0, (double)v * gain));  // dsp.clip
-    return c * c;
+// clip(mid*gain)^2 of four samples: the product and the clip in float32 (the plane is float32
+// anyway), the squares summed in float64
+__device__ __forceinline__ double clip_sq4(float4 v, float gain) {
+    const float a = fminf(1.0f, fmaxf(-1.0f, v.x * gain)), b = fminf(1.0f, fmaxf(-1.0f, v.y * gain));
+    const float c = fminf(1.0f, fmaxf(-1.0f, v.z * gain)), d = fminf(1.0f, fmaxf(-1.0f, v.w * gain));
+    return (double)a * a + (double)b * b + ((double)c * c + (double)d * d);
+}
+__device__ __forceinline__ double clip_sq(float v, float gain) {
+    const float c = fminf(1.0f, fmaxf(-1.0f, v * gain));  // dsp.clip
+    return (double)c * c;
 }
 
 __global__ void __launch_bounds__(256)
@@ -39,6 +46,7 @@ clip_sumsq_kernel(const float* __restrict__ mid, long long piece, int divisions,
         state->correction[step - 1] = c_prev;  // no CTA of this launch reads this slot
         state->steps_done = step;
     }
+    const float gain_f = (float)gain;
     const long long p = blockIdx.y;
     const long long per = (piece + gridDim.x - 1) / gridDim.x;
     const long long lo = p * piece + (long long)blockIdx.x * per;
@@ -50,16 +58,15 @@ clip_sumsq_kernel(const float* __restrict__ mid, long long piece, int divisions,
         if (body_lo > hi) body_lo = hi;
         long long body_hi = hi & ~3LL;
         if (body_hi < body_lo) body_hi = body_lo;
-        if ((long long)threadIdx.x < body_lo - lo) acc += clip_sq(mid[lo + threadIdx.x], gain);       // head (< 4)
-        if ((long long)threadIdx.x < hi - body_hi) acc += clip_sq(mid[body_hi + threadIdx.x], gain);  // tail (< 4)
+        if ((long long)threadIdx.x < body_lo - lo) acc += clip_sq(mid[lo + threadIdx.x], gain_f);       // head (< 4)
+        if ((long long)threadIdx.x < hi - body_hi) acc += clip_sq(mid[body_hi + threadIdx.x], gain_f);  // tail (< 4)
         const float4* body = reinterpret_cast<const float4*>(mid + body_lo);
         const long long nvec = (body_hi - body_lo) >> 2;
         for (long long i = threadIdx.x; i < nvec; i += 2 * blockDim.x) {
             const float4 a = body[i];
             const long long i2 = i + blockDim.x;
             const float4 b = i2 < nvec ? body[i2] : make_float4(0.f, 0.f, 0.f, 0.f);
-            acc += clip_sq(a.x, gain) + clip_sq(a.y, gain) + clip_sq(a.z, gain) + clip_sq(a.w, gain);
-            acc += clip_sq(b.x, gain) + clip_sq(b.y, gain) + clip_sq(b.z, gain) + clip_sq(b.w, gain);
+            acc += clip_sq4(a, gain_f) + clip_sq4(b, gain_f);
         }
     }
     const double total = block_sum(acc, red);

@@ -199,7 +199,7 @@ struct DesignArgs {
 
 // Matching curve m[k] = mean|rfft(reference)| / max(eps, mean|rfft(target)|) from the per-(piece,
 // slot) partial sums of analyze.cu, over the loudest pieces only (match_frequencies.py:42,93-94).
-// grid = (ceil(n_lin/32), 2 channels); block = 32 bins x 8 slices of the (piece, slot) items.
+// grid = (ceil(n_lin/16), 2 channels); block = 16 bins x 16 slices of the (piece, slot) items.
 struct PrefetchList {
     const void* ptr[14];
     long long bytes[14];
@@ -216,7 +216,8 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 
 __global__ void __launch_bounds__(256)
 spectrum_mean_kernel(DesignArgs a, int n_lin, int fft_size, double eps, PrefetchList pf) {
-    __shared__ double part_t[8][33], part_r[8][33];
+    constexpr int BINS = 16, SLICES = 16;
+    __shared__ double part_t[SLICES][BINS + 1], part_r[SLICES][BINS + 1];
     __shared__ double red_d[32];
     __shared__ float red_f[32];
     MGB_DYN_SMEM(smem);  // loudest-piece masks: [div_t] then [div_r] bytes
@@ -243,22 +244,22 @@ spectrum_mean_kernel(DesignArgs a, int n_lin, int fft_size, double eps, Prefetch
         for (int p = threadIdx.x; p < a.div_t; p += blockDim.x) a.mask_t[p] = mask_t[p];
         for (int p = threadIdx.x; p < a.div_r; p += blockDim.x) a.mask_r[p] = mask_r[p];
     }
-    const int bx = threadIdx.x & 31, sy = threadIdx.x >> 5;
-    const int k = blockIdx.x * 32 + bx;
+    const int bx = threadIdx.x % BINS, sy = threadIdx.x / BINS;
+    const int k = blockIdx.x * BINS + bx;
     const int ch = blockIdx.y;
     double st = 0.0, sr = 0.0;
     if (k < n_lin) {
         const int items_t = a.div_t * a.slots_t, items_r = a.div_r * a.slots_r;
-        for (int it = sy; it < items_t; it += 8)
+        for (int it = sy; it < items_t; it += SLICES)
             if (mask_t[it / a.slots_t]) st += (double)a.spec_part_t[((long long)it * 2 + ch) * n_lin + k];
-        for (int it = sy; it < items_r; it += 8)
+        for (int it = sy; it < items_r; it += SLICES)
             if (mask_r[it / a.slots_r]) sr += (double)a.spec_part_r[((long long)it * 2 + ch) * n_lin + k];
     }
     part_t[sy][bx] = st;
     part_r[sy][bx] = sr;
     __syncthreads();
     if (sy == 0 && k < n_lin) {
-        for (int q = 1; q < 8; ++q) {
+        for (int q = 1; q < SLICES; ++q) {
             st += part_t[q][bx];
             sr += part_r[q][bx];
         }
@@ -508,7 +509,7 @@ int launch_design(const mgb_plan& plan, const mgb_track_layout& layout, const Wo
         add(plan.d_lw_alpha, ng * 8);
         add(plan.d_lw_rows, (long long)plan.lowess_nrows * plan.lowess_k * 8);
         add(plan.d_hann, F * 8);
-        MGB_TRY(launch("spectrum_mean_kernel", spectrum_mean_kernel, dim3((plan.n_lin + 31) / 32, 2), dim3(256),
+        MGB_TRY(launch("spectrum_mean_kernel", spectrum_mean_kernel, dim3((plan.n_lin + 15) / 16, 2), dim3(256),
                        (size_t)(layout.target_divisions + layout.reference_divisions + 16), stream, a, plan.n_lin,
                        plan.fft_size, plan.min_value, pf));
     }

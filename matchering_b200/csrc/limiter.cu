@@ -182,8 +182,8 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
             float g = 0.0f;
             if (i >= vlo && i < vhi) {
                 const float2 v = base[i];
-                const double a = fmax(fabs((double)v.x), fabs((double)v.y)) * pre;
-                g = (float)(1.0 - thr / fmax(a, thr));
+                const double a = (double)fmaxf(fabsf(v.x), fabsf(v.y)) * pre;
+                if (a > thr) g = (float)(1.0 - thr / a);  // frames at or below the threshold need no division
             }
             G[i] = g;
             Wk[i] = g;

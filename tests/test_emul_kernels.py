@@ -171,3 +171,32 @@ def test_unsupported_configs_fail_loudly():
     lim = port.OracleLimiterConfig(hold_filter_order=2)
     with pytest.raises(plan_mod.UnsupportedConfig):
         plan_mod.build_tables(port.OracleConfig(limiter=lim))
+
+
+def test_pipeline_entry_points_match_single_track_path(lib, golden):
+    """mgb_pipeline_* (batch entry, several slots) gives the same samples as the stage calls."""
+    g = golden("pipeline_small.npz")
+    cfg = port.OracleConfig(max_piece_size=float(g["max_piece_size_s"]))
+    from emul_harness import get_emul_plan
+    ep = get_emul_plan(cfg)
+    handle = C.c_void_p()
+    _native.check(lib, lib.mgb_pipeline_create(C.byref(ep.struct), 40000, 40000, 2, C.byref(handle)))
+    try:
+        outs, slots = [], []
+        for k in range(3):  # more submissions than slots: a slot gets reused
+            t = aligned_copy(g["target"][: 40000 - 7 * k], np.float32)
+            r = aligned_copy(g["reference"], np.float32)
+            o = aligned((len(t), 2), np.float32)
+            slot = C.c_int32()
+            _native.check(lib, lib.mgb_pipeline_submit(handle, ptr(t), len(t), ptr(r), len(r), ptr(o), C.byref(slot)))
+            outs.append(o)
+            slots.append(slot.value)
+        assert slots == [0, 1, 0]
+        st = _native.TrackState()
+        _native.check(lib, lib.mgb_pipeline_wait(handle, 1, C.byref(st)))
+        assert st.steps_done == 4
+        assert np.abs(outs[0] - g["limited"]).max() < TOL
+        want = port.main(g["target"][: 40000 - 7].astype(np.float64), g["reference"].astype(np.float64), cfg)[0]
+        assert np.abs(outs[1] - want).max() < TOL
+    finally:
+        lib.mgb_pipeline_destroy(handle)

@@ -248,3 +248,16 @@ def test_process_files_end_to_end(torch_cuda, tmp_path):
     got_16, _ = wavio.read(str(tmp_path / "o16.wav"))
     assert np.abs(got_f - want[2]).max() < TOL
     assert np.abs(got_16 - want[0]).max() < 1.0 / 32767 + TOL
+
+
+def test_batch_pipeline_matches_single_track_path(torch_cuda):
+    """master_many (three tracks in flight, copies overlapped with kernels) vs stages.main."""
+    import port
+    from matchering_b200 import stages
+    from matchering_b200.batch import master_many
+    cfg = _config(max_piece_size=3.0)
+    pairs = [(port.synth_target(300000 + 1111 * k, 20 + k), port.synth_reference(280000, 40 + k)) for k in range(5)]
+    got = master_many(pairs, cfg, depth=3)
+    for (t, r), o in zip(pairs, got):
+        want = stages.main(t, r, cfg)[0]
+        assert o.shape == want.shape and np.abs(o - want).max() < 1e-6
