@@ -189,6 +189,9 @@ def run_b200(args) -> dict:
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        # keep stdout for the one JSON line: NCCL prints its version banner there at VERSION level
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=device)
 
     port = oracle()  # synthetic-input recipes + the cpu_baseline leg only
@@ -217,20 +220,49 @@ def run_b200(args) -> dict:
         host_r.append(r)
         dev_t.append(t.to(device))
         dev_r.append(r.to(device))
-    session = TrackSession(plan, n, n)
-    out_dev = torch.empty((n, 2), dtype=torch.float32, device=device)
+    # two tracks in flight on two streams: one track's small latency-bound kernels (FIR design: two
+    # CTAs) overlap the other's streaming kernels
+    n_lanes = 2
+    sessions = [TrackSession(plan, n, n) for _ in range(n_lanes)]
+    lane_streams = [torch.cuda.Stream(device=device) for _ in range(n_lanes)]
+    lane_out = [torch.empty((n, 2), dtype=torch.float32, device=device) for _ in range(n_lanes)]
+    session = sessions[0]
+    out_dev = lane_out[0]
     out_host = torch.empty((n, 2), dtype=torch.float32).pin_memory()
     stage_t = torch.empty((n, 2), dtype=torch.float32, device=device)
     stage_r = torch.empty((n, 2), dtype=torch.float32, device=device)
     p_plan, p_layout = C.byref(plan.struct), C.byref(session.layout)
     ws, st = session.workspace.data_ptr(), session.state.data_ptr()
 
-    def step_device(k):
+    def step_on(k, sess, out, stream_ptr):
         t, r = dev_t[k % n_sets], dev_r[k % n_sets]
-        _native.check(lib, lib.mgb_match_levels(p_plan, p_layout, t.data_ptr(), r.data_ptr(), ws, st, sptr))
-        _native.check(lib, lib.mgb_match_frequencies(p_plan, p_layout, t.data_ptr(), session.result.data_ptr(), None, ws, st, sptr))
-        _native.check(lib, lib.mgb_correct_levels(p_plan, p_layout, ws, st, sptr))
-        _native.check(lib, lib.mgb_finalize(p_plan, p_layout, session.result.data_ptr(), out_dev.data_ptr(), None, None, ws, st, sptr))
+        lay, w, s_ = C.byref(sess.layout), sess.workspace.data_ptr(), sess.state.data_ptr()
+        _native.check(lib, lib.mgb_match_levels(p_plan, lay, t.data_ptr(), r.data_ptr(), w, s_, stream_ptr))
+        _native.check(lib, lib.mgb_match_frequencies(p_plan, lay, t.data_ptr(), sess.result.data_ptr(), None, w, s_, stream_ptr))
+        _native.check(lib, lib.mgb_correct_levels(p_plan, lay, w, s_, stream_ptr))
+        _native.check(lib, lib.mgb_finalize(p_plan, lay, sess.result.data_ptr(), out.data_ptr(), None, None, w, s_, stream_ptr))
+
+    def step_device(k):  # one stream, one track at a time (profiling pass, single-track latency)
+        step_on(k, session, out_dev, sptr)
+
+    def timed_lanes(steps, warmup):
+        """K tracks, alternating over the lanes; CUDA events on the main stream bracket all of them."""
+        for k in range(warmup):
+            step_on(k, sessions[k % n_lanes], lane_out[k % n_lanes], C.c_void_p(lane_streams[k % n_lanes].cuda_stream))
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = lib.mgb_launch_count()
+        e0.record(stream)
+        for ls in lane_streams:
+            ls.wait_event(e0)
+        for k in range(steps):
+            lane = k % n_lanes
+            step_on(warmup + k, sessions[lane], lane_out[lane], C.c_void_p(lane_streams[lane].cuda_stream))
+        for ls in lane_streams:
+            stream.wait_stream(ls)
+        e1.record(stream)
+        barrier()
+        return e0.elapsed_time(e1), lib.mgb_launch_count() - launches0
 
     def step_host(k):
         t, r = host_t[k % n_sets], host_r[k % n_sets]
@@ -281,7 +313,8 @@ def run_b200(args) -> dict:
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    dev_ms, launches = timed(step_device, args.steps, args.warmup)
+    dev_ms, launches = timed_lanes(args.steps, args.warmup)
+    dev_serial_ms, _ = timed(step_device, args.steps, args.warmup)
     e2e_single_ms, _ = timed(step_host, args.steps, max(3, args.warmup))
     e2e_ms = timed_pipeline(args.steps, max(3, args.warmup))
     clocks = sampler.stop() if rank == 0 else None
@@ -289,12 +322,13 @@ def run_b200(args) -> dict:
 
     # max over ranks of the device times
     if world > 1:
-        tms = torch.tensor([dev_ms, e2e_ms, e2e_single_ms], dtype=torch.float64, device=device)
+        tms = torch.tensor([dev_ms, e2e_ms, e2e_single_ms, dev_serial_ms], dtype=torch.float64, device=device)
         gathered = [torch.zeros_like(tms) for _ in range(world)]
         dist.all_gather(gathered, tms)
         dev_ms = max(float(g[0]) for g in gathered)
         e2e_ms = max(float(g[1]) for g in gathered)
         e2e_single_ms = max(float(g[2]) for g in gathered)
+        dev_serial_ms = max(float(g[3]) for g in gathered)
     frames_total = world * args.steps * n
     value = frames_total / (dev_ms * 1e-3) / SAMPLE_RATE
     e2e_value = frames_total / (e2e_ms * 1e-3) / SAMPLE_RATE
@@ -356,7 +390,9 @@ def run_b200(args) -> dict:
             "dtype": "f32", "data": "synthetic", "samples_per_sec": frames_total / (dev_ms * 1e-3),
             "config": {"workload": f"config 2: {args.seconds:.0f}-s stereo 44.1 kHz synthetic track vs {args.seconds:.0f}-s reference, "
                                    "full pipeline stages.main(need_default), one track per GPU per step",
-                       "frames_per_track": n, "tracks_per_step": world,
+                       "frames_per_track": n, "tracks_per_step": world, "tracks_in_flight_per_gpu": n_lanes,
+                       "one_track_at_a_time": {"value": frames_total / (dev_serial_ms * 1e-3) / SAMPLE_RATE,
+                                               "ms_per_step": dev_serial_ms / args.steps},
                        "l2": "inputs larger than L2: 3 rotating tracks per rank, ~290 MB touched per step",
                        "precision": "float32 I/O and FFTs, float64 reductions / FIR design / IIR state"},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,

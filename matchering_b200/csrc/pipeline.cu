@@ -26,6 +26,8 @@ struct Slot {
     bool busy = false;
 #ifndef MGB_EMULATE
     cudaEvent_t h2d_done = nullptr, compute_done = nullptr, d2h_done = nullptr;
+    cudaStream_t compute = nullptr;  // one compute stream per slot: the small latency-bound kernels of
+                                     // one track (FIR design: 2 CTAs) overlap another track's streaming ones
 #endif
 };
 
@@ -104,6 +106,7 @@ int mgb_pipeline_create(const mgb_plan* plan, int64_t max_target_frames, int64_t
         MGB_CUDA_OK(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
         MGB_CUDA_OK(cudaEventCreateWithFlags(&s.compute_done, cudaEventDisableTiming));
         MGB_CUDA_OK(cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming));
+        MGB_CUDA_OK(cudaStreamCreateWithFlags(&s.compute, cudaStreamNonBlocking));
 #endif
     }
     *out = p;
@@ -129,6 +132,7 @@ int mgb_pipeline_destroy(mgb_pipeline* p) {
         if (s.h2d_done) cudaEventDestroy(s.h2d_done);
         if (s.compute_done) cudaEventDestroy(s.compute_done);
         if (s.d2h_done) cudaEventDestroy(s.d2h_done);
+        if (s.compute) cudaStreamDestroy(s.compute);
 #endif
     }
 #ifndef MGB_EMULATE
@@ -173,8 +177,8 @@ int mgb_pipeline_submit(mgb_pipeline* p, const float* h_target_lr, int64_t targe
     MGB_CUDA_OK(cudaMemcpyAsync(s.d_target, h_target_lr, tb, cudaMemcpyHostToDevice, p->s_h2d));
     MGB_CUDA_OK(cudaMemcpyAsync(s.d_reference, h_reference_lr, rb, cudaMemcpyHostToDevice, p->s_h2d));
     MGB_CUDA_OK(cudaEventRecord(s.h2d_done, p->s_h2d));
-    MGB_CUDA_OK(cudaStreamWaitEvent(p->s_compute, s.h2d_done, 0));
-    void* sc = (void*)p->s_compute;
+    MGB_CUDA_OK(cudaStreamWaitEvent(s.compute, s.h2d_done, 0));
+    void* sc = (void*)s.compute;
 #endif
     MGB_TRY(mgb_match_levels(&p->plan, &s.layout, s.d_target, s.d_reference, s.d_workspace, s.d_state, sc));
     MGB_TRY(mgb_match_frequencies(&p->plan, &s.layout, s.d_target, s.d_result, nullptr, s.d_workspace, s.d_state, sc));
@@ -184,7 +188,7 @@ int mgb_pipeline_submit(mgb_pipeline* p, const float* h_target_lr, int64_t targe
     memcpy(h_out_limited, s.d_out, tb);
     memcpy(s.h_state, s.d_state, sizeof(mgb_track_state));
 #else
-    MGB_CUDA_OK(cudaEventRecord(s.compute_done, p->s_compute));
+    MGB_CUDA_OK(cudaEventRecord(s.compute_done, s.compute));
     MGB_CUDA_OK(cudaStreamWaitEvent(p->s_d2h, s.compute_done, 0));
     MGB_CUDA_OK(cudaMemcpyAsync(h_out_limited, s.d_out, tb, cudaMemcpyDeviceToHost, p->s_d2h));
     MGB_CUDA_OK(cudaMemcpyAsync(s.h_state, s.d_state, sizeof(mgb_track_state), cudaMemcpyDeviceToHost, p->s_d2h));
