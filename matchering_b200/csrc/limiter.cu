@@ -34,7 +34,11 @@ constexpr int SPAN_EPT_MAX = kLimiterSpanEptMax;
 // Exclusive carry of the recurrence y = u + p*y_prev across the block: given each thread's local
 // end value B (zero initial state over its elements), returns the state just before the thread's
 // first element when the state before the block's first element is c0.
-// scratch: >= 32 doubles.  Contains barriers: every thread of the block must call.
+// One barrier: warps scan their own 32 values with shuffles, publish the warp totals, and then EVERY
+// warp scans the (at most 32) totals itself instead of waiting for one warp to do it.
+// scratch: >= 32 doubles, and must not be the buffer the previous call used (callers alternate
+// between two), which is what makes the leading "scratch is free again" barrier unnecessary.
+// Every thread of the block must call.
 __device__ __forceinline__ double scan_carry(double B, const ScanPow* t, double c0, double* scratch) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double v = B;
@@ -43,23 +47,19 @@ __device__ __forceinline__ double scan_carry(double B, const ScanPow* t, double 
         const double up = __shfl_up_sync(0xffffffffu, v, d);
         if (lane >= d) v += t->ql[d] * up;
     }
-    __syncthreads();  // scratch reuse
     if (lane == 31) scratch[warp] = v;
     __syncthreads();
-    if (warp == 0) {
-        double w = lane < NT / 32 ? scratch[lane] : 0.0;
+    double w = lane < NT / 32 ? scratch[lane] : 0.0;
 #pragma unroll
-        for (int d = 1; d < NT / 32; d <<= 1) {
-            const double up = __shfl_up_sync(0xffffffffu, w, d);
-            if (lane >= d) w += t->qw[d] * up;
-        }
-        if (lane < NT / 32) scratch[lane] = w;
+    for (int d = 1; d < NT / 32; d <<= 1) {
+        const double up = __shfl_up_sync(0xffffffffu, w, d);
+        if (lane >= d) w += t->qw[d] * up;
     }
-    __syncthreads();
-    const double warp_carry = warp > 0 ? scratch[warp - 1] : 0.0;
+    // state at the end of the previous warp (zero block carry): inclusive total of warps 0..warp-1
+    const double warp_carry = __shfl_sync(0xffffffffu, w, (warp + 31) & 31);
     double prev = __shfl_up_sync(0xffffffffu, v, 1);
     if (lane == 0) prev = 0.0;
-    return prev + t->ql[lane] * (warp_carry + t->qw[warp] * c0);
+    return prev + t->ql[lane] * ((warp > 0 ? warp_carry : 0.0) + t->qw[warp] * c0);
 }
 
 __device__ __forceinline__ void publish(double* value, int* flag, double v, int state) {
@@ -133,9 +133,11 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
     double* Fd = reinterpret_cast<double*>(smem);                 // [CAP] float64 work plane
     float* Aenv = reinterpret_cast<float*>(smem) + CAP;           // [CAP] attack envelope, aliases Fd's upper half
     float* G = reinterpret_cast<float*>(smem + (size_t)CAP * 8);  // [CAP] hard-clip gain, later max(g, g_att)
-    float* Wk = G + CAP;                                          // [CAP + pad] doubling plane, later the hold envelope
+    float* Wk = G + CAP;                                          // [CAP] suffix maxima, later the hold envelope
+    constexpr int kLevels = 6;  // runs of up to 63 whole blocks
+    __shared__ float blockmax[kLevels][NT + 32];
     __shared__ ScanPow pw3[3];
-    __shared__ double scratch[32];
+    __shared__ double scratch_a[32], scratch_b[32];  // scan_carry alternates between them
     __shared__ double bcast[2];
     __shared__ int chunk_s;
     const ScanPow* pow_att = &pw3[0];
@@ -186,59 +188,76 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
                 if (a > thr) g = (float)(1.0 - thr / a);  // frames at or below the threshold need no division
             }
             G[i] = g;
-            Wk[i] = g;
         }
-        for (int i = CAP + tid; i < CAP + gm.pad; i += NT) Wk[i] = 0.0f;
     }
     __syncthreads();
 
-    // ---- P2: both running maxima from one doubling ladder over g ------------------------------------
-    //   A[n] = max g[n-reach .. n+reach]                        (hyrax.py:35-37)
+    // ---- P2: both running maxima of g ----------------------------------------------------------------
+    //   A[n] = max g[n-reach .. n+reach]                                 (hyrax.py:35-37)
     //   H[n] = max A[n-hold+1 .. n] = max g[n-hold+1-reach .. n+reach]   (hyrax.py:38-40)
-    // Wk holds m_pw[i] = max g[i .. i+pw-1]; a window of length w is max(m_pw[i], m_pw[i+w-pw]).
+    // Every thread owns EPT consecutive samples: their prefix and suffix maxima inside the block
+    // (PF, SF) and the block maximum; a sparse table over the 512 block maxima answers any run of
+    // whole blocks in two reads.  A window [l, r] is then max(SF[l], whole blocks between, PF[r]):
+    // about 7 shared-memory reads per sample for BOTH windows, where log-step doubling over the
+    // samples needed ~9 full passes.
     {
-        const int win_a = 2 * reach + 1, win_h = win_a + hold - 1;
-        float v[EPT];
-        int pw = 1;
-        auto double_step = [&]() {
+        float* PF = reinterpret_cast<float*>(smem);  // [CAP] lower half of Fd's bytes (Aenv is the upper half)
+        float* SF = Wk;                              // [CAP]
+        float x[EPT];
+        const int base = tid * EPT;
 #pragma unroll
-            for (int k = 0; k < EPT; ++k) {
-                const int i = tid + k * NT;
-                v[k] = fmaxf(Wk[i], Wk[i + pw]);
-            }
-            __syncthreads();
+        for (int e = 0; e < EPT; ++e) x[e] = G[base + e];
+        float run = 0.0f;  // g >= 0
 #pragma unroll
-            for (int k = 0; k < EPT; ++k) Wk[tid + k * NT] = v[k];
+        for (int e = 0; e < EPT; ++e) {
+            run = fmaxf(run, x[e]);
+            PF[base + e] = run;
+        }
+        blockmax[0][tid] = run;
+        if (tid < 32) {
+#pragma unroll
+            for (int j = 0; j < kLevels; ++j) blockmax[j][NT + tid] = 0.0f;
+        }
+        run = 0.0f;
+#pragma unroll
+        for (int e = EPT - 1; e >= 0; --e) {
+            run = fmaxf(run, x[e]);
+            SF[base + e] = run;
+        }
+        __syncthreads();
+        for (int j = 1; j < kLevels; ++j) {  // blockmax[j][t] = max of blocks t .. t + 2^j - 1
+            blockmax[j][tid] = fmaxf(blockmax[j - 1][tid], blockmax[j - 1][tid + (1 << (j - 1))]);
             __syncthreads();
-            pw *= 2;
+        }
+        auto whole_blocks = [&](int a, int b) -> float {  // blocks a..b inclusive, a <= b
+            const int j = 31 - __clz(b - a + 1);
+            return fmaxf(blockmax[j][a], blockmax[j][b - (1 << j) + 1]);
         };
-        while (pw * 2 <= win_a) double_step();
-        {
-            const int rem = win_a - pw;
-#pragma unroll
-            for (int k = 0; k < EPT; ++k) {
-                const int i = tid + k * NT;
-                const float m = fmaxf(Wk[i], Wk[i + rem]);
-                if (i + reach < CAP) Aenv[i + reach] = m;
-                if (i < reach) Aenv[i] = 0.0f;
+        auto window = [&](int l, int r, int br, float pr) -> float {
+            const int bl = l / EPT;
+            if (bl == br) {  // shorter than a block: scan it
+                float m = 0.0f;
+                for (int i = l; i <= r; ++i) m = fmaxf(m, G[i]);
+                return m;
             }
+            float m = fmaxf(SF[l], pr);
+            if (br - bl > 1) m = fmaxf(m, whole_blocks(bl + 1, br - 1));
+            return m;
+        };
+        float h[EPT];
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const int i = base + e;
+            const int r = min(i + reach, CAP - 1);
+            const int br = r / EPT;
+            const float pr = PF[r];
+            Aenv[i] = window(max(i - reach, 0), r, br, pr);
+            h[e] = window(max(i - reach - hold + 1, 0), r, br, pr);
         }
-        while (pw * 2 <= win_h) double_step();
-        {
-            const int rem = win_h - pw, shift = reach + hold - 1;
+        __syncthreads();  // SF (= Wk) fully read
 #pragma unroll
-            for (int k = 0; k < EPT; ++k) {
-                const int i = tid + k * NT;
-                v[k] = fmaxf(Wk[i], Wk[i + rem]);
-            }
-            __syncthreads();
-#pragma unroll
-            for (int k = 0; k < EPT; ++k) {
-                const int i = tid + k * NT;
-                if (i + shift < CAP) Wk[i + shift] = v[k];
-            }
-            __syncthreads();
-        }
+        for (int e = 0; e < EPT; ++e) Wk[base + e] = h[e];
+        __syncthreads();
     }
     if (vlo > 0) {  // lfilter starts from rest: the envelope before the first sample is 0, not a window max
         for (int i = tid; i < vlo; i += NT) Wk[i] = 0.0f;
@@ -260,7 +279,7 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
             acc = u - lp.hold_a1 * acc;
             hold_y[e] = acc;
         }
-        const double carry = scan_carry(acc, pow_hold, 0.0, scratch);
+        const double carry = scan_carry(acc, pow_hold, 0.0, scratch_a);
 #pragma unroll
         for (int e = 0; e < CORE_EPT; ++e) hold_y[e] += pow_hold->pe[e + 1] * carry;
         if (tid == NT - 1) publish(&slot->hold_agg, &slot->hold_flag, hold_y[CORE_EPT - 1], 1);
@@ -301,7 +320,7 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
             y[e] = acc;
         }
         const double c0 = (double)Aenv[0];  // state before the first element: steady state
-        const double carry = scan_carry(acc, pow_att, c0, scratch);  // barriers: Aenv fully read
+        const double carry = scan_carry(acc, pow_att, c0, scratch_b);  // barrier inside: Aenv fully read
 #pragma unroll
         for (int e = 0; e < EPT; ++e) Fd[tid * EPT + e] = y[e] + pow_att->pe[e + 1] * carry;
     }
@@ -329,7 +348,7 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
             y[e] = acc;
         }
         const double c0 = Fd[CAP - 1];
-        const double carry = scan_carry(acc, pow_att, c0, scratch);
+        const double carry = scan_carry(acc, pow_att, c0, scratch_a);
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
             const int i = CAP - 1 - (tid * EPT + e);
@@ -374,7 +393,7 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
             acc = u - lp.release_a1 * acc;
             rel_y[e] = acc;
         }
-        const double carry = scan_carry(acc, pow_rel, 0.0, scratch);
+        const double carry = scan_carry(acc, pow_rel, 0.0, scratch_b);
 #pragma unroll
         for (int e = 0; e < CORE_EPT; ++e) rel_y[e] += pow_rel->pe[e + 1] * carry;
         if (tid == NT - 1) publish(&slot->rel_agg, &slot->rel_flag, rel_y[CORE_EPT - 1], 1);
@@ -436,9 +455,8 @@ int limiter_geometry(const mgb_limiter_params& lp, LimiterGeom* g) {
     if (ept < 11) ept = 11;
     g->ept = ept;
     const int win_h = 2 * lp.reach + lp.hold;
-    int pad = 32;
-    while (pad < win_h) pad *= 2;
-    g->pad = pad;
+    g->pad = 0;
+    MGB_REQUIRE(win_h / ept < 60, MGB_ERR_UNSUPPORTED, "limiter: attack + hold window of %d samples is too long", win_h);
     MGB_REQUIRE(ept <= SPAN_EPT_MAX, MGB_ERR_UNSUPPORTED,
                 "limiter: halo of %d samples exceeds the kernel's span", g->span - LC);
     return MGB_OK;
