@@ -223,6 +223,11 @@ int mgb_pipeline_create(const mgb_plan* plan, int64_t max_target_frames, int64_t
                         mgb_pipeline** out);
 int mgb_pipeline_submit(mgb_pipeline* p, const float* h_target_lr, int64_t target_frames, const float* h_reference_lr,
                         int64_t reference_frames, float* h_out_limited, int32_t* slot_out);
+/* Same with PCM host buffers (what audio files hold): interleaved int16 or packed int24 in, the
+ * limited result out as int16 / int24; a quarter to a half of the PCIe bytes of the float32 entry. */
+int mgb_pipeline_submit_pcm(mgb_pipeline* p, const void* h_target_pcm, int32_t target_bits, int64_t target_frames,
+                            const void* h_reference_pcm, int32_t reference_bits, int64_t reference_frames,
+                            void* h_out_pcm, int32_t out_bits, int32_t* slot_out);
 int mgb_pipeline_wait(mgb_pipeline* p, int32_t slot, mgb_track_state* state_out);
 int mgb_pipeline_streams(mgb_pipeline* p, void** h2d, void** compute, void** d2h);
 int mgb_pipeline_destroy(mgb_pipeline* p);
@@ -231,6 +236,13 @@ int mgb_pipeline_destroy(mgb_pipeline* p);
  * to stages.main; core.py:53-62 / soundfile's default read dtype). */
 int mgb_convert_f64_to_f32(const double* d_in, float* d_out, int64_t count, void* stream);
 int mgb_convert_f32_to_f64(const float* d_in, double* d_out, int64_t count, void* stream);
+
+/* PCM <-> float32 on the device, the conversions libsndfile performs at the reference's file
+ * boundary (matchering/loader.py:35 sf.read -> x / 2^(bits-1); matchering/saver.py:32 sf.write ->
+ * lrint(x * (2^(bits-1) - 1)), clipped).  bits = 16 (int16) or 24 (packed little-endian triplets);
+ * `count` = samples (frames * channels). */
+int mgb_pcm_decode(const void* d_pcm, int32_t bits, float* d_out, int64_t count, void* stream);
+int mgb_pcm_encode(const float* d_in, int32_t bits, void* d_pcm, int64_t count, void* stream);
 
 /* ---- building blocks exported for the parity tests (tests/ only) ------------------------------ */
 /* forward or inverse (dir = +1 / -1) complex FFT of `batch` frames of n points through the same

@@ -50,6 +50,31 @@ class MasteringPipeline:
         self._pending[slot.value] = (target, reference, out)
         return slot.value
 
+    def submit_pcm(self, target, reference, out) -> int:
+        """PCM host buffers (what audio files hold): int16 arrays of shape (frames, 2), or uint8
+        arrays of shape (frames, 6) for packed little-endian 24-bit.  `out` chooses the result's
+        width the same way.  A quarter to a half of the PCIe bytes of `submit`."""
+        def describe(a):
+            a_np = a.numpy() if isinstance(a, torch.Tensor) else a
+            if a_np.dtype == np.int16 and a_np.ndim == 2 and a_np.shape[1] == 2:
+                bits = 16
+            elif a_np.dtype == np.uint8 and a_np.ndim == 2 and a_np.shape[1] == 6:
+                bits = 24
+            else:
+                raise TypeError("PCM buffers are int16 (frames, 2) or uint8 (frames, 6)")
+            assert a_np.flags["C_CONTIGUOUS"]
+            return a_np.ctypes.data, bits, a_np.shape[0]
+        tp, tb, tn = describe(target)
+        rp, rb, rn = describe(reference)
+        op, ob, on = describe(out)
+        assert on == tn
+        slot = C.c_int32()
+        with torch.cuda.device(self.device):
+            _native.check(self.lib, self.lib.mgb_pipeline_submit_pcm(self._handle, tp, tb, tn, rp, rb, rn, op, ob,
+                                                                     C.byref(slot)))
+        self._pending[slot.value] = (target, reference, out)
+        return slot.value
+
     def wait(self, slot: int) -> _native.TrackState:
         st = _native.TrackState()
         _native.check(self.lib, self.lib.mgb_pipeline_wait(self._handle, slot, C.byref(st)))

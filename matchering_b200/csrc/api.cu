@@ -534,6 +534,15 @@ int mgb_convert_f32_to_f64(const float* d_in, double* d_out, int64_t count, void
     return launch_convert_f32_f64(d_in, d_out, count, (cudaStream_t)stream);
 }
 
+int mgb_pcm_decode(const void* d_pcm, int32_t bits, float* d_out, int64_t count, void* stream) {
+    MGB_REQUIRE(d_pcm && d_out && count >= 0, MGB_ERR_INVALID, "pcm_decode: bad arguments");
+    return launch_pcm_decode(d_pcm, bits, d_out, count, (cudaStream_t)stream);
+}
+int mgb_pcm_encode(const float* d_in, int32_t bits, void* d_pcm, int64_t count, void* stream) {
+    MGB_REQUIRE(d_pcm && d_in && count >= 0, MGB_ERR_INVALID, "pcm_encode: bad arguments");
+    return launch_pcm_encode(d_in, bits, d_pcm, count, (cudaStream_t)stream);
+}
+
 int mgb_test_fft(int32_t n, int32_t is_f64, int32_t dir, const void* d_in, void* d_out, int32_t batch,
                  const void* d_twiddles, void* stream) {
     MGB_REQUIRE(d_in && d_out && d_twiddles && batch > 0, MGB_ERR_INVALID, "test_fft: bad arguments");

@@ -137,6 +137,67 @@ __global__ void convert_f32_f64_kernel(const float* __restrict__ in, double* __r
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) out[i] = (double)in[i];
 }
 
+// ---- PCM <-> float32 at the file boundary (loader / saver) ---------------------------
+// decode: libsndfile's integer -> float read, x / 2^(bits-1)  (what sf.read hands the reference,
+// matchering/loader.py:35).  encode: its float -> integer write, lrint(x * (2^(bits-1) - 1)) with
+// clipping (matchering/saver.py:32).  24-bit samples are packed little-endian triplets.
+__global__ void __launch_bounds__(256)
+pcm16_decode_kernel(const short* __restrict__ in, float* __restrict__ out, long long count) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long pairs = count >> 1;
+    const short2* in2 = reinterpret_cast<const short2*>(in);
+    float2* out2 = reinterpret_cast<float2*>(out);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += stride) {
+        const short2 v = in2[i];
+        out2[i] = make_float2((float)v.x * (1.0f / 32768.0f), (float)v.y * (1.0f / 32768.0f));
+    }
+    if ((count & 1) && blockIdx.x == 0 && threadIdx.x == 0) out[count - 1] = (float)in[count - 1] * (1.0f / 32768.0f);
+}
+
+__global__ void __launch_bounds__(256)
+pcm24_decode_kernel(const unsigned char* __restrict__ in, float* __restrict__ out, long long count) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        const unsigned char* p = in + 3 * i;
+        int v = (int)p[0] | ((int)p[1] << 8) | ((int)(signed char)p[2] << 16);
+        out[i] = (float)v * (1.0f / 8388608.0f);
+    }
+}
+
+__device__ __forceinline__ int quantize(float x, float top) {
+    const float q = rintf(x * top);  // round half to even, like lrint
+    return (int)fminf(top, fmaxf(-top - 1.0f, q));
+}
+
+__global__ void __launch_bounds__(256)
+pcm16_encode_kernel(const float* __restrict__ in, short* __restrict__ out, long long count) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long pairs = count >> 1;
+    const float2* in2 = reinterpret_cast<const float2*>(in);
+    short2* out2 = reinterpret_cast<short2*>(out);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += stride) {
+        const float2 v = in2[i];
+        short2 q;
+        q.x = (short)quantize(v.x, 32767.0f);
+        q.y = (short)quantize(v.y, 32767.0f);
+        out2[i] = q;
+    }
+    if ((count & 1) && blockIdx.x == 0 && threadIdx.x == 0) out[count - 1] = (short)quantize(in[count - 1], 32767.0f);
+}
+
+__global__ void __launch_bounds__(256)
+pcm24_encode_kernel(const float* __restrict__ in, unsigned char* __restrict__ out, long long count) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        // 8388607 is exactly representable in float32; the product is rounded once before rintf
+        const int q = quantize(in[i], 8388607.0f);
+        unsigned char* p = out + 3 * i;
+        p[0] = (unsigned char)(q & 0xff);
+        p[1] = (unsigned char)((q >> 8) & 0xff);
+        p[2] = (unsigned char)((q >> 16) & 0xff);
+    }
+}
+
 unsigned grid_for(long long items, int per_block) {
     long long blocks = (items + per_block - 1) / per_block;
     const long long cap = (long long)num_sms() * 8;
@@ -188,6 +249,28 @@ int launch_convert_f64_f32(const double* in, float* out, int64_t count, cudaStre
 int launch_convert_f32_f64(const float* in, double* out, int64_t count, cudaStream_t stream) {
     return launch("convert_f32_f64_kernel", convert_f32_f64_kernel, dim3(grid_for(count, 1024)), dim3(256), 0, stream, in,
                   out, (long long)count);
+}
+
+int launch_pcm_decode(const void* in, int bits, float* out, int64_t count, cudaStream_t stream) {
+    if (bits == 16)
+        return launch("pcm16_decode_kernel", pcm16_decode_kernel, dim3(grid_for(count / 2 + 1, 1024)), dim3(256), 0, stream,
+                      (const short*)in, out, (long long)count);
+    if (bits == 24)
+        return launch("pcm24_decode_kernel", pcm24_decode_kernel, dim3(grid_for(count, 1024)), dim3(256), 0, stream,
+                      (const unsigned char*)in, out, (long long)count);
+    set_error("pcm decode: %d-bit samples have no kernel (16 and 24 do)", bits);
+    return MGB_ERR_UNSUPPORTED;
+}
+
+int launch_pcm_encode(const float* in, int bits, void* out, int64_t count, cudaStream_t stream) {
+    if (bits == 16)
+        return launch("pcm16_encode_kernel", pcm16_encode_kernel, dim3(grid_for(count / 2 + 1, 1024)), dim3(256), 0, stream, in,
+                      (short*)out, (long long)count);
+    if (bits == 24)
+        return launch("pcm24_encode_kernel", pcm24_encode_kernel, dim3(grid_for(count, 1024)), dim3(256), 0, stream, in,
+                      (unsigned char*)out, (long long)count);
+    set_error("pcm encode: %d-bit samples have no kernel (16 and 24 do)", bits);
+    return MGB_ERR_UNSUPPORTED;
 }
 
 }  // namespace mgb

@@ -178,16 +178,18 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
     // ---- P1: hard-clip gain g = 1 - thr/max(|L|,|R|,thr) over the span (dsp.py:117-121, hyrax.py:87)
     {
         const float2* base = in + ga;
+        float2 v[EPT];  // all of the thread's loads are issued before the first use: one DRAM latency, not EPT
 #pragma unroll
         for (int k = 0; k < EPT; ++k) {
             const int i = tid + k * NT;
+            v[k] = (i >= vlo && i < vhi) ? __ldg(base + i) : make_float2(0.0f, 0.0f);
+        }
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+            const double a = (double)fmaxf(fabsf(v[k].x), fabsf(v[k].y)) * pre;
             float g = 0.0f;
-            if (i >= vlo && i < vhi) {
-                const float2 v = base[i];
-                const double a = (double)fmaxf(fabsf(v.x), fabsf(v.y)) * pre;
-                if (a > thr) g = (float)(1.0 - thr / a);  // frames at or below the threshold need no division
-            }
-            G[i] = g;
+            if (a > thr) g = (float)(1.0 - thr / a);  // frames at or below the threshold need no division
+            G[tid + k * NT] = g;
         }
     }
     __syncthreads();
@@ -421,14 +423,25 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
     __syncthreads();
 
     // ---- P7: apply (hyrax.py:99, stages.py:203) -----------------------------------------------------
-    for (int k = tid; k < core_n; k += NT) {
-        const float2 v = in[s0 + k];
-        const double gain = Fd[k] * pre * post;
+    {
+        float2 v[CORE_EPT];
+#pragma unroll
+        for (int q = 0; q < CORE_EPT; ++q) {
+            const int k = tid + q * NT;
+            v[q] = k < core_n ? __ldg(in + s0 + k) : make_float2(0.0f, 0.0f);
+        }
+#pragma unroll
+        for (int q = 0; q < CORE_EPT; ++q) {
+            const int k = tid + q * NT;
+            if (k < core_n) {
+                const double gain = Fd[k] * pre * post;
 #ifdef MGB_LIM_DEBUG
-        out[s0 + k] = make_float2((float)Fd[k], G[cidx + k]);
+                out[s0 + k] = make_float2((float)Fd[k], G[cidx + k]);
 #else
-        out[s0 + k] = make_float2((float)((double)v.x * gain), (float)((double)v.y * gain));
+                out[s0 + k] = make_float2((float)((double)v[q].x * gain), (float)((double)v[q].y * gain));
 #endif
+            }
+        }
     }
 }
 

@@ -20,6 +20,8 @@ struct Slot {
     float* d_result = nullptr;
     float* d_out = nullptr;
     void* d_workspace = nullptr;
+    void* d_pcm_in = nullptr;   // raw PCM of target then reference (submit_pcm)
+    void* d_pcm_out = nullptr;  // quantised result
     mgb_track_state* d_state = nullptr;
     mgb_track_state* h_state = nullptr;  // pinned
     mgb_track_layout layout;
@@ -93,8 +95,11 @@ int mgb_pipeline_create(const mgb_plan* plan, int64_t max_target_frames, int64_t
         s.d_result = (float*)dev_alloc((size_t)max_target_frames * 8);
         s.d_out = (float*)dev_alloc((size_t)max_target_frames * 8);
         s.d_workspace = dev_alloc((size_t)p->workspace_bytes);
+        s.d_pcm_in = dev_alloc((size_t)(max_target_frames + max_reference_frames) * 6 + 512);
+        s.d_pcm_out = dev_alloc((size_t)max_target_frames * 6 + 256);
         s.d_state = (mgb_track_state*)dev_alloc(sizeof(mgb_track_state));
-        if (!s.d_target || !s.d_reference || !s.d_result || !s.d_out || !s.d_workspace || !s.d_state) {
+        if (!s.d_target || !s.d_reference || !s.d_result || !s.d_out || !s.d_workspace || !s.d_state || !s.d_pcm_in ||
+            !s.d_pcm_out) {
             set_error("pipeline: device allocation failed");
             mgb_pipeline_destroy(p);
             return MGB_ERR_CUDA;
@@ -124,6 +129,8 @@ int mgb_pipeline_destroy(mgb_pipeline* p) {
         dev_free(s.d_result);
         dev_free(s.d_out);
         dev_free(s.d_workspace);
+        dev_free(s.d_pcm_in);
+        dev_free(s.d_pcm_out);
         dev_free(s.d_state);
 #ifdef MGB_EMULATE
         free(s.h_state);
@@ -191,6 +198,58 @@ int mgb_pipeline_submit(mgb_pipeline* p, const float* h_target_lr, int64_t targe
     MGB_CUDA_OK(cudaEventRecord(s.compute_done, s.compute));
     MGB_CUDA_OK(cudaStreamWaitEvent(p->s_d2h, s.compute_done, 0));
     MGB_CUDA_OK(cudaMemcpyAsync(h_out_limited, s.d_out, tb, cudaMemcpyDeviceToHost, p->s_d2h));
+    MGB_CUDA_OK(cudaMemcpyAsync(s.h_state, s.d_state, sizeof(mgb_track_state), cudaMemcpyDeviceToHost, p->s_d2h));
+    MGB_CUDA_OK(cudaEventRecord(s.d2h_done, p->s_d2h));
+#endif
+    s.busy = true;
+    if (slot_out) *slot_out = idx;
+    return MGB_OK;
+}
+
+int mgb_pipeline_submit_pcm(mgb_pipeline* p, const void* h_target_pcm, int32_t target_bits, int64_t target_frames,
+                            const void* h_reference_pcm, int32_t reference_bits, int64_t reference_frames,
+                            void* h_out_pcm, int32_t out_bits, int32_t* slot_out) {
+    MGB_REQUIRE(p && h_target_pcm && h_reference_pcm && h_out_pcm, MGB_ERR_INVALID, "pipeline: NULL argument");
+    MGB_REQUIRE((target_bits == 16 || target_bits == 24) && (reference_bits == 16 || reference_bits == 24) &&
+                    (out_bits == 16 || out_bits == 24),
+                MGB_ERR_UNSUPPORTED, "pipeline: PCM widths must be 16 or 24 bits");
+    MGB_REQUIRE(target_frames <= p->max_target && reference_frames <= p->max_reference, MGB_ERR_INVALID,
+                "pipeline: track longer than the pipeline was created for");
+    const int idx = p->next;
+    p->next = (p->next + 1) % (int)p->slots.size();
+    Slot& s = p->slots[idx];
+    MGB_TRY(mgb_pipeline_wait(p, idx, nullptr));
+    MGB_TRY(mgb_track_layout_init(&p->plan, target_frames, reference_frames, &s.layout));
+    MGB_REQUIRE(s.layout.workspace_bytes <= p->workspace_bytes, MGB_ERR_WORKSPACE, "pipeline: workspace too small");
+    const size_t tb = (size_t)target_frames * 2 * (target_bits / 8), rb = (size_t)reference_frames * 2 * (reference_bits / 8);
+    const size_t ob = (size_t)target_frames * 2 * (out_bits / 8);
+    unsigned char* pcm_t = (unsigned char*)s.d_pcm_in;
+    unsigned char* pcm_r = pcm_t + (tb + 255) / 256 * 256;
+#ifdef MGB_EMULATE
+    memcpy(pcm_t, h_target_pcm, tb);
+    memcpy(pcm_r, h_reference_pcm, rb);
+    void* sc = nullptr;
+#else
+    MGB_CUDA_OK(cudaMemcpyAsync(pcm_t, h_target_pcm, tb, cudaMemcpyHostToDevice, p->s_h2d));
+    MGB_CUDA_OK(cudaMemcpyAsync(pcm_r, h_reference_pcm, rb, cudaMemcpyHostToDevice, p->s_h2d));
+    MGB_CUDA_OK(cudaEventRecord(s.h2d_done, p->s_h2d));
+    MGB_CUDA_OK(cudaStreamWaitEvent(s.compute, s.h2d_done, 0));
+    void* sc = (void*)s.compute;
+#endif
+    MGB_TRY(mgb_pcm_decode(pcm_t, target_bits, s.d_target, target_frames * 2, sc));
+    MGB_TRY(mgb_pcm_decode(pcm_r, reference_bits, s.d_reference, reference_frames * 2, sc));
+    MGB_TRY(mgb_match_levels(&p->plan, &s.layout, s.d_target, s.d_reference, s.d_workspace, s.d_state, sc));
+    MGB_TRY(mgb_match_frequencies(&p->plan, &s.layout, s.d_target, s.d_result, nullptr, s.d_workspace, s.d_state, sc));
+    MGB_TRY(mgb_correct_levels(&p->plan, &s.layout, s.d_workspace, s.d_state, sc));
+    MGB_TRY(mgb_finalize(&p->plan, &s.layout, s.d_result, s.d_out, nullptr, nullptr, s.d_workspace, s.d_state, sc));
+    MGB_TRY(mgb_pcm_encode(s.d_out, out_bits, s.d_pcm_out, target_frames * 2, sc));
+#ifdef MGB_EMULATE
+    memcpy(h_out_pcm, s.d_pcm_out, ob);
+    memcpy(s.h_state, s.d_state, sizeof(mgb_track_state));
+#else
+    MGB_CUDA_OK(cudaEventRecord(s.compute_done, s.compute));
+    MGB_CUDA_OK(cudaStreamWaitEvent(p->s_d2h, s.compute_done, 0));
+    MGB_CUDA_OK(cudaMemcpyAsync(h_out_pcm, s.d_pcm_out, ob, cudaMemcpyDeviceToHost, p->s_d2h));
     MGB_CUDA_OK(cudaMemcpyAsync(s.h_state, s.d_state, sizeof(mgb_track_state), cudaMemcpyDeviceToHost, p->s_d2h));
     MGB_CUDA_OK(cudaEventRecord(s.d2h_done, p->s_d2h));
 #endif

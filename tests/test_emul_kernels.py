@@ -200,3 +200,60 @@ def test_pipeline_entry_points_match_single_track_path(lib, golden):
         assert np.abs(outs[1] - want).max() < TOL
     finally:
         lib.mgb_pipeline_destroy(handle)
+
+
+def _to_pcm24(x):
+    q = np.clip(np.rint(x.astype(np.float64) * 8388607.0), -8388608, 8388607).astype(np.int64) & 0xFFFFFF
+    return np.stack([q & 0xFF, (q >> 8) & 0xFF, (q >> 16) & 0xFF], axis=-1).astype(np.uint8).reshape(len(x), 6)
+
+
+def _from_pcm24(b):
+    b = b.reshape(-1, 3).astype(np.int64)
+    v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
+    v = np.where(v >= 1 << 23, v - (1 << 24), v)
+    return (v / 8388608.0).reshape(-1, 2)
+
+
+def test_pcm_conversions_are_bit_exact(lib):
+    rng = np.random.default_rng(4)
+    x = np.clip(0.7 * rng.standard_normal((5001, 2)), -1.2, 1.2).astype(np.float32)
+    xin = aligned_copy(x)
+    q16 = aligned((5001, 2), np.int16)
+    _native.check(lib, lib.mgb_pcm_encode(ptr(xin), 16, ptr(q16), x.size, None))
+    want16 = np.clip(np.rint(x * np.float32(32767.0)), -32768, 32767).astype(np.int16)
+    assert np.array_equal(q16, want16)
+    q24 = aligned((5001, 6), np.uint8)
+    _native.check(lib, lib.mgb_pcm_encode(ptr(xin), 24, ptr(q24), x.size, None))
+    want24 = np.clip(np.rint(x * np.float32(8388607.0)), -8388608, 8388607).astype(np.int64)
+    got24 = (_from_pcm24(q24) * 8388608.0).astype(np.int64)
+    assert np.array_equal(got24, want24)
+    back = aligned((5001, 2), np.float32)
+    _native.check(lib, lib.mgb_pcm_decode(ptr(q16), 16, ptr(back), x.size, None))
+    assert np.array_equal(back, q16.astype(np.float32) / np.float32(32768.0))
+    _native.check(lib, lib.mgb_pcm_decode(ptr(q24), 24, ptr(back), x.size, None))
+    assert np.array_equal(back, _from_pcm24(q24).astype(np.float32))
+
+
+def test_pipeline_pcm_entry(lib, golden):
+    """PCM16 in / PCM24 out through the batch entry == decode, float pipeline, encode."""
+    g = golden("pipeline_small.npz")
+    cfg = port.OracleConfig(max_piece_size=float(g["max_piece_size_s"]))
+    from emul_harness import get_emul_plan
+    ep = get_emul_plan(cfg)
+    t16 = aligned_copy(np.clip(np.rint(g["target"] * 32767.0), -32768, 32767).astype(np.int16))
+    r24 = aligned_copy(_to_pcm24(g["reference"]))
+    out24 = aligned((len(t16), 6), np.uint8)
+    handle = C.c_void_p()
+    _native.check(lib, lib.mgb_pipeline_create(C.byref(ep.struct), 40000, 40000, 2, C.byref(handle)))
+    try:
+        slot = C.c_int32()
+        _native.check(lib, lib.mgb_pipeline_submit_pcm(handle, ptr(t16), 16, len(t16), ptr(r24), 24, len(r24), ptr(out24), 24,
+                                                       C.byref(slot)))
+        _native.check(lib, lib.mgb_pipeline_wait(handle, slot.value, None))
+    finally:
+        lib.mgb_pipeline_destroy(handle)
+    t = t16.astype(np.float64) / 32768.0
+    r = _from_pcm24(r24)
+    want = port.main(t, r, cfg)[0]
+    got = _from_pcm24(out24) * (8388608.0 / 8388607.0)
+    assert np.abs(got - want).max() < TOL + 1.0 / 8388607

@@ -261,3 +261,24 @@ def test_batch_pipeline_matches_single_track_path(torch_cuda):
     for (t, r), o in zip(pairs, got):
         want = stages.main(t, r, cfg)[0]
         assert o.shape == want.shape and np.abs(o - want).max() < 1e-6
+
+
+def test_pcm_batch_entry(torch_cuda):
+    """int16 in / int16 out through the batch pipeline == decode, float pipeline, encode (bit-exact
+    up to one LSB where the float32 result sits on a rounding boundary)."""
+    import port
+    from matchering_b200 import stages
+    from matchering_b200.batch import MasteringPipeline
+    cfg = _config(max_piece_size=3.0)
+    t = port.synth_target(300000, 3)
+    r = port.synth_reference(280000, 4)
+    t16 = np.clip(np.rint(t * 32767.0), -32768, 32767).astype(np.int16)
+    r16 = np.clip(np.rint(r * 32767.0), -32768, 32767).astype(np.int16)
+    out16 = np.zeros((300000, 2), dtype=np.int16)
+    with MasteringPipeline(cfg, 300000, 280000, depth=2) as pipe:
+        st = pipe.wait(pipe.submit_pcm(t16, r16, out16))
+    assert st.steps_done == 4
+    want = stages.main(t16.astype(np.float32) / np.float32(32768.0), r16.astype(np.float32) / np.float32(32768.0), cfg)[0]
+    want16 = np.clip(np.rint(want * np.float32(32767.0)), -32768, 32767).astype(np.int16)
+    assert np.abs(out16.astype(np.int32) - want16.astype(np.int32)).max() <= 1
+    assert (out16 != want16).mean() < 1e-3
