@@ -6,7 +6,7 @@ from .loader import load
 from .log import Code, ModuleError, debug, debug_line, info
 from .results import Result
 from .saver import save
-from .stages import main
+from .stages import main_device
 from .utils import get_temp_folder
 
 _DEFAULT_CONFIG = None
@@ -38,7 +38,7 @@ def process(target: str, reference: str, results: list, config: Config = None,
             or not (target_audio.shape[0] > config.fft_size and reference_audio.shape[0] > config.fft_size)):
         raise ModuleError(Code.ERROR_VALIDATION)
 
-    limited, plain, normalized = main(
+    limited, plain, normalized = main_device(
         target_audio, reference_audio, config,
         need_default=any(r.use_limiter for r in results),
         need_no_limiter=any(not r.use_limiter and not r.normalize for r in results),
@@ -48,6 +48,23 @@ def process(target: str, reference: str, results: list, config: Config = None,
     info(Code.INFO_EXPORTING)
     for wanted in results:
         audio = limited if wanted.use_limiter else (normalized if wanted.normalize else plain)
-        save(wanted.file, audio, config.internal_sample_rate, wanted.subtype)
+        _export(wanted, audio, config.internal_sample_rate)
     debug_line()
     info(Code.INFO_COMPLETED)
+
+
+def _export(wanted: Result, audio, sample_rate: int) -> None:
+    """16/24-bit WAV results are quantised on the device and written as they come back (a quarter of
+    the device->host bytes of a float64 array); everything else takes the reference's route through
+    a host float array and `save`."""
+    from .results import real_soundfile
+    is_wav = wanted.file.lower().endswith(".wav")
+    if is_wav and wanted.subtype in ("PCM_16", "PCM_24") and real_soundfile() is None:
+        from . import wavio
+        from .engine import encode_pcm
+        bits = int(wanted.subtype[4:])
+        debug(f"Saving the RESULT {sample_rate} Hz Stereo {wanted.subtype} to: '{wanted.file}'...")
+        wavio.write_pcm(wanted.file, encode_pcm(audio, bits), sample_rate, bits)
+        debug(f"'{wanted.file}' is saved")
+    else:
+        save(wanted.file, audio.cpu().numpy().astype("float64"), sample_rate, wanted.subtype)

@@ -94,7 +94,7 @@ Workspace carve_workspace(const mgb_plan& plan, const mgb_track_layout& L, void*
     w.mask_t = take(L.target_divisions);
     w.mask_r = take(L.reference_divisions);
     w.design_stride = (design_doubles_per_channel(plan) + 31) / 32 * 32;
-    w.design = (double*)take(2 * w.design_stride * 8);
+    w.design = (double*)take(4 * w.design_stride * 8);
     w.h_mid = (float2*)take((F + 1) * 8);
     w.h_side = (float2*)take((F + 1) * 8);
     w.mid_plane = (float*)take(L.target_frames * 4);
@@ -558,7 +558,7 @@ int mgb_test_design_fir(const mgb_plan* plan, const double* d_avg, double* d_fir
     memset(&ws, 0, sizeof(ws));
     ws.design_stride = (design_doubles_per_channel(*plan) + 31) / 32 * 32;
     ws.design = (double*)d_workspace;
-    ws.h_mid = (float2*)((unsigned char*)d_workspace + align256(2 * ws.design_stride * 8));
+    ws.h_mid = (float2*)((unsigned char*)d_workspace + align256(4 * ws.design_stride * 8));
     ws.h_side = ws.h_mid + (plan->fft_size + 1 + 31) / 32 * 32;
     mgb_track_layout L;
     memset(&L, 0, sizeof(L));

@@ -267,7 +267,7 @@ spectrum_mean_kernel(DesignArgs a, int n_lin, int fft_size, double eps, Prefetch
         // normalisation 1/coef are applied to the means instead of to the samples
         const double norm_t = lv.c0 / ((double)lv.loud_t * (double)a.frames_per_piece_t * (double)fft_size);
         const double norm_r = 1.0 / (lv.coef * (double)lv.loud_r * (double)a.frames_per_piece_r * (double)fft_size);
-        a.scratch[(long long)ch * a.stride + k] = (sr * norm_r) / fmax(eps, st * norm_t);
+        a.scratch[(long long)(2 * ch) * a.stride + k] = (sr * norm_r) / fmax(eps, st * norm_t);
     }
 }
 
@@ -285,14 +285,18 @@ design_kernel(mgb_plan plan, DesignArgs a) {
     double* re = reinterpret_cast<double*>(smem);
     double* im = re + DesignSmem<F>::kPlane;
     const int tid = threadIdx.x, nthr = blockDim.x;
-    const int ch = blockIdx.x;
+    const int ch = blockIdx.x >> 1;
+    const int parity = blockIdx.x & 1;  // which half of the FIR spectrum this CTA produces (step G)
     const int NL = plan.n_log;
     const cpx<double>* tw = (const cpx<double>*)plan.d_tw_f64_F;
 
-    double* base = a.scratch + (long long)ch * a.stride;
-    double* m = base;                    // [HB] matching curve
-    double* s = base + 2 * HB;           // [HB] smoothed curve on the linear grid
-    double* fir = base + 3 * HB + 4 * NL;  // [F]
+    // scratch blocks: [channel][parity]; the matching curve m (and, on the operator path, the smoothed
+    // curve s) are produced into the parity-0 block by the kernels that ran before
+    double* base0 = a.scratch + (long long)(2 * ch) * a.stride;
+    double* base = base0 + (long long)parity * a.stride;
+    double* m = base;                       // [HB] matching curve
+    double* s = (a.s_ready ? base0 : base) + 2 * HB;  // [HB] smoothed curve on the linear grid
+    double* fir = base + 3 * HB + 4 * NL;   // [F]
 
     const double eps = plan.min_value;
     double c0 = 1.0, coef = 1.0;
@@ -308,7 +312,9 @@ design_kernel(mgb_plan plan, DesignArgs a) {
             const double ar = a.avg_override[(long long)(2 + ch) * HB + k];
             m[k] = ar / fmax(eps, at);
         }
-    }  // otherwise spectrum_mean_kernel has already written m
+    } else if (parity == 1 && !a.s_ready) {
+        for (int k = tid; k < HB; k += nthr) m[k] = base0[k];  // own copy: the direct chain works in place
+    }  // otherwise spectrum_mean_kernel / ratio_kernel has already written m into the parity-0 block
     __syncthreads();
 
     // ---- B-E: smoothing on the log-frequency grid, unless the operator kernel already produced s ---
@@ -324,40 +330,44 @@ design_kernel(mgb_plan plan, DesignArgs a) {
             const int src = (i + F / 2) & (F - 1);
             const double v = re[fft_pad(src)] * inv * plan.d_hann[i];
             fir[i] = v;
-            if (a.fir_out) a.fir_out[(long long)ch * F + i] = v;
+            if (a.fir_out && parity == 0) a.fir_out[(long long)ch * F + i] = v;
         }
         __syncthreads();
     }
 
     // ---- G: spectrum of the FIR on the 2F grid, bins 0..F ---------------------------------------
-    // even bins 2j = FFT_F(fir)[j]; odd bins 2j+1 = FFT_F(fir[n] * exp(-i*pi*n/F))[j]
+    // even bins 2j = FFT_F(fir)[j]; odd bins 2j+1 = FFT_F(fir[n] * exp(-i*pi*n/F))[j].  Two CTAs per
+    // channel: both have just designed the same FIR (steps A-F are cheap and deterministic), one
+    // transforms it for the even bins, the other for the odd bins.
     {
         float2* H = ch == 0 ? a.h_mid : a.h_side;
         const double scale = c0 / (2.0 * (double)F);
-        auto first_even = [&](int i) { return cpx<double>{fir[i], 0.0}; };
-        fft_run<F, +1, kDesignThreads, double>(re, im, tw, first_even, SmemStore<double>{re, im}, false, true);
-        __syncthreads();
-        for (int j = tid; j <= F / 2; j += nthr) {
-            const int jj = j & (F - 1);
-            H[2 * j] = make_float2((float)(re[fft_pad(jj)] * scale), (float)(im[fft_pad(jj)] * scale));
+        if (parity == 0) {
+            auto first_even = [&](int i) { return cpx<double>{fir[i], 0.0}; };
+            fft_run<F, +1, kDesignThreads, double>(re, im, tw, first_even, SmemStore<double>{re, im}, false, true);
+            __syncthreads();
+            for (int j = tid; j <= F / 2; j += nthr) {
+                const int jj = j & (F - 1);
+                H[2 * j] = make_float2((float)(re[fft_pad(jj)] * scale), (float)(im[fft_pad(jj)] * scale));
+            }
+        } else {
+            auto first_odd = [&](int i) {
+                double sn, cs;
+                sincospi(-(double)i / (double)F, &sn, &cs);
+                return cpx<double>{fir[i] * cs, fir[i] * sn};
+            };
+            fft_run<F, +1, kDesignThreads, double>(re, im, tw, first_odd, SmemStore<double>{re, im}, false, true);
+            __syncthreads();
+            for (int j = tid; j < F / 2; j += nthr)
+                H[2 * j + 1] = make_float2((float)(re[fft_pad(j)] * scale), (float)(im[fft_pad(j)] * scale));
         }
-        __syncthreads();
-        auto first_odd = [&](int i) {
-            double sn, cs;
-            sincospi(-(double)i / (double)F, &sn, &cs);
-            return cpx<double>{fir[i] * cs, fir[i] * sn};
-        };
-        fft_run<F, +1, kDesignThreads, double>(re, im, tw, first_odd, SmemStore<double>{re, im}, false, true);
-        __syncthreads();
-        for (int j = tid; j < F / 2; j += nthr)
-            H[2 * j + 1] = make_float2((float)(re[fft_pad(j)] * scale), (float)(im[fft_pad(j)] * scale));
     }
 }
 
 __global__ void ratio_kernel(const double* __restrict__ avg, double* __restrict__ scratch, long long stride, int n_lin,
                              double eps) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x, ch = blockIdx.y;
-    if (k < n_lin) scratch[(long long)ch * stride + k] = avg[(long long)(2 + ch) * n_lin + k] / fmax(eps, avg[(long long)ch * n_lin + k]);
+    if (k < n_lin) scratch[(long long)(2 * ch) * stride + k] = avg[(long long)(2 + ch) * n_lin + k] / fmax(eps, avg[(long long)ch * n_lin + k]);
 }
 
 // ---- the smoothing as a Config-only matrix ------------------------------------------------------
@@ -398,8 +408,8 @@ smooth_operator_kernel(const double* __restrict__ S, double* __restrict__ scratc
     const int r = blockIdx.x * 8 + warp;
     if (r >= n_lin) return;
     const double* row = S + (long long)r * n_lin;
-    const double* m0 = scratch;
-    const double* m1 = scratch + stride;
+    const double* m0 = scratch;               // channel 0, parity-0 block
+    const double* m1 = scratch + 2 * stride;  // channel 1, parity-0 block
     double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
     int c = lane;
     for (; c + 32 < n_lin; c += 64) {
@@ -417,13 +427,13 @@ smooth_operator_kernel(const double* __restrict__ S, double* __restrict__ scratc
     const double sa = warp_sum(a0 + a1), sb = warp_sum(b0 + b1);
     if (lane == 0) {
         scratch[2LL * n_lin + r] = sa;
-        scratch[stride + 2LL * n_lin + r] = sb;
+        scratch[2 * stride + 2LL * n_lin + r] = sb;
     }
 }
 
 template <int F>
 int launch_design_t(const mgb_plan& plan, const DesignArgs& a, cudaStream_t stream) {
-    return launch("design_kernel", design_kernel<F>, dim3(2), dim3(kDesignThreads), DesignSmem<F>::kBytes, stream, plan, a);
+    return launch("design_kernel", design_kernel<F>, dim3(4), dim3(kDesignThreads), DesignSmem<F>::kBytes, stream, plan, a);
 }
 
 }  // namespace

@@ -14,7 +14,7 @@ struct Workspace {
     float* absmax_part_r;   // [Dr*Sr + 1]
     unsigned char* mask_t;  // [Dt] loudest-piece mask of the target
     unsigned char* mask_r;  // [Dr]
-    double* design;         // [2][design_stride] float64 vectors of the FIR design, per channel
+    double* design;         // [2 channels][2 CTAs][design_stride] float64 vectors of the FIR design
     float2* h_mid;          // [F+1] spectrum of the mid FIR on the 2F grid (bins 0..F), c0/(2F) folded in
     float2* h_side;         // [F+1]
     float* mid_plane;       // [T] mid channel of the convolution result

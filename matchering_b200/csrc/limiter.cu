@@ -105,7 +105,7 @@ struct LimiterGeom {
     int ept;                      // span elements per thread (odd)
     int span;                     // samples of g the chunk touches
     int filt;                     // samples the attack filter needs to run over (LC + left + warm)
-    int pad;                      // zeroed floats past the span arrays (>= the largest doubling step)
+    int levels;                   // sparse-table levels the running maxima need (runs of < 2^(levels+1) blocks)
 };
 
 // powers of the three poles, computed once per parameter set (not per CTA: pow() is slow)
@@ -216,10 +216,7 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
             PF[base + e] = run;
         }
         blockmax[0][tid] = run;
-        if (tid < 32) {
-#pragma unroll
-            for (int j = 0; j < kLevels; ++j) blockmax[j][NT + tid] = 0.0f;
-        }
+        if (tid < 32) blockmax[0][NT + tid] = 0.0f;
         run = 0.0f;
 #pragma unroll
         for (int e = EPT - 1; e >= 0; --e) {
@@ -227,10 +224,20 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
             SF[base + e] = run;
         }
         __syncthreads();
-        for (int j = 1; j < kLevels; ++j) {  // blockmax[j][t] = max of blocks t .. t + 2^j - 1
-            blockmax[j][tid] = fmaxf(blockmax[j - 1][tid], blockmax[j - 1][tid + (1 << (j - 1))]);
-            __syncthreads();
+        // sparse table over the block maxima, blockmax[j][t] = max of blocks t .. t + 2^j - 1: every
+        // thread builds its own column straight from level 0 (at most 2^jmax reads), so the levels
+        // need no barriers between them
+        {
+            float m = blockmax[0][tid];
+            int have = 1;
+            for (int j = 1; j <= gm.levels; ++j) {
+                const int want = 1 << j;
+                for (int q = have; q < want; ++q) m = fmaxf(m, blockmax[0][min(tid + q, NT + 31)]);
+                have = want;
+                blockmax[j][tid] = m;
+            }
         }
+        __syncthreads();
         auto whole_blocks = [&](int a, int b) -> float {  // blocks a..b inclusive, a <= b
             const int j = 31 - __clz(b - a + 1);
             return fmaxf(blockmax[j][a], blockmax[j][b - (1 << j) + 1]);
@@ -468,8 +475,11 @@ int limiter_geometry(const mgb_limiter_params& lp, LimiterGeom* g) {
     if (ept < 11) ept = 11;
     g->ept = ept;
     const int win_h = 2 * lp.reach + lp.hold;
-    g->pad = 0;
-    MGB_REQUIRE(win_h / ept < 60, MGB_ERR_UNSUPPORTED, "limiter: attack + hold window of %d samples is too long", win_h);
+    const int max_blocks = win_h / ept + 1;  // whole blocks strictly inside the widest window
+    MGB_REQUIRE(max_blocks < 32, MGB_ERR_UNSUPPORTED, "limiter: attack + hold window of %d samples is too long", win_h);
+    int levels = 0;
+    while ((2 << levels) <= max_blocks) ++levels;
+    g->levels = levels;
     MGB_REQUIRE(ept <= SPAN_EPT_MAX, MGB_ERR_UNSUPPORTED,
                 "limiter: halo of %d samples exceeds the kernel's span", g->span - LC);
     return MGB_OK;
@@ -496,7 +506,7 @@ int launch_limiter(const mgb_limiter_params& lp, const float2* in, float2* out, 
     MGB_REQUIRE(frames > 6, MGB_ERR_INVALID, "limiter: the input must be longer than filtfilt's padlen (6)");
     MGB_REQUIRE(tables != nullptr, MGB_ERR_INVALID, "limiter: pole tables missing");
     const int64_t chunks = (frames + LC - 1) / LC;
-    const size_t smem = (size_t)g.ept * NT * 16 + (size_t)g.pad * 4;
+    const size_t smem = (size_t)g.ept * NT * 16;
 #define MGB_LIMITER_CASE(E)                                                                                       \
     case E:                                                                                                       \
         return launch("limiter_kernel", limiter_kernel<E>, dim3((unsigned)chunks), dim3(NT), smem, stream, lp, g, in, \

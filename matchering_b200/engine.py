@@ -175,3 +175,18 @@ class TrackSession:
         """One device->host read of the job's scalars (synchronises)."""
         raw = self.state.cpu().numpy().tobytes()
         return _native.TrackState.from_buffer_copy(raw)
+
+
+def encode_pcm(t: torch.Tensor, bits: int):
+    """float32 CUDA (frames, 2) -> host numpy PCM: int16 (frames, 2) or packed 24-bit uint8 (frames, 6),
+    quantised on the device (lrint(x * (2^(bits-1) - 1)), clipped: libsndfile's float -> int write)."""
+    lib = _native.load()
+    frames = t.shape[0]
+    if bits == 16:
+        out = torch.empty((frames, 2), dtype=torch.int16, device=t.device)
+    elif bits == 24:
+        out = torch.empty((frames, 6), dtype=torch.uint8, device=t.device)
+    else:
+        raise ValueError("PCM width must be 16 or 24")
+    _native.check(lib, lib.mgb_pcm_encode(t.data_ptr(), bits, out.data_ptr(), frames * 2, _stream_ptr(t.device)))
+    return out.cpu().numpy()

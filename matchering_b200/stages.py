@@ -17,6 +17,14 @@ def main(target, reference, config: Config, need_default: bool = True, need_no_l
     reference's loader produces, or float32) or torch tensors.  Returns
     (result, result_no_limiter, result_no_limiter_normalized), None where not requested, in the
     caller's array type."""
+    outs = main_device(target, reference, config, need_default, need_no_limiter, need_no_limiter_normalized)
+    return tuple(None if t is None else to_host_like(t, target) for t in outs)
+
+
+def main_device(target, reference, config: Config, need_default: bool = True, need_no_limiter: bool = False,
+                need_no_limiter_normalized: bool = False):
+    """Same as `main`, but the results stay on the device as float32 CUDA tensors (the caller may
+    quantise them there, see core.process)."""
     plan = get_plan(config)
     device = plan.device
     if target.ndim != 2 or reference.ndim != 2 or target.shape[1] != 2 or reference.shape[1] != 2:
@@ -59,5 +67,4 @@ def main(target, reference, config: Config, need_default: bool = True, need_no_l
                 debug(f"RMS correction #{step + 1}: {to_db(st.correction[step])}")
             debug("The limiter is not needed!" if not st.limiter_engaged else "The limiter was applied")
 
-        out = tuple(None if t is None else to_host_like(t, target) for t in (limited, plain, normalized))
-    return out
+    return limited, plain, normalized

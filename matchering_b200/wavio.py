@@ -84,3 +84,15 @@ def write(path: str, array: np.ndarray, sample_rate: int, subtype: str) -> None:
         body += b"\x00"
     with open(path, "wb") as f:
         f.write(b"RIFF" + struct.pack("<I", len(body)) + body)
+
+
+def write_pcm(path: str, pcm: np.ndarray, sample_rate: int, bits: int, channels: int = 2) -> None:
+    """Already-quantised samples (int16 (frames, ch) or packed 24-bit uint8 (frames, 3*ch)) -> WAV."""
+    payload = np.ascontiguousarray(pcm).tobytes()
+    block = channels * bits // 8
+    fmt = struct.pack("<HHIIHH", _PCM, channels, int(sample_rate), int(sample_rate) * block, block, bits)
+    body = b"WAVE" + b"fmt " + struct.pack("<I", len(fmt)) + fmt + b"data" + struct.pack("<I", len(payload)) + payload
+    if len(payload) & 1:
+        body += b"\x00"
+    with open(path, "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", len(body)) + body)
