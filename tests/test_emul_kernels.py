@@ -257,3 +257,43 @@ def test_pipeline_pcm_entry(lib, golden):
     want = port.main(t, r, cfg)[0]
     got = _from_pcm24(out24) * (8388608.0 / 8388607.0)
     assert np.abs(got - want).max() < TOL + 1.0 / 8388607
+
+
+@pytest.mark.parametrize("steps", [0, 1, 3])
+def test_rms_correction_step_counts(lib, steps):
+    cfg = port.OracleConfig(fft_size=1024, max_piece_size=0.3, rms_correction_steps=steps)
+    t, r = port.synth_target(40000, 31), port.synth_reference(35000, 32)
+    outs, st, _, _, _ = run_pipeline(cfg, t, r)
+    _compare(outs, port.main(t.astype(np.float64), r.astype(np.float64), cfg, True, True, True))
+    assert st.steps_done == steps
+
+
+def test_shortest_legal_tracks_single_piece(lib):
+    """Just over fft_size: one piece, one STFT frame, two convolution frames, one limiter chunk."""
+    cfg = port.OracleConfig(fft_size=1024)
+    t, r = port.synth_target(1500, 41), port.synth_reference(1025, 42)
+    outs, st, _, _, L = run_pipeline(cfg, t, r)
+    assert (L.target_divisions, L.target_piece, L.reference_divisions) == (1, 1500, 1)
+    assert st.target_loud_pieces == 1 and st.reference_loud_pieces == 1  # sqrt(r*r) >= r (SURVEY appendix C.4)
+    _compare(outs, port.main(t.astype(np.float64), r.astype(np.float64), cfg, True, True, True))
+
+
+def test_very_quiet_target_and_clipping_reference(lib):
+    """Large level-matching gain (target 80 dB down) and a reference that peaks above the threshold
+    (normalize leaves it alone, dsp.py:98)."""
+    cfg = port.OracleConfig(fft_size=1024, max_piece_size=0.4)
+    t = (1e-4 * port.synth_target(30000, 51)).astype(np.float32)
+    r = np.clip(1.5 * port.synth_reference(30000, 52), -1.0, 1.0).astype(np.float32)
+    outs, st, _, _, _ = run_pipeline(cfg, t, r)
+    want = port.main(t.astype(np.float64), r.astype(np.float64), cfg, True, True, True)
+    assert st.final_amplitude_coef == 1.0 and st.rms_coefficient > 1000
+    _compare(outs, want)
+
+
+def test_too_short_pieces_are_rejected(lib):
+    from emul_harness import get_emul_plan
+    cfg = port.OracleConfig(fft_size=4096, max_piece_size=0.1)  # 4410-sample pieces at most
+    ep = get_emul_plan(cfg)
+    L = _native.TrackLayout()
+    rc = lib.mgb_track_layout_init(C.byref(ep.struct), 5000, 5000, C.byref(L))  # 2 pieces of 2500 < fft_size
+    assert rc == _native.MGB_ERR_UNSUPPORTED

@@ -282,3 +282,64 @@ def test_pcm_batch_entry(torch_cuda):
     want16 = np.clip(np.rint(want * np.float32(32767.0)), -32768, 32767).astype(np.int16)
     assert np.abs(out16.astype(np.int32) - want16.astype(np.int32)).max() <= 1
     assert (out16 != want16).mean() < 1e-3
+
+
+@pytest.mark.parametrize("steps", [0, 1, 3])
+def test_rms_correction_step_counts(torch_cuda, steps):
+    import port
+    from matchering_b200 import stages
+    cfg = _config(fft_size=1024, max_piece_size=0.3, rms_correction_steps=steps)
+    t, r = port.synth_target(40000, 31), port.synth_reference(35000, 32)
+    _compare(stages.main(t, r, cfg, True, True, True),
+             port.main(t.astype(np.float64), r.astype(np.float64), cfg, True, True, True))
+
+
+def test_shortest_legal_tracks_and_extreme_levels(torch_cuda):
+    import port
+    from matchering_b200 import stages
+    cfg = _config(fft_size=1024)
+    t, r = port.synth_target(1500, 41), port.synth_reference(1025, 42)
+    _compare(stages.main(t, r, cfg, True, True, True),
+             port.main(t.astype(np.float64), r.astype(np.float64), cfg, True, True, True))
+    cfg = _config(fft_size=1024, max_piece_size=0.4)
+    t = (1e-4 * port.synth_target(30000, 51)).astype(np.float32)
+    r = np.clip(1.5 * port.synth_reference(30000, 52), -1.0, 1.0).astype(np.float32)
+    _compare(stages.main(t, r, cfg, True, True, True),
+             port.main(t.astype(np.float64), r.astype(np.float64), cfg, True, True, True))
+
+
+def test_unsupported_configs_fail_loudly(torch_cuda):
+    from matchering_b200 import stages
+    from matchering_b200.plan import UnsupportedConfig
+    import matchering_b200 as mg
+    x = np.zeros((20000, 2), dtype=np.float32)
+    for cfg in (_config(fft_size=512), _config(lowess_it=1), _config(limiter=mg.LimiterConfig(release_filter_order=2)),
+                _config(fft_size=4096, max_piece_size=0.1)):
+        with pytest.raises(UnsupportedConfig):
+            stages.main(x[:5000], x[:5000], cfg)
+
+
+def test_direct_smoothing_path_matches_operator_path(torch_cuda, lib, golden):
+    """mgb_plan.d_smooth_op == NULL makes design_kernel run spline/LOWESS/spline itself."""
+    torch = torch_cuda
+    import ctypes as C
+    from matchering_b200 import _native
+    from matchering_b200.engine import TrackSession, get_plan, to_device_f32
+    g = golden("pipeline_small.npz")
+    cfg = _config(max_piece_size=float(g["max_piece_size_s"]))
+    plan = get_plan(cfg)
+    t, r = to_device_f32(g["target"], plan.device), to_device_f32(g["reference"], plan.device)
+    firs = []
+    saved = plan.struct.d_smooth_op
+    try:
+        for op in (saved, None):
+            plan.struct.d_smooth_op = op
+            s = TrackSession(plan, t.shape[0], r.shape[0])
+            fir = torch.zeros((2, cfg.fft_size), dtype=torch.float64, device=plan.device)
+            s.match_levels(t, r)
+            s.match_frequencies(t, fir)
+            firs.append(fir.cpu().numpy())
+    finally:
+        plan.struct.d_smooth_op = saved
+    assert np.abs(firs[0] - firs[1]).max() < 1e-12
+    assert np.abs(firs[0][0] - g["fir_mid"]).max() < 1e-7
