@@ -130,8 +130,12 @@ typedef struct mgb_track_layout {
 int mgb_version(void);
 const char* mgb_last_error_string(void);
 
-/* Runtime switches for A/B measurements: "tma" (1 = cp.async.bulk frame loads, default; 0 = plain
- * coalesced loads).  Returns MGB_ERR_INVALID for an unknown name. */
+/* Runtime switches for A/B measurements and tests.  "tma": 1 = cp.async.bulk frame loads (default),
+ * 0 = plain coalesced loads.  "twiddle_chain": convolution FFTs build twiddle powers in registers
+ * (1, default) or read them all from the table (0).  "design_direct": mgb_test_design_fir runs the
+ * spline/LOWESS chain directly even when the plan has a smoothing operator.  "lookback_inclusive":
+ * 0 makes limiter chunks publish aggregates only, so every look-back walks to its cut-off.
+ * Returns MGB_ERR_INVALID for an unknown name. */
 int mgb_set_option(const char* name, int value);
 
 /* Measurement hooks (bench.py): number of kernel launches made by this library so far; and, while

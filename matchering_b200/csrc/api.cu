@@ -13,6 +13,7 @@ namespace mgb {
 
 int g_use_tma = 1;
 int g_twiddle_chain = 1;
+int g_lookback_inclusive = 1;
 
 #ifndef MGB_EMULATE
 long long g_launch_count = 0;
@@ -226,6 +227,10 @@ int mgb_set_option(const char* name, int value) {
     }
     if (strcmp(name, "twiddle_chain") == 0) {
         g_twiddle_chain = value ? 1 : 0;
+        return MGB_OK;
+    }
+    if (strcmp(name, "lookback_inclusive") == 0) {
+        g_lookback_inclusive = value ? 1 : 0;
         return MGB_OK;
     }
     if (strcmp(name, "design_direct") == 0) {

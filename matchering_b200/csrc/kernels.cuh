@@ -28,10 +28,14 @@ struct Workspace {
     int64_t total_bytes;
 };
 
+// One chunk's published scan state: value and status travel in ONE aligned 16-byte word, so a
+// reader gets a consistent pair from a single load (no flag-then-fence-then-value round trips).
+struct alignas(16) LookbackWord {
+    double value;         // status 1: the chunk's zero-carry aggregate; status 2: its inclusive end state
+    long long status;     // 0 = nothing yet
+};
 struct LookbackSlot {
-    double hold_agg, hold_inc, rel_agg, rel_inc;
-    int hold_flag, rel_flag;  // 0 = nothing, 1 = aggregate published, 2 = inclusive published
-    int pad[2];
+    LookbackWord hold, rel;
 };
 
 // powers of a pole for a blocked scan with `ept` elements per thread (limiter.cu)
@@ -94,6 +98,7 @@ int fill_twiddles(int n, int is_f64, void* table, cudaStream_t stream);
 int twiddle_count(int n);
 
 extern int g_use_tma;
+extern int g_lookback_inclusive;  // limiter chunks publish their inclusive state (1, default) or aggregates only (0, tests)
 extern int g_twiddle_chain;  // convolution FFTs: build twiddle powers in registers (1) or read them all (0)
 
 }  // namespace mgb

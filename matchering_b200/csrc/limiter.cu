@@ -62,42 +62,51 @@ __device__ __forceinline__ double scan_carry(double B, const ScanPow* t, double 
     return prev + t->ql[lane] * ((warp > 0 ? warp_carry : 0.0) + t->qw[warp] * c0);
 }
 
-__device__ __forceinline__ void publish(double* value, int* flag, double v, int state) {
-    *(volatile double*)value = v;
-    __threadfence();
-    *(volatile int*)flag = state;
+// 16-byte publish / poll of a LookbackWord through L2 (st.cg / ld.cg: coherent device-wide).
+__device__ __forceinline__ void publish(LookbackWord* w, double v, int status) {
+#ifdef MGB_EMULATE
+    w->value = v;
+    w->status = status;
+#else
+    asm volatile("st.global.cg.v2.u64 [%0], {%1, %2};" ::"l"(w), "l"(__double_as_longlong(v)), "l"((long long)status) : "memory");
+#endif
+}
+__device__ __forceinline__ int poll(const LookbackWord* w, double* v) {
+#ifdef MGB_EMULATE
+    *v = w->value;
+    return (int)w->status;
+#else
+    long long a, b;
+    asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(w) : "memory");
+    *v = __longlong_as_double(a);
+    return (int)b;
+#endif
 }
 
 // Carry into chunk `chunk` of a first-order recurrence whose per-chunk multiplier is P = pc[1]
-// (decoupled look-back).  One warp inspects 32 predecessors at a time: every lane reads one
-// predecessor's published value, the window is cut at the nearest predecessor whose INCLUSIVE
-// state is known, and the lanes' values are combined with weights P^lane by a warp reduction.
-// The walk stops when whatever lies further back weighs less than 1e-13 (all values are <= 1).
-// Called by all 32 lanes of one warp.
+// (decoupled look-back).  One warp inspects 32 predecessors at a time: every lane polls one
+// predecessor's word, the window is cut at the nearest predecessor whose INCLUSIVE state is known,
+// each lane weighs its value by P^distance, and one warp reduction at the very end adds them up.
+// The walk stops when whatever lies further back weighs less than 1e-9 (all values are gains in
+// [0, 1], so that bounds the absolute error of the carry).  Called by all 32 lanes of one warp.
 __device__ __forceinline__ double lookback(LookbackSlot* slots, int chunk, bool release, const double* pc) {
     const int lane = threadIdx.x & 31;
-    double carry = 0.0, mult = 1.0;
-    for (int base = chunk - 1; base >= 0 && mult > 1e-13; base -= 32) {
+    double acc = 0.0, mult = 1.0;
+    for (int base = chunk - 1; base >= 0 && mult > 1e-9; base -= 32) {
         const int j = base - lane;
-        int f = 2;         // before the first chunk: inclusive state 0 (lfilter starts from rest)
+        int st = 2;  // before the first chunk: inclusive state 0 (lfilter starts from rest)
         double val = 0.0;
         if (j >= 0) {
-            LookbackSlot* s = slots + j;
-            int* flag = release ? &s->rel_flag : &s->hold_flag;
-            while ((f = *(volatile int*)flag) == 0) __nanosleep(20);
-            __threadfence();
-            val = (f == 2) ? *(volatile double*)(release ? &s->rel_inc : &s->hold_inc)
-                           : *(volatile double*)(release ? &s->rel_agg : &s->hold_agg);
+            const LookbackWord* w = release ? &slots[j].rel : &slots[j].hold;
+            while ((st = poll(w, &val)) == 0) __nanosleep(20);
         }
-        const unsigned inclusive = __ballot_sync(0xffffffffu, f == 2);
+        const unsigned inclusive = __ballot_sync(0xffffffffu, st == 2);
         const int first = inclusive ? __ffs((int)inclusive) - 1 : 32;
-        double part = lane <= first ? pc[lane] * val : 0.0;
-        part = warp_sum(part);
-        carry += mult * part;
+        if (lane <= first) acc += mult * pc[lane] * val;
         if (inclusive) break;
         mult *= pc[32];
     }
-    return carry;
+    return warp_sum(acc);
 }
 
 struct LimiterGeom {
@@ -105,6 +114,7 @@ struct LimiterGeom {
     int ept;                      // span elements per thread (odd)
     int span;                     // samples of g the chunk touches
     int filt;                     // samples the attack filter needs to run over (LC + left + warm)
+    int publish_inclusive;        // 0: chunks publish aggregates only (test switch: every look-back then walks to the cut-off)
     int levels;                   // sparse-table levels the running maxima need (runs of < 2^(levels+1) blocks)
 };
 
@@ -291,7 +301,7 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
         const double carry = scan_carry(acc, pow_hold, 0.0, scratch_a);
 #pragma unroll
         for (int e = 0; e < CORE_EPT; ++e) hold_y[e] += pow_hold->pe[e + 1] * carry;
-        if (tid == NT - 1) publish(&slot->hold_agg, &slot->hold_flag, hold_y[CORE_EPT - 1], 1);
+        if (tid == NT - 1) publish(&slot->hold, hold_y[CORE_EPT - 1], 1);
     }
 
     // ---- P4: g_att = filtfilt one-pole over A (hyrax.py:48-51) -------------------------------------
@@ -379,7 +389,7 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
             hold_y[e] += pow_hold->pe[e + 1] * lead * hold_cin;
             Fd[tid * CORE_EPT + e] = hold_y[e];
         }
-        if (tid == NT - 1) publish(&slot->hold_inc, &slot->hold_flag, hold_y[CORE_EPT - 1], 2);
+        if (tid == NT - 1 && gm.publish_inclusive) publish(&slot->hold, hold_y[CORE_EPT - 1], 2);
     }
     __syncthreads();
 
@@ -405,7 +415,7 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
         const double carry = scan_carry(acc, pow_rel, 0.0, scratch_b);
 #pragma unroll
         for (int e = 0; e < CORE_EPT; ++e) rel_y[e] += pow_rel->pe[e + 1] * carry;
-        if (tid == NT - 1) publish(&slot->rel_agg, &slot->rel_flag, rel_y[CORE_EPT - 1], 1);
+        if (tid == NT - 1) publish(&slot->rel, rel_y[CORE_EPT - 1], 1);
         if (tid < 32) {
             const double cr = lookback(slots, chunk, true, pow_rel->pc);
             if (tid == 0) bcast[1] = cr;
@@ -425,7 +435,7 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
             Fd[tid * CORE_EPT + e] = 1.0 - fmax((double)G[i], g_rel);  // hyrax.py:97
 #endif
         }
-        if (tid == NT - 1) publish(&slot->rel_inc, &slot->rel_flag, rel_y[CORE_EPT - 1], 2);
+        if (tid == NT - 1 && gm.publish_inclusive) publish(&slot->rel, rel_y[CORE_EPT - 1], 2);
     }
     __syncthreads();
 
@@ -480,6 +490,7 @@ int limiter_geometry(const mgb_limiter_params& lp, LimiterGeom* g) {
     int levels = 0;
     while ((2 << levels) <= max_blocks) ++levels;
     g->levels = levels;
+    g->publish_inclusive = g_lookback_inclusive;
     MGB_REQUIRE(ept <= SPAN_EPT_MAX, MGB_ERR_UNSUPPORTED,
                 "limiter: halo of %d samples exceeds the kernel's span", g->span - LC);
     return MGB_OK;

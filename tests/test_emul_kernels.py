@@ -297,3 +297,17 @@ def test_too_short_pieces_are_rejected(lib):
     L = _native.TrackLayout()
     rc = lib.mgb_track_layout_init(C.byref(ep.struct), 5000, 5000, C.byref(L))  # 2 pieces of 2500 < fft_size
     assert rc == _native.MGB_ERR_UNSUPPORTED
+
+
+def test_limiter_lookback_through_aggregates_only(lib, golden):
+    """With inclusive states withheld every chunk's carry is rebuilt from its predecessors'
+    zero-carry aggregates, weighted by the pole's per-chunk decay, down to the 1e-9 cut-off (on a GPU
+    this is what a chunk sees while its predecessors are still in flight)."""
+    x = port.synth_limiter_input(4608 * 40 + 123, seed=9)
+    want = port.limit(x.astype(np.float64), port.OracleConfig())
+    lib.mgb_set_option(b"lookback_inclusive", 0)
+    try:
+        out, _ = _limit(lib, x, port.OracleConfig())
+    finally:
+        lib.mgb_set_option(b"lookback_inclusive", 1)
+    assert np.abs(out - want).max() < 3e-7
