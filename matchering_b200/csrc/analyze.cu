@@ -25,8 +25,8 @@ namespace {
 template <int F>
 struct AnalyzeSmem {
     static constexpr int kRawBytes = ((F + 2) * 8 + 15) / 16 * 16;
-    static constexpr int kPlaneFloats = fft_padded_size(F);
-    static constexpr int kBytes = kRawBytes + 2 * kPlaneFloats * 4 + 16 /*barrier*/ + 32 * 8 + 32 * 4 + 32;
+    static constexpr int kPlaneBytes = (int)((PackedPlanes::bytes(F) + 15) / 16 * 16);
+    static constexpr int kBytes = kRawBytes + kPlaneBytes + 16 /*barrier*/ + 32 * 8 + 32 * 4 + 32;
 };
 
 struct AnalyzeFirst {
@@ -56,9 +56,8 @@ analyze_kernel(const float2* __restrict__ x, long long frames, long long piece, 
     using L = AnalyzeSmem<F>;
     MGB_DYN_SMEM(smem);
     float2* raw = reinterpret_cast<float2*>(smem);
-    float* re = reinterpret_cast<float*>(smem + L::kRawBytes);
-    float* im = re + L::kPlaneFloats;
-    unsigned char* tail = reinterpret_cast<unsigned char*>(im + L::kPlaneFloats);
+    const PackedPlanes planes{reinterpret_cast<float2*>(smem + L::kRawBytes)};
+    unsigned char* tail = smem + L::kRawBytes + L::kPlaneBytes;
     tail += (16 - (reinterpret_cast<uintptr_t>(tail) & 15)) & 15;
     TmaBarrier* bar = reinterpret_cast<TmaBarrier*>(tail);
     double* red_d = reinterpret_cast<double*>(tail + 16);
@@ -114,21 +113,21 @@ analyze_kernel(const float2* __restrict__ x, long long frames, long long piece, 
         first.raw = raw + off;
         first.sumsq = &sumsq;
         first.peak = &peak;
-        fft_first_pass<F, +1, THREADS, float>(re, im, tw, first, /*in_place=*/false);
+        fft_first_pass<F, +1, THREADS, float>(planes, tw, first, /*in_place=*/false);
         __syncthreads();  // planes written, landing buffer consumed by every thread
         if (use_tma && tid == 0 && f + 1 < f_hi) {
             fence_proxy_async();
             issue(f + 1);  // overlaps the remaining passes of this frame
         }
-        fft_remaining<F, +1, THREADS, float>(re, im, tw, SmemStore<float>{re, im}, /*last_in_place=*/true);
+        fft_remaining<F, +1, THREADS, float>(planes, tw, PlaneStore<PackedPlanes>{planes}, /*last_in_place=*/true);
         __syncthreads();
 #pragma unroll
         for (int b = 0; b < BINS; ++b) {
             const int k = tid + b * THREADS;
             if (k < HB) {
                 const int kn = (F - k) & (F - 1);
-                const float zr = re[fft_pad(k)], zi = im[fft_pad(k)];
-                const float nr = re[fft_pad(kn)], ni = im[fft_pad(kn)];
+                const cpx<float> zk = planes.load(k), zn = planes.load(kn);
+                const float zr = zk.x, zi = zk.y, nr = zn.x, ni = zn.y;
                 // rfft(mid)[k] = (Z[k] + conj(Z[F-k]))/2 ; rfft(side)[k] = (Z[k] - conj(Z[F-k]))/(2i)
                 const float mr = zr + nr, mi = zi - ni;
                 const float sr = zi + ni, si = nr - zr;

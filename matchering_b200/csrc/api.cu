@@ -130,22 +130,31 @@ static int check_aligned(const void* p, const char* name) {
 // ------------------------------------------------------------------------------------------------
 // FFT test harness: one frame per CTA through fft_run, global -> shared -> global
 // ------------------------------------------------------------------------------------------------
+template <typename T> struct TestPlanes { using type = SplitPlanes<T>; };
+template <> struct TestPlanes<float> { using type = PackedPlanes; };  // what the float32 kernels use
+
 template <int N, int DIR, typename T, int THREADS>
 __global__ void __launch_bounds__(THREADS) test_fft_kernel(const cpx<T>* __restrict__ in, cpx<T>* __restrict__ out,
                                                            const cpx<T>* __restrict__ tw) {
     MGB_DYN_SMEM(smem);
-    T* re = reinterpret_cast<T*>(smem);
-    T* im = re + fft_padded_size(N);
+    using P = typename TestPlanes<T>::type;
+    P planes;
+    if constexpr (sizeof(T) == 4) {
+        planes.z = reinterpret_cast<float2*>(smem);
+    } else {
+        planes.re = reinterpret_cast<T*>(smem);
+        planes.im = planes.re + P::elems(N);
+    }
     const cpx<T>* src = in + (long long)blockIdx.x * N;
     cpx<T>* dst = out + (long long)blockIdx.x * N;
     auto first = [&](int i) { return src[i]; };
     auto last = [&](int i, cpx<T> v) { dst[i] = v; };
-    fft_run<N, DIR, THREADS, T>(re, im, tw, first, last, false, false);
+    fft_run<N, DIR, THREADS, T, sizeof(T) == 4>(planes, tw, first, last, false, false);
 }
 
 template <int N, typename T, int THREADS>
 static int launch_test_fft_t(int dir, const void* in, void* out, int batch, const void* tw, cudaStream_t stream) {
-    const size_t smem = 2 * (size_t)fft_padded_size(N) * sizeof(T);
+    const size_t smem = TestPlanes<T>::type::bytes(N);
     if (dir > 0)
         return launch("test_fft_kernel", test_fft_kernel<N, +1, T, THREADS>, dim3(batch), dim3(THREADS), smem, stream,
                       (const cpx<T>*)in, (cpx<T>*)out, (const cpx<T>*)tw);

@@ -27,8 +27,8 @@ namespace {
 template <int F>
 struct ConvSmem {
     static constexpr int N = 2 * F;
-    static constexpr int kPlane = fft_padded_size(N);
-    static constexpr int kBytes = 2 * kPlane * 4 + 16 + 32 * 8 + 32 * 8 + 32 * 4 + 32;
+    static constexpr int kPlaneBytes = (int)((PackedPlanes::bytes(N) + 15) / 16 * 16);
+    static constexpr int kBytes = kPlaneBytes + 16 + 32 * 8 + 32 * 8 + 32 * 4 + 32;
 };
 
 struct ConvFirst {
@@ -57,10 +57,10 @@ convolve_kernel(const float2* __restrict__ x, long long frames, long long piece,
     constexpr int THREADS = N / 16;
     using L = ConvSmem<F>;
     MGB_DYN_SMEM(smem);
-    float* re = reinterpret_cast<float*>(smem);
-    float* im = re + L::kPlane;
-    float2* raw = reinterpret_cast<float2*>(smem);  // aliases the planes until the first pass has gathered
-    unsigned char* tail = reinterpret_cast<unsigned char*>(im + L::kPlane);
+    const PackedPlanes planes{reinterpret_cast<float2*>(smem)};
+    float2* raw = reinterpret_cast<float2*>(smem);  // the landing buffer IS the frame's storage: unpadded
+                                                    // until the first pass has gathered it, padded after
+    unsigned char* tail = smem + L::kPlaneBytes;
     tail += (16 - (reinterpret_cast<uintptr_t>(tail) & 15)) & 15;
     TmaBarrier* bar = reinterpret_cast<TmaBarrier*>(tail);
     double* red_a = reinterpret_cast<double*>(tail + 16);
@@ -98,16 +98,16 @@ convolve_kernel(const float2* __restrict__ x, long long frames, long long piece,
     }
 
     // ---- forward transform of z = mid + i*side ---------------------------------------------------
-    fft_first_pass<N, +1, THREADS, float>(re, im, tw, first, /*in_place=*/true);
+    fft_first_pass<N, +1, THREADS, float>(planes, tw, first, /*in_place=*/true);
     __syncthreads();
-    fft_remaining<N, +1, THREADS, float, CHAIN>(re, im, tw, SmemStore<float>{re, im}, true);
+    fft_remaining<N, +1, THREADS, float, CHAIN>(planes, tw, PlaneStore<PackedPlanes>{planes}, true);
     __syncthreads();
 
     // ---- apply both FIR spectra on the pair (k, N-k) ---------------------------------------------
     for (int k = tid; k <= F; k += THREADS) {
         const int kn = (N - k) & (N - 1);
-        const int ak = fft_pad(k), an = fft_pad(kn);
-        const float zr = re[ak], zi = im[ak], nr = re[an], ni = im[an];
+        const cpx<float> zk = planes.load(k), zn = planes.load(kn);
+        const float zr = zk.x, zi = zk.y, nr = zn.x, ni = zn.y;
         // M = (Z[k] + conj Z[N-k])/2 ; S = (Z[k] - conj Z[N-k])/(2i)
         const float mr = 0.5f * (zr + nr), mi = 0.5f * (zi - ni);
         const float sr = 0.5f * (zi + ni), si = 0.5f * (nr - zr);
@@ -115,19 +115,15 @@ convolve_kernel(const float2* __restrict__ x, long long frames, long long piece,
         const float pmr = hm.x * mr - hm.y * mi, pmi = hm.x * mi + hm.y * mr;
         const float psr = hs.x * sr - hs.y * si, psi = hs.x * si + hs.y * sr;
         // Y[k] = Pm + i Ps ; Y[N-k] = conj(Pm) + i conj(Ps)
-        re[ak] = pmr - psi;
-        im[ak] = pmi + psr;
-        if (kn != k) {
-            re[an] = pmr + psi;
-            im[an] = psr - pmi;
-        }
+        planes.store(k, cpx<float>{pmr - psi, pmi + psr});
+        if (kn != k) planes.store(kn, cpx<float>{pmr + psi, psr - pmi});
     }
     __syncthreads();
 
     // ---- inverse transform, in place ------------------------------------------------------------------
-    fft_first_pass<N, -1, THREADS, float>(re, im, tw, SmemLoad<float>{re, im}, /*in_place=*/true);
+    fft_first_pass<N, -1, THREADS, float>(planes, tw, PlaneLoad<PackedPlanes>{planes}, /*in_place=*/true);
     __syncthreads();
-    fft_remaining<N, -1, THREADS, float, CHAIN>(re, im, tw, SmemStore<float>{re, im}, /*last_in_place=*/true);
+    fft_remaining<N, -1, THREADS, float, CHAIN>(planes, tw, PlaneStore<PackedPlanes>{planes}, /*last_in_place=*/true);
     __syncthreads();
 
     // ---- epilogue: circular index F-1+o is output sample n0+o; coalesced stores, mid/side -> L/R
@@ -146,15 +142,16 @@ convolve_kernel(const float2* __restrict__ x, long long frames, long long piece,
     for (int k = 0; k < F / THREADS; ++k) {
         const int o = tid + k * THREADS;
         if (o < valid) {
-            const int a = fft_pad(F - 1 + o);
-            const float m = re[a], sd = im[a];
+            const cpx<float> y = planes.load(F - 1 + o);
+            const float m = y.x, sd = y.y;
             const float l = m + sd, r = m - sd;
             res[o] = make_float2(l, r);
             midp[o] = m;
             peak = fmaxf(peak, fmaxf(fabsf(l), fabsf(r)));
             if (o < count_to) {
-                const double c = fmin(1.0, fmax(-1.0, (double)m));  // dsp.clip
-                if (o < boundary) sq_a += c * c; else sq_b += c * c;
+                const float cf = fminf(1.0f, fmaxf(-1.0f, m));  // dsp.clip
+                const double c2 = (double)cf * (double)cf;
+                if (o < boundary) sq_a += c2; else sq_b += c2;
             }
         }
     }

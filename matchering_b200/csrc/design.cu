@@ -284,6 +284,7 @@ design_kernel(mgb_plan plan, DesignArgs a) {
     MGB_DYN_SMEM(smem);
     double* re = reinterpret_cast<double*>(smem);
     double* im = re + DesignSmem<F>::kPlane;
+    const SplitPlanes<double> planes{re, im};
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int ch = blockIdx.x >> 1;
     const int parity = blockIdx.x & 1;  // which half of the FIR spectrum this CTA produces (step G)
@@ -323,7 +324,7 @@ design_kernel(mgb_plan plan, DesignArgs a) {
     // ---- F: fir = ifftshift(irfft(s)) * hann (match_frequencies.py:98-99) ---------------------
     {
         auto first = [&](int i) { return cpx<double>{s[i <= F / 2 ? i : F - i], 0.0}; };
-        fft_run<F, -1, kDesignThreads, double>(re, im, tw, first, SmemStore<double>{re, im}, false, true);
+        fft_run<F, -1, kDesignThreads, double>(planes, tw, first, PlaneStore<SplitPlanes<double>>{planes}, false, true);
         __syncthreads();
         const double inv = 1.0 / (double)F;
         for (int i = tid; i < F; i += nthr) {
@@ -344,7 +345,7 @@ design_kernel(mgb_plan plan, DesignArgs a) {
         const double scale = c0 / (2.0 * (double)F);
         if (parity == 0) {
             auto first_even = [&](int i) { return cpx<double>{fir[i], 0.0}; };
-            fft_run<F, +1, kDesignThreads, double>(re, im, tw, first_even, SmemStore<double>{re, im}, false, true);
+            fft_run<F, +1, kDesignThreads, double>(planes, tw, first_even, PlaneStore<SplitPlanes<double>>{planes}, false, true);
             __syncthreads();
             for (int j = tid; j <= F / 2; j += nthr) {
                 const int jj = j & (F - 1);
@@ -356,7 +357,7 @@ design_kernel(mgb_plan plan, DesignArgs a) {
                 sincospi(-(double)i / (double)F, &sn, &cs);
                 return cpx<double>{fir[i] * cs, fir[i] * sn};
             };
-            fft_run<F, +1, kDesignThreads, double>(re, im, tw, first_odd, SmemStore<double>{re, im}, false, true);
+            fft_run<F, +1, kDesignThreads, double>(planes, tw, first_odd, PlaneStore<SplitPlanes<double>>{planes}, false, true);
             __syncthreads();
             for (int j = tid; j < F / 2; j += nthr)
                 H[2 * j + 1] = make_float2((float)(re[fft_pad(j)] * scale), (float)(im[fft_pad(j)] * scale));

@@ -14,8 +14,7 @@
 
 namespace mgb {
 
-// shared-memory index padding: one extra word per 32 keeps the stride-R scatters of the first
-// pass conflict-free
+// padded index of the split (re / im) layout, see SplitPlanes below
 __device__ __host__ __forceinline__ constexpr int fft_pad(int i) { return i + (i >> 5); }
 __device__ __host__ constexpr int fft_padded_size(int n) { return n + (n >> 5) + 1; }
 
@@ -181,24 +180,50 @@ __device__ __forceinline__ void fft_pass(const cpx<T>* __restrict__ tw, Load loa
     }
 }
 
+// Where a frame lives in shared memory between passes.
+// SplitPlanes: two padded arrays (re / im), one extra word per 32 -- used by the float64 transforms.
+// PackedPlanes: one padded float2 array, one extra element per 16 -- used by the float32 kernels:
+// a point is one 8-byte access instead of two 4-byte ones, which halves the shared-memory
+// instructions of kernels that are bound by instruction issue.  Both paddings keep the stride-R
+// scatters of the early passes and the unit-stride gathers conflict-free.
 template <typename T>
-struct SmemLoad {
-    const T* re;
-    const T* im;
-    __device__ __forceinline__ cpx<T> operator()(int i) const {
-        const int a = fft_pad(i);
-        return cpx<T>{re[a], im[a]};
-    }
-};
-template <typename T>
-struct SmemStore {
+struct SplitPlanes {
     T* re;
     T* im;
-    __device__ __forceinline__ void operator()(int i, cpx<T> v) const {
-        const int a = fft_pad(i);
+    static __device__ __host__ constexpr int pad(int i) { return i + (i >> 5); }
+    static __device__ __host__ constexpr int elems(int n) { return n + (n >> 5) + 1; }
+    static __device__ __host__ constexpr size_t bytes(int n) { return 2 * (size_t)elems(n) * sizeof(T); }
+    __device__ __forceinline__ cpx<T> load(int i) const {
+        const int a = pad(i);
+        return cpx<T>{re[a], im[a]};
+    }
+    __device__ __forceinline__ void store(int i, cpx<T> v) const {
+        const int a = pad(i);
         re[a] = v.x;
         im[a] = v.y;
     }
+};
+struct PackedPlanes {
+    float2* z;
+    static __device__ __host__ constexpr int pad(int i) { return i + (i >> 4); }
+    static __device__ __host__ constexpr int elems(int n) { return n + (n >> 4) + 1; }
+    static __device__ __host__ constexpr size_t bytes(int n) { return (size_t)elems(n) * sizeof(float2); }
+    __device__ __forceinline__ cpx<float> load(int i) const {
+        const float2 v = z[pad(i)];
+        return cpx<float>{v.x, v.y};
+    }
+    __device__ __forceinline__ void store(int i, cpx<float> v) const { z[pad(i)] = make_float2(v.x, v.y); }
+};
+template <typename P>
+struct PlaneLoad {
+    P p;
+    __device__ __forceinline__ auto operator()(int i) const { return p.load(i); }
+};
+template <typename P>
+struct PlaneStore {
+    P p;
+    template <typename V>
+    __device__ __forceinline__ void operator()(int i, V v) const { p.store(i, v); }
 };
 
 // Radix schedule of an N-point transform.  Sizes outside this list are rejected by the C ABI.
@@ -215,26 +240,23 @@ template <int N>
 __host__ __device__ constexpr int fft_threads() { return N / 16; }
 
 // First pass of the transform: `first` supplies the input points (logical index -> value), results
-// go to (re, im).  `in_place` says whether `first` reads (re, im) itself (then a barrier separates
-// the gathers from the scatters).  No trailing barrier.
-template <int N, int DIR, int THREADS, typename T, typename First>
-__device__ __forceinline__ void fft_first_pass(T* re, T* im, const cpx<T>* __restrict__ tw, First first,
-                                               bool in_place) {
-    SmemStore<T> ss{re, im};
-    fft_pass<N, Radices<N>::r[0], 1, DIR, THREADS, T, false>(tw, first, ss, in_place);  // NS = 1: no twiddles
+// go to the planes.  `in_place` says whether `first` reads the planes itself (then a barrier
+// separates the gathers from the scatters).  No trailing barrier.
+template <int N, int DIR, int THREADS, typename T, typename Planes, typename First>
+__device__ __forceinline__ void fft_first_pass(Planes pl, const cpx<T>* __restrict__ tw, First first, bool in_place) {
+    fft_pass<N, Radices<N>::r[0], 1, DIR, THREADS, T, false>(tw, first, PlaneStore<Planes>{pl}, in_place);  // NS = 1: no twiddles
 }
 
-// Remaining passes, in place on (re, im); the caller has put a barrier after the first pass.
-// `last` consumes the output points in natural order (`last_in_place`: it writes (re, im)).
+// Remaining passes, in place on the planes; the caller has put a barrier after the first pass.
+// `last` consumes the output points in natural order (`last_in_place`: it writes the planes).
 // On return all `last` stores have been ISSUED (no trailing barrier).
-template <int N, int DIR, int THREADS, typename T, bool CHAIN = false, typename Last>
-__device__ __forceinline__ void fft_remaining(T* re, T* im, const cpx<T>* __restrict__ tw, Last last,
-                                              bool last_in_place) {
+template <int N, int DIR, int THREADS, typename T, bool CHAIN = false, typename Planes, typename Last>
+__device__ __forceinline__ void fft_remaining(Planes pl, const cpx<T>* __restrict__ tw, Last last, bool last_in_place) {
     using Rd = Radices<N>;
     constexpr int R0 = Rd::r[0], R1 = Rd::r[1], R2 = Rd::r[2], R3 = Rd::r[3];
     constexpr int NP = Rd::n;
-    SmemLoad<T> sl{re, im};
-    SmemStore<T> ss{re, im};
+    PlaneLoad<Planes> sl{pl};
+    PlaneStore<Planes> ss{pl};
     static_assert(NP >= 2 && NP <= 4, "2..4 passes supported");
     constexpr int o1 = 0;  // pass 0 has NS = 1: no twiddles stored
     if constexpr (NP == 2) {
@@ -255,12 +277,12 @@ __device__ __forceinline__ void fft_remaining(T* re, T* im, const cpx<T>* __rest
 }
 
 // Whole transform: first pass, barrier, remaining passes.
-template <int N, int DIR, int THREADS, typename T, bool CHAIN = false, typename First, typename Last>
-__device__ __forceinline__ void fft_run(T* re, T* im, const cpx<T>* __restrict__ tw, First first, Last last,
+template <int N, int DIR, int THREADS, typename T, bool CHAIN = false, typename Planes, typename First, typename Last>
+__device__ __forceinline__ void fft_run(Planes pl, const cpx<T>* __restrict__ tw, First first, Last last,
                                         bool first_in_place, bool last_in_place) {
-    fft_first_pass<N, DIR, THREADS, T>(re, im, tw, first, first_in_place);
+    fft_first_pass<N, DIR, THREADS, T>(pl, tw, first, first_in_place);
     __syncthreads();
-    fft_remaining<N, DIR, THREADS, T, CHAIN>(re, im, tw, last, last_in_place);
+    fft_remaining<N, DIR, THREADS, T, CHAIN>(pl, tw, last, last_in_place);
 }
 
 // number of stored twiddles (pass 0 stores none)

@@ -364,11 +364,11 @@ def test_config3_shape_96k(torch_cuda):
     rr = torch.from_numpy(r).cuda().repeat(10, 1)
     full = stages.main(tt, rr, cfg, True, False, False)[0]
     assert full.shape == (n1 * 10, 2) and bool(torch.isfinite(full).all())
+    # the limiter pins the peak at the threshold; the reference peaks at tanh(3) < threshold, so the
+    # result is scaled by the same final amplitude coefficient as the one-minute run
     peak = float(full.abs().max())
-    assert abs(peak - cfg.threshold) < 1e-5  # loud reference: final amplitude coefficient is 1
-    # the limited result never gains level anywhere
-    lim_gain = full.abs().amax(dim=1)
-    assert float(lim_gain.max()) <= cfg.threshold + 1e-6
+    assert abs(peak - float(np.abs(want[0]).max())) < 1e-5
+    assert peak <= cfg.threshold
 
 
 def test_config4_shape_batch_of_tracks(torch_cuda):
@@ -385,4 +385,6 @@ def test_config4_shape_batch_of_tracks(torch_cuda):
     outs = master_many(pairs, cfg, depth=3)
     for (t, r), o in zip(pairs[:3], outs[:3]):
         assert np.abs(o - stages.main(t, r, cfg)[0]).max() < 1e-6
-    assert all(np.isfinite(o).all() and abs(np.abs(o).max() - cfg.threshold) < 1e-5 for o in outs)
+    for (t, r), o in zip(pairs, outs):
+        coef = min(1.0, float(np.abs(r).max()) / cfg.threshold)  # normalize_reference's coefficient
+        assert np.isfinite(o).all() and abs(float(np.abs(o).max()) - cfg.threshold * coef) < 1e-5
