@@ -40,6 +40,7 @@ def parse_args():
     ap.add_argument("--seconds", type=float, default=180.0, help="track length (config 2: 180)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--reference-sample-seconds", type=float, default=30.0)
+    ap.add_argument("--lanes", type=int, default=2, help="tracks in flight per GPU for the device-resident number")
     ap.add_argument("--opt", action="append", default=[], help="library switch name=value (A/B measurements)")
     return ap.parse_args()
 
@@ -222,7 +223,7 @@ def run_b200(args) -> dict:
         dev_r.append(r.to(device))
     # two tracks in flight on two streams: one track's small latency-bound kernels (FIR design: two
     # CTAs) overlap the other's streaming kernels
-    n_lanes = 2
+    n_lanes = max(1, args.lanes)
     sessions = [TrackSession(plan, n, n) for _ in range(n_lanes)]
     lane_streams = [torch.cuda.Stream(device=device) for _ in range(n_lanes)]
     lane_out = [torch.empty((n, 2), dtype=torch.float32, device=device) for _ in range(n_lanes)]

@@ -62,11 +62,14 @@ clip_sumsq_kernel(const float* __restrict__ mid, long long piece, int divisions,
         if ((long long)threadIdx.x < hi - body_hi) acc += clip_sq(mid[body_hi + threadIdx.x], gain_f);  // tail (< 4)
         const float4* body = reinterpret_cast<const float4*>(mid + body_lo);
         const long long nvec = (body_hi - body_lo) >> 2;
-        for (long long i = threadIdx.x; i < nvec; i += 2 * blockDim.x) {
-            const float4 a = body[i];
-            const long long i2 = i + blockDim.x;
-            const float4 b = i2 < nvec ? body[i2] : make_float4(0.f, 0.f, 0.f, 0.f);
-            acc += clip_sq4(a, gain_f) + clip_sq4(b, gain_f);
+        for (long long i = threadIdx.x; i < nvec; i += 4 * blockDim.x) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long iu = i + (long long)u * blockDim.x;
+                v[u] = iu < nvec ? body[iu] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            acc += (clip_sq4(v[0], gain_f) + clip_sq4(v[1], gain_f)) + (clip_sq4(v[2], gain_f) + clip_sq4(v[3], gain_f));
         }
     }
     const double total = block_sum(acc, red);

@@ -402,28 +402,52 @@ transpose_kernel(const double* __restrict__ in, double* __restrict__ out, int n)
         if (bx + r < n && by + tx < n) out[(long long)(bx + r) * n + by + tx] = tile[tx][r];
 }
 
-// s[ch] = S m[ch] for both channels; one warp per row, grid = ceil(n_lin / 8).
-__global__ void __launch_bounds__(256)
+// s[ch] = S m[ch] for both channels; one warp per row, four rows per CTA.  Each lane streams its
+// share of the row with 16-byte loads, four of them in flight, so the 33.6 MB matrix moves at HBM
+// speed instead of at one-load-latency per iteration.
+__global__ void __launch_bounds__(128)
 smooth_operator_kernel(const double* __restrict__ S, double* __restrict__ scratch, long long stride, int n_lin) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int r = blockIdx.x * 8 + warp;
+    const int r = blockIdx.x * 4 + warp;
     if (r >= n_lin) return;
     const double* row = S + (long long)r * n_lin;
     const double* m0 = scratch;               // channel 0, parity-0 block
     const double* m1 = scratch + 2 * stride;  // channel 1, parity-0 block
     double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-    int c = lane;
-    for (; c + 32 < n_lin; c += 64) {
-        const double w0 = row[c], w1 = row[c + 32];
-        a0 += w0 * m0[c];
-        a1 += w1 * m0[c + 32];
-        b0 += w0 * m1[c];
-        b1 += w1 * m1[c + 32];
+    // rows start at r*n_lin doubles: 16-byte aligned only for even r*n_lin, so peel to alignment
+    int c0 = ((reinterpret_cast<uintptr_t>(row) & 15) != 0) ? 1 : 0;
+    if (c0 && lane == 0) {
+        a0 += row[0] * m0[0];
+        b0 += row[0] * m1[0];
     }
-    if (c < n_lin) {
-        const double w0 = row[c];
-        a0 += w0 * m0[c];
-        b0 += w0 * m1[c];
+    const int pairs = (n_lin - c0) >> 1;
+    const double2* row2 = reinterpret_cast<const double2*>(row + c0);
+    int p = lane;
+    for (; p + 96 < pairs; p += 128) {
+        double2 w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) w[u] = row2[p + 32 * u];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int c = c0 + 2 * (p + 32 * u);
+            a0 += w[u].x * m0[c];
+            a1 += w[u].y * m0[c + 1];
+            b0 += w[u].x * m1[c];
+            b1 += w[u].y * m1[c + 1];
+        }
+    }
+    for (; p < pairs; p += 32) {
+        const double2 w = row2[p];
+        const int c = c0 + 2 * p;
+        a0 += w.x * m0[c];
+        a1 += w.y * m0[c + 1];
+        b0 += w.x * m1[c];
+        b1 += w.y * m1[c + 1];
+    }
+    const int tail = c0 + 2 * pairs;  // at most one element left
+    if (tail < n_lin && lane == 0) {
+        a0 += row[tail] * m0[tail];
+        b0 += row[tail] * m1[tail];
     }
     const double sa = warp_sum(a0 + a1), sb = warp_sum(b0 + b1);
     if (lane == 0) {
@@ -531,7 +555,7 @@ int launch_design(const mgb_plan& plan, const mgb_track_layout& layout, const Wo
                            a.scratch, a.stride, plan.n_lin, plan.min_value));
             a.avg_override = nullptr;
         }
-        MGB_TRY(launch("smooth_operator_kernel", smooth_operator_kernel, dim3((plan.n_lin + 7) / 8), dim3(256), 0, stream,
+        MGB_TRY(launch("smooth_operator_kernel", smooth_operator_kernel, dim3((plan.n_lin + 3) / 4), dim3(128), 0, stream,
                        plan.d_smooth_op, a.scratch, a.stride, plan.n_lin));
         a.s_ready = 1;
     }
