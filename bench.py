@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument("--seconds", type=float, default=180.0, help="track length (config 2: 180)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--reference-sample-seconds", type=float, default=30.0)
-    ap.add_argument("--lanes", type=int, default=2, help="tracks in flight per GPU for the device-resident number")
+    ap.add_argument("--lanes", type=int, default=3, help="tracks in flight per GPU for the device-resident number")
     ap.add_argument("--opt", action="append", default=[], help="library switch name=value (A/B measurements)")
     return ap.parse_args()
 
