@@ -61,10 +61,18 @@ inline int launch(const char* what, void (*kernel)(KA...), dim3 grid, dim3 block
     if (grid.x == 0 || grid.y == 0 || grid.z == 0) return MGB_OK;
     g_launch_count++;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) {
-            set_error("%s: cudaFuncSetAttribute(%zu B smem): %s", what, smem, cudaGetErrorString(e));
-            return MGB_ERR_CUDA;
+        // opt in to large dynamic shared memory once per kernel and size (a driver call per launch
+        // would sit on the critical path of an 11-launch, sub-millisecond pipeline)
+        static thread_local const void* done_kernel = nullptr;
+        static thread_local size_t done_smem = 0;
+        if (done_kernel != (const void*)kernel || done_smem < smem) {
+            cudaError_t e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) {
+                set_error("%s: cudaFuncSetAttribute(%zu B smem): %s", what, smem, cudaGetErrorString(e));
+                return MGB_ERR_CUDA;
+            }
+            done_kernel = (const void*)kernel;
+            done_smem = smem;
         }
     }
     if (g_profile) profile_mark(what, stream, true);
