@@ -248,6 +248,14 @@ int mgb_convert_f32_to_f64(const float* d_in, double* d_out, int64_t count, void
 int mgb_pcm_decode(const void* d_pcm, int32_t bits, float* d_out, int64_t count, void* stream);
 int mgb_pcm_encode(const float* d_in, int32_t bits, void* d_pcm, int64_t count, void* stream);
 
+/* Checker reductions on the device (matchering/checker.py:64-88,140-142; dsp.count_max_peaks
+ * dsp.py:49-54).  mgb_check_peaks: d_scratch16 (16 bytes, device) receives {float peak; pad;
+ * uint64 count of samples with isclose(|x|, peak)} for `frames` stereo frames.
+ * mgb_check_equality: d_scratch8 receives the uint64 number of samples where the two signals are
+ * not allclose (0 => the reference would raise ERROR_TARGET_EQUALS_REFERENCE). */
+int mgb_check_peaks(const float* d_lr, int64_t frames, void* d_scratch16, void* stream);
+int mgb_check_equality(const float* d_a_lr, const float* d_b_lr, int64_t frames, void* d_scratch8, void* stream);
+
 /* ---- building blocks exported for the parity tests (tests/ only) ------------------------------ */
 /* forward or inverse (dir = +1 / -1) complex FFT of `batch` frames of n points through the same
  * shared-memory kernel the pipeline uses; is_f64 selects the double variant (n in {F, 2F}). */

@@ -27,12 +27,10 @@ def process(target: str, reference: str, results: list, config: Config = None,
         raise NotImplementedError("previews are outside this build's scope (SURVEY.md section 8f)")
     temp_folder = config.temp_folder if config.temp_folder else get_temp_folder(results)
 
-    target_audio, target_rate = load(target, "target", temp_folder)
-    target_audio, target_rate = check(target_audio, target_rate, config, "target")
-    reference_audio, reference_rate = load(reference, "reference", temp_folder)
-    reference_audio, reference_rate = check(reference_audio, reference_rate, config, "reference")
+    target_audio, target_rate = _load_and_check(target, "target", temp_folder, config)
+    reference_audio, reference_rate = _load_and_check(reference, "reference", temp_folder, config)
     if not config.allow_equality:
-        check_equality(target_audio, reference_audio)
+        _check_equality_any(target_audio, reference_audio)
     if (not (target_rate == reference_rate == config.internal_sample_rate)
             or not (target_audio.shape[1] == reference_audio.shape[1] == 2)
             or not (target_audio.shape[0] > config.fft_size and reference_audio.shape[0] > config.fft_size)):
@@ -68,3 +66,24 @@ def _export(wanted: Result, audio, sample_rate: int) -> None:
         debug(f"'{wanted.file}' is saved")
     else:
         save(wanted.file, audio.cpu().numpy().astype("float64"), sample_rate, wanted.subtype)
+
+
+def _load_and_check(file: str, name: str, temp_folder: str, config: Config):
+    """16/24-bit PCM WAV at the internal rate is decoded and checked on the device; everything else
+    goes through the host loader and checker like in the reference."""
+    from .device_io import check_on_device, load_to_device
+    on_device = load_to_device(file, name, config)
+    if on_device is not None:
+        return check_on_device(on_device, config, name), config.internal_sample_rate
+    audio, rate = load(file, name, temp_folder)
+    return check(audio, rate, config, name)
+
+
+def _check_equality_any(target_audio, reference_audio) -> None:
+    import torch
+    if isinstance(target_audio, torch.Tensor) and isinstance(reference_audio, torch.Tensor):
+        from .device_io import check_equality_on_device
+        check_equality_on_device(target_audio, reference_audio)
+    else:
+        as_np = lambda a: a.cpu().numpy() if isinstance(a, torch.Tensor) else a
+        check_equality(as_np(target_audio), as_np(reference_audio))

@@ -557,6 +557,28 @@ int mgb_pcm_encode(const float* d_in, int32_t bits, void* d_pcm, int64_t count, 
     return launch_pcm_encode(d_in, bits, d_pcm, count, (cudaStream_t)stream);
 }
 
+int mgb_check_peaks(const float* d_lr, int64_t frames, void* d_scratch16, void* stream) {
+    MGB_REQUIRE(d_lr && d_scratch16 && frames > 0, MGB_ERR_INVALID, "check_peaks: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+#ifdef MGB_EMULATE
+    memset(d_scratch16, 0, 16);
+#else
+    if (cudaMemsetAsync(d_scratch16, 0, 16, st) != cudaSuccess) return cuda_status("memset");
+#endif
+    return launch_peak_count(d_lr, frames * 2, (float*)d_scratch16, (unsigned long long*)((char*)d_scratch16 + 8), st);
+}
+
+int mgb_check_equality(const float* d_a_lr, const float* d_b_lr, int64_t frames, void* d_scratch8, void* stream) {
+    MGB_REQUIRE(d_a_lr && d_b_lr && d_scratch8 && frames > 0, MGB_ERR_INVALID, "check_equality: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+#ifdef MGB_EMULATE
+    memset(d_scratch8, 0, 8);
+#else
+    if (cudaMemsetAsync(d_scratch8, 0, 8, st) != cudaSuccess) return cuda_status("memset");
+#endif
+    return launch_count_different(d_a_lr, d_b_lr, frames * 2, (unsigned long long*)d_scratch8, st);
+}
+
 int mgb_test_fft(int32_t n, int32_t is_f64, int32_t dir, const void* d_in, void* d_out, int32_t batch,
                  const void* d_twiddles, void* stream) {
     MGB_REQUIRE(d_in && d_out && d_twiddles && batch > 0, MGB_ERR_INVALID, "test_fft: bad arguments");

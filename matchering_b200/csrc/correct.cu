@@ -201,6 +201,37 @@ pcm24_encode_kernel(const float* __restrict__ in, unsigned char* __restrict__ ou
     }
 }
 
+// ---- checker reductions (matchering/checker.py:64-88, dsp.count_max_peaks dsp.py:49-54) ------------
+// number of samples with |x| "close" to `peak` in numpy.isclose's sense (rtol 1e-5, atol 1e-8)
+__global__ void __launch_bounds__(256)
+count_close_kernel(const float* __restrict__ x, long long count, const float* __restrict__ peak_bits,
+                   unsigned long long* __restrict__ out) {
+    const double peak = (double)*peak_bits;
+    const double tol = 1e-8 + 1e-5 * peak;
+    unsigned long long local = 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+        local += (fabs(fabs((double)x[i]) - peak) <= tol) ? 1ull : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, local);
+}
+
+// number of samples where two equally long signals differ beyond numpy.allclose's tolerance
+__global__ void __launch_bounds__(256)
+count_different_kernel(const float* __restrict__ a, const float* __restrict__ b, long long count,
+                       unsigned long long* __restrict__ out) {
+    unsigned long long local = 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        const double x = a[i], y = b[i];
+        local += (fabs(x - y) <= 1e-8 + 1e-5 * fabs(y)) ? 0ull : 1ull;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, local);
+}
+
 unsigned grid_for(long long items, int per_block) {
     long long blocks = (items + per_block - 1) / per_block;
     const long long cap = (long long)num_sms() * 8;
@@ -274,6 +305,19 @@ int launch_pcm_encode(const float* in, int bits, void* out, int64_t count, cudaS
                       (unsigned char*)out, (long long)count);
     set_error("pcm encode: %d-bit samples have no kernel (16 and 24 do)", bits);
     return MGB_ERR_UNSUPPORTED;
+}
+
+int launch_peak_count(const float* x, int64_t count, float* peak_bits, unsigned long long* n_close, cudaStream_t stream) {
+    // peak_bits and n_close must be zeroed by the caller
+    MGB_TRY(launch("absmax_kernel", absmax_kernel, dim3(grid_for(count / 2, 1024)), dim3(256), 0, stream, (const float2*)x,
+                   (long long)(count / 2), peak_bits));
+    return launch("count_close_kernel", count_close_kernel, dim3(grid_for(count, 1024)), dim3(256), 0, stream, x,
+                  (long long)count, (const float*)peak_bits, n_close);
+}
+
+int launch_count_different(const float* a, const float* b, int64_t count, unsigned long long* n_diff, cudaStream_t stream) {
+    return launch("count_different_kernel", count_different_kernel, dim3(grid_for(count, 1024)), dim3(256), 0, stream, a, b,
+                  (long long)count, n_diff);
 }
 
 }  // namespace mgb

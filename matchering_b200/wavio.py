@@ -96,3 +96,32 @@ def write_pcm(path: str, pcm: np.ndarray, sample_rate: int, bits: int, channels:
         body += b"\x00"
     with open(path, "wb") as f:
         f.write(b"RIFF" + struct.pack("<I", len(body)) + body)
+
+
+def read_pcm(path: str):
+    """Raw 16- or 24-bit PCM of a WAV file without converting it on the host:
+    -> (samples, sample_rate, channels, bits) with samples int16 (frames, ch) or packed 24-bit uint8
+    (frames, 3*ch); None when the file is not 16/24-bit PCM WAV."""
+    with open(path, "rb") as f:
+        data = f.read()
+    if len(data) < 12 or data[:4] != b"RIFF" or data[8:12] != b"WAVE":
+        return None
+    pos, fmt, payload = 12, None, None
+    while pos + 8 <= len(data):
+        cid, size = data[pos:pos + 4], struct.unpack("<I", data[pos + 4:pos + 8])[0]
+        if cid == b"fmt ":
+            fmt = data[pos + 8:pos + 8 + size]
+        elif cid == b"data":
+            payload = memoryview(data)[pos + 8:pos + 8 + size]
+        pos += 8 + size + (size & 1)
+    if fmt is None or payload is None or len(fmt) < 16:
+        return None
+    tag, channels, rate, _, _, bits = struct.unpack("<HHIIHH", fmt[:16])
+    if tag == _EXTENSIBLE and len(fmt) >= 26:
+        tag = struct.unpack("<H", fmt[24:26])[0]
+    if tag != _PCM or bits not in (16, 24) or channels < 1:
+        return None
+    block = channels * bits // 8
+    frames = len(payload) // block
+    raw = np.frombuffer(payload[: frames * block], dtype=np.int16 if bits == 16 else np.uint8)
+    return raw.reshape(frames, channels if bits == 16 else 3 * channels), int(rate), int(channels), int(bits)

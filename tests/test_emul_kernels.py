@@ -311,3 +311,23 @@ def test_limiter_lookback_through_aggregates_only(lib, golden):
     finally:
         lib.mgb_set_option(b"lookback_inclusive", 1)
     assert np.abs(out - want).max() < 3e-7
+
+
+def test_checker_reductions(lib):
+    rng = np.random.default_rng(6)
+    x = (0.5 * rng.standard_normal((20001, 2))).astype(np.float32)
+    x[100, 0] = x[2000, 1] = -(np.abs(x).max() + 0.25)  # two samples at the (negative) peak
+    xin = aligned_copy(x)
+    scratch = aligned((16,), np.uint8)
+    _native.check(lib, lib.mgb_check_peaks(ptr(xin), len(x), ptr(scratch), None))
+    peak, hits = float(scratch[:4].view(np.float32)[0]), int(scratch[8:].view(np.uint64)[0])
+    want_peak = np.abs(x).max()
+    want_hits = np.count_nonzero(np.logical_or(np.isclose(x, want_peak), np.isclose(x, -want_peak)))  # dsp.py:49-54
+    assert peak == want_peak and hits == want_hits == 2
+    y = aligned_copy(x)
+    diff = aligned((8,), np.uint8)
+    _native.check(lib, lib.mgb_check_equality(ptr(xin), ptr(y), len(x), ptr(diff), None))
+    assert int(diff.view(np.uint64)[0]) == 0
+    y[5, 1] += 0.01
+    _native.check(lib, lib.mgb_check_equality(ptr(xin), ptr(y), len(x), ptr(diff), None))
+    assert int(diff.view(np.uint64)[0]) == 1

@@ -388,3 +388,34 @@ def test_config4_shape_batch_of_tracks(torch_cuda):
     for (t, r), o in zip(pairs, outs):
         coef = min(1.0, float(np.abs(r).max()) / cfg.threshold)  # normalize_reference's coefficient
         assert np.isfinite(o).all() and abs(float(np.abs(o).max()) - cfg.threshold * coef) < 1e-5
+
+
+def test_process_pcm_files_stay_on_the_device(torch_cuda, tmp_path):
+    """mg.process on 16-bit (mono target!) and 24-bit PCM WAV: decode, checks, mastering and
+    quantisation all on the device; result against the oracle fed the same decoded samples."""
+    import matchering_b200 as mg
+    import port
+    from matchering_b200 import wavio
+    from matchering_b200.log import ModuleError
+    n = 44100 * 6
+    t = port.synth_target(n, 3)[:, :1]                       # mono
+    r = port.synth_reference(n + 500, 4)
+    wavio.write(str(tmp_path / "t16.wav"), t, 44100, "PCM_16")
+    wavio.write(str(tmp_path / "r24.wav"), r, 44100, "PCM_24")
+    seen = []
+    mg.log(info_handler=seen.append, warning_handler=seen.append)
+    try:
+        mg.process(str(tmp_path / "t16.wav"), str(tmp_path / "r24.wav"), [mg.pcm24(str(tmp_path / "o24.wav"))],
+                   config=mg.Config(max_piece_size=2.0))
+    finally:
+        mg.log()
+    assert "The TARGET audio is mono. Converting it to stereo..." in seen
+    t_dec, _ = wavio.read(str(tmp_path / "t16.wav"))
+    r_dec, _ = wavio.read(str(tmp_path / "r24.wav"))
+    want = port.main(np.repeat(t_dec, 2, axis=1), r_dec, port.OracleConfig(max_piece_size=2.0))[0]
+    got, sr = wavio.read(str(tmp_path / "o24.wav"))
+    assert sr == 44100 and np.abs(got - want).max() < TOL + 2.0 / 8388607
+    # the same file twice is refused like in the reference (checker.py:140-142)
+    wavio.write(str(tmp_path / "s.wav"), r, 44100, "PCM_16")
+    with pytest.raises(ModuleError):
+        mg.process(str(tmp_path / "s.wav"), str(tmp_path / "s.wav"), [mg.pcm16(str(tmp_path / "x.wav"))])
