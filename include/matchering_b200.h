@@ -115,7 +115,9 @@ typedef struct mgb_track_state {
     int32_t reference_loud_pieces;
     int32_t limiter_engaged;      /* 0 when hyrax.py:83-85 takes its early-out                     */
     int32_t steps_done;
-    int32_t reserved[3];
+    float fir_peak_mid_bits;      /* max |H_mid[k]| of the designed FIR spectrum (as applied)         */
+    float fir_peak_side_bits;     /* max |H_side[k]|                                                  */
+    int32_t reserved;
 } mgb_track_state;
 
 /* Geometry of one mastering job, computed by mgb_track_layout from sizes + plan (host side). */

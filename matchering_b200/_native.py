@@ -75,7 +75,9 @@ class TrackState(C.Structure):
         ("reference_loud_pieces", C.c_int32),
         ("limiter_engaged", C.c_int32),
         ("steps_done", C.c_int32),
-        ("reserved", C.c_int32 * 3),
+        ("fir_peak_mid_bits", C.c_float),
+        ("fir_peak_side_bits", C.c_float),
+        ("reserved", C.c_int32),
     ]
 
 

@@ -26,22 +26,27 @@ template <int F>
 struct AnalyzeSmem {
     static constexpr int kRawBytes = ((F + 2) * 8 + 15) / 16 * 16;
     static constexpr int kPlaneBytes = (int)((PackedPlanes::bytes(F) + 15) / 16 * 16);
-    static constexpr int kBytes = kRawBytes + kPlaneBytes + 16 /*barrier*/ + 32 * 8 + 32 * 4 + 32;
+    static constexpr int kBytes = kRawBytes + kPlaneBytes + 16 /*barrier*/ + 32 * 8 + 96 * 4 + 32;
 };
 
 struct AnalyzeFirst {
     const float2* raw;    // frame start inside the landing buffer
     const float2* fixup;  // global address of the one sample the bulk copy could not cover (or null)
     int fix_index;
+    float side_scale;  // power of two: z = mid + i * side_scale * side (see balance_factor)
     double* sumsq;
     float* peak;
-    __device__ __forceinline__ cpx<float> operator()(int i) const {
+    __device__ __forceinline__ float2 sample(int i) const {
         float2 v = raw[i];
         if (i == fix_index) v = *fixup;
+        return v;
+    }
+    __device__ __forceinline__ cpx<float> operator()(int i) const {
+        const float2 v = sample(i);
         const double mid = ((double)v.x + (double)v.y) * 0.5;
         *sumsq += mid * mid;
         *peak = fmaxf(*peak, fmaxf(fabsf(v.x), fabsf(v.y)));
-        return cpx<float>{(float)mid, (float)(mid - (double)v.y)};
+        return cpx<float>{(float)mid, (float)(mid - (double)v.y) * side_scale};
     }
 };
 
@@ -62,6 +67,7 @@ analyze_kernel(const float2* __restrict__ x, long long frames, long long piece, 
     TmaBarrier* bar = reinterpret_cast<TmaBarrier*>(tail);
     double* red_d = reinterpret_cast<double*>(tail + 16);
     float* red_f = reinterpret_cast<float*>(tail + 16 + 32 * 8);
+    float* red_f2 = red_f + 32;  // [64] scratch of block_max2
 
     const int tid = threadIdx.x;
     const int slot = blockIdx.x;
@@ -113,6 +119,19 @@ analyze_kernel(const float2* __restrict__ x, long long frames, long long piece, 
         first.raw = raw + off;
         first.sumsq = &sumsq;
         first.peak = &peak;
+        // balance the frame's two channels before they share a transform (see balance_factor)
+        float max_mid = 0.0f, max_side = 0.0f;
+#pragma unroll
+        for (int k = 0; k < F / THREADS; ++k) {
+            const float2 v = first.sample(tid + k * THREADS);
+            max_mid = fmaxf(max_mid, fabsf(v.x + v.y));
+            max_side = fmaxf(max_side, fabsf(v.x - v.y));
+        }
+        block_max2(max_mid, max_side, red_f2);
+        const float g_side = balance_factor(max_mid, max_side);
+        const float inv_g = 0.5f / g_side;  // exact (power of two); folds the 1/2 of the spectrum split
+        const bool side_silent = max_side == 0.0f;
+        first.side_scale = g_side;
         fft_first_pass<F, +1, THREADS, float>(planes, tw, first, /*in_place=*/false);
         __syncthreads();  // planes written, landing buffer consumed by every thread
         if (use_tma && tid == 0 && f + 1 < f_hi) {
@@ -132,7 +151,7 @@ analyze_kernel(const float2* __restrict__ x, long long frames, long long piece, 
                 const float mr = zr + nr, mi = zi - ni;
                 const float sr = zi + ni, si = nr - zr;
                 acc_mid[b] += 0.5f * sqrtf(mr * mr + mi * mi);
-                acc_side[b] += 0.5f * sqrtf(sr * sr + si * si);
+                if (!side_silent) acc_side[b] += inv_g * sqrtf(sr * sr + si * si);
             }
         }
         __syncthreads();  // planes free for the next frame

@@ -142,6 +142,35 @@ __device__ __forceinline__ float block_max(float v, float* scratch) {
     return scratch[0];
 }
 
+// Block-wide maxima of two non-negative floats at once; both results valid in every thread.
+// `scratch` holds >= 64 floats.  All threads must call.
+__device__ __forceinline__ void block_max2(float& a, float& b, float* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    a = warp_max(a);
+    b = warp_max(b);
+    __syncthreads();
+    if (lane == 0) {
+        scratch[warp] = a;
+        scratch[32 + warp] = b;
+    }
+    __syncthreads();
+    float ta = (lane < nwarps) ? scratch[lane] : 0.0f;
+    float tb = (lane < nwarps) ? scratch[32 + lane] : 0.0f;
+    a = warp_max(ta);
+    b = warp_max(tb);
+}
+
+// Power-of-two factor that brings `small` up to the scale of `large` (exact in floating point).
+// mid and side ride one complex FFT as z = mid + i*g*side: the transform's rounding noise is
+// relative to the LARGER part, so without the factor a quiet channel would inherit the loud one's
+// noise (and a matching FIR with a huge gain on the quiet channel would amplify it).
+__device__ __forceinline__ float balance_factor(float large, float small) {
+    if (!(small > 0.0f) || !(large > 0.0f)) return 1.0f;
+    int e = (int)floorf(log2f(large / small));
+    e = e < -60 ? -60 : (e > 60 ? 60 : e);
+    return exp2f((float)e);
+}
+
 // Non-negative floats order like their bit patterns: atomic max through the integer unit.
 __device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
     atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));

@@ -28,7 +28,7 @@ template <int F>
 struct ConvSmem {
     static constexpr int N = 2 * F;
     static constexpr int kPlaneBytes = (int)((PackedPlanes::bytes(N) + 15) / 16 * 16);
-    static constexpr int kBytes = kPlaneBytes + 16 + 32 * 8 + 32 * 8 + 32 * 4 + 32;
+    static constexpr int kBytes = kPlaneBytes + 16 + 32 * 8 + 32 * 8 + 64 * 4 + 32;
 };
 
 struct ConvFirst {
@@ -36,14 +36,20 @@ struct ConvFirst {
     int lo, hi;         // indices of the buffer that lie inside the signal: [lo, hi)
     const float2* fixup;
     int fix_index;
-    __device__ __forceinline__ cpx<float> operator()(int i) const {
+    float side_scale;   // power of two: z = mid + i * side_scale * side (see balance_factor)
+    __device__ __forceinline__ float2 sample(int i) const {
         float2 v = make_float2(0.0f, 0.0f);
         if (i >= lo && i < hi) {
             v = raw[i];
             if (i == fix_index) v = *fixup;
         }
-        const float mid = (v.x + v.y) * 0.5f;  // exact sum rounded once, as (float)(((double)L+R)/2)
-        return cpx<float>{mid, mid - v.y};
+        return v;
+    }
+    __device__ __forceinline__ cpx<float> operator()(int i) const {
+        const float2 v = sample(i);
+        // each channel from L and R directly, one rounding each: (L-R)/2 is the reference's mid - R, and
+        // forming it from the already rounded mid would put mid's rounding error into a quiet side
+        return cpx<float>{(v.x + v.y) * 0.5f, (v.x - v.y) * 0.5f * side_scale};
     }
 };
 
@@ -97,7 +103,21 @@ convolve_kernel(const float2* __restrict__ x, long long frames, long long piece,
         __syncthreads();
     }
 
-    // ---- forward transform of z = mid + i*side ---------------------------------------------------
+    // ---- balance the two channels of this frame (see balance_factor) -----------------------------------
+    float max_mid = 0.0f, max_side = 0.0f;
+#pragma unroll
+    for (int k = 0; k < N / THREADS; ++k) {
+        const float2 v = first.sample(tid + k * THREADS);
+        max_mid = fmaxf(max_mid, fabsf(v.x + v.y));
+        max_side = fmaxf(max_side, fabsf(v.x - v.y));
+    }
+    block_max2(max_mid, max_side, red_f);
+    const float g_side = balance_factor(max_mid, max_side);  // >= 1 when the side is the quiet one, < 1 otherwise
+    const float inv_g = 1.0f / g_side;                         // exact: a power of two
+    const bool mid_silent = max_mid == 0.0f, side_silent = max_side == 0.0f;
+    first.side_scale = g_side;
+
+    // ---- forward transform of z = mid + i*g*side ---------------------------------------------------
     fft_first_pass<N, +1, THREADS, float>(planes, tw, first, /*in_place=*/true);
     __syncthreads();
     fft_remaining<N, +1, THREADS, float, CHAIN>(planes, tw, PlaneStore<PackedPlanes>{planes}, true);
@@ -108,12 +128,13 @@ convolve_kernel(const float2* __restrict__ x, long long frames, long long piece,
         const int kn = (N - k) & (N - 1);
         const cpx<float> zk = planes.load(k), zn = planes.load(kn);
         const float zr = zk.x, zi = zk.y, nr = zn.x, ni = zn.y;
-        // M = (Z[k] + conj Z[N-k])/2 ; S = (Z[k] - conj Z[N-k])/(2i)
+        // M = (Z[k] + conj Z[N-k])/2 ; g S = (Z[k] - conj Z[N-k])/(2i)
         const float mr = 0.5f * (zr + nr), mi = 0.5f * (zi - ni);
-        const float sr = 0.5f * (zi + ni), si = 0.5f * (nr - zr);
+        const float sr = 0.5f * (zi + ni) * inv_g, si = 0.5f * (nr - zr) * inv_g;
         const float2 hm = h_mid[k], hs = h_side[k];
-        const float pmr = hm.x * mr - hm.y * mi, pmi = hm.x * mi + hm.y * mr;
-        const float psr = hs.x * sr - hs.y * si, psi = hs.x * si + hs.y * sr;
+        // a channel that is exactly silent in this frame stays exactly silent, as in the reference
+        const float pmr = mid_silent ? 0.0f : hm.x * mr - hm.y * mi, pmi = mid_silent ? 0.0f : hm.x * mi + hm.y * mr;
+        const float psr = side_silent ? 0.0f : hs.x * sr - hs.y * si, psi = side_silent ? 0.0f : hs.x * si + hs.y * sr;
         // Y[k] = Pm + i Ps ; Y[N-k] = conj(Pm) + i conj(Ps)
         planes.store(k, cpx<float>{pmr - psi, pmi + psr});
         if (kn != k) planes.store(kn, cpx<float>{pmr + psi, psr - pmi});
@@ -143,7 +164,8 @@ convolve_kernel(const float2* __restrict__ x, long long frames, long long piece,
         const int o = tid + k * THREADS;
         if (o < valid) {
             const cpx<float> y = planes.load(F - 1 + o);
-            const float m = y.x, sd = y.y;
+            // (the inverse transform leaves rounding dust in a channel whose spectrum was exactly zero)
+            const float m = mid_silent ? 0.0f : y.x, sd = side_silent ? 0.0f : y.y;
             const float l = m + sd, r = m - sd;
             res[o] = make_float2(l, r);
             midp[o] = m;

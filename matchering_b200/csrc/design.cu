@@ -240,6 +240,9 @@ spectrum_mean_kernel(DesignArgs a, int n_lin, int fft_size, double eps, Prefetch
         if (threadIdx.x == 0) {
             levels_store(lv, a.state);
             a.state->conv_peak_bits = 0.0f;
+            a.state->fir_peak_mid_bits = 0.0f;
+            a.state->fir_peak_side_bits = 0.0f;
+            a.state->reserved = 0;
         }
         for (int p = threadIdx.x; p < a.div_t; p += blockDim.x) a.mask_t[p] = mask_t[p];
         for (int p = threadIdx.x; p < a.div_r; p += blockDim.x) a.mask_r[p] = mask_r[p];
@@ -343,13 +346,16 @@ design_kernel(mgb_plan plan, DesignArgs a) {
     {
         float2* H = ch == 0 ? a.h_mid : a.h_side;
         const double scale = c0 / (2.0 * (double)F);
+        float hpeak = 0.0f;  // max |H| of this CTA's bins: the convolution compares the two channels' peaks
         if (parity == 0) {
             auto first_even = [&](int i) { return cpx<double>{fir[i], 0.0}; };
             fft_run<F, +1, kDesignThreads, double>(planes, tw, first_even, PlaneStore<SplitPlanes<double>>{planes}, false, true);
             __syncthreads();
             for (int j = tid; j <= F / 2; j += nthr) {
                 const int jj = j & (F - 1);
-                H[2 * j] = make_float2((float)(re[fft_pad(jj)] * scale), (float)(im[fft_pad(jj)] * scale));
+                const float2 h = make_float2((float)(re[fft_pad(jj)] * scale), (float)(im[fft_pad(jj)] * scale));
+                H[2 * j] = h;
+                hpeak = fmaxf(hpeak, sqrtf(h.x * h.x + h.y * h.y));
             }
         } else {
             auto first_odd = [&](int i) {
@@ -359,9 +365,15 @@ design_kernel(mgb_plan plan, DesignArgs a) {
             };
             fft_run<F, +1, kDesignThreads, double>(planes, tw, first_odd, PlaneStore<SplitPlanes<double>>{planes}, false, true);
             __syncthreads();
-            for (int j = tid; j < F / 2; j += nthr)
-                H[2 * j + 1] = make_float2((float)(re[fft_pad(j)] * scale), (float)(im[fft_pad(j)] * scale));
+            for (int j = tid; j < F / 2; j += nthr) {
+                const float2 h = make_float2((float)(re[fft_pad(j)] * scale), (float)(im[fft_pad(j)] * scale));
+                H[2 * j + 1] = h;
+                hpeak = fmaxf(hpeak, sqrtf(h.x * h.x + h.y * h.y));
+            }
         }
+        __shared__ float red_peak[32];
+        hpeak = block_max(hpeak, red_peak);
+        if (tid == 0 && a.state) atomic_max_nonneg(ch == 0 ? &a.state->fir_peak_mid_bits : &a.state->fir_peak_side_bits, hpeak);
     }
 }
 

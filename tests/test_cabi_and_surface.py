@@ -32,7 +32,7 @@ def test_cuda_library_loads_and_exports_every_symbol():
     # struct layouts the binding assumes (sizes of the C structs, computed from the header's fields)
     assert C.sizeof(_native.LimiterParams) == 8 + 4 * 4 + 7 * 8
     assert C.sizeof(_native.TrackLayout) == 4 * 8 + 4 * 4 + 8
-    assert C.sizeof(_native.TrackState) == 6 * 8 + 16 * 8 + 2 * 8 + 4 + 4 * 4 + 3 * 4
+    assert C.sizeof(_native.TrackState) == 6 * 8 + 16 * 8 + 2 * 8 + 4 + 4 * 4 + 3 * 4  # the last three: fir peaks + reserved
 
 
 def test_emulator_library_exports_every_symbol():

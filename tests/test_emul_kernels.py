@@ -331,3 +331,22 @@ def test_checker_reductions(lib):
     y[5, 1] += 0.01
     _native.check(lib, lib.mgb_check_equality(ptr(xin), ptr(y), len(x), ptr(diff), None))
     assert int(diff.view(np.uint64)[0]) == 1
+
+
+@pytest.mark.parametrize("side_level", [0.0, 1e-4])
+def test_mono_and_near_mono_targets(lib, side_level):
+    """A (nearly) mono target against a wide reference makes the side FIR ~1e4..1e6 times larger
+    than the mid FIR.  mid and side share one complex transform per frame; without the per-frame
+    power-of-two balancing the mid channel's rounding noise would swamp the side channel."""
+    cfg = port.OracleConfig(fft_size=1024, max_piece_size=0.4)
+    rng = np.random.default_rng(77)
+    mid = port.synth_target(30000, 71)[:, :1]
+    wobble = (side_level * rng.standard_normal((30000, 1))).astype(np.float32)
+    t = np.ascontiguousarray(np.concatenate([mid + wobble, mid - wobble], axis=1))
+    r = port.synth_reference(30000, 72)
+    outs, st, _, _, _ = run_pipeline(cfg, t, r)
+    assert st.fir_peak_side_bits > 30 * st.fir_peak_mid_bits
+    want = port.main(t.astype(np.float64), r.astype(np.float64), cfg, True, True, True)
+    _compare(outs, want)
+    if side_level == 0.0:
+        assert np.array_equal(outs[1][:, 0], outs[1][:, 1])  # stays exactly mono, like the reference
