@@ -33,20 +33,10 @@ struct AnalyzeFirst {
     const float2* raw;    // frame start inside the landing buffer
     const float2* fixup;  // global address of the one sample the bulk copy could not cover (or null)
     int fix_index;
-    float side_scale;  // power of two: z = mid + i * side_scale * side (see balance_factor)
-    double* sumsq;
-    float* peak;
     __device__ __forceinline__ float2 sample(int i) const {
         float2 v = raw[i];
         if (i == fix_index) v = *fixup;
         return v;
-    }
-    __device__ __forceinline__ cpx<float> operator()(int i) const {
-        const float2 v = sample(i);
-        const double mid = ((double)v.x + (double)v.y) * 0.5;
-        *sumsq += mid * mid;
-        *peak = fmaxf(*peak, fmaxf(fabsf(v.x), fabsf(v.y)));
-        return cpx<float>{(float)mid, (float)(mid - (double)v.y) * side_scale};
     }
 };
 
@@ -67,7 +57,7 @@ analyze_kernel(const float2* __restrict__ x, long long frames, long long piece, 
     TmaBarrier* bar = reinterpret_cast<TmaBarrier*>(tail);
     double* red_d = reinterpret_cast<double*>(tail + 16);
     float* red_f = reinterpret_cast<float*>(tail + 16 + 32 * 8);
-    float* red_f2 = red_f + 32;  // [64] scratch of block_max2
+    unsigned* red_u = reinterpret_cast<unsigned*>(red_f + 32);  // [4] two alternating slots of block_max2
 
     const int tid = threadIdx.x;
     const int slot = blockIdx.x;
@@ -84,6 +74,7 @@ analyze_kernel(const float2* __restrict__ x, long long frames, long long piece, 
     for (int b = 0; b < BINS; ++b) acc_mid[b] = acc_side[b] = 0.0f;
 
     if (use_tma && tid == 0) tma_barrier_init(bar);
+    if (tid == 0) red_u[0] = red_u[1] = red_u[2] = red_u[3] = 0u;
     __syncthreads();
 
     // Bulk copies need 16-byte aligned global addresses; a frame may start on an odd sample, so
@@ -117,22 +108,30 @@ analyze_kernel(const float2* __restrict__ x, long long frames, long long piece, 
             __syncthreads();
         }
         first.raw = raw + off;
-        first.sumsq = &sumsq;
-        first.peak = &peak;
-        // balance the frame's two channels before they share a transform (see balance_factor)
+        // the thread's 16 input points: mid / side, sum(mid^2) in float64, the peak, and the frame's
+        // channel balance before the two channels share a transform (see balance_factor)
+        cpx<float> z[F / THREADS];
         float max_mid = 0.0f, max_side = 0.0f;
 #pragma unroll
-        for (int k = 0; k < F / THREADS; ++k) {
-            const float2 v = first.sample(tid + k * THREADS);
-            max_mid = fmaxf(max_mid, fabsf(v.x + v.y));
-            max_side = fmaxf(max_side, fabsf(v.x - v.y));
+        for (int r = 0; r < F / THREADS; ++r) {
+            const float2 v = first.sample(tid + r * THREADS);
+            const double mid = ((double)v.x + (double)v.y) * 0.5;
+            sumsq += mid * mid;
+            peak = fmaxf(peak, fmaxf(fabsf(v.x), fabsf(v.y)));
+            z[r].x = (float)mid;
+            z[r].y = (float)(mid - (double)v.y);
+            max_mid = fmaxf(max_mid, fabsf(z[r].x));
+            max_side = fmaxf(max_side, fabsf(z[r].y));
         }
-        block_max2(max_mid, max_side, red_f2);
+        unsigned* slot = red_u + 2 * ((f - f_lo) & 1);
+        if (tid == 0) red_u[2 * ((f - f_lo + 1) & 1)] = red_u[2 * ((f - f_lo + 1) & 1) + 1] = 0u;  // next frame's slot
+        block_max2(max_mid, max_side, slot);
         const float g_side = balance_factor(max_mid, max_side);
         const float inv_g = 0.5f / g_side;  // exact (power of two); folds the 1/2 of the spectrum split
         const bool side_silent = max_side == 0.0f;
-        first.side_scale = g_side;
-        fft_first_pass<F, +1, THREADS, float>(planes, tw, first, /*in_place=*/false);
+#pragma unroll
+        for (int r = 0; r < F / THREADS; ++r) z[r].y *= g_side;
+        fft_first_pass_regs<F, +1, THREADS, float>(planes, z, /*barrier_before_store=*/false);
         __syncthreads();  // planes written, landing buffer consumed by every thread
         if (use_tma && tid == 0 && f + 1 < f_hi) {
             fence_proxy_async();

@@ -143,21 +143,31 @@ __device__ __forceinline__ float block_max(float v, float* scratch) {
 }
 
 // Block-wide maxima of two non-negative floats at once; both results valid in every thread.
-// `scratch` holds >= 64 floats.  All threads must call.
-__device__ __forceinline__ void block_max2(float& a, float& b, float* scratch) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
-    a = warp_max(a);
-    b = warp_max(b);
-    __syncthreads();
-    if (lane == 0) {
-        scratch[warp] = a;
-        scratch[32 + warp] = b;
+// Non-negative floats order like their bit patterns, so each warp reduces with one integer
+// redux.sync per value and its lane 0 folds the result into shared memory with an atomic max: one
+// barrier in all.  `slot` (2 unsigned words in shared memory) must be zero on entry; callers that
+// loop alternate between two slots and clear the idle one.  All threads must call.
+__device__ __forceinline__ unsigned warp_max_bits(unsigned v) {
+#ifdef MGB_EMULATE
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned other = __shfl_xor_sync(0xffffffffu, v, o);
+        v = other > v ? other : v;
+    }
+    return v;
+#else
+    return __reduce_max_sync(0xffffffffu, v);
+#endif
+}
+__device__ __forceinline__ void block_max2(float& a, float& b, unsigned* slot) {
+    const unsigned ua = warp_max_bits(__float_as_uint(a)), ub = warp_max_bits(__float_as_uint(b));
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(&slot[0], ua);
+        atomicMax(&slot[1], ub);
     }
     __syncthreads();
-    float ta = (lane < nwarps) ? scratch[lane] : 0.0f;
-    float tb = (lane < nwarps) ? scratch[32 + lane] : 0.0f;
-    a = warp_max(ta);
-    b = warp_max(tb);
+    a = __uint_as_float(slot[0]);
+    b = __uint_as_float(slot[1]);
 }
 
 // Power-of-two factor that brings `small` up to the scale of `large` (exact in floating point).

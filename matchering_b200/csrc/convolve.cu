@@ -36,7 +36,6 @@ struct ConvFirst {
     int lo, hi;         // indices of the buffer that lie inside the signal: [lo, hi)
     const float2* fixup;
     int fix_index;
-    float side_scale;   // power of two: z = mid + i * side_scale * side (see balance_factor)
     __device__ __forceinline__ float2 sample(int i) const {
         float2 v = make_float2(0.0f, 0.0f);
         if (i >= lo && i < hi) {
@@ -44,12 +43,6 @@ struct ConvFirst {
             if (i == fix_index) v = *fixup;
         }
         return v;
-    }
-    __device__ __forceinline__ cpx<float> operator()(int i) const {
-        const float2 v = sample(i);
-        // each channel from L and R directly, one rounding each: (L-R)/2 is the reference's mid - R, and
-        // forming it from the already rounded mid would put mid's rounding error into a quiet side
-        return cpx<float>{(v.x + v.y) * 0.5f, (v.x - v.y) * 0.5f * side_scale};
     }
 };
 
@@ -72,6 +65,7 @@ convolve_kernel(const float2* __restrict__ x, long long frames, long long piece,
     double* red_a = reinterpret_cast<double*>(tail + 16);
     double* red_b = red_a + 32;
     float* red_f = reinterpret_cast<float*>(red_b + 32);
+    unsigned* red_u = reinterpret_cast<unsigned*>(red_f + 32);  // [2] slot of block_max2
 
     const int tid = threadIdx.x;
     const long long n0 = (long long)blockIdx.x * F;
@@ -86,6 +80,7 @@ convolve_kernel(const float2* __restrict__ x, long long frames, long long piece,
     first.hi = (int)(hi - origin);
     first.fixup = nullptr;
     first.fix_index = -1;
+    if (tid == 0) red_u[0] = red_u[1] = 0u;
     if (use_tma) {
         if (tid == 0) tma_barrier_init(bar);
         __syncthreads();
@@ -103,22 +98,28 @@ convolve_kernel(const float2* __restrict__ x, long long frames, long long piece,
         __syncthreads();
     }
 
-    // ---- balance the two channels of this frame (see balance_factor) -----------------------------------
+    // ---- the thread's 16 input points, mid / side, and the frame's channel balance (balance_factor) -----
+    cpx<float> z[N / THREADS];
     float max_mid = 0.0f, max_side = 0.0f;
 #pragma unroll
-    for (int k = 0; k < N / THREADS; ++k) {
-        const float2 v = first.sample(tid + k * THREADS);
-        max_mid = fmaxf(max_mid, fabsf(v.x + v.y));
-        max_side = fmaxf(max_side, fabsf(v.x - v.y));
+    for (int r = 0; r < N / THREADS; ++r) {
+        const float2 v = first.sample(tid + r * THREADS);
+        // each channel from L and R directly, one rounding each: (L-R)/2 is the reference's mid - R, and
+        // forming it from the already rounded mid would put mid's rounding error into a quiet side
+        z[r].x = (v.x + v.y) * 0.5f;
+        z[r].y = (v.x - v.y) * 0.5f;
+        max_mid = fmaxf(max_mid, fabsf(z[r].x));
+        max_side = fmaxf(max_side, fabsf(z[r].y));
     }
-    block_max2(max_mid, max_side, red_f);
+    block_max2(max_mid, max_side, red_u);  // its barrier also ends everybody's reads of the landing buffer
     const float g_side = balance_factor(max_mid, max_side);  // >= 1 when the side is the quiet one, < 1 otherwise
     const float inv_g = 1.0f / g_side;                         // exact: a power of two
     const bool mid_silent = max_mid == 0.0f, side_silent = max_side == 0.0f;
-    first.side_scale = g_side;
+#pragma unroll
+    for (int r = 0; r < N / THREADS; ++r) z[r].y *= g_side;
 
     // ---- forward transform of z = mid + i*g*side ---------------------------------------------------
-    fft_first_pass<N, +1, THREADS, float>(planes, tw, first, /*in_place=*/true);
+    fft_first_pass_regs<N, +1, THREADS, float>(planes, z, /*barrier_before_store=*/false);
     __syncthreads();
     fft_remaining<N, +1, THREADS, float, CHAIN>(planes, tw, PlaneStore<PackedPlanes>{planes}, true);
     __syncthreads();

@@ -247,6 +247,19 @@ __device__ __forceinline__ void fft_first_pass(Planes pl, const cpx<T>* __restri
     fft_pass<N, Radices<N>::r[0], 1, DIR, THREADS, T, false>(tw, first, PlaneStore<Planes>{pl}, in_place);  // NS = 1: no twiddles
 }
 
+// First pass when the caller already holds the thread's R = N/THREADS input points in registers
+// (v[r] = point tid + r*THREADS), e.g. because it had to look at them before transforming.
+template <int N, int DIR, int THREADS, typename T, typename Planes>
+__device__ __forceinline__ void fft_first_pass_regs(Planes pl, cpx<T>* v, bool barrier_before_store) {
+    constexpr int R = Radices<N>::r[0];
+    static_assert(N / R == THREADS, "one butterfly per thread in the first pass");
+    if (barrier_before_store) __syncthreads();
+    Dft<R, DIR, T>::run(v);
+    const int j0 = threadIdx.x * R;  // NS = 1
+#pragma unroll
+    for (int q = 0; q < R; ++q) pl.store(j0 + q, v[q]);
+}
+
 // Remaining passes, in place on the planes; the caller has put a barrier after the first pass.
 // `last` consumes the output points in natural order (`last_in_place`: it writes the planes).
 // On return all `last` stores have been ISSUED (no trailing barrier).
