@@ -13,6 +13,7 @@ namespace mgb {
 
 int g_use_tma = 1;
 int g_twiddle_chain = 1;
+int g_conv_fused = 1;
 int g_lookback_inclusive = 1;
 
 #ifndef MGB_EMULATE
@@ -198,15 +199,41 @@ static bool radix_schedule(int n, int* npass, int r[4]) {
         default: return false;
     }
 }
-int twiddle_count(int n) {
-    int npass, r[4];
-    if (!radix_schedule(n, &npass, r)) return -1;
+template <int N>
+static bool inverse_radices_of(int* npass, int r[4]) {
+    if constexpr (InverseRadices<N>::fused) {
+        *npass = InverseRadices<N>::n;
+        for (int i = 0; i < 4; ++i) r[i] = InverseRadices<N>::r[i];
+        return true;
+    } else {
+        return false;
+    }
+}
+// the second schedule the fused convolution keeps behind the forward one in the 2F float table
+static bool inverse_schedule(int n, int* npass, int r[4]) {
+    switch (n) {
+        case 8192: return inverse_radices_of<8192>(npass, r);
+        case 16384: return inverse_radices_of<16384>(npass, r);
+        default: return false;
+    }
+}
+static int schedule_count(int npass, const int r[4]) {
     int total = 0, ns = r[0];
     for (int p = 1; p < npass; ++p) {
         total += (r[p] - 1) * ns;
         ns *= r[p];
     }
     return total;
+}
+int twiddle_count(int n) {
+    int npass, r[4];
+    if (!radix_schedule(n, &npass, r)) return -1;
+    return schedule_count(npass, r);
+}
+int inverse_twiddle_count(int n) {
+    int npass, r[4];
+    if (!inverse_schedule(n, &npass, r)) return 0;
+    return schedule_count(npass, r);
 }
 int fill_twiddles(int n, int is_f64, void* table, cudaStream_t stream) {
     int npass, r[4];
@@ -216,6 +243,12 @@ int fill_twiddles(int n, int is_f64, void* table, cudaStream_t stream) {
                       npass, r[0], r[1], r[2], r[3]);
     return launch("fft_twiddle_kernel", fft_twiddle_kernel<float>, dim3(16), dim3(256), 0, stream, (cpx<float>*)table,
                   npass, r[0], r[1], r[2], r[3]);
+}
+int fill_inverse_twiddles(int n, cpx<float>* table, cudaStream_t stream) {
+    int npass, r[4];
+    if (!inverse_schedule(n, &npass, r)) return MGB_OK;
+    return launch("fft_twiddle_kernel", fft_twiddle_kernel<float>, dim3(16), dim3(256), 0, stream,
+                  table + twiddle_count(n), npass, r[0], r[1], r[2], r[3]);
 }
 
 }  // namespace mgb
@@ -232,6 +265,10 @@ int mgb_set_option(const char* name, int value) {
     MGB_REQUIRE(name != nullptr, MGB_ERR_INVALID, "option name is NULL");
     if (strcmp(name, "tma") == 0) {
         g_use_tma = value ? 1 : 0;
+        return MGB_OK;
+    }
+    if (strcmp(name, "conv_fused") == 0) {
+        g_conv_fused = value ? 1 : 0;
         return MGB_OK;
     }
     if (strcmp(name, "twiddle_chain") == 0) {
@@ -305,7 +342,7 @@ int mgb_plan_twiddle_bytes(int32_t fft_size, int64_t bytes_out[5]) {
     const int cf = twiddle_count(fft_size), c2 = twiddle_count(2 * fft_size);
     MGB_REQUIRE(cf > 0 && c2 > 0, MGB_ERR_UNSUPPORTED, "fft_size %d has no kernel", fft_size);
     bytes_out[0] = (int64_t)cf * 8;
-    bytes_out[1] = (int64_t)c2 * 8;
+    bytes_out[1] = (int64_t)(c2 + inverse_twiddle_count(2 * fft_size)) * 8;
     bytes_out[2] = (int64_t)cf * 16;
     bytes_out[3] = (int64_t)c2 * 16;
     bytes_out[4] = (int64_t)align256(3 * sizeof(ScanPow));
@@ -320,6 +357,7 @@ int mgb_plan_fill_twiddles(const mgb_plan* plan, void* stream) {
     MGB_TRY(check_aligned(plan->d_tw_f64_F, "d_tw_f64_F"));
     MGB_TRY(fill_twiddles(plan->fft_size, 0, plan->d_tw_f32_F, st));
     MGB_TRY(fill_twiddles(2 * plan->fft_size, 0, plan->d_tw_f32_2F, st));
+    MGB_TRY(fill_inverse_twiddles(2 * plan->fft_size, (cpx<float>*)plan->d_tw_f32_2F, st));
     MGB_TRY(fill_twiddles(plan->fft_size, 1, plan->d_tw_f64_F, st));
     if (plan->d_tw_f64_2F && plan->fft_size <= 4096) MGB_TRY(fill_twiddles(2 * plan->fft_size, 1, plan->d_tw_f64_2F, st));
     if (!plan->d_limiter_tables) return MGB_OK;  // FFT-only plans (tests); mgb_finalize insists on the tables

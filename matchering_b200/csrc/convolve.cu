@@ -46,32 +46,22 @@ struct ConvFirst {
     }
 };
 
-template <int F, bool CHAIN>
-__global__ void __launch_bounds__(F / 8, (F <= 4096 ? 2 : 1))
-convolve_kernel(const float2* __restrict__ x, long long frames, long long piece, int divisions,
-                const cpx<float>* __restrict__ tw, const float2* __restrict__ h_mid,
-                const float2* __restrict__ h_side, float2* __restrict__ result, float* __restrict__ mid_plane,
-                double* __restrict__ piece_sums, mgb_track_state* __restrict__ state, int use_tma) {
+// ---- shared by both kernels: frame load + channel balance, FIR spectra on a pair, the epilogue -----
+struct ConvBalance {
+    float inv_g;
+    bool mid_silent, side_silent;
+};
+
+// Loads the frame's 2F input samples (clipped to the signal) into the landing buffer, hands every thread
+// its 16 points z[r] = mid + i*g*side of index tid + r*THREADS.  On return every thread is past a
+// barrier that follows its last read of the landing buffer.
+template <int F>
+__device__ __forceinline__ ConvBalance conv_load_frame(const float2* __restrict__ x, long long frames, long long origin,
+                                                       float2* raw, TmaBarrier* bar, unsigned* red_u, int use_tma,
+                                                       cpx<float>* z) {
     constexpr int N = 2 * F;
     constexpr int THREADS = N / 16;
-    using L = ConvSmem<F>;
-    MGB_DYN_SMEM(smem);
-    const PackedPlanes planes{reinterpret_cast<float2*>(smem)};
-    float2* raw = reinterpret_cast<float2*>(smem);  // the landing buffer IS the frame's storage: unpadded
-                                                    // until the first pass has gathered it, padded after
-    unsigned char* tail = smem + L::kPlaneBytes;
-    tail += (16 - (reinterpret_cast<uintptr_t>(tail) & 15)) & 15;
-    TmaBarrier* bar = reinterpret_cast<TmaBarrier*>(tail);
-    double* red_a = reinterpret_cast<double*>(tail + 16);
-    double* red_b = red_a + 32;
-    float* red_f = reinterpret_cast<float*>(red_b + 32);
-    unsigned* red_u = reinterpret_cast<unsigned*>(red_f + 32);  // [2] slot of block_max2
-
     const int tid = threadIdx.x;
-    const long long n0 = (long long)blockIdx.x * F;
-    const long long origin = n0 - F / 2;
-
-    // ---- load the frame's 2F input samples (clipped to the signal) -----------------------------
     const long long lo = origin < 0 ? 0 : origin;
     const long long hi = (origin + N < frames) ? origin + N : frames;  // exclusive
     ConvFirst first;
@@ -97,9 +87,6 @@ convolve_kernel(const float2* __restrict__ x, long long frames, long long piece,
         for (long long n = lo + tid; n < hi; n += THREADS) raw[n - origin] = x[n];
         __syncthreads();
     }
-
-    // ---- the thread's 16 input points, mid / side, and the frame's channel balance (balance_factor) -----
-    cpx<float> z[N / THREADS];
     float max_mid = 0.0f, max_side = 0.0f;
 #pragma unroll
     for (int r = 0; r < N / THREADS; ++r) {
@@ -113,58 +100,59 @@ convolve_kernel(const float2* __restrict__ x, long long frames, long long piece,
     }
     block_max2(max_mid, max_side, red_u);  // its barrier also ends everybody's reads of the landing buffer
     const float g_side = balance_factor(max_mid, max_side);  // >= 1 when the side is the quiet one, < 1 otherwise
-    const float inv_g = 1.0f / g_side;                         // exact: a power of two
-    const bool mid_silent = max_mid == 0.0f, side_silent = max_side == 0.0f;
 #pragma unroll
     for (int r = 0; r < N / THREADS; ++r) z[r].y *= g_side;
+    ConvBalance b;
+    b.inv_g = 1.0f / g_side;  // exact: a power of two
+    b.mid_silent = max_mid == 0.0f;
+    b.side_silent = max_side == 0.0f;
+    return b;
+}
 
-    // ---- forward transform of z = mid + i*g*side ---------------------------------------------------
-    fft_first_pass_regs<N, +1, THREADS, float>(planes, z, /*barrier_before_store=*/false);
-    __syncthreads();
-    fft_remaining<N, +1, THREADS, float, CHAIN>(planes, tw, PlaneStore<PackedPlanes>{planes}, true);
-    __syncthreads();
+// Z[k], Z[N-k] of z = mid + i*g*side  ->  Y[k], Y[N-k] of the filtered pair (k <= F indexes the FIR spectra).
+__device__ __forceinline__ void conv_apply_pair(cpx<float>& zk, cpx<float>& zn, int k, const float2* __restrict__ h_mid,
+                                                const float2* __restrict__ h_side, const ConvBalance& bal) {
+    const float zr = zk.x, zi = zk.y, nr = zn.x, ni = zn.y;
+    // M = (Z[k] + conj Z[N-k])/2 ; g S = (Z[k] - conj Z[N-k])/(2i)
+    const float mr = 0.5f * (zr + nr), mi = 0.5f * (zi - ni);
+    const float sr = 0.5f * (zi + ni) * bal.inv_g, si = 0.5f * (nr - zr) * bal.inv_g;
+    const float2 hm = h_mid[k], hs = h_side[k];
+    // a channel that is exactly silent in this frame stays exactly silent, as in the reference
+    const float pmr = bal.mid_silent ? 0.0f : hm.x * mr - hm.y * mi, pmi = bal.mid_silent ? 0.0f : hm.x * mi + hm.y * mr;
+    const float psr = bal.side_silent ? 0.0f : hs.x * sr - hs.y * si, psi = bal.side_silent ? 0.0f : hs.x * si + hs.y * sr;
+    // Y[k] = Pm + i Ps ; Y[N-k] = conj(Pm) + i conj(Ps)
+    zk = cpx<float>{pmr - psi, pmi + psr};
+    zn = cpx<float>{pmr + psi, psr - pmi};
+}
 
-    // ---- apply both FIR spectra on the pair (k, N-k) ---------------------------------------------
-    for (int k = tid; k <= F; k += THREADS) {
-        const int kn = (N - k) & (N - 1);
-        const cpx<float> zk = planes.load(k), zn = planes.load(kn);
-        const float zr = zk.x, zi = zk.y, nr = zn.x, ni = zn.y;
-        // M = (Z[k] + conj Z[N-k])/2 ; g S = (Z[k] - conj Z[N-k])/(2i)
-        const float mr = 0.5f * (zr + nr), mi = 0.5f * (zi - ni);
-        const float sr = 0.5f * (zi + ni) * inv_g, si = 0.5f * (nr - zr) * inv_g;
-        const float2 hm = h_mid[k], hs = h_side[k];
-        // a channel that is exactly silent in this frame stays exactly silent, as in the reference
-        const float pmr = mid_silent ? 0.0f : hm.x * mr - hm.y * mi, pmi = mid_silent ? 0.0f : hm.x * mi + hm.y * mr;
-        const float psr = side_silent ? 0.0f : hs.x * sr - hs.y * si, psi = side_silent ? 0.0f : hs.x * si + hs.y * sr;
-        // Y[k] = Pm + i Ps ; Y[N-k] = conj(Pm) + i conj(Ps)
-        planes.store(k, cpx<float>{pmr - psi, pmi + psr});
-        if (kn != k) planes.store(kn, cpx<float>{pmr + psi, psr - pmi});
-    }
-    __syncthreads();
-
-    // ---- inverse transform, in place ------------------------------------------------------------------
-    fft_first_pass<N, -1, THREADS, float>(planes, tw, PlaneLoad<PackedPlanes>{planes}, /*in_place=*/true);
-    __syncthreads();
-    fft_remaining<N, -1, THREADS, float, CHAIN>(planes, tw, PlaneStore<PackedPlanes>{planes}, /*last_in_place=*/true);
-    __syncthreads();
-
-    // ---- epilogue: circular index F-1+o is output sample n0+o; coalesced stores, mid/side -> L/R
-    // (dsp.ms_to_lr), the first RMS-correction step's sum of clip(mid)^2 per piece, the peak ---------
-    const int valid = (int)((frames - n0 < F) ? frames - n0 : F);
-    const long long counted = piece * divisions;  // samples that enter the piece RMS (dsp.unfold)
-    const long long pa = n0 / piece;
-    const long long brel = (pa + 1) * piece - n0;  // first output of the next piece
-    const int boundary = (int)(brel < F ? brel : F);
-    const int count_to = (int)((counted - n0 < 0) ? 0 : (counted - n0 < F ? counted - n0 : F));
+// Output side of a frame: circular index F-1+o of the inverse transform is output sample n0+o.
+// mid/side -> L/R (dsp.ms_to_lr), the first RMS-correction step's sum of clip(mid)^2 per piece, the peak.
+template <int F>
+struct ConvEpilogue {
+    float2* res;
+    float* midp;
+    int valid, boundary, count_to;
+    long long pa;
+    int divisions;
+    bool mid_silent, side_silent;
     double sq_a = 0.0, sq_b = 0.0;
     float peak = 0.0f;
-    float2* res = result + n0;
-    float* midp = mid_plane + n0;
-#pragma unroll
-    for (int k = 0; k < F / THREADS; ++k) {
-        const int o = tid + k * THREADS;
+    __device__ __forceinline__ ConvEpilogue(float2* result, float* mid_plane, long long n0, long long frames,
+                                            long long piece, int divisions_, const ConvBalance& bal) {
+        res = result + n0;
+        midp = mid_plane + n0;
+        valid = (int)((frames - n0 < F) ? frames - n0 : F);
+        const long long counted = piece * divisions_;  // samples that enter the piece RMS (dsp.unfold)
+        pa = n0 / piece;
+        const long long brel = (pa + 1) * piece - n0;  // first output of the next piece
+        boundary = (int)(brel < F ? brel : F);
+        count_to = (int)((counted - n0 < 0) ? 0 : (counted - n0 < F ? counted - n0 : F));
+        divisions = divisions_;
+        mid_silent = bal.mid_silent;
+        side_silent = bal.side_silent;
+    }
+    __device__ __forceinline__ void emit(int o, cpx<float> y) {
         if (o < valid) {
-            const cpx<float> y = planes.load(F - 1 + o);
             // (the inverse transform leaves rounding dust in a channel whose spectrum was exactly zero)
             const float m = mid_silent ? 0.0f : y.x, sd = side_silent ? 0.0f : y.y;
             const float l = m + sd, r = m - sd;
@@ -178,14 +166,182 @@ convolve_kernel(const float2* __restrict__ x, long long frames, long long piece,
             }
         }
     }
-    const double ta = block_sum(sq_a, red_a);
-    const double tb = block_sum(sq_b, red_b);
-    const float pk = block_max(peak, red_f);
-    if (tid == 0) {
-        if (pa < divisions && ta != 0.0) atomicAdd(&piece_sums[pa], ta);
-        if (pa + 1 < divisions && tb != 0.0) atomicAdd(&piece_sums[pa + 1], tb);
-        atomic_max_nonneg(&state->conv_peak_bits, pk);
+    __device__ __forceinline__ void finish(double* red_a, double* red_b, float* red_f, double* piece_sums,
+                                           mgb_track_state* state) {
+        const double ta = block_sum(sq_a, red_a);
+        const double tb = block_sum(sq_b, red_b);
+        const float pk = block_max(peak, red_f);
+        if (threadIdx.x == 0) {
+            if (pa < divisions && ta != 0.0) atomicAdd(&piece_sums[pa], ta);
+            if (pa + 1 < divisions && tb != 0.0) atomicAdd(&piece_sums[pa + 1], tb);
+            atomic_max_nonneg(&state->conv_peak_bits, pk);
+        }
     }
+};
+
+template <int F>
+struct ConvPointers {
+    PackedPlanes planes;
+    float2* raw;
+    TmaBarrier* bar;
+    double *red_a, *red_b;
+    float* red_f;
+    unsigned* red_u;
+    __device__ __forceinline__ explicit ConvPointers(unsigned char* smem) {
+        planes = PackedPlanes{reinterpret_cast<float2*>(smem)};
+        raw = reinterpret_cast<float2*>(smem);  // the landing buffer IS the frame's storage: unpadded
+                                                // until the first pass has gathered it, padded after
+        unsigned char* tail = smem + ConvSmem<F>::kPlaneBytes;
+        tail += (16 - (reinterpret_cast<uintptr_t>(tail) & 15)) & 15;
+        bar = reinterpret_cast<TmaBarrier*>(tail);
+        red_a = reinterpret_cast<double*>(tail + 16);
+        red_b = red_a + 32;
+        red_f = reinterpret_cast<float*>(red_b + 32);
+        red_u = reinterpret_cast<unsigned*>(red_f + 32);  // [2] slot of block_max2
+    }
+};
+
+// ---- generic kernel: every pass through shared memory (any radix schedule) -------------------------
+template <int F, bool CHAIN>
+__global__ void __launch_bounds__(F / 8, (F <= 4096 ? 2 : 1))
+convolve_kernel(const float2* __restrict__ x, long long frames, long long piece, int divisions,
+                const cpx<float>* __restrict__ tw, const float2* __restrict__ h_mid,
+                const float2* __restrict__ h_side, float2* __restrict__ result, float* __restrict__ mid_plane,
+                double* __restrict__ piece_sums, mgb_track_state* __restrict__ state, int use_tma) {
+    constexpr int N = 2 * F;
+    constexpr int THREADS = N / 16;
+    MGB_DYN_SMEM(smem);
+    const ConvPointers<F> sp(smem);
+    const PackedPlanes planes = sp.planes;
+    const int tid = threadIdx.x;
+    const long long n0 = (long long)blockIdx.x * F;
+
+    cpx<float> z[N / THREADS];
+    const ConvBalance bal = conv_load_frame<F>(x, frames, n0 - F / 2, sp.raw, sp.bar, sp.red_u, use_tma, z);
+
+    // ---- forward transform of z = mid + i*g*side ---------------------------------------------------
+    fft_first_pass_regs<N, +1, THREADS, float>(planes, z, /*barrier_before_store=*/false);
+    __syncthreads();
+    fft_remaining<N, +1, THREADS, float, CHAIN>(planes, tw, PlaneStore<PackedPlanes>{planes}, true);
+    __syncthreads();
+
+    // ---- apply both FIR spectra on the pair (k, N-k) ---------------------------------------------
+    for (int k = tid; k <= F; k += THREADS) {
+        const int kn = (N - k) & (N - 1);
+        cpx<float> zk = planes.load(k), zn = planes.load(kn);
+        conv_apply_pair(zk, zn, k, h_mid, h_side, bal);
+        planes.store(k, zk);
+        if (kn != k) planes.store(kn, zn);
+    }
+    __syncthreads();
+
+    // ---- inverse transform, in place ------------------------------------------------------------------
+    fft_first_pass<N, -1, THREADS, float>(planes, tw, PlaneLoad<PackedPlanes>{planes}, /*in_place=*/true);
+    __syncthreads();
+    fft_remaining<N, -1, THREADS, float, CHAIN>(planes, tw, PlaneStore<PackedPlanes>{planes}, /*last_in_place=*/true);
+    __syncthreads();
+
+    // ---- epilogue: coalesced stores -------------------------------------------------------------------
+    ConvEpilogue<F> ep(result, mid_plane, n0, frames, piece, divisions, bal);
+#pragma unroll
+    for (int k = 0; k < F / THREADS; ++k) {
+        const int o = tid + k * THREADS;
+        if (o < ep.valid) ep.emit(o, planes.load(F - 1 + o));
+    }
+    ep.finish(sp.red_a, sp.red_b, sp.red_f, piece_sums, state);
+}
+
+// ---- fused kernel: the frame makes 6 trips through shared memory instead of 9.5 ---------------------
+// The forward schedule ends and the inverse schedule (InverseRadices) starts with a radix-8 pass of
+// N/8 = 2*THREADS butterflies, butterfly j touching the points j + r*N/8 in both.  A thread takes the
+// butterflies j and N/8 - j: between them they hold every pair Z[k], Z[N-k] the FIR spectra need, so
+// the last forward pass, the spectral product and the first inverse pass happen in registers.  The
+// inverse schedule also ends with a radix-8 pass over j + r*N/8: outputs q = 4..7 of butterfly j are
+// the circular indices F + j + (q-4)*N/8, i.e. output samples j + 1 + (q-4)*N/8 -- contiguous across
+// the block, so the epilogue runs straight from registers (outputs q < 4 are never formed, except
+// index F-1 = output 0).
+template <int F, bool CHAIN>
+__global__ void __launch_bounds__(F / 8, (F <= 4096 ? 2 : 1))
+convolve_fused_kernel(const float2* __restrict__ x, long long frames, long long piece, int divisions,
+                      const cpx<float>* __restrict__ tw, const float2* __restrict__ h_mid,
+                      const float2* __restrict__ h_side, float2* __restrict__ result, float* __restrict__ mid_plane,
+                      double* __restrict__ piece_sums, mgb_track_state* __restrict__ state, int use_tma) {
+    constexpr int N = 2 * F;
+    constexpr int THREADS = N / 16;
+    constexpr int NB8 = N / 8;
+    using Fwd = Radices<N>;
+    using Inv = InverseRadices<N>;
+    static_assert(Inv::fused && Fwd::r[Fwd::n - 1] == 8 && Inv::r[0] == 8 && Inv::r[Inv::n - 1] == 8, "schedule");
+    static_assert(fft_last_pass_ns<Fwd>() == NB8 && fft_last_pass_ns<Inv>() == NB8 && NB8 == 2 * THREADS, "schedule");
+    const cpx<float>* tw_inv = tw + fft_schedule_twiddles<Fwd>();
+    MGB_DYN_SMEM(smem);
+    const ConvPointers<F> sp(smem);
+    const PackedPlanes planes = sp.planes;
+    const PlaneLoad<PackedPlanes> sl{planes};
+    const int tid = threadIdx.x;
+    const long long n0 = (long long)blockIdx.x * F;
+
+    ConvBalance bal;
+    {
+        cpx<float> z[N / THREADS];
+        bal = conv_load_frame<F>(x, frames, n0 - F / 2, sp.raw, sp.bar, sp.red_u, use_tma, z);
+        fft_first_pass_regs<N, +1, THREADS, float>(planes, z, /*barrier_before_store=*/false);
+    }
+    __syncthreads();
+    fft_middle<N, +1, THREADS, float, CHAIN, Fwd>(planes, tw);
+
+    // ---- last forward pass, FIR spectra, first inverse pass ----------------------------------------
+    {
+        const int ja = tid, jb = tid == 0 ? NB8 / 2 : NB8 - tid;
+        cpx<float> a[8], b[8];
+        fft_gather<8, NB8>(sl, ja, a);
+        fft_gather<8, NB8>(sl, jb, b);
+        __syncthreads();  // in place: everybody has gathered before anybody scatters
+        const cpx<float>* tw_last = tw + fft_last_pass_twiddles<Fwd>();
+        fft_butterfly<8, NB8, +1, CHAIN>(tw_last, ja, a);  // a[q] = Z[ja + q*NB8]
+        fft_butterfly<8, NB8, +1, CHAIN>(tw_last, jb, b);  // b[q] = Z[jb + q*NB8]
+        if (tid != 0) {
+            // N - (ja + q*NB8) = jb + (7-q)*NB8
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                conv_apply_pair(a[q], b[7 - q], ja + q * NB8, h_mid, h_side, bal);
+                conv_apply_pair(b[q], a[7 - q], jb + q * NB8, h_mid, h_side, bal);
+            }
+        } else {
+            // butterflies 0 and N/16 pair with themselves: a[q] <-> a[8-q], b[q] <-> b[7-q]
+            cpx<float> t = a[0];
+            conv_apply_pair(a[0], t, 0, h_mid, h_side, bal);
+            t = a[4];
+            conv_apply_pair(a[4], t, F, h_mid, h_side, bal);
+#pragma unroll
+            for (int q = 1; q < 4; ++q) conv_apply_pair(a[q], a[8 - q], q * NB8, h_mid, h_side, bal);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) conv_apply_pair(b[q], b[7 - q], NB8 / 2 + q * NB8, h_mid, h_side, bal);
+        }
+        Dft<8, -1, float>::run(a);
+        Dft<8, -1, float>::run(b);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) planes.store(ja * 8 + q, a[q]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) planes.store(jb * 8 + q, b[q]);
+    }
+    __syncthreads();
+    fft_middle<N, -1, THREADS, float, CHAIN, Inv>(planes, tw_inv);
+
+    // ---- last inverse pass straight into the epilogue ------------------------------------------------
+    ConvEpilogue<F> ep(result, mid_plane, n0, frames, piece, divisions, bal);
+    const cpx<float>* tw_last = tw_inv + fft_last_pass_twiddles<Inv>();
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const int j = tid + p * THREADS;
+        cpx<float> v[8];
+        fft_gather<8, NB8>(sl, j, v);
+        fft_butterfly<8, NB8, -1, CHAIN>(tw_last, j, v);  // v[q] = y[j + q*NB8]
+#pragma unroll
+        for (int q = 4; q < 8; ++q) ep.emit(j + 1 + (q - 4) * NB8, v[q]);  // (o = F for j = NB8-1, q = 7: not valid)
+        if (j == NB8 - 1) ep.emit(0, v[3]);
+    }
+    ep.finish(sp.red_a, sp.red_b, sp.red_f, piece_sums, state);
 }
 
 template <int F>
@@ -194,6 +350,9 @@ int launch_convolve_t(const mgb_plan& plan, const mgb_track_layout& layout, cons
     const long long T = layout.target_frames;
     const unsigned nframes = (unsigned)((T + F - 1) / F);
     auto kernel = g_twiddle_chain ? convolve_kernel<F, true> : convolve_kernel<F, false>;
+    if constexpr (InverseRadices<2 * F>::fused) {
+        if (g_conv_fused) kernel = g_twiddle_chain ? convolve_fused_kernel<F, true> : convolve_fused_kernel<F, false>;
+    }
     return launch("convolve_kernel", kernel, dim3(nframes), dim3(F / 8), ConvSmem<F>::kBytes, stream, target, T,
                   (long long)layout.target_piece, layout.target_divisions, (const cpx<float>*)plan.d_tw_f32_2F,
                   (const float2*)ws.h_mid, (const float2*)ws.h_side, result, ws.mid_plane, ws.piece_sums, state,

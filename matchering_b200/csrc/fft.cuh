@@ -289,6 +289,84 @@ __device__ __forceinline__ void fft_remaining(Planes pl, const cpx<T>* __restric
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Pieces for kernels that keep the ends of a transform in registers (convolve.cu): the passes between
+// the first and the last one, and a single butterfly without its scatter.
+// ------------------------------------------------------------------------------------------------
+// Inverse schedules of the fused convolution: they START with the radix-8 pass whose inputs are exactly
+// the outputs of the forward schedule's last radix-8 pass (points j + r*N/8), and end with a radix-8
+// pass of two butterflies per thread whose outputs are contiguous across the block.
+template <int N> struct InverseRadices { static constexpr bool fused = false; };
+template <> struct InverseRadices<8192>  { static constexpr bool fused = true; static constexpr int n = 4; static constexpr int r[4] = {8, 16, 8, 8}; };
+template <> struct InverseRadices<16384> { static constexpr bool fused = true; static constexpr int n = 4; static constexpr int r[4] = {8, 16, 16, 8}; };
+
+template <typename Rd>
+__host__ __device__ constexpr int fft_schedule_twiddles() {
+    int total = 0, ns = Rd::r[0];
+    for (int p = 1; p < Rd::n; ++p) {
+        total += (Rd::r[p] - 1) * ns;
+        ns *= Rd::r[p];
+    }
+    return total;
+}
+// NS (transform length already built) of the schedule's last pass, and the offset of that pass's
+// twiddles inside the schedule's table
+template <typename Rd>
+__host__ __device__ constexpr int fft_last_pass_ns() {
+    int ns = 1;
+    for (int p = 0; p < Rd::n - 1; ++p) ns *= Rd::r[p];
+    return ns;
+}
+template <typename Rd>
+__host__ __device__ constexpr int fft_last_pass_twiddles() {
+    return fft_schedule_twiddles<Rd>() - (Rd::r[Rd::n - 1] - 1) * fft_last_pass_ns<Rd>();
+}
+
+// Passes 1 .. n-2 of schedule Rd, in place, a barrier after each (the caller has put one after pass 0).
+template <int N, int DIR, int THREADS, typename T, bool CHAIN, typename Rd, typename Planes>
+__device__ __forceinline__ void fft_middle(Planes pl, const cpx<T>* __restrict__ tw) {
+    constexpr int R0 = Rd::r[0], R1 = Rd::r[1], R2 = Rd::r[2];
+    PlaneLoad<Planes> sl{pl};
+    PlaneStore<Planes> ss{pl};
+    static_assert(Rd::n >= 2 && Rd::n <= 4, "2..4 passes supported");
+    if constexpr (Rd::n >= 3) {
+        fft_pass<N, R1, R0, DIR, THREADS, T, CHAIN>(tw, sl, ss, true);
+        __syncthreads();
+    }
+    if constexpr (Rd::n >= 4) {
+        fft_pass<N, R2, R0 * R1, DIR, THREADS, T, CHAIN>(tw + (R1 - 1) * R0, sl, ss, true);
+        __syncthreads();
+    }
+}
+
+// The R inputs of butterfly j of a pass with NB = N/R butterflies.
+template <int R, int NB, typename T, typename Load>
+__device__ __forceinline__ void fft_gather(Load load, int j, cpx<T>* v) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = load(j + r * NB);
+}
+// Twiddle (index k = j mod NS) and radix-R DFT of one gathered butterfly; outputs belong at
+// (j - k)*R + k + q*NS.
+template <int R, int NS, int DIR, bool CHAIN, typename T>
+__device__ __forceinline__ void fft_butterfly(const cpx<T>* __restrict__ tw, int k, cpx<T>* v) {
+    if constexpr (NS > 1) {
+        if constexpr (CHAIN && R > 2) {
+            cpx<T> w[R];
+            load_twiddles<R, NS, DIR, true, T>(tw, k, w);
+#pragma unroll
+            for (int r = 1; r < R; ++r) v[r] = cmul(v[r], w[r]);
+        } else {
+#pragma unroll
+            for (int r = 1; r < R; ++r) {
+                cpx<T> w = tw[(r - 1) * NS + k];
+                if constexpr (DIR < 0) w.y = -w.y;
+                v[r] = cmul(v[r], w);
+            }
+        }
+    }
+    Dft<R, DIR, T>::run(v);
+}
+
 // Whole transform: first pass, barrier, remaining passes.
 template <int N, int DIR, int THREADS, typename T, bool CHAIN = false, typename Planes, typename First, typename Last>
 __device__ __forceinline__ void fft_run(Planes pl, const cpx<T>* __restrict__ tw, First first, Last last,

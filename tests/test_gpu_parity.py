@@ -127,6 +127,25 @@ def test_pipeline_other_configs_against_oracle(torch_cuda, fft_size, sr, seconds
     _compare(got, want)
 
 
+@pytest.mark.parametrize("fft_size", [4096, 8192])
+def test_generic_convolution_kernel_against_oracle(torch_cuda, lib, fft_size):
+    """These sizes normally take the fused convolution kernel; the all-shared-memory one must agree too."""
+    import port
+    from matchering_b200 import stages
+    cfg = _config(fft_size=fft_size, max_piece_size=1.0)
+    n = 44100 * 4 + 5
+    t, r = port.synth_target(n, 21), port.synth_reference(n - 999, 22)
+    lib.mgb_set_option(b"conv_fused", 0)
+    try:
+        got = stages.main(t, r, cfg, True, True, True)
+    finally:
+        lib.mgb_set_option(b"conv_fused", 1)
+    fused = stages.main(t, r, cfg, True, True, True)
+    want = port.main(t.astype(np.float64), r.astype(np.float64), cfg, True, True, True)
+    _compare(got, want)
+    _compare(fused, want)
+
+
 def test_pipeline_half_minute_against_oracle(torch_cuda, tma):
     """30 s at the default Config (3 pieces, ~320 convolution frames, ~290 limiter chunks)."""
     import port
