@@ -37,6 +37,35 @@ __global__ void __launch_bounds__(256)
 clip_sumsq_kernel(const float* __restrict__ mid, long long piece, int divisions, int step, double eps,
                   mgb_track_state* __restrict__ state, const double* __restrict__ prev_sums, double* __restrict__ sums) {
     __shared__ double red[32];
+    const long long p = blockIdx.y;
+    const long long per = (piece + gridDim.x - 1) / gridDim.x;
+    const long long lo = p * piece + (long long)blockIdx.x * per;
+    long long hi = lo + per;
+    if (hi > (p + 1) * piece) hi = (p + 1) * piece;
+    if (hi < lo) hi = lo;
+    long long body_lo = (lo + 3) & ~3LL;
+    if (body_lo > hi) body_lo = hi;
+    long long body_hi = hi & ~3LL;
+    if (body_hi < body_lo) body_hi = body_lo;
+    const float4* body = reinterpret_cast<const float4*>(mid + body_lo);
+    const long long nvec = (body_hi - body_lo) >> 2;
+    const long long stride = 4LL * blockDim.x;
+    auto fetch = [&](long long i, float4* v) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long iu = i + (long long)u * blockDim.x;
+            v[u] = iu < nvec ? body[iu] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    // the first loads do not depend on the coefficient: they go out before the prologue's chain of
+    // dependent reads, which then costs no extra DRAM round trip
+    float4 v[4];
+    long long i = threadIdx.x;
+    fetch(i, v);
+    float edge_a = 0.0f, edge_b = 0.0f;  // head / tail (< 4 samples each) outside the 16-byte aligned body
+    if ((long long)threadIdx.x < body_lo - lo) edge_a = mid[lo + threadIdx.x];
+    if ((long long)threadIdx.x < hi - body_hi) edge_b = mid[body_hi + threadIdx.x];
+
     // prologue, identical in every CTA: the previous step's coefficient from its per-piece sums, and
     // the gain accumulated so far (stages.py:161-168 applied lazily)
     const double c_prev = correction_coefficient(prev_sums, divisions, piece, eps, state->reference_match_rms, red);
@@ -47,30 +76,15 @@ clip_sumsq_kernel(const float* __restrict__ mid, long long piece, int divisions,
         state->steps_done = step;
     }
     const float gain_f = (float)gain;
-    const long long p = blockIdx.y;
-    const long long per = (piece + gridDim.x - 1) / gridDim.x;
-    const long long lo = p * piece + (long long)blockIdx.x * per;
-    long long hi = lo + per;
-    if (hi > (p + 1) * piece) hi = (p + 1) * piece;
-    double acc = 0.0;
-    if (lo < hi) {
-        long long body_lo = (lo + 3) & ~3LL;
-        if (body_lo > hi) body_lo = hi;
-        long long body_hi = hi & ~3LL;
-        if (body_hi < body_lo) body_hi = body_lo;
-        if ((long long)threadIdx.x < body_lo - lo) acc += clip_sq(mid[lo + threadIdx.x], gain_f);       // head (< 4)
-        if ((long long)threadIdx.x < hi - body_hi) acc += clip_sq(mid[body_hi + threadIdx.x], gain_f);  // tail (< 4)
-        const float4* body = reinterpret_cast<const float4*>(mid + body_lo);
-        const long long nvec = (body_hi - body_lo) >> 2;
-        for (long long i = threadIdx.x; i < nvec; i += 4 * blockDim.x) {
-            float4 v[4];
+    double acc = (double)0.0;
+    acc += clip_sq(edge_a, gain_f) + clip_sq(edge_b, gain_f);  // (zero where there is no edge sample)
+    while (i < nvec) {
+        float4 w[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const long long iu = i + (long long)u * blockDim.x;
-                v[u] = iu < nvec ? body[iu] : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            acc += (clip_sq4(v[0], gain_f) + clip_sq4(v[1], gain_f)) + (clip_sq4(v[2], gain_f) + clip_sq4(v[3], gain_f));
-        }
+        for (int u = 0; u < 4; ++u) w[u] = v[u];
+        i += stride;
+        if (i < nvec) fetch(i, v);  // next batch in flight while this one is reduced
+        acc += (clip_sq4(w[0], gain_f) + clip_sq4(w[1], gain_f)) + (clip_sq4(w[2], gain_f) + clip_sq4(w[3], gain_f));
     }
     const double total = block_sum(acc, red);
     if (threadIdx.x == 0 && total != 0.0) atomicAdd(&sums[p], total);
