@@ -260,6 +260,17 @@ int mgb_pcm_encode(const float* d_in, int32_t bits, void* d_pcm, int64_t count, 
 int mgb_check_peaks(const float* d_lr, int64_t frames, void* d_scratch16, void* stream);
 int mgb_check_equality(const float* d_a_lr, const float* d_b_lr, int64_t frames, void* d_scratch8, void* stream);
 
+/* Preview creator on the device (matchering/preview_creator.py:30-94; dsp.strided_app_2d,
+ * batch_rms_2d, fade: dsp.py:128-152).
+ * mgb_window_energy: d_energy[w] = sum of L^2 + R^2 (float64) over the window [w*step, w*step+window)
+ * for w < count -- the argmax of the reference's per-window RMS picks the preview.
+ * mgb_preview_piece: d_out = clip(d_in, +-clip_to) (clip_to <= 0: no clip; the reference clips the
+ * target at the threshold) with linspace(0, 1, fade_frames) fades at both ends (0: no fade). */
+int mgb_window_energy(const float* d_lr, int64_t frames, int64_t window, int64_t step, int32_t count, double* d_energy,
+                      void* stream);
+int mgb_preview_piece(const float* d_in_lr, float* d_out_lr, int64_t frames, double clip_to, int64_t fade_frames,
+                      void* stream);
+
 /* ---- building blocks exported for the parity tests (tests/ only) ------------------------------ */
 /* forward or inverse (dir = +1 / -1) complex FFT of `batch` frames of n points through the same
  * shared-memory kernel the pipeline uses; is_f64 selects the double variant (n in {F, 2F}). */

@@ -23,8 +23,6 @@ def process(target: str, reference: str, results: list, config: Config = None,
     info(Code.INFO_LOADING)
     if not results:
         raise RuntimeError("The result list is empty")
-    if preview_target or preview_result:
-        raise NotImplementedError("previews are outside this build's scope (SURVEY.md section 8f)")
     temp_folder = config.temp_folder if config.temp_folder else get_temp_folder(results)
 
     target_audio, target_rate = _load_and_check(target, "target", temp_folder, config)
@@ -47,11 +45,15 @@ def process(target: str, reference: str, results: list, config: Config = None,
     for wanted in results:
         audio = limited if wanted.use_limiter else (normalized if wanted.normalize else plain)
         _export(wanted, audio, config.internal_sample_rate)
+    if preview_target or preview_result:
+        from .preview_creator import create_preview
+        first = next(item for item in (limited, plain, normalized) if item is not None)
+        create_preview(target_audio, first, config, preview_target, preview_result)
     debug_line()
     info(Code.INFO_COMPLETED)
 
 
-def _export(wanted: Result, audio, sample_rate: int) -> None:
+def _export(wanted: Result, audio, sample_rate: int, name: str = "result") -> None:
     """16/24-bit WAV results are quantised on the device and written as they come back (a quarter of
     the device->host bytes of a float64 array); everything else takes the reference's route through
     a host float array and `save`."""
@@ -61,11 +63,11 @@ def _export(wanted: Result, audio, sample_rate: int) -> None:
         from . import wavio
         from .engine import encode_pcm
         bits = int(wanted.subtype[4:])
-        debug(f"Saving the RESULT {sample_rate} Hz Stereo {wanted.subtype} to: '{wanted.file}'...")
+        debug(f"Saving the {name.upper()} {sample_rate} Hz Stereo {wanted.subtype} to: '{wanted.file}'...")
         wavio.write_pcm(wanted.file, encode_pcm(audio, bits), sample_rate, bits)
         debug(f"'{wanted.file}' is saved")
     else:
-        save(wanted.file, audio.cpu().numpy().astype("float64"), sample_rate, wanted.subtype)
+        save(wanted.file, audio.cpu().numpy().astype("float64"), sample_rate, wanted.subtype, name)
 
 
 def _load_and_check(file: str, name: str, temp_folder: str, config: Config):

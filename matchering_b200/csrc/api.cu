@@ -617,6 +617,31 @@ int mgb_check_equality(const float* d_a_lr, const float* d_b_lr, int64_t frames,
     return launch_count_different(d_a_lr, d_b_lr, frames * 2, (unsigned long long*)d_scratch8, st);
 }
 
+int mgb_window_energy(const float* d_lr, int64_t frames, int64_t window, int64_t step, int32_t count, double* d_energy,
+                      void* stream) {
+    MGB_REQUIRE(d_lr && d_energy && window > 0 && step > 0 && count > 0, MGB_ERR_INVALID, "window_energy: bad arguments");
+    MGB_REQUIRE((int64_t)(count - 1) * step + window <= frames, MGB_ERR_INVALID,
+                "window_energy: %d windows of %lld frames every %lld do not fit in %lld frames", count, (long long)window,
+                (long long)step, (long long)frames);
+    MGB_REQUIRE(count <= 65535, MGB_ERR_INVALID, "window_energy: too many windows (%d)", count);
+    cudaStream_t st = (cudaStream_t)stream;
+#ifdef MGB_EMULATE
+    memset(d_energy, 0, sizeof(double) * count);
+#else
+    if (cudaMemsetAsync(d_energy, 0, sizeof(double) * count, st) != cudaSuccess) return cuda_status("memset");
+#endif
+    return launch_window_energy((const float2*)d_lr, window, step, count, d_energy, st);
+}
+
+int mgb_preview_piece(const float* d_in_lr, float* d_out_lr, int64_t frames, double clip_to, int64_t fade_frames,
+                      void* stream) {
+    MGB_REQUIRE(d_in_lr && d_out_lr && frames > 0, MGB_ERR_INVALID, "preview_piece: bad arguments");
+    MGB_REQUIRE(fade_frames >= 0 && 2 * fade_frames <= frames, MGB_ERR_INVALID,
+                "preview_piece: two fades of %lld frames do not fit in %lld", (long long)fade_frames, (long long)frames);
+    return launch_preview_piece((const float2*)d_in_lr, (float2*)d_out_lr, frames, (float)clip_to, fade_frames,
+                                (cudaStream_t)stream);
+}
+
 int mgb_test_fft(int32_t n, int32_t is_f64, int32_t dir, const void* d_in, void* d_out, int32_t batch,
                  const void* d_twiddles, void* stream) {
     MGB_REQUIRE(d_in && d_out && d_twiddles && batch > 0, MGB_ERR_INVALID, "test_fft: bad arguments");

@@ -246,6 +246,48 @@ count_different_kernel(const float* __restrict__ a, const float* __restrict__ b,
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, local);
 }
 
+// ---- preview creator (matchering/preview_creator.py:30-94; dsp.strided_app_2d / batch_rms_2d / fade
+// dsp.py:128-152) --------------------------------------------------------------------------------------
+// energy[w] = sum over window w = [w*step, w*step + window) of L^2 + R^2 (float64): the argmax of the
+// reference's per-window RMS.  grid = (slices, windows): a CTA sums one slice of one window.
+__global__ void __launch_bounds__(256)
+window_energy_kernel(const float2* __restrict__ x, long long window, long long step, double* __restrict__ energy) {
+    __shared__ double red[32];
+    const long long w = blockIdx.y;
+    const long long per = (window + gridDim.x - 1) / gridDim.x;
+    const long long lo = blockIdx.x * per;
+    const long long hi = lo + per < window ? lo + per : window;
+    const float2* src = x + w * step;
+    double acc = 0.0;
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const float2 v = src[i];
+        acc += (double)v.x * (double)v.x + (double)v.y * (double)v.y;
+    }
+    const double total = block_sum(acc, red);
+    if (threadIdx.x == 0 && total != 0.0) atomicAdd(&energy[w], total);
+}
+
+// out = clip(in, +-clip_to) (clip_to <= 0: no clip) with linear fades of `fade` frames at both ends:
+// fade_in = linspace(0, 1, fade), fade_out its mirror (dsp.fade).
+__global__ void __launch_bounds__(256)
+preview_piece_kernel(const float2* __restrict__ in, float2* __restrict__ out, long long frames, float clip_to,
+                     long long fade) {
+    const double ramp = fade > 1 ? 1.0 / (double)(fade - 1) : 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < frames; i += stride) {
+        float2 v = in[i];
+        if (clip_to > 0.0f) {
+            v.x = fminf(clip_to, fmaxf(-clip_to, v.x));
+            v.y = fminf(clip_to, fmaxf(-clip_to, v.y));
+        }
+        double g = 1.0;
+        if (i < fade) g = (i == fade - 1 && fade > 1) ? 1.0 : (double)i * ramp;
+        const long long j = frames - 1 - i;  // distance from the end
+        if (j < fade) g *= (j == fade - 1 && fade > 1) ? 1.0 : (double)j * ramp;
+        out[i] = make_float2((float)((double)v.x * g), (float)((double)v.y * g));
+    }
+}
+
 unsigned grid_for(long long items, int per_block) {
     long long blocks = (items + per_block - 1) / per_block;
     const long long cap = (long long)num_sms() * 8;
@@ -327,6 +369,20 @@ int launch_peak_count(const float* x, int64_t count, float* peak_bits, unsigned 
                    (long long)(count / 2), peak_bits));
     return launch("count_close_kernel", count_close_kernel, dim3(grid_for(count, 1024)), dim3(256), 0, stream, x,
                   (long long)count, (const float*)peak_bits, n_close);
+}
+
+int launch_window_energy(const float2* x, int64_t window, int64_t step, int count, double* energy, cudaStream_t stream) {
+    long long slices = (4LL * num_sms() + count - 1) / count;
+    const long long useful = (window + 4095) / 4096;
+    if (slices > useful) slices = useful;
+    if (slices < 1) slices = 1;
+    return launch("window_energy_kernel", window_energy_kernel, dim3((unsigned)slices, (unsigned)count), dim3(256), 0, stream,
+                  x, (long long)window, (long long)step, energy);
+}
+
+int launch_preview_piece(const float2* in, float2* out, int64_t frames, float clip_to, int64_t fade, cudaStream_t stream) {
+    return launch("preview_piece_kernel", preview_piece_kernel, dim3(grid_for(frames, 1024)), dim3(256), 0, stream, in, out,
+                  (long long)frames, clip_to, (long long)fade);
 }
 
 int launch_count_different(const float* a, const float* b, int64_t count, unsigned long long* n_diff, cudaStream_t stream) {

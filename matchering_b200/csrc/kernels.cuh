@@ -80,6 +80,8 @@ int launch_scale(const float2* in, float2* out, int64_t frames, const double* ga
 int launch_absmax(const float2* in, int64_t frames, float* out_bits, cudaStream_t stream);
 int launch_peak_count(const float* x, int64_t count, float* peak_bits, unsigned long long* n_close, cudaStream_t stream);
 int launch_count_different(const float* a, const float* b, int64_t count, unsigned long long* n_diff, cudaStream_t stream);
+int launch_window_energy(const float2* x, int64_t window, int64_t step, int count, double* energy, cudaStream_t stream);
+int launch_preview_piece(const float2* in, float2* out, int64_t frames, float clip_to, int64_t fade, cudaStream_t stream);
 int launch_pcm_decode(const void* in, int bits, float* out, int64_t count, cudaStream_t stream);
 int launch_pcm_encode(const float* in, int bits, void* out, int64_t count, cudaStream_t stream);
 int launch_convert_f64_f32(const double* in, float* out, int64_t count, cudaStream_t stream);

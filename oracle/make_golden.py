@@ -73,6 +73,25 @@ def main():
     np.savez_compressed(os.path.join(OUT, "limiter.npz"), x=x, y_44100=y44, y_96000=y96,
                         gain_attack=att.astype(np.float32), gain_release=rel.astype(np.float32),
                         envelope=slided.astype(np.float32))
+    # ---- G4: preview creator: the loudest 6-s window of the result, clipped target, fades ---------
+    from matchering import Result, preview_creator
+    cfg4 = Config(internal_sample_rate=2000, preview_size=6, preview_analysis_step=2)
+    n4 = 30000
+    target4 = (2.5 * port.synth_target(n4, 41)).astype(np.float32)
+    result4 = (port.synth_reference(n4, 42) * (0.2 + np.abs(np.sin(np.linspace(0, 9, n4))))[:, None]).astype(np.float32)
+    saved = {}
+    original_save = preview_creator.save
+    preview_creator.save = lambda file, arr, sr, subtype, name: saved.__setitem__(name, arr.copy())
+    try:
+        preview_creator.create_preview(target4.astype(np.float64), result4.astype(np.float64), cfg4,
+                                       Result("t.wav", "PCM_16"), Result("r.wav", "PCM_16"))
+    finally:
+        preview_creator.save = original_save
+    index4 = port.preview_pieces(target4, result4, cfg4)[0]
+    np.savez_compressed(os.path.join(OUT, "preview.npz"), target=target4, result=result4, sample_rate=2000,
+                        preview_size_s=6, preview_analysis_step_s=2, index=index4, every=7,
+                        target_piece=saved["target preview"][::7], result_piece=saved["result preview"][::7],
+                        target_piece_head=saved["target preview"][:300], result_piece_tail=saved["result preview"][-300:])
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
 

@@ -311,6 +311,34 @@ def main(target: np.ndarray, reference: np.ndarray, cfg, need_default=True,
     return out, (result if need_no_limiter else None), out_norm
 
 
+# --------------------------------------------------------------------------- preview creator
+def preview_pieces(target: np.ndarray, result: np.ndarray, cfg):
+    """preview_creator.create_preview (matchering/preview_creator.py:30-94) up to the two arrays it
+    saves: windows of preview_size every preview_analysis_step (dsp.strided_app_2d, dsp.py:128-141),
+    the window where the RESULT is loudest (dsp.batch_rms_2d, dsp.py:144-145), the same window of
+    the target clipped at the threshold, both with linear fades (dsp.fade, dsp.py:148-155) unless
+    the window is the whole track.  -> (window index, target piece, result piece)"""
+    size, step = int(cfg.preview_size), int(cfg.preview_analysis_step)
+    target = np.clip(np.asarray(target, dtype=np.float64), -cfg.threshold, cfg.threshold)
+    result = np.asarray(result, dtype=np.float64)
+    n = result.shape[0]
+    if size > n:
+        index, lo, hi = 0, 0, n
+    else:
+        count = (n - size) // step + 1
+        energy = np.array([np.sum(result[w * step:w * step + size] ** 2) for w in range(count)])
+        index = int(np.argmax(np.sqrt(energy / (2 * size))))
+        lo, hi = index * step, index * step + size
+    t_piece, r_piece = target[lo:hi].copy(), result[lo:hi].copy()
+    if hi - lo != n:
+        fade = int(min(cfg.preview_fade_size, (hi - lo) // cfg.preview_fade_coefficient))
+        ramp = np.linspace(0, 1, fade)
+        for piece in (t_piece, r_piece):
+            piece[:fade] *= ramp[:, None]
+            piece[len(piece) - fade:] *= ramp[::-1, None]
+    return index, t_piece, r_piece
+
+
 # --------------------------------------------------------------------------- synthetic inputs
 _PINK_B = [0.049922035, -0.095993537, 0.050612699, -0.004408786]
 _PINK_A = [1.0, -2.494956002, 2.017265875, -0.522189400]

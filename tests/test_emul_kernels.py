@@ -362,3 +362,30 @@ def test_mono_and_near_mono_targets(lib, side_level):
     _compare(outs, want)
     if side_level == 0.0:
         assert np.array_equal(outs[1][:, 0], outs[1][:, 1])  # stays exactly mono, like the reference
+
+
+def test_preview_kernels_match_golden(lib, golden):
+    """mgb_window_energy + mgb_preview_piece against the reference's create_preview (tests/golden/preview.npz)."""
+    g = golden("preview.npz")
+    sr, every = int(g["sample_rate"]), int(g["every"])
+    size, step = int(g["preview_size_s"]) * sr, int(g["preview_analysis_step_s"]) * sr
+    target, result = aligned_copy(g["target"]), aligned_copy(g["result"])
+    n = len(result)
+    count = (n - size) // step + 1
+    energy = aligned((count,), np.float64)
+    _native.check(lib, lib.mgb_window_energy(ptr(result), n, size, step, count, ptr(energy), None))
+    want = np.array([np.sum(g["result"][w * step:w * step + size].astype(np.float64) ** 2) for w in range(count)])
+    assert np.abs(energy - want).max() < 1e-9 * want.max()
+    index = int(np.argmax(np.sqrt(energy / (2 * size))))
+    assert index == int(g["index"])
+    fade = min(1 * sr, size // 8)
+    thr = port.OracleConfig().threshold
+    for src, clip_to, piece, edge, where in ((target, thr, g["target_piece"], g["target_piece_head"], slice(0, 300)),
+                                             (result, 0.0, g["result_piece"], g["result_piece_tail"], slice(-300, None))):
+        out = aligned((size, 2), np.float32)
+        _native.check(lib, lib.mgb_preview_piece(ptr(src[index * step:]), ptr(out), size, clip_to, fade, None))
+        assert np.abs(out[::every] - piece).max() < 2e-7 and np.abs(out[where] - edge).max() < 2e-7
+        assert out[0].tolist() == [0.0, 0.0] and out[-1].tolist() == [0.0, 0.0]
+    # more windows than fit, or fades longer than the piece, are refused
+    assert lib.mgb_window_energy(ptr(result), n, size, step, count + 1, ptr(energy), None) == _native.MGB_ERR_INVALID
+    assert lib.mgb_preview_piece(ptr(result), ptr(out), 100, 0.0, 51, None) == _native.MGB_ERR_INVALID

@@ -438,3 +438,46 @@ def test_process_pcm_files_stay_on_the_device(torch_cuda, tmp_path):
     wavio.write(str(tmp_path / "s.wav"), r, 44100, "PCM_16")
     with pytest.raises(ModuleError):
         mg.process(str(tmp_path / "s.wav"), str(tmp_path / "s.wav"), [mg.pcm16(str(tmp_path / "x.wav"))])
+
+
+def test_preview_pieces_match_golden(torch_cuda, golden):
+    """matchering_b200.preview_creator against the reference's create_preview (tests/golden/preview.npz)."""
+    import matchering_b200 as mg
+    from matchering_b200.preview_creator import preview_pieces
+    g = golden("preview.npz")
+    cfg = mg.Config(internal_sample_rate=int(g["sample_rate"]), preview_size=int(g["preview_size_s"]),
+                    preview_analysis_step=int(g["preview_analysis_step_s"]))
+    every = int(g["every"])
+    index, t_piece, r_piece = preview_pieces(g["target"], g["result"], cfg)
+    t_piece, r_piece = t_piece.cpu().numpy(), r_piece.cpu().numpy()
+    assert index == int(g["index"])
+    assert np.abs(t_piece[::every] - g["target_piece"]).max() < 2e-7
+    assert np.abs(r_piece[::every] - g["result_piece"]).max() < 2e-7
+    assert np.abs(t_piece[:300] - g["target_piece_head"]).max() < 2e-7
+    assert np.abs(r_piece[-300:] - g["result_piece_tail"]).max() < 2e-7
+    assert np.abs(t_piece).max() <= cfg.threshold  # the target piece is clipped at the threshold
+
+
+def test_process_with_previews(torch_cuda, tmp_path):
+    """mg.process(..., preview_target=, preview_result=): the loudest 30-s window of the result, from both signals."""
+    import matchering_b200 as mg
+    import port
+    from matchering_b200 import wavio
+    n = 44100 * 50 + 3
+    t = port.synth_target(n, 5)
+    r = port.synth_reference(n, 6)
+    wavio.write(str(tmp_path / "t.wav"), t, 44100, "PCM_24")
+    wavio.write(str(tmp_path / "r.wav"), r, 44100, "PCM_24")
+    mg.process(str(tmp_path / "t.wav"), str(tmp_path / "r.wav"), [mg.pcm24(str(tmp_path / "o.wav"))],
+               preview_target=mg.pcm16(str(tmp_path / "pt.wav")), preview_result=mg.Result(str(tmp_path / "pr.wav"), "FLOAT"))
+    t_file, _ = wavio.read(str(tmp_path / "t.wav"))
+    r_file, _ = wavio.read(str(tmp_path / "r.wav"))
+    cfg = mg.Config()
+    result = port.main(t_file, r_file, port.config_from(cfg), True, False, False)[0]
+    index, want_t, want_r = port.preview_pieces(t_file, result, cfg)
+    got_t, _ = wavio.read(str(tmp_path / "pt.wav"))
+    got_r, _ = wavio.read(str(tmp_path / "pr.wav"))
+    assert got_t.shape == want_t.shape == (30 * 44100, 2) and got_r.shape == want_r.shape
+    assert np.abs(got_r - want_r).max() < TOL
+    assert np.abs(got_t - want_t).max() < 1.6 / 32768
+    assert got_r[0].tolist() == [0.0, 0.0]

@@ -92,3 +92,21 @@ def test_main_against_reference(reference_package, sr, seconds):
     got = port.main(t, r, cfg, True, True, True)
     for a, b in zip(got, want):
         assert np.abs(a - b).max() < 1e-12
+
+
+@pytest.mark.parametrize("n,whole", [(30000, False), (9000, True), (12000 + 4000 * 3, False)])
+def test_preview_pieces_against_reference(reference_package, monkeypatch, n, whole):
+    """oracle/port.py::preview_pieces against the unmodified create_preview (its two `save` calls captured)."""
+    from matchering import Config, Result, preview_creator
+    cfg = Config(internal_sample_rate=2000, preview_size=6, preview_analysis_step=2)
+    saved = {}
+    monkeypatch.setattr(preview_creator, "save", lambda file, arr, sr, subtype, name: saved.__setitem__(name, arr.copy()))
+    target = 2.5 * port.synth_target(n, 41).astype(np.float64)
+    result = port.synth_reference(n, 42).astype(np.float64) * (0.2 + np.abs(np.sin(np.linspace(0, 9, n))))[:, None]
+    keep_t, keep_r = target.copy(), result.copy()
+    preview_creator.create_preview(target, result, cfg, Result("t.wav", "PCM_16"), Result("r.wav", "PCM_16"))
+    index, t_piece, r_piece = port.preview_pieces(keep_t, keep_r, cfg)
+    assert np.array_equal(saved["target preview"], t_piece) and np.array_equal(saved["result preview"], r_piece)
+    assert (len(r_piece) == n) == whole
+    if not whole:
+        assert r_piece[0].tolist() == [0.0, 0.0] and r_piece[-1].tolist() == [0.0, 0.0]
