@@ -116,6 +116,7 @@ struct LimiterGeom {
     int filt;                     // samples the attack filter needs to run over (LC + left + warm)
     int publish_inclusive;        // 0: chunks publish aggregates only (test switch: every look-back then walks to the cut-off)
     int levels;                   // sparse-table levels the running maxima need (runs of < 2^(levels+1) blocks)
+    int shared_core;              // both windows are wide enough for the per-thread shared-core evaluation
 };
 
 // powers of the three poles, computed once per parameter set (not per CTA: pow() is slow)
@@ -264,14 +265,50 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
             return m;
         };
         float h[EPT];
+        if (gm.shared_core) {
+            // The thread's EPT windows of one kind share most of their samples: with b = base,
+            //   A window e = [b+e-reach, b+EPT-2-reach] + coreA + [b+reach+1, b+e+reach]
+            //   H window e = [b+e-reach-hold+1, b+EPT-1-reach-hold] + coreH + the same right part
+            // where coreA = [b+EPT-1-reach, b+reach] and coreH = [b+EPT-reach-hold, b+reach] do not
+            // depend on e.  Two table queries per thread instead of 2*EPT; the parts left and right of
+            // the cores are EPT-1 samples each, combined by running maxima in registers.  g >= 0, so
+            // samples outside the span count as 0, which is what truncating the window does.
+            auto gat = [&](int i) -> float { return (i >= 0 && i < CAP) ? G[i] : 0.0f; };
+            float la[EPT], lh[EPT], rt[EPT];
 #pragma unroll
-        for (int e = 0; e < EPT; ++e) {
-            const int i = base + e;
-            const int r = min(i + reach, CAP - 1);
+            for (int e = 0; e < EPT - 1; ++e) {
+                la[e] = gat(base - reach + e);
+                lh[e] = gat(base - reach - hold + 1 + e);
+                rt[e + 1] = gat(base + reach + 1 + e);
+            }
+            la[EPT - 1] = lh[EPT - 1] = rt[0] = 0.0f;
+#pragma unroll
+            for (int e = EPT - 2; e >= 0; --e) {  // suffix maxima of the left parts
+                la[e] = fmaxf(la[e], la[e + 1]);
+                lh[e] = fmaxf(lh[e], lh[e + 1]);
+            }
+#pragma unroll
+            for (int e = 1; e < EPT; ++e) rt[e] = fmaxf(rt[e], rt[e - 1]);  // prefix maxima of the right part
+            const int r = min(base + reach, CAP - 1);
             const int br = r / EPT;
             const float pr = PF[r];
-            Aenv[i] = window(max(i - reach, 0), r, br, pr);
-            h[e] = window(max(i - reach - hold + 1, 0), r, br, pr);
+            const float core_a = window(max(base + EPT - 1 - reach, 0), r, br, pr);
+            const float core_h = window(max(base + EPT - reach - hold, 0), r, br, pr);
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                Aenv[base + e] = fmaxf(core_a, fmaxf(la[e], rt[e]));
+                h[e] = fmaxf(core_h, fmaxf(lh[e], rt[e]));
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                const int i = base + e;
+                const int r = min(i + reach, CAP - 1);
+                const int br = r / EPT;
+                const float pr = PF[r];
+                Aenv[i] = window(max(i - reach, 0), r, br, pr);
+                h[e] = window(max(i - reach - hold + 1, 0), r, br, pr);
+            }
         }
         __syncthreads();  // SF (= Wk) fully read
 #pragma unroll
@@ -491,6 +528,8 @@ int limiter_geometry(const mgb_limiter_params& lp, LimiterGeom* g) {
     while ((2 << levels) <= max_blocks) ++levels;
     g->levels = levels;
     g->publish_inclusive = g_lookback_inclusive;
+    // the cores [b+ept-1-reach, b+reach] and [b+ept-reach-hold, b+reach] must not be empty
+    g->shared_core = (2 * lp.reach >= ept - 1 && 2 * lp.reach + lp.hold >= ept) ? 1 : 0;
     MGB_REQUIRE(ept <= SPAN_EPT_MAX, MGB_ERR_UNSUPPORTED,
                 "limiter: halo of %d samples exceeds the kernel's span", g->span - LC);
     return MGB_OK;

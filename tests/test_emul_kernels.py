@@ -164,6 +164,17 @@ def test_limiter_edge_lengths(lib, n):
     assert np.abs(out - want).max() < 3e-7
 
 
+@pytest.mark.parametrize("sr,attack", [(4000, 1.0), (8000, 1.0), (44100, 0.1), (44100, 4.0)])
+def test_limiter_narrow_and_wide_windows(lib, sr, attack):
+    """Attack windows of 3..350 samples: narrow ones take the per-sample window evaluation, the others the
+    shared-core one (limiter.cu, P2)."""
+    cfg = port.OracleConfig(internal_sample_rate=sr, limiter=port.OracleLimiterConfig(attack=attack))
+    x = port.synth_limiter_input(12000, seed=sr + int(10 * attack))
+    out, engaged = _limit(lib, x, cfg)
+    want = port.limit(x.astype(np.float64), cfg)
+    assert engaged == 1 and np.abs(out - want).max() < 3e-7
+
+
 def test_limiter_not_engaged_copies_input(lib):
     x = (0.2 * port.synth_limiter_input(6000, 2)).astype(np.float32)
     out, engaged = _limit(lib, x, port.OracleConfig())
