@@ -115,7 +115,6 @@ struct LimiterGeom {
     int span;                     // samples of g the chunk touches
     int filt;                     // samples the attack filter needs to run over (LC + left + warm)
     int publish_inclusive;        // 0: chunks publish aggregates only (test switch: every look-back then walks to the cut-off)
-    int levels;                   // sparse-table levels the running maxima need (runs of < 2^(levels+1) blocks)
     int shared_core;              // both windows are wide enough for the per-thread shared-core evaluation
 };
 
@@ -145,11 +144,11 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
     float* Aenv = reinterpret_cast<float*>(smem) + CAP;           // [CAP] attack envelope, aliases Fd's upper half
     float* G = reinterpret_cast<float*>(smem + (size_t)CAP * 8);  // [CAP] hard-clip gain, later max(g, g_att)
     float* Wk = G + CAP;                                          // [CAP] suffix maxima, later the hold envelope
-    constexpr int kLevels = 6;  // runs of up to 63 whole blocks
-    __shared__ float blockmax[kLevels][NT + 32];
+    __shared__ float blockmax[NT];
     __shared__ ScanPow pw3[3];
     __shared__ double scratch_a[32], scratch_b[32];  // scan_carry alternates between them
     __shared__ double bcast[2];
+    __shared__ double warp_edge[NT / 32];
     __shared__ int chunk_s;
     const ScanPow* pow_att = &pw3[0];
     const ScanPow* pow_hold = &pw3[1];
@@ -209,10 +208,8 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
     //   A[n] = max g[n-reach .. n+reach]                                 (hyrax.py:35-37)
     //   H[n] = max A[n-hold+1 .. n] = max g[n-hold+1-reach .. n+reach]   (hyrax.py:38-40)
     // Every thread owns EPT consecutive samples: their prefix and suffix maxima inside the block
-    // (PF, SF) and the block maximum; a sparse table over the 512 block maxima answers any run of
-    // whole blocks in two reads.  A window [l, r] is then max(SF[l], whole blocks between, PF[r]):
-    // about 7 shared-memory reads per sample for BOTH windows, where log-step doubling over the
-    // samples needed ~9 full passes.
+    // (PF, SF) and the block maximum.  A window [l, r] is max(SF[l], whole blocks between, PF[r]).
+    float hc[CORE_EPT + 1];  // H at span indices cidx + tid*CORE_EPT - 1 + e
     {
         float* PF = reinterpret_cast<float*>(smem);  // [CAP] lower half of Fd's bytes (Aenv is the upper half)
         float* SF = Wk;                              // [CAP]
@@ -226,8 +223,7 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
             run = fmaxf(run, x[e]);
             PF[base + e] = run;
         }
-        blockmax[0][tid] = run;
-        if (tid < 32) blockmax[0][NT + tid] = 0.0f;
+        blockmax[tid] = run;
         run = 0.0f;
 #pragma unroll
         for (int e = EPT - 1; e >= 0; --e) {
@@ -235,23 +231,10 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
             SF[base + e] = run;
         }
         __syncthreads();
-        // sparse table over the block maxima, blockmax[j][t] = max of blocks t .. t + 2^j - 1: every
-        // thread builds its own column straight from level 0 (at most 2^jmax reads), so the levels
-        // need no barriers between them
-        {
-            float m = blockmax[0][tid];
-            int have = 1;
-            for (int j = 1; j <= gm.levels; ++j) {
-                const int want = 1 << j;
-                for (int q = have; q < want; ++q) m = fmaxf(m, blockmax[0][min(tid + q, NT + 31)]);
-                have = want;
-                blockmax[j][tid] = m;
-            }
-        }
-        __syncthreads();
-        auto whole_blocks = [&](int a, int b) -> float {  // blocks a..b inclusive, a <= b
-            const int j = 31 - __clz(b - a + 1);
-            return fmaxf(blockmax[j][a], blockmax[j][b - (1 << j) + 1]);
+        auto whole_blocks = [&](int a, int b) -> float {  // blocks a..b inclusive (a run of at most ~a dozen)
+            float m = 0.0f;
+            for (int q = a; q <= b; ++q) m = fmaxf(m, blockmax[q]);
+            return m;
         };
         auto window = [&](int l, int r, int br, float pr) -> float {
             const int bl = l / EPT;
@@ -264,81 +247,92 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
             if (br - bl > 1) m = fmaxf(m, whole_blocks(bl + 1, br - 1));
             return m;
         };
-        float h[EPT];
+        auto gat = [&](int i) -> float { return (i >= 0 && i < CAP) ? G[i] : 0.0f; };  // g >= 0: outside counts as 0
+        // The thread's consecutive windows of one kind share most of their samples: for the EPT windows
+        // [b+e-reach, b+e+reach] (b = base) the core [b+EPT-1-reach, b+reach] does not depend on e; what
+        // lies left and right of it are EPT-1 samples each, combined by running maxima in registers.
+        // One table query per thread and kind instead of one per sample.
         if (gm.shared_core) {
-            // The thread's EPT windows of one kind share most of their samples: with b = base,
-            //   A window e = [b+e-reach, b+EPT-2-reach] + coreA + [b+reach+1, b+e+reach]
-            //   H window e = [b+e-reach-hold+1, b+EPT-1-reach-hold] + coreH + the same right part
-            // where coreA = [b+EPT-1-reach, b+reach] and coreH = [b+EPT-reach-hold, b+reach] do not
-            // depend on e.  Two table queries per thread instead of 2*EPT; the parts left and right of
-            // the cores are EPT-1 samples each, combined by running maxima in registers.  g >= 0, so
-            // samples outside the span count as 0, which is what truncating the window does.
-            auto gat = [&](int i) -> float { return (i >= 0 && i < CAP) ? G[i] : 0.0f; };
-            float la[EPT], lh[EPT], rt[EPT];
+            float la[EPT], rt[EPT];
 #pragma unroll
             for (int e = 0; e < EPT - 1; ++e) {
                 la[e] = gat(base - reach + e);
-                lh[e] = gat(base - reach - hold + 1 + e);
                 rt[e + 1] = gat(base + reach + 1 + e);
             }
-            la[EPT - 1] = lh[EPT - 1] = rt[0] = 0.0f;
+            la[EPT - 1] = rt[0] = 0.0f;
 #pragma unroll
-            for (int e = EPT - 2; e >= 0; --e) {  // suffix maxima of the left parts
-                la[e] = fmaxf(la[e], la[e + 1]);
-                lh[e] = fmaxf(lh[e], lh[e + 1]);
-            }
+            for (int e = EPT - 2; e >= 0; --e) la[e] = fmaxf(la[e], la[e + 1]);  // suffix maxima of the left part
 #pragma unroll
-            for (int e = 1; e < EPT; ++e) rt[e] = fmaxf(rt[e], rt[e - 1]);  // prefix maxima of the right part
+            for (int e = 1; e < EPT; ++e) rt[e] = fmaxf(rt[e], rt[e - 1]);       // prefix maxima of the right part
             const int r = min(base + reach, CAP - 1);
-            const int br = r / EPT;
-            const float pr = PF[r];
-            const float core_a = window(max(base + EPT - 1 - reach, 0), r, br, pr);
-            const float core_h = window(max(base + EPT - reach - hold, 0), r, br, pr);
+            const float core = window(max(base + EPT - 1 - reach, 0), r, r / EPT, PF[r]);
 #pragma unroll
-            for (int e = 0; e < EPT; ++e) {
-                Aenv[base + e] = fmaxf(core_a, fmaxf(la[e], rt[e]));
-                h[e] = fmaxf(core_h, fmaxf(lh[e], rt[e]));
-            }
+            for (int e = 0; e < EPT; ++e) Aenv[base + e] = fmaxf(core, fmaxf(la[e], rt[e]));
         } else {
 #pragma unroll
             for (int e = 0; e < EPT; ++e) {
                 const int i = base + e;
                 const int r = min(i + reach, CAP - 1);
-                const int br = r / EPT;
-                const float pr = PF[r];
-                Aenv[i] = window(max(i - reach, 0), r, br, pr);
-                h[e] = window(max(i - reach - hold + 1, 0), r, br, pr);
+                Aenv[i] = window(max(i - reach, 0), r, r / EPT, PF[r]);
             }
         }
-        __syncthreads();  // SF (= Wk) fully read
+        // H for the thread's own CORE_EPT core samples and the one before them (the filters below run
+        // over the core in this very mapping, so H never goes through shared memory for another thread):
+        // windows [bh+e-reach-hold+1, bh+e+reach], e = 0..CORE_EPT
+        const int bh = cidx + tid * CORE_EPT - 1;
+        if (gm.shared_core) {
+            float lh[CORE_EPT + 1], rh[CORE_EPT + 1];
 #pragma unroll
-        for (int e = 0; e < EPT; ++e) Wk[base + e] = h[e];
-        __syncthreads();
+            for (int e = 0; e < CORE_EPT; ++e) {
+                lh[e] = gat(bh - reach - hold + 1 + e);
+                rh[e + 1] = gat(bh + reach + 1 + e);
+            }
+            lh[CORE_EPT] = rh[0] = 0.0f;
+#pragma unroll
+            for (int e = CORE_EPT - 1; e >= 0; --e) lh[e] = fmaxf(lh[e], lh[e + 1]);
+#pragma unroll
+            for (int e = 1; e <= CORE_EPT; ++e) rh[e] = fmaxf(rh[e], rh[e - 1]);
+            const int r = min(bh + reach, CAP - 1);
+            const float core = window(max(bh + CORE_EPT + 1 - reach - hold, 0), r, r / EPT, PF[r]);
+#pragma unroll
+            for (int e = 0; e <= CORE_EPT; ++e) hc[e] = fmaxf(core, fmaxf(lh[e], rh[e]));
+        } else {
+#pragma unroll
+            for (int e = 0; e <= CORE_EPT; ++e) {
+                const int r = min(bh + e + reach, CAP - 1);
+                hc[e] = window(max(bh + e - reach - hold + 1, 0), r, r / EPT, PF[r]);
+            }
+        }
+        // lfilter starts from rest: the envelope before the first sample is 0, not a window maximum
+#pragma unroll
+        for (int e = 0; e <= CORE_EPT; ++e)
+            if (bh + e < vlo) hc[e] = 0.0f;
     }
-    if (vlo > 0) {  // lfilter starts from rest: the envelope before the first sample is 0, not a window max
-        for (int i = tid; i < vlo; i += NT) Wk[i] = 0.0f;
-        __syncthreads();
-    }
-    const float* H = Wk;
 
     // ---- P3: hold_out = lfilter(butter(1, f_hold), H), zero-carry pass (hyrax.py:61-66) -------------
     // The chunk's aggregate is published now; the carry from the previous chunks is only needed after
     // the attack filter below, which gives the predecessors time to publish theirs.
     LookbackSlot* slot = slots + chunk;
     double hold_y[CORE_EPT];
+    double prev_last;  // the previous thread's last hold sample (zero carry into the chunk)
+    float* Hown = Wk + tid * (CORE_EPT + 1);  // the thread's own H samples, parked until the release filter
     {
         double acc = 0.0;
 #pragma unroll
         for (int e = 0; e < CORE_EPT; ++e) {
-            const int i = cidx + tid * CORE_EPT + e;
-            const double u = lp.hold_b0 * (double)H[i] + lp.hold_b1 * (double)H[i - 1];
+            const double u = lp.hold_b0 * (double)hc[e + 1] + lp.hold_b1 * (double)hc[e];
             acc = u - lp.hold_a1 * acc;
             hold_y[e] = acc;
         }
+        // (the barrier inside also ends P2: every thread is done with PF, SF and the sparse table)
         const double carry = scan_carry(acc, pow_hold, 0.0, scratch_a);
 #pragma unroll
         for (int e = 0; e < CORE_EPT; ++e) hold_y[e] += pow_hold->pe[e + 1] * carry;
         if (tid == NT - 1) publish(&slot->hold, hold_y[CORE_EPT - 1], 1);
+        prev_last = __shfl_up_sync(0xffffffffu, hold_y[CORE_EPT - 1], 1);
+        if ((tid & 31) == 31) warp_edge[tid >> 5] = hold_y[CORE_EPT - 1];  // read by the next warp's lane 0 in P5
+#pragma unroll
+        for (int e = 0; e <= CORE_EPT; ++e) Hown[e] = hc[e];  // SF (= Wk) is free now; only this thread reads these back
     }
 
     // ---- P4: g_att = filtfilt one-pole over A (hyrax.py:48-51) -------------------------------------
@@ -419,31 +413,24 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
     }
     __syncthreads();  // also: every thread is done reading Fd as the attack filter's plane
     const double hold_cin = bcast[0];
+    double hold_prev;  // hold_out just before the thread's first sample
     {
         const double lead = pow_hold->ql[tid & 31] * pow_hold->qw[tid >> 5];  // pole^(tid*CORE_EPT)
+        if ((tid & 31) == 0 && tid > 0) prev_last = warp_edge[(tid >> 5) - 1];
+        hold_prev = tid == 0 ? hold_cin : prev_last + lead * hold_cin;
 #pragma unroll
-        for (int e = 0; e < CORE_EPT; ++e) {
-            hold_y[e] += pow_hold->pe[e + 1] * lead * hold_cin;
-            Fd[tid * CORE_EPT + e] = hold_y[e];
-        }
+        for (int e = 0; e < CORE_EPT; ++e) hold_y[e] += pow_hold->pe[e + 1] * lead * hold_cin;
         if (tid == NT - 1 && gm.publish_inclusive) publish(&slot->hold, hold_y[CORE_EPT - 1], 2);
     }
-    __syncthreads();
 
     // ---- P6: release_out = lfilter(butter(1, f_rel), max(H, hold_out)) (hyrax.py:68-73) -------------
     {
         double rel_y[CORE_EPT];
         double acc = 0.0;
-        double prev_in;
-        {
-            const int i = cidx + tid * CORE_EPT - 1;
-            const double hprev = tid == 0 ? hold_cin : Fd[tid * CORE_EPT - 1];
-            prev_in = fmax((double)H[i], hprev);
-        }
+        double prev_in = fmax((double)Hown[0], hold_prev);
 #pragma unroll
         for (int e = 0; e < CORE_EPT; ++e) {
-            const int i = cidx + tid * CORE_EPT + e;
-            const double cur = fmax((double)H[i], hold_y[e]);
+            const double cur = fmax((double)Hown[e + 1], hold_y[e]);
             const double u = lp.release_b0 * cur + lp.release_b1 * prev_in;
             prev_in = cur;
             acc = u - lp.release_a1 * acc;
@@ -521,12 +508,6 @@ int limiter_geometry(const mgb_limiter_params& lp, LimiterGeom* g) {
     if (!(ept & 1)) ept += 1;  // odd stride: the blocked scans read shared memory conflict-free
     if (ept < 11) ept = 11;
     g->ept = ept;
-    const int win_h = 2 * lp.reach + lp.hold;
-    const int max_blocks = win_h / ept + 1;  // whole blocks strictly inside the widest window
-    MGB_REQUIRE(max_blocks < 32, MGB_ERR_UNSUPPORTED, "limiter: attack + hold window of %d samples is too long", win_h);
-    int levels = 0;
-    while ((2 << levels) <= max_blocks) ++levels;
-    g->levels = levels;
     g->publish_inclusive = g_lookback_inclusive;
     // the cores [b+ept-1-reach, b+reach] and [b+ept-reach-hold, b+reach] must not be empty
     g->shared_core = (2 * lp.reach >= ept - 1 && 2 * lp.reach + lp.hold >= ept) ? 1 : 0;
