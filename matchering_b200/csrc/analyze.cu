@@ -8,7 +8,7 @@
 //
 // Work item = (piece p, slot s): a contiguous run of the piece's F-sample frames.  Each frame is
 // brought into shared memory by one TMA bulk copy (cp.async.bulk, raw interleaved L/R), turned
-// into z = mid + i*side while it is gathered for the first FFT pass (sum(mid^2) in float64 and
+// into z = mid + i*side while it is gathered for the first FFT pass (sum(mid^2) accumulated in float64 and
 // max|x| are accumulated on the way), transformed with ONE complex F-point FFT, and split into
 // |rfft(mid)| and |rfft(side)| from the pair Z[k], Z[F-k].  The magnitudes are summed over the
 // slot's frames in registers and written once per work item; which pieces count ("loudest") is
@@ -115,11 +115,11 @@ analyze_kernel(const float2* __restrict__ x, long long frames, long long piece, 
 #pragma unroll
         for (int r = 0; r < F / THREADS; ++r) {
             const float2 v = first.sample(tid + r * THREADS);
-            const double mid = ((double)v.x + (double)v.y) * 0.5;
-            sumsq += mid * mid;
+            // mid and side from L and R directly, one rounding each, exactly as the convolution forms them
+            z[r].x = (v.x + v.y) * 0.5f;
+            z[r].y = (v.x - v.y) * 0.5f;
+            sumsq = fma((double)z[r].x, (double)z[r].x, sumsq);
             peak = fmaxf(peak, fmaxf(fabsf(v.x), fabsf(v.y)));
-            z[r].x = (float)mid;
-            z[r].y = (float)(mid - (double)v.y);
             max_mid = fmaxf(max_mid, fabsf(z[r].x));
             max_side = fmaxf(max_side, fabsf(z[r].y));
         }
