@@ -149,8 +149,8 @@ analyze_kernel(const float2* __restrict__ x, long long frames, long long piece, 
                 // rfft(mid)[k] = (Z[k] + conj(Z[F-k]))/2 ; rfft(side)[k] = (Z[k] - conj(Z[F-k]))/(2i)
                 const float mr = zr + nr, mi = zi - ni;
                 const float sr = zi + ni, si = nr - zr;
-                acc_mid[b] += 0.5f * sqrtf(mr * mr + mi * mi);
-                if (!side_silent) acc_side[b] += inv_g * sqrtf(sr * sr + si * si);
+                acc_mid[b] += 0.5f * sqrt_approx(mr * mr + mi * mi);
+                if (!side_silent) acc_side[b] += inv_g * sqrt_approx(sr * sr + si * si);
             }
         }
         __syncthreads();  // planes free for the next frame

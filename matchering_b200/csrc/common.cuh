@@ -181,6 +181,19 @@ __device__ __forceinline__ float balance_factor(float large, float small) {
     return exp2f((float)e);
 }
 
+// sqrt with the special-function unit alone (sqrt.approx: one MUFU, relative error <= 2^-23) instead of
+// sqrtf's correctly rounded sequence (nine instructions and a branch).  For magnitudes that are summed
+// over hundreds of frames the half ulp does not matter; the issue slots do.
+__device__ __forceinline__ float sqrt_approx(float x) {
+#ifdef MGB_EMULATE
+    return sqrtf(x);
+#else
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#endif
+}
+
 // Non-negative floats order like their bit patterns: atomic max through the integer unit.
 __device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
     atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
