@@ -189,6 +189,11 @@ def run_b200(args) -> dict:
         raise SystemExit("bench.py --impl b200 needs a CUDA device: there is no CPU fallback")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    bound_cores = None
+    if world > 1:
+        # several ranks share the host: each stays on the cores (and memory) next to its own GPU
+        from matchering_b200.sharding import bind_host_thread_near_gpu
+        bound_cores = bind_host_thread_near_gpu(local_rank)
     if world > 1:
         # keep stdout for the one JSON line: NCCL prints its version banner there at VERSION level
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
@@ -414,6 +419,7 @@ def run_b200(args) -> dict:
                        "one_track_at_a_time": {"value": frames_total / (dev_serial_ms * 1e-3) / SAMPLE_RATE,
                                                "ms_per_step": dev_serial_ms / args.steps},
                        "l2": "inputs larger than L2: 3 rotating tracks per rank, ~290 MB touched per step",
+                       "host_cores_bound_per_rank": bound_cores,
                        "precision": "float32 I/O and FFTs, float64 reductions / FIR design / IIR state"},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": 2 * n * 8, "d2h_bytes_per_step": n * 8,

@@ -70,6 +70,21 @@ static void dev_free(void* p) { cudaFree(p); }
 
 extern "C" {
 
+// (inside mgb_pipeline_create: a failed CUDA call releases what was created so far)
+#ifdef MGB_EMULATE
+#define MGB_CUDA_OR_DESTROY(call) (void)0
+#else
+#define MGB_CUDA_OR_DESTROY(call)                                                     \
+    do {                                                                              \
+        cudaError_t e_ = (call);                                                      \
+        if (e_ != cudaSuccess) {                                                      \
+            set_error("%s: %s", #call, cudaGetErrorString(e_));                       \
+            mgb_pipeline_destroy(p);                                                  \
+            return MGB_ERR_CUDA;                                                      \
+        }                                                                             \
+    } while (0)
+#endif
+
 int mgb_pipeline_create(const mgb_plan* plan, int64_t max_target_frames, int64_t max_reference_frames, int32_t depth,
                         mgb_pipeline** out) {
     MGB_REQUIRE(plan && out, MGB_ERR_INVALID, "pipeline: NULL argument");
@@ -85,9 +100,9 @@ int mgb_pipeline_create(const mgb_plan* plan, int64_t max_target_frames, int64_t
     p->workspace_bytes = biggest.workspace_bytes + (8 << 20);
     p->slots.resize(depth);
 #ifndef MGB_EMULATE
-    MGB_CUDA_OK(cudaStreamCreateWithFlags(&p->s_h2d, cudaStreamNonBlocking));
-    MGB_CUDA_OK(cudaStreamCreateWithFlags(&p->s_compute, cudaStreamNonBlocking));
-    MGB_CUDA_OK(cudaStreamCreateWithFlags(&p->s_d2h, cudaStreamNonBlocking));
+    MGB_CUDA_OR_DESTROY(cudaStreamCreateWithFlags(&p->s_h2d, cudaStreamNonBlocking));
+    MGB_CUDA_OR_DESTROY(cudaStreamCreateWithFlags(&p->s_compute, cudaStreamNonBlocking));
+    MGB_CUDA_OR_DESTROY(cudaStreamCreateWithFlags(&p->s_d2h, cudaStreamNonBlocking));
 #endif
     for (auto& s : p->slots) {
         s.d_target = (float*)dev_alloc((size_t)max_target_frames * 8);
@@ -107,11 +122,11 @@ int mgb_pipeline_create(const mgb_plan* plan, int64_t max_target_frames, int64_t
 #ifdef MGB_EMULATE
         s.h_state = (mgb_track_state*)malloc(sizeof(mgb_track_state));
 #else
-        MGB_CUDA_OK(cudaMallocHost((void**)&s.h_state, sizeof(mgb_track_state)));
-        MGB_CUDA_OK(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
-        MGB_CUDA_OK(cudaEventCreateWithFlags(&s.compute_done, cudaEventDisableTiming));
-        MGB_CUDA_OK(cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming));
-        MGB_CUDA_OK(cudaStreamCreateWithFlags(&s.compute, cudaStreamNonBlocking));
+        MGB_CUDA_OR_DESTROY(cudaMallocHost((void**)&s.h_state, sizeof(mgb_track_state)));
+        MGB_CUDA_OR_DESTROY(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
+        MGB_CUDA_OR_DESTROY(cudaEventCreateWithFlags(&s.compute_done, cudaEventDisableTiming));
+        MGB_CUDA_OR_DESTROY(cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming));
+        MGB_CUDA_OR_DESTROY(cudaStreamCreateWithFlags(&s.compute, cudaStreamNonBlocking));
 #endif
     }
     *out = p;

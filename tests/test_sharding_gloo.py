@@ -51,3 +51,13 @@ def test_single_process_is_identity():
     from matchering_b200 import sharding
     assert sharding.tracks_for_rank(5, 0, 1) == [0, 1, 2, 3, 4]
     assert sharding.gather_throughput(123, 4.5, device=None) == (123, 4.5)
+
+
+def test_numa_binding_is_a_no_op_without_a_gpu():
+    import os
+    import torch
+    from matchering_b200.sharding import bind_host_thread_near_gpu
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without a GPU")
+    before = os.sched_getaffinity(0)
+    assert bind_host_thread_near_gpu(0) is None and os.sched_getaffinity(0) == before
