@@ -14,7 +14,6 @@ namespace mgb {
 int g_use_tma = 1;
 int g_twiddle_chain = 1;
 int g_conv_fused = 1;
-int g_l2_prefetch = 1;
 int g_lookback_inclusive = 1;
 
 #ifndef MGB_EMULATE
@@ -266,10 +265,6 @@ int mgb_set_option(const char* name, int value) {
     MGB_REQUIRE(name != nullptr, MGB_ERR_INVALID, "option name is NULL");
     if (strcmp(name, "tma") == 0) {
         g_use_tma = value ? 1 : 0;
-        return MGB_OK;
-    }
-    if (strcmp(name, "l2_prefetch") == 0) {
-        g_l2_prefetch = value ? 1 : 0;
         return MGB_OK;
     }
     if (strcmp(name, "conv_fused") == 0) {

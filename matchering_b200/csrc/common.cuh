@@ -217,7 +217,6 @@ __device__ __forceinline__ void tma_barrier_wait(TmaBarrier* b, uint32_t phase_i
     while (b->phase_done <= phase_index) ::emul::yield();
 }
 __device__ __forceinline__ void fence_proxy_async() {}
-__device__ __forceinline__ void tma_prefetch_l2(const void*, uint32_t) {}
 #else
 struct __align__(8) TmaBarrier {
     unsigned long long bar;
@@ -239,12 +238,6 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
         "l"(gmem_src), "r"(bytes), "r"(smem_u32(&b->bar))
         : "memory");
-}
-// Bulk prefetch into L2 (cp.async.bulk.prefetch.L2): one instruction asks for a whole frame that a LATER
-// CTA will load, so that CTA's copy finds it in L2 instead of waiting for DRAM.  Address and size are
-// multiples of 16 bytes.
-__device__ __forceinline__ void tma_prefetch_l2(const void* gmem_src, uint32_t bytes) {
-    if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void tma_barrier_wait(TmaBarrier* b, uint32_t phase_index) {
     const uint32_t parity = phase_index & 1u;

@@ -58,7 +58,7 @@ struct ConvBalance {
 template <int F>
 __device__ __forceinline__ ConvBalance conv_load_frame(const float2* __restrict__ x, long long frames, long long origin,
                                                        float2* raw, TmaBarrier* bar, unsigned* red_u, int use_tma,
-                                                       int ahead, cpx<float>* z) {
+                                                       cpx<float>* z) {
     constexpr int N = 2 * F;
     constexpr int THREADS = N / 16;
     const int tid = threadIdx.x;
@@ -81,12 +81,7 @@ __device__ __forceinline__ ConvBalance conv_load_frame(const float2* __restrict_
             first.fixup = x + (hi - 1);
             count -= 1;
         }
-        if (tid == 0) {
-            tma_load_1d(raw + (lo - origin), x + lo, (uint32_t)(count * 8), bar);
-            // the F new samples of the frame that this SM slot's next-but-`ahead` CTA will load: by then in L2
-            const long long plo = origin + (long long)ahead * F + F;  // (its first F samples are this wave's reads)
-            if (ahead > 0 && plo >= 0 && plo + F <= frames) tma_prefetch_l2(x + plo, (uint32_t)F * 8u);
-        }
+        if (tid == 0) tma_load_1d(raw + (lo - origin), x + lo, (uint32_t)(count * 8), bar);
         tma_barrier_wait(bar, 0);
     } else {
         for (long long n = lo + tid; n < hi; n += THREADS) raw[n - origin] = x[n];
@@ -222,7 +217,7 @@ convolve_kernel(const float2* __restrict__ x, long long frames, long long piece,
     const long long n0 = (long long)blockIdx.x * F;
 
     cpx<float> z[N / THREADS];
-    const ConvBalance bal = conv_load_frame<F>(x, frames, n0 - F / 2, sp.raw, sp.bar, sp.red_u, use_tma & 1, use_tma >> 1, z);
+    const ConvBalance bal = conv_load_frame<F>(x, frames, n0 - F / 2, sp.raw, sp.bar, sp.red_u, use_tma, z);
 
     // ---- forward transform of z = mid + i*g*side ---------------------------------------------------
     fft_first_pass_regs<N, +1, THREADS, float>(planes, z, /*barrier_before_store=*/false);
@@ -289,7 +284,7 @@ convolve_fused_kernel(const float2* __restrict__ x, long long frames, long long 
     ConvBalance bal;
     {
         cpx<float> z[N / THREADS];
-        bal = conv_load_frame<F>(x, frames, n0 - F / 2, sp.raw, sp.bar, sp.red_u, use_tma & 1, use_tma >> 1, z);
+        bal = conv_load_frame<F>(x, frames, n0 - F / 2, sp.raw, sp.bar, sp.red_u, use_tma, z);
         fft_first_pass_regs<N, +1, THREADS, float>(planes, z, /*barrier_before_store=*/false);
     }
     __syncthreads();
@@ -361,8 +356,7 @@ int launch_convolve_t(const mgb_plan& plan, const mgb_track_layout& layout, cons
     return launch("convolve_kernel", kernel, dim3(nframes), dim3(F / 8), ConvSmem<F>::kBytes, stream, target, T,
                   (long long)layout.target_piece, layout.target_divisions, (const cpx<float>*)plan.d_tw_f32_2F,
                   (const float2*)ws.h_mid, (const float2*)ws.h_side, result, ws.mid_plane, ws.piece_sums, state,
-                  // bit 0: bulk-copy loads; the rest: how many frames ahead to prefetch into L2 (one wave of CTAs)
-                  g_use_tma | ((g_l2_prefetch ? 2 * num_sms() : 0) << 1));
+                  g_use_tma);
 }
 
 }  // namespace

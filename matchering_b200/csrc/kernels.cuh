@@ -103,7 +103,6 @@ int twiddle_count(int n);
 
 extern int g_use_tma;
 extern int g_lookback_inclusive;  // limiter chunks publish their inclusive state (1, default) or aggregates only (0, tests)
-extern int g_l2_prefetch;    // convolution / limiter: ask L2 for the data of the CTA one wave ahead (1)
 extern int g_conv_fused;     // convolution: ends of both transforms in registers where the schedule allows (1)
 extern int g_twiddle_chain;  // convolution FFTs: build twiddle powers in registers (1) or read them all (0)
 

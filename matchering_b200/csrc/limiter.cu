@@ -116,7 +116,6 @@ struct LimiterGeom {
     int filt;                     // samples the attack filter needs to run over (LC + left + warm)
     int publish_inclusive;        // 0: chunks publish aggregates only (test switch: every look-back then walks to the cut-off)
     int shared_core;              // both windows are wide enough for the per-thread shared-core evaluation
-    int ahead;                    // chunks ahead whose samples this CTA asks L2 for (0: none)
 };
 
 // powers of the three poles, computed once per parameter set (not per CTA: pow() is slow)
@@ -187,13 +186,6 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
     const double thr = lp.threshold;
 
     // ---- P1: hard-clip gain g = 1 - thr/max(|L|,|R|,thr) over the span (dsp.py:117-121, hyrax.py:87)
-    if (tid == 0 && gm.ahead > 0) {  // the core of the chunk one wave of CTAs ahead: in L2 by the time it is wanted
-        const long long p0 = s0 + (long long)gm.ahead * LC;
-        if (p0 < frames) {
-            const long long cnt = (frames - p0 < LC ? frames - p0 : LC) & ~1LL;
-            tma_prefetch_l2(in + p0, (uint32_t)(cnt * 8));
-        }
-    }
     {
         const float2* base = in + ga;
         float2 v[EPT];  // all of the thread's loads are issued before the first use: one DRAM latency, not EPT
@@ -517,7 +509,6 @@ int limiter_geometry(const mgb_limiter_params& lp, LimiterGeom* g) {
     if (ept < 11) ept = 11;
     g->ept = ept;
     g->publish_inclusive = g_lookback_inclusive;
-    g->ahead = g_l2_prefetch ? 2 * num_sms() : 0;
     // the cores [b+ept-1-reach, b+reach] and [b+ept-reach-hold, b+reach] must not be empty
     g->shared_core = (2 * lp.reach >= ept - 1 && 2 * lp.reach + lp.hold >= ept) ? 1 : 0;
     MGB_REQUIRE(ept <= SPAN_EPT_MAX, MGB_ERR_UNSUPPORTED,
