@@ -157,6 +157,7 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
     const int tid = threadIdx.x;
     const double pre = pre_gain ? *pre_gain : 1.0;
     const double post = post_gain ? *post_gain : 1.0;
+    const double scale = pre * post;
 
     if (tid == 0) chunk_s = atomicAdd(ticket, 1);
     {
@@ -196,9 +197,12 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
         }
 #pragma unroll
         for (int k = 0; k < EPT; ++k) {
+            // g = 1 - thr/a = (a - thr)/a: the difference in float64 (it decides which frames are touched at
+            // all, and cancels when a is close to thr), the quotient in float32 -- g is kept as float32 anyway
             const double a = (double)fmaxf(fabsf(v[k].x), fabsf(v[k].y)) * pre;
+            const double over = a - thr;
             float g = 0.0f;
-            if (a > thr) g = (float)(1.0 - thr / a);  // frames at or below the threshold need no division
+            if (over > 0.0) g = __fdiv_rn((float)over, (float)a);
             G[tid + k * NT] = g;
         }
     }
@@ -475,10 +479,11 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
         for (int q = 0; q < CORE_EPT; ++q) {
             const int k = tid + q * NT;
             if (k < core_n) {
-                const double gain = Fd[k] * pre * post;
 #ifdef MGB_LIM_DEBUG
                 out[s0 + k] = make_float2((float)Fd[k], G[cidx + k]);
 #else
+                // (in float64 to the end: a frame the hard clip brings to the threshold must round to it exactly)
+                const double gain = Fd[k] * scale;
                 out[s0 + k] = make_float2((float)((double)v[q].x * gain), (float)((double)v[q].y * gain));
 #endif
             }
