@@ -368,3 +368,20 @@ def synth_limiter_input(n: int, seed: int) -> np.ndarray:
     rng = np.random.default_rng(seed)
     x = (rng.uniform(0, 1, (n, 2)) * 3 - 1.5) * (0.3 + 0.7 * np.abs(np.sin(np.linspace(0, 500, n))))[:, None]
     return np.ascontiguousarray(x.astype(np.float32))
+
+
+def synth_tonal(n: int, seed: int, sample_rate: int = 44100) -> np.ndarray:
+    """Decaying harmonic notes with random panning between stretches of exact digital silence
+    (head and tail): pieces and frames with zero energy, strongly coloured spectra."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) / sample_rate
+    x = np.zeros((n, 2))
+    for _ in range(12):
+        f0, start, dur, pan = rng.uniform(60, 2000), rng.uniform(0.1, t[-1] - 0.2), rng.uniform(0.05, 0.6), rng.uniform(0, 1)
+        env = np.where(t >= start, np.exp(-(t - start) / dur), 0.0)
+        tone = sum(np.sin(2 * np.pi * f0 * h * t + rng.uniform(0, 6)) / h for h in range(1, 6))
+        x[:, 0] += pan * env * tone * 0.2
+        x[:, 1] += (1 - pan) * env * tone * 0.2
+    x[: int(0.1 * sample_rate)] = 0.0
+    x[n - int(0.05 * sample_rate):] = 0.0
+    return np.ascontiguousarray(x.astype(np.float32))

@@ -400,3 +400,19 @@ def test_preview_kernels_match_golden(lib, golden):
     # more windows than fit, or fades longer than the piece, are refused
     assert lib.mgb_window_energy(ptr(result), n, size, step, count + 1, ptr(energy), None) == _native.MGB_ERR_INVALID
     assert lib.mgb_preview_piece(ptr(result), ptr(out), 100, 0.0, 51, None) == _native.MGB_ERR_INVALID
+
+
+@pytest.mark.parametrize("one_sided", [False, True])
+def test_tonal_material_with_digital_silence(lib, one_sided):
+    """Notes between stretches of exact zeros (silent pieces and frames), optionally with the right
+    channel silent and a DC offset on the left."""
+    cfg = port.OracleConfig(max_piece_size=0.3)
+    n = 44100 * 2
+    t = 0.5 * port.synth_tonal(n, 1)
+    r = np.tanh(2.0 * port.synth_tonal(n + 500, 2)).astype(np.float32)
+    if one_sided:
+        t[:, 1] = 0.0
+        t[:, 0] += 0.05
+    outs, st, _, _, _ = run_pipeline(cfg, t, r)
+    want = port.main(t.astype(np.float64), r.astype(np.float64), cfg, True, True, True)
+    _compare(outs, want)

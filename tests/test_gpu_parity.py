@@ -481,3 +481,19 @@ def test_process_with_previews(torch_cuda, tmp_path):
     assert np.abs(got_r - want_r).max() < TOL
     assert np.abs(got_t - want_t).max() < 1.6 / 32768
     assert got_r[0].tolist() == [0.0, 0.0]
+
+
+@pytest.mark.parametrize("one_sided", [False, True])
+def test_tonal_material_with_digital_silence(torch_cuda, one_sided):
+    import port
+    from matchering_b200 import stages
+    cfg = _config(max_piece_size=1.5)
+    n = 44100 * 8
+    t = 0.5 * port.synth_tonal(n, 1)
+    r = np.tanh(2.0 * port.synth_tonal(n + 500, 2)).astype(np.float32)
+    if one_sided:
+        t[:, 1] = 0.0
+        t[:, 0] += 0.05
+    got = stages.main(t, r, cfg, True, True, True)
+    want = port.main(t.astype(np.float64), r.astype(np.float64), cfg, True, True, True)
+    _compare(got, want)
