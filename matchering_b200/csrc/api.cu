@@ -14,6 +14,7 @@ namespace mgb {
 int g_use_tma = 1;
 int g_twiddle_chain = 1;
 int g_conv_fused = 1;
+int g_clip_ctas_per_sm = 3;
 int g_lookback_inclusive = 1;
 
 #ifndef MGB_EMULATE
@@ -265,6 +266,11 @@ int mgb_set_option(const char* name, int value) {
     MGB_REQUIRE(name != nullptr, MGB_ERR_INVALID, "option name is NULL");
     if (strcmp(name, "tma") == 0) {
         g_use_tma = value ? 1 : 0;
+        return MGB_OK;
+    }
+    if (strcmp(name, "clip_ctas_per_sm") == 0) {
+        MGB_REQUIRE(value >= 1 && value <= 16, MGB_ERR_INVALID, "clip_ctas_per_sm must be 1..16");
+        g_clip_ctas_per_sm = value;
         return MGB_OK;
     }
     if (strcmp(name, "conv_fused") == 0) {

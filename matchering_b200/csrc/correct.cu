@@ -301,7 +301,7 @@ unsigned grid_for(long long items, int per_block) {
 int launch_clip_sumsq(const mgb_plan& plan, const mgb_track_layout& layout, const Workspace& ws, int step,
                       mgb_track_state* state, cudaStream_t stream) {
     const int div = layout.target_divisions;
-    long long per_piece = (3LL * num_sms() + div - 1) / div;
+    long long per_piece = ((long long)g_clip_ctas_per_sm * num_sms() + div - 1) / div;
     const long long max_useful = (layout.target_piece + 8191) / 8192;
     if (per_piece > max_useful) per_piece = max_useful;
     if (per_piece < 1) per_piece = 1;
