@@ -24,9 +24,8 @@ namespace {
 
 template <int F>
 struct AnalyzeSmem {
+    static constexpr int kRawBytes = ((F + 2) * 8 + 15) / 16 * 16;
     static constexpr int kPlaneBytes = (int)((PackedPlanes::bytes(F) + 15) / 16 * 16);
-    // the landing buffer of the bulk copies doubles as the second plane buffer of the transform
-    static constexpr int kRawBytes = kPlaneBytes > ((F + 2) * 8 + 15) / 16 * 16 ? kPlaneBytes : ((F + 2) * 8 + 15) / 16 * 16;
     static constexpr int kBytes = kRawBytes + kPlaneBytes + 16 /*barrier*/ + 32 * 8 + 96 * 4 + 32;
 };
 
@@ -42,7 +41,7 @@ struct AnalyzeFirst {
 };
 
 template <int F>
-__global__ void __launch_bounds__(F / 16, (F <= 4096 ? 3 : 1))
+__global__ void __launch_bounds__(F / 16)
 analyze_kernel(const float2* __restrict__ x, long long frames, long long piece, int divisions, int slots,
                const cpx<float>* __restrict__ tw, float* __restrict__ spec_part, double* __restrict__ sumsq_part,
                float* __restrict__ absmax_part, int use_tma) {
@@ -53,8 +52,6 @@ analyze_kernel(const float2* __restrict__ x, long long frames, long long piece, 
     MGB_DYN_SMEM(smem);
     float2* raw = reinterpret_cast<float2*>(smem);
     const PackedPlanes planes{reinterpret_cast<float2*>(smem + L::kRawBytes)};
-    const PackedPlanes planes_b{raw};  // (free once the first pass has gathered the frame)
-    constexpr bool kEndsInPlanes = fft_pingpong_ends_in_first<F>();  // else the spectrum ends in the landing buffer
     unsigned char* tail = smem + L::kRawBytes + L::kPlaneBytes;
     tail += (16 - (reinterpret_cast<uintptr_t>(tail) & 15)) & 15;
     TmaBarrier* bar = reinterpret_cast<TmaBarrier*>(tail);
@@ -136,19 +133,18 @@ analyze_kernel(const float2* __restrict__ x, long long frames, long long piece, 
         for (int r = 0; r < F / THREADS; ++r) z[r].y *= g_side;
         fft_first_pass_regs<F, +1, THREADS, float>(planes, z, /*barrier_before_store=*/false);
         __syncthreads();  // planes written, landing buffer consumed by every thread
-        // the remaining passes bounce between the two buffers: one barrier per pass
-        fft_remaining_pingpong<F, +1, THREADS, float>(planes, planes_b, tw);
-        const PackedPlanes spectrum = kEndsInPlanes ? planes : planes_b;
-        if (kEndsInPlanes && use_tma && tid == 0 && f + 1 < f_hi) {
+        if (use_tma && tid == 0 && f + 1 < f_hi) {
             fence_proxy_async();
-            issue(f + 1);  // the landing buffer is free again: the copy overlaps the magnitudes below
+            issue(f + 1);  // overlaps the remaining passes of this frame
         }
+        fft_remaining<F, +1, THREADS, float>(planes, tw, PlaneStore<PackedPlanes>{planes}, /*last_in_place=*/true);
+        __syncthreads();
 #pragma unroll
         for (int b = 0; b < BINS; ++b) {
             const int k = tid + b * THREADS;
             if (k < HB) {
                 const int kn = (F - k) & (F - 1);
-                const cpx<float> zk = spectrum.load(k), zn = spectrum.load(kn);
+                const cpx<float> zk = planes.load(k), zn = planes.load(kn);
                 const float zr = zk.x, zi = zk.y, nr = zn.x, ni = zn.y;
                 // rfft(mid)[k] = (Z[k] + conj(Z[F-k]))/2 ; rfft(side)[k] = (Z[k] - conj(Z[F-k]))/(2i)
                 const float mr = zr + nr, mi = zi - ni;
@@ -157,11 +153,7 @@ analyze_kernel(const float2* __restrict__ x, long long frames, long long piece, 
                 if (!side_silent) acc_side[b] += inv_g * sqrt_approx(sr * sr + si * si);
             }
         }
-        __syncthreads();  // both buffers free for the next frame
-        if (!kEndsInPlanes && use_tma && tid == 0 && f + 1 < f_hi) {
-            fence_proxy_async();
-            issue(f + 1);
-        }
+        __syncthreads();  // planes free for the next frame
     }
 
     // the piece's tail beyond its last whole frame counts for the RMS and the peak, not the spectrum

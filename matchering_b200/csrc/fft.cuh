@@ -367,30 +367,6 @@ __device__ __forceinline__ void fft_butterfly(const cpx<T>* __restrict__ tw, int
     Dft<R, DIR, T>::run(v);
 }
 
-// Remaining passes between TWO plane buffers: pass 1 reads `a` (where the first pass left the frame)
-// and writes `b`, pass 2 reads `b` and writes `a`, ...  A pass then needs no barrier between its
-// gathers and its scatters: one barrier per pass instead of two.  Ends with a barrier; the result
-// is in `a` when the schedule has an odd number of passes in total (n = 3), else in `b`.
-template <int N, int DIR, int THREADS, typename T, bool CHAIN = false, typename Planes>
-__device__ __forceinline__ void fft_remaining_pingpong(Planes a, Planes b, const cpx<T>* __restrict__ tw) {
-    using Rd = Radices<N>;
-    constexpr int R0 = Rd::r[0], R1 = Rd::r[1], R2 = Rd::r[2], R3 = Rd::r[3];
-    static_assert(Rd::n >= 2 && Rd::n <= 4, "2..4 passes supported");
-    fft_pass<N, R1, R0, DIR, THREADS, T, CHAIN>(tw, PlaneLoad<Planes>{a}, PlaneStore<Planes>{b}, false);
-    __syncthreads();
-    if constexpr (Rd::n >= 3) {
-        fft_pass<N, R2, R0 * R1, DIR, THREADS, T, CHAIN>(tw + (R1 - 1) * R0, PlaneLoad<Planes>{b}, PlaneStore<Planes>{a}, false);
-        __syncthreads();
-    }
-    if constexpr (Rd::n >= 4) {
-        fft_pass<N, R3, R0 * R1 * R2, DIR, THREADS, T, CHAIN>(tw + (R1 - 1) * R0 + (R2 - 1) * R0 * R1, PlaneLoad<Planes>{a},
-                                                             PlaneStore<Planes>{b}, false);
-        __syncthreads();
-    }
-}
-template <int N>
-__host__ __device__ constexpr bool fft_pingpong_ends_in_first() { return Radices<N>::n == 3 || Radices<N>::n == 1; }
-
 // Whole transform: first pass, barrier, remaining passes.
 template <int N, int DIR, int THREADS, typename T, bool CHAIN = false, typename Planes, typename First, typename Last>
 __device__ __forceinline__ void fft_run(Planes pl, const cpx<T>* __restrict__ tw, First first, Last last,
