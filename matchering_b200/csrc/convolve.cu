@@ -88,15 +88,20 @@ __device__ __forceinline__ ConvBalance conv_load_frame(const float2* __restrict_
         __syncthreads();
     }
     float max_mid = 0.0f, max_side = 0.0f;
-#pragma unroll
-    for (int r = 0; r < N / THREADS; ++r) {
-        const float2 v = first.sample(tid + r * THREADS);
-        // each channel from L and R directly, one rounding each: (L-R)/2 is the reference's mid - R, and
-        // forming it from the already rounded mid would put mid's rounding error into a quiet side
+    // each channel from L and R directly, one rounding each: (L-R)/2 is the reference's mid - R, and
+    // forming it from the already rounded mid would put mid's rounding error into a quiet side
+    auto take = [&](int r, float2 v) {
         z[r].x = (v.x + v.y) * 0.5f;
         z[r].y = (v.x - v.y) * 0.5f;
         max_mid = fmaxf(max_mid, fabsf(z[r].x));
         max_side = fmaxf(max_side, fabsf(z[r].y));
+    };
+    if (lo == origin && hi == origin + N) {  // a frame inside the signal (all but the first and the last few):
+#pragma unroll                               // no bounds, no fix-up, nothing per sample but the load
+        for (int r = 0; r < N / THREADS; ++r) take(r, raw[tid + r * THREADS]);
+    } else {
+#pragma unroll
+        for (int r = 0; r < N / THREADS; ++r) take(r, first.sample(tid + r * THREADS));
     }
     block_max2(max_mid, max_side, red_u);  // its barrier also ends everybody's reads of the landing buffer
     const float g_side = balance_factor(max_mid, max_side);  // >= 1 when the side is the quiet one, < 1 otherwise
@@ -135,6 +140,7 @@ struct ConvEpilogue {
     long long pa;
     int divisions;
     bool mid_silent, side_silent;
+    bool full;  // every output of the frame exists, is counted, and belongs to piece pa: nothing to test per sample
     double sq_a = 0.0, sq_b = 0.0;
     float peak = 0.0f;
     __device__ __forceinline__ ConvEpilogue(float2* result, float* mid_plane, long long n0, long long frames,
@@ -150,6 +156,16 @@ struct ConvEpilogue {
         divisions = divisions_;
         mid_silent = bal.mid_silent;
         side_silent = bal.side_silent;
+        full = valid == F && boundary == F && count_to == F;
+    }
+    __device__ __forceinline__ void emit_full(int o, cpx<float> y) {  // emit() when `full`
+        const float m = mid_silent ? 0.0f : y.x, sd = side_silent ? 0.0f : y.y;
+        const float l = m + sd, r = m - sd;
+        res[o] = make_float2(l, r);
+        midp[o] = m;
+        peak = fmaxf(peak, fmaxf(fabsf(l), fabsf(r)));
+        const float cf = fminf(1.0f, fmaxf(-1.0f, m));  // dsp.clip
+        sq_a += (double)cf * (double)cf;
     }
     __device__ __forceinline__ void emit(int o, cpx<float> y) {
         if (o < valid) {
@@ -166,15 +182,28 @@ struct ConvEpilogue {
             }
         }
     }
+    // one barrier: every warp leaves its three partial results in shared memory, warp 0 folds them
     __device__ __forceinline__ void finish(double* red_a, double* red_b, float* red_f, double* piece_sums,
                                            mgb_track_state* state) {
-        const double ta = block_sum(sq_a, red_a);
-        const double tb = block_sum(sq_b, red_b);
-        const float pk = block_max(peak, red_f);
-        if (threadIdx.x == 0) {
-            if (pa < divisions && ta != 0.0) atomicAdd(&piece_sums[pa], ta);
-            if (pa + 1 < divisions && tb != 0.0) atomicAdd(&piece_sums[pa + 1], tb);
-            atomic_max_nonneg(&state->conv_peak_bits, pk);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+        const double wa = warp_sum(sq_a);
+        const double wb = full ? 0.0 : warp_sum(sq_b);
+        const float wp = warp_max(peak);
+        if (lane == 0) {
+            red_a[warp] = wa;
+            red_b[warp] = wb;
+            red_f[warp] = wp;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const double ta = warp_sum(lane < nwarps ? red_a[lane] : 0.0);
+            const double tb = full ? 0.0 : warp_sum(lane < nwarps ? red_b[lane] : 0.0);
+            const float pk = warp_max(lane < nwarps ? red_f[lane] : 0.0f);
+            if (lane == 0) {
+                if (pa < divisions && ta != 0.0) atomicAdd(&piece_sums[pa], ta);
+                if (pa + 1 < divisions && tb != 0.0) atomicAdd(&piece_sums[pa + 1], tb);
+                atomic_max_nonneg(&state->conv_peak_bits, pk);
+            }
         }
     }
 };
@@ -337,9 +366,16 @@ convolve_fused_kernel(const float2* __restrict__ x, long long frames, long long 
         cpx<float> v[8];
         fft_gather<8, NB8>(sl, j, v);
         fft_butterfly<8, NB8, -1, CHAIN>(tw_last, j, v);  // v[q] = y[j + q*NB8]
+        if (ep.full) {
 #pragma unroll
-        for (int q = 4; q < 8; ++q) ep.emit(j + 1 + (q - 4) * NB8, v[q]);  // (o = F for j = NB8-1, q = 7: not valid)
-        if (j == NB8 - 1) ep.emit(0, v[3]);
+            for (int q = 4; q < 7; ++q) ep.emit_full(j + 1 + (q - 4) * NB8, v[q]);
+            if (j != NB8 - 1) ep.emit_full(j + 1 + 3 * NB8, v[7]);  // (o = F for j = NB8-1: not an output)
+            else ep.emit_full(0, v[3]);
+        } else {
+#pragma unroll
+            for (int q = 4; q < 8; ++q) ep.emit(j + 1 + (q - 4) * NB8, v[q]);  // (o = F for j = NB8-1, q = 7: not valid)
+            if (j == NB8 - 1) ep.emit(0, v[3]);
+        }
     }
     ep.finish(sp.red_a, sp.red_b, sp.red_f, piece_sums, state);
 }
