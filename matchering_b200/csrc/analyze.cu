@@ -112,9 +112,7 @@ analyze_kernel(const float2* __restrict__ x, long long frames, long long piece, 
         // channel balance before the two channels share a transform (see balance_factor)
         cpx<float> z[F / THREADS];
         float max_mid = 0.0f, max_side = 0.0f;
-#pragma unroll
-        for (int r = 0; r < F / THREADS; ++r) {
-            const float2 v = first.sample(tid + r * THREADS);
+        auto take = [&](int r, float2 v) {
             // mid and side from L and R directly, one rounding each, exactly as the convolution forms them
             z[r].x = (v.x + v.y) * 0.5f;
             z[r].y = (v.x - v.y) * 0.5f;
@@ -122,6 +120,13 @@ analyze_kernel(const float2* __restrict__ x, long long frames, long long piece, 
             peak = fmaxf(peak, fmaxf(fabsf(v.x), fabsf(v.y)));
             max_mid = fmaxf(max_mid, fabsf(z[r].x));
             max_side = fmaxf(max_side, fabsf(z[r].y));
+        };
+        if (first.fix_index < 0) {  // (all frames but possibly the signal's last one)
+#pragma unroll
+            for (int r = 0; r < F / THREADS; ++r) take(r, first.raw[tid + r * THREADS]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < F / THREADS; ++r) take(r, first.sample(tid + r * THREADS));
         }
         unsigned* slot = red_u + 2 * ((f - f_lo) & 1);
         if (tid == 0) red_u[2 * ((f - f_lo + 1) & 1)] = red_u[2 * ((f - f_lo + 1) & 1) + 1] = 0u;  // next frame's slot

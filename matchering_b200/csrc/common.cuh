@@ -176,9 +176,11 @@ __device__ __forceinline__ void block_max2(float& a, float& b, unsigned* slot) {
 // noise (and a matching FIR with a huge gain on the quiet channel would amplify it).
 __device__ __forceinline__ float balance_factor(float large, float small) {
     if (!(small > 0.0f) || !(large > 0.0f)) return 1.0f;
-    int e = (int)floorf(log2f(large / small));
+    // the difference of the two binary exponents is within one of floor(log2(large / small)), which is
+    // all the balancing needs; integer work on the bit patterns instead of log2f, a division and exp2f
+    int e = (int)((__float_as_uint(large) >> 23) & 0xffu) - (int)((__float_as_uint(small) >> 23) & 0xffu);
     e = e < -60 ? -60 : (e > 60 ? 60 : e);
-    return exp2f((float)e);
+    return __uint_as_float((unsigned)(127 + e) << 23);
 }
 
 // sqrt with the special-function unit alone (sqrt.approx: one MUFU, relative error <= 2^-23) instead of

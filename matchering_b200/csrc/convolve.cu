@@ -49,7 +49,7 @@ struct ConvFirst {
 // ---- shared by both kernels: frame load + channel balance, FIR spectra on a pair, the epilogue -----
 struct ConvBalance {
     float inv_g;
-    bool mid_silent, side_silent;
+    bool mid_silent, side_silent, any_silent;
 };
 
 // Loads the frame's 2F input samples (clipped to the signal) into the landing buffer, hands every thread
@@ -111,6 +111,7 @@ __device__ __forceinline__ ConvBalance conv_load_frame(const float2* __restrict_
     b.inv_g = 1.0f / g_side;  // exact: a power of two
     b.mid_silent = max_mid == 0.0f;
     b.side_silent = max_side == 0.0f;
+    b.any_silent = b.mid_silent || b.side_silent;
     return b;
 }
 
@@ -122,9 +123,12 @@ __device__ __forceinline__ void conv_apply_pair(cpx<float>& zk, cpx<float>& zn, 
     const float mr = 0.5f * (zr + nr), mi = 0.5f * (zi - ni);
     const float sr = 0.5f * (zi + ni) * bal.inv_g, si = 0.5f * (nr - zr) * bal.inv_g;
     const float2 hm = h_mid[k], hs = h_side[k];
-    // a channel that is exactly silent in this frame stays exactly silent, as in the reference
-    const float pmr = bal.mid_silent ? 0.0f : hm.x * mr - hm.y * mi, pmi = bal.mid_silent ? 0.0f : hm.x * mi + hm.y * mr;
-    const float psr = bal.side_silent ? 0.0f : hs.x * sr - hs.y * si, psi = bal.side_silent ? 0.0f : hs.x * si + hs.y * sr;
+    float pmr = hm.x * mr - hm.y * mi, pmi = hm.x * mi + hm.y * mr;
+    float psr = hs.x * sr - hs.y * si, psi = hs.x * si + hs.y * sr;
+    if (bal.any_silent) {  // (uniform over the CTA) a channel that is exactly silent in this frame stays exactly
+        if (bal.mid_silent) pmr = pmi = 0.0f;   // silent, as in the reference
+        if (bal.side_silent) psr = psi = 0.0f;
+    }
     // Y[k] = Pm + i Ps ; Y[N-k] = conj(Pm) + i conj(Ps)
     zk = cpx<float>{pmr - psi, pmi + psr};
     zn = cpx<float>{pmr + psi, psr - pmi};
@@ -139,8 +143,8 @@ struct ConvEpilogue {
     int valid, boundary, count_to;
     long long pa;
     int divisions;
-    bool mid_silent, side_silent;
-    bool full;  // every output of the frame exists, is counted, and belongs to piece pa: nothing to test per sample
+    bool mid_silent, side_silent, any_silent;
+    bool full;  // every output of the frame exists, is counted, belongs to piece pa, no channel is silent: nothing to test per sample
     double sq_a = 0.0, sq_b = 0.0;
     float peak = 0.0f;
     __device__ __forceinline__ ConvEpilogue(float2* result, float* mid_plane, long long n0, long long frames,
@@ -156,10 +160,11 @@ struct ConvEpilogue {
         divisions = divisions_;
         mid_silent = bal.mid_silent;
         side_silent = bal.side_silent;
-        full = valid == F && boundary == F && count_to == F;
+        any_silent = bal.any_silent;
+        full = valid == F && boundary == F && count_to == F && !any_silent;
     }
-    __device__ __forceinline__ void emit_full(int o, cpx<float> y) {  // emit() when `full`
-        const float m = mid_silent ? 0.0f : y.x, sd = side_silent ? 0.0f : y.y;
+    __device__ __forceinline__ void emit_full(int o, cpx<float> y) {  // emit() when `full` (which implies: no silent channel)
+        const float m = y.x, sd = y.y;
         const float l = m + sd, r = m - sd;
         res[o] = make_float2(l, r);
         midp[o] = m;

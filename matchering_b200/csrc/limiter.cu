@@ -116,6 +116,7 @@ struct LimiterGeom {
     int filt;                     // samples the attack filter needs to run over (LC + left + warm)
     int publish_inclusive;        // 0: chunks publish aggregates only (test switch: every look-back then walks to the cut-off)
     int shared_core;              // both windows are wide enough for the per-thread shared-core evaluation
+    int margin;                   // zeros kept on both sides of G so that window reads need no bounds test (multiple of 4)
 };
 
 // powers of the three poles, computed once per parameter set (not per CTA: pow() is slow)
@@ -142,8 +143,9 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
     MGB_DYN_SMEM(smem);
     double* Fd = reinterpret_cast<double*>(smem);                 // [CAP] float64 work plane
     float* Aenv = reinterpret_cast<float*>(smem) + CAP;           // [CAP] attack envelope, aliases Fd's upper half
-    float* G = reinterpret_cast<float*>(smem + (size_t)CAP * 8);  // [CAP] hard-clip gain, later max(g, g_att)
-    float* Wk = G + CAP;                                          // [CAP] suffix maxima, later the hold envelope
+    // [margin zeros][CAP hard-clip gain, later max(g, g_att)][margin zeros]: window samples outside the span read as 0
+    float* G = reinterpret_cast<float*>(smem + (size_t)CAP * 8) + gm.margin;
+    float* Wk = G + CAP + gm.margin;                              // [CAP] suffix maxima, later the hold envelope
     __shared__ float blockmax[NT];
     __shared__ ScanPow pw3[3];
     __shared__ double scratch_a[32], scratch_b[32];  // scan_carry alternates between them
@@ -187,6 +189,10 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
     const double thr = lp.threshold;
 
     // ---- P1: hard-clip gain g = 1 - thr/max(|L|,|R|,thr) over the span (dsp.py:117-121, hyrax.py:87)
+    for (int i = tid; i < gm.margin; i += NT) {
+        G[-1 - i] = 0.0f;
+        G[CAP + i] = 0.0f;
+    }
     {
         const float2* base = in + ga;
         float2 v[EPT];  // all of the thread's loads are issued before the first use: one DRAM latency, not EPT
@@ -251,7 +257,7 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
             if (br - bl > 1) m = fmaxf(m, whole_blocks(bl + 1, br - 1));
             return m;
         };
-        auto gat = [&](int i) -> float { return (i >= 0 && i < CAP) ? G[i] : 0.0f; };  // g >= 0: outside counts as 0
+        auto gat = [&](int i) -> float { return G[i]; };  // (outside the span: the zero margins; g >= 0, so 0 is neutral)
         // The thread's consecutive windows of one kind share most of their samples: for the EPT windows
         // [b+e-reach, b+e+reach] (b = base) the core [b+EPT-1-reach, b+reach] does not depend on e; what
         // lies left and right of it are EPT-1 samples each, combined by running maxima in registers.
@@ -516,6 +522,7 @@ int limiter_geometry(const mgb_limiter_params& lp, LimiterGeom* g) {
     g->publish_inclusive = g_lookback_inclusive;
     // the cores [b+ept-1-reach, b+reach] and [b+ept-reach-hold, b+reach] must not be empty
     g->shared_core = (2 * lp.reach >= ept - 1 && 2 * lp.reach + lp.hold >= ept) ? 1 : 0;
+    g->margin = (lp.reach + lp.hold + ept + 3) / 4 * 4;  // the furthest a window part reaches outside [0, CAP)
     MGB_REQUIRE(ept <= SPAN_EPT_MAX, MGB_ERR_UNSUPPORTED,
                 "limiter: halo of %d samples exceeds the kernel's span", g->span - LC);
     return MGB_OK;
@@ -542,7 +549,7 @@ int launch_limiter(const mgb_limiter_params& lp, const float2* in, float2* out, 
     MGB_REQUIRE(frames > 6, MGB_ERR_INVALID, "limiter: the input must be longer than filtfilt's padlen (6)");
     MGB_REQUIRE(tables != nullptr, MGB_ERR_INVALID, "limiter: pole tables missing");
     const int64_t chunks = (frames + LC - 1) / LC;
-    const size_t smem = (size_t)g.ept * NT * 16;
+    const size_t smem = (size_t)g.ept * NT * 16 + (size_t)g.margin * 8;
 #define MGB_LIMITER_CASE(E)                                                                                       \
     case E:                                                                                                       \
         return launch("limiter_kernel", limiter_kernel<E>, dim3((unsigned)chunks), dim3(NT), smem, stream, lp, g, in, \
