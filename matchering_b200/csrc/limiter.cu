@@ -146,7 +146,7 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
     // [margin zeros][CAP hard-clip gain, later max(g, g_att)][margin zeros]: window samples outside the span read as 0
     float* G = reinterpret_cast<float*>(smem + (size_t)CAP * 8) + gm.margin;
     float* Wk = G + CAP + gm.margin;                              // [CAP] suffix maxima, later the hold envelope
-    __shared__ float blockmax[NT], block_pf[NT], block_sf[NT];
+    __shared__ float blockmax[NT];
     __shared__ ScanPow pw3[3];
     __shared__ double scratch_a[32], scratch_b[32];  // scan_carry alternates between them
     __shared__ double bcast[2];
@@ -234,19 +234,6 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
             PF[base + e] = run;
         }
         blockmax[tid] = run;
-        {
-            // prefix / suffix maxima of the block maxima inside aligned groups of 8 blocks (8 lanes of a
-            // warp: segmented shuffles, a lane whose source lies outside its group gets its own value back):
-            // a run of whole blocks that crosses a group boundary is then two reads plus one per group in between
-            float bp = run, bs = run;
-#pragma unroll
-            for (int d = 1; d < 8; d <<= 1) {
-                bp = fmaxf(bp, __shfl_up_sync(0xffffffffu, bp, d, 8));
-                bs = fmaxf(bs, __shfl_down_sync(0xffffffffu, bs, d, 8));
-            }
-            block_pf[tid] = bp;
-            block_sf[tid] = bs;
-        }
         run = 0.0f;
 #pragma unroll
         for (int e = EPT - 1; e >= 0; --e) {
@@ -254,15 +241,9 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
             SF[base + e] = run;
         }
         __syncthreads();
-        auto whole_blocks = [&](int a, int b) -> float {  // blocks a..b inclusive
-            const int ga = a >> 3, gb = b >> 3;
+        auto whole_blocks = [&](int a, int b) -> float {  // blocks a..b inclusive (a run of at most ~a dozen)
             float m = 0.0f;
-            if (ga == gb) {
-                for (int q = a; q <= b; ++q) m = fmaxf(m, blockmax[q]);
-            } else {
-                m = fmaxf(block_sf[a], block_pf[b]);
-                for (int g = ga + 1; g < gb; ++g) m = fmaxf(m, block_pf[8 * g + 7]);
-            }
+            for (int q = a; q <= b; ++q) m = fmaxf(m, blockmax[q]);
             return m;
         };
         auto window = [&](int l, int r, int br, float pr) -> float {

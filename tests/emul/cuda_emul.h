@@ -216,7 +216,6 @@ static inline long long __double_as_longlong(double d) { long long i; std::memcp
 static inline double __longlong_as_double(long long i) { double d; std::memcpy(&d, &i, 8); return d; }
 static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
-static inline float __fdividef(float a, float b) { return a / b; }
 static inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 static inline float __double2float_rn(double d) { return (float)d; }
 static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
