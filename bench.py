@@ -7,9 +7,11 @@ step (tracks shard one-per-GPU, no data-path collective; NCCL only gathers the t
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
   python bench.py --impl reference --steps K --warmup W    # the reference's CPU algorithm (oracle port)
 
-One JSON line on stdout (rank 0).  `value` = device-resident throughput (inputs already in HBM),
-`e2e` = the same job through the C ABI's host-buffer entry point (mgb_process_host: pinned host
-float32 in, H2D + four stages + D2H inside the timed region).
+One JSON line on stdout (rank 0).  `value` = device-resident throughput (inputs already in HBM,
+`--lanes` tracks in flight; the one-track-at-a-time figure is in `config`), `e2e` = the same job through
+the C ABI's host-buffer batch entry (mgb_pipeline_submit/wait: pinned host float32 in and out, H2D +
+four stages + D2H inside the timed region; `e2e.pcm16` with int16 buffers, `e2e.single_call` =
+mgb_process_host).
 """
 from __future__ import annotations
 
@@ -226,7 +228,7 @@ def run_b200(args) -> dict:
         host_r.append(r)
         dev_t.append(t.to(device))
         dev_r.append(r.to(device))
-    # two tracks in flight on two streams: one track's small latency-bound kernels (FIR design: two
+    # `--lanes` tracks in flight on as many streams: one track's small latency-bound kernels (FIR design: four
     # CTAs) overlap the other's streaming kernels
     n_lanes = max(1, args.lanes)
     sessions = [TrackSession(plan, n, n) for _ in range(n_lanes)]
