@@ -236,8 +236,6 @@ template <> struct Radices<4096>  { static constexpr int n = 3; static constexpr
 template <> struct Radices<8192>  { static constexpr int n = 4; static constexpr int r[4] = {16, 8, 8, 8}; };
 template <> struct Radices<16384> { static constexpr int n = 4; static constexpr int r[4] = {16, 16, 8, 8}; };
 
-template <int N>
-__host__ __device__ constexpr int fft_threads() { return N / 16; }
 
 // First pass of the transform: `first` supplies the input points (logical index -> value), results
 // go to the planes.  `in_place` says whether `first` reads the planes itself (then a barrier
@@ -374,17 +372,6 @@ __device__ __forceinline__ void fft_run(Planes pl, const cpx<T>* __restrict__ tw
     fft_first_pass<N, DIR, THREADS, T>(pl, tw, first, first_in_place);
     __syncthreads();
     fft_remaining<N, DIR, THREADS, T, CHAIN>(pl, tw, last, last_in_place);
-}
-
-// number of stored twiddles (pass 0 stores none)
-template <int N>
-__host__ __device__ constexpr int fft_twiddle_stored() {
-    int total = 0, ns = Radices<N>::r[0];
-    for (int p = 1; p < Radices<N>::n; ++p) {
-        total += (Radices<N>::r[p] - 1) * ns;
-        ns *= Radices<N>::r[p];
-    }
-    return total;
 }
 
 // Fill the twiddle table of a transform with the given radix schedule (double-precision sincospi,
