@@ -497,3 +497,33 @@ def test_tonal_material_with_digital_silence(torch_cuda, one_sided):
     got = stages.main(t, r, cfg, True, True, True)
     want = port.main(t.astype(np.float64), r.astype(np.float64), cfg, True, True, True)
     _compare(got, want)
+
+
+def test_single_call_host_entry(torch_cuda, lib):
+    """mgb_process_host: host buffers in, all three outputs and the scalars back, one call."""
+    import ctypes as C
+    torch = torch_cuda
+    import port
+    from matchering_b200 import _native, stages
+    from matchering_b200.engine import TrackSession, get_plan
+    cfg = _config(max_piece_size=2.0)
+    n, m = 250007, 240000
+    t = torch.from_numpy(port.synth_target(n, 61)).pin_memory()
+    r = torch.from_numpy(port.synth_reference(m, 62)).pin_memory()
+    plan = get_plan(cfg)
+    s = TrackSession(plan, n, m)
+    dev = plan.device
+    d_t, d_r = torch.empty((n, 2), device=dev), torch.empty((m, 2), device=dev)
+    d_out = torch.empty((n, 2), device=dev)
+    outs = [torch.zeros((n, 2)).pin_memory() for _ in range(3)]
+    state = _native.TrackState()
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    _native.check(lib, lib.mgb_process_host(C.byref(plan.struct), C.byref(s.layout), t.data_ptr(), r.data_ptr(),
+                                            outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), d_t.data_ptr(),
+                                            d_r.data_ptr(), s.result.data_ptr(), d_out.data_ptr(), s.workspace.data_ptr(),
+                                            s.state.data_ptr(), C.byref(state), stream))
+    torch.cuda.synchronize()
+    want = stages.main(t.numpy(), r.numpy(), cfg, True, True, True)
+    for got, ref in zip(outs, want):
+        assert np.abs(got.numpy() - ref).max() < 1e-6
+    assert state.steps_done == 4 and state.limiter_engaged == 1
