@@ -62,6 +62,33 @@ __device__ __forceinline__ double scan_carry(double B, const ScanPow* t, double 
     return prev + t->ql[lane] * ((warp > 0 ? warp_carry : 0.0) + t->qw[warp] * c0);
 }
 
+// The same for a recurrence that runs from the block's LAST element to its first (thread NT-1 first):
+// B is the thread's local end value after its elements were taken in descending order, *c0 the state
+// just beyond the block's last element (read after the barrier, so the caller may have written it to
+// shared memory just before the call); returns the state just beyond the thread's last element.
+__device__ __forceinline__ double scan_carry_rev(double B, const ScanPow* t, const double* c0, double* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rl = 31 - lane, rw = NT / 32 - 1 - warp;  // ranks in processing order
+    double v = B;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double up = __shfl_down_sync(0xffffffffu, v, d);
+        if (rl >= d) v += t->ql[d] * up;
+    }
+    if (lane == 0) scratch[rw] = v;
+    __syncthreads();
+    double w = lane < NT / 32 ? scratch[lane] : 0.0;
+#pragma unroll
+    for (int d = 1; d < NT / 32; d <<= 1) {
+        const double up = __shfl_up_sync(0xffffffffu, w, d);
+        if (lane >= d) w += t->qw[d] * up;
+    }
+    const double warp_carry = __shfl_sync(0xffffffffu, w, (rw + 31) & 31);
+    double prev = __shfl_down_sync(0xffffffffu, v, 1);
+    if (rl == 0) prev = 0.0;
+    return prev + t->ql[rl] * ((rw > 0 ? warp_carry : 0.0) + t->qw[rw] * (*c0));
+}
+
 // 16-byte publish / poll of a LookbackWord through L2 (st.cg / ld.cg: coherent device-wide).
 __device__ __forceinline__ void publish(LookbackWord* w, double v, int status) {
 #ifdef MGB_EMULATE
@@ -372,6 +399,9 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
         __syncthreads();
     }
     {
+        // forward over the thread's own samples, then backward over the same samples in the same registers:
+        // the backward scan runs across the block in descending thread order, so the forward result never
+        // goes through shared memory
         double y[EPT];
         double acc = 0.0;
 #pragma unroll
@@ -382,37 +412,34 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
         const double c0 = (double)Aenv[0];  // state before the first element: steady state
         const double carry = scan_carry(acc, pow_att, c0, scratch_b);  // barrier inside: Aenv fully read
 #pragma unroll
-        for (int e = 0; e < EPT; ++e) Fd[tid * EPT + e] = y[e] + pow_att->pe[e + 1] * carry;
-    }
-    __syncthreads();
-    if (edge_r) {
-        // past the extension's last sample (frames+5) the backward pass sees that value held
-        const int ilast = (int)(frames + 5 - ga);
-        if (ilast < CAP - 1) {
-            const double held = Fd[ilast];
-            __syncthreads();
+        for (int e = 0; e < EPT; ++e) y[e] += pow_att->pe[e + 1] * carry;
+        if (edge_r) {
+            // past the extension's last sample (frames+5) the backward pass sees that value held
+            const int ilast = (int)(frames + 5 - ga);
+            if (ilast < CAP - 1) {
 #pragma unroll
-            for (int k = 0; k < EPT; ++k) {
-                const int i = tid + k * NT;
-                if (i > ilast) Fd[i] = held;
+                for (int e = 0; e < EPT; ++e)
+                    if (tid * EPT + e == ilast) bcast[1] = y[e];
+                __syncthreads();
+                const double held = bcast[1];
+#pragma unroll
+                for (int e = 0; e < EPT; ++e)
+                    if (tid * EPT + e > ilast) y[e] = held;
+                __syncthreads();  // bcast[1] is written again just below
             }
-            __syncthreads();
         }
-    }
-    {
-        double y[EPT];
-        double acc = 0.0;
+        if (tid == NT - 1) bcast[1] = y[EPT - 1];  // the backward pass starts from the forward pass's last value
+        acc = 0.0;
 #pragma unroll
-        for (int e = 0; e < EPT; ++e) {
-            acc = (1.0 - c) * Fd[CAP - 1 - (tid * EPT + e)] + c * acc;
+        for (int e = EPT - 1; e >= 0; --e) {
+            acc = (1.0 - c) * y[e] + c * acc;
             y[e] = acc;
         }
-        const double c0 = Fd[CAP - 1];
-        const double carry = scan_carry(acc, pow_att, c0, scratch_a);
+        const double back = scan_carry_rev(acc, pow_att, &bcast[1], scratch_a);
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
-            const int i = CAP - 1 - (tid * EPT + e);
-            if (i >= cidx && i < cidx + LC) G[i] = fmaxf(G[i], (float)(y[e] + pow_att->pe[e + 1] * carry));
+            const int i = tid * EPT + e;
+            if (i >= cidx && i < cidx + LC) G[i] = fmaxf(G[i], (float)(y[e] + pow_att->pe[EPT - e] * back));
         }
     }
 
