@@ -178,7 +178,6 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
     __shared__ double scratch_a[32], scratch_b[32];  // scan_carry alternates between them
     __shared__ double bcast[2];
     __shared__ double warp_edge[NT / 32];
-    __shared__ float att_first;  // A at span index 0
     __shared__ int chunk_s;
     const ScanPow* pow_att = &pw3[0];
     const ScanPow* pow_hold = &pw3[1];
@@ -208,7 +207,7 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
         return;
     }
 
-    const int reach = gm.reach, hold = gm.hold, HL = gm.left;
+    const int reach = gm.reach, hold = gm.hold, HL = gm.left, FL = gm.filt;
     const long long ga = s0 - HL - reach;  // sample at span index 0
     const int cidx = HL + reach;           // span index of the chunk's first sample
     // span indices that fall inside the signal: [vlo, vhi)
@@ -248,8 +247,6 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
     // Every thread owns EPT consecutive samples: their prefix and suffix maxima inside the block
     // (PF, SF) and the block maximum.  A window [l, r] is max(SF[l], whole blocks between, PF[r]).
     float hc[CORE_EPT + 1];  // H at span indices cidx + tid*CORE_EPT - 1 + e
-    float av[EPT];           // A at span indices tid*EPT + e: stays with its thread unless the chunk touches an end of the signal
-    const bool edge_l = vlo > reach, edge_r = vhi < reach + gm.filt;  // (then filtfilt's odd extension is in the span)
     {
         float* PF = reinterpret_cast<float*>(smem);  // [CAP] lower half of Fd's bytes (Aenv is the upper half)
         float* SF = Wk;                              // [CAP]
@@ -307,20 +304,15 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
             const int r = min(base + reach, CAP - 1);
             const float core = window(max(base + EPT - 1 - reach, 0), r, r / EPT, PF[r]);
 #pragma unroll
-            for (int e = 0; e < EPT; ++e) av[e] = fmaxf(core, fmaxf(la[e], rt[e]));
+            for (int e = 0; e < EPT; ++e) Aenv[base + e] = fmaxf(core, fmaxf(la[e], rt[e]));
         } else {
 #pragma unroll
             for (int e = 0; e < EPT; ++e) {
                 const int i = base + e;
                 const int r = min(i + reach, CAP - 1);
-                av[e] = window(max(i - reach, 0), r, r / EPT, PF[r]);
+                Aenv[i] = window(max(i - reach, 0), r, r / EPT, PF[r]);
             }
         }
-        if (edge_l || edge_r) {  // the extension below needs other threads' values
-#pragma unroll
-            for (int e = 0; e < EPT; ++e) Aenv[base + e] = av[e];
-        }
-        if (tid == 0) att_first = av[0];
         // H for the thread's own CORE_EPT core samples and the one before them (the filters below run
         // over the core in this very mapping, so H never goes through shared memory for another thread):
         // windows [bh+e-reach-hold+1, bh+e+reach], e = 0..CORE_EPT
@@ -385,6 +377,7 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
     // holding the extension's end value constant further out reproduces that state exactly.  Only
     // chunks that touch an end of the signal see the extension.
     const double c = lp.attack_c;
+    const bool edge_l = vlo > reach, edge_r = vhi < reach + FL;
     if (edge_l || edge_r) {
         const int i0 = vlo, iL = vhi - 1;  // span indices of samples 0 and frames-1
         float fix[EPT];
@@ -404,10 +397,6 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
 #pragma unroll
         for (int k = 0; k < EPT; ++k) Aenv[tid + k * NT] = fix[k];
         __syncthreads();
-#pragma unroll
-        for (int e = 0; e < EPT; ++e) av[e] = Aenv[tid * EPT + e];
-        if (tid == 0) att_first = av[0];
-        __syncthreads();
     }
     {
         // forward over the thread's own samples, then backward over the same samples in the same registers:
@@ -417,11 +406,11 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
         double acc = 0.0;
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
-            acc = (1.0 - c) * (double)av[e] + c * acc;
+            acc = (1.0 - c) * (double)Aenv[tid * EPT + e] + c * acc;
             y[e] = acc;
         }
-        const double c0 = (double)att_first;  // state before the first element: steady state
-        const double carry = scan_carry(acc, pow_att, c0, scratch_b);
+        const double c0 = (double)Aenv[0];  // state before the first element: steady state
+        const double carry = scan_carry(acc, pow_att, c0, scratch_b);  // barrier inside: Aenv fully read
 #pragma unroll
         for (int e = 0; e < EPT; ++e) y[e] += pow_att->pe[e + 1] * carry;
         if (edge_r) {
