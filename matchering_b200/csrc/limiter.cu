@@ -498,19 +498,26 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
         }
         if (tid == NT - 1 && gm.publish_inclusive) publish(&slot->rel, rel_y[CORE_EPT - 1], 2);
     }
+#ifdef MGB_LIM_DEBUG
     __syncthreads();
+#else
+    __syncwarp();  // a warp applies the gains of its own 32*CORE_EPT consecutive samples: no block barrier
+#endif
 
     // ---- P7: apply (hyrax.py:99, stages.py:203) -----------------------------------------------------
+    // The gains sit in shared memory in the filters' mapping (thread t: samples t*CORE_EPT ..); lane l of
+    // warp w now takes samples w*32*CORE_EPT + l + 32 q, so that every global access is 32 neighbours.
     {
+        const int wbase = (tid >> 5) * (32 * CORE_EPT) + (tid & 31);
         float2 v[CORE_EPT];
 #pragma unroll
         for (int q = 0; q < CORE_EPT; ++q) {
-            const int k = tid + q * NT;
+            const int k = wbase + q * 32;
             v[q] = k < core_n ? __ldg(in + s0 + k) : make_float2(0.0f, 0.0f);
         }
 #pragma unroll
         for (int q = 0; q < CORE_EPT; ++q) {
-            const int k = tid + q * NT;
+            const int k = wbase + q * 32;
             if (k < core_n) {
 #ifdef MGB_LIM_DEBUG
                 out[s0 + k] = make_float2((float)Fd[k], G[cidx + k]);
