@@ -57,7 +57,9 @@ def oracle():
 # clocks: sample nvidia-smi while the timed region runs
 # --------------------------------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi polled every 100 ms in a child process that is started EARLY (its start-up can take
+    seconds on a cold box); the samples that count are the ones time-stamped inside the timed window."""
+    QUERY = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -65,6 +67,7 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.path = None
+        self.t_begin = self.t_end = None
 
     def start(self):
         try:
@@ -76,34 +79,58 @@ class ClockSampler:
         except (OSError, FileNotFoundError):
             self.proc = None
 
+    def begin(self, wait_s: float = 15.0):
+        """Start of the timed window; waits (bounded) until the poller has produced its first line."""
+        if self.proc is not None:
+            deadline = time.time() + wait_s
+            while time.time() < deadline and os.path.getsize(self.path) == 0 and self.proc.poll() is None:
+                time.sleep(0.05)
+        self.t_begin = time.time()
+
+    def end(self):
+        self.t_end = time.time()
+
+    @staticmethod
+    def _stamp(text: str):
+        import datetime
+        try:
+            return datetime.datetime.strptime(text.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
+
     def stop(self) -> dict:
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvidia-smi unavailable"]}
+        if self.t_end is None:
+            self.end()
         time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, smax, reasons = [], None, set()
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         with open(self.path) as f:
             for line in f:
                 parts = [p.strip() for p in line.split(",")]
-                if len(parts) < 9:
+                if len(parts) < 10:
                     continue
                 try:
-                    sm.append(float(parts[1]))
-                    smax = float(parts[2])
+                    rows.append((self._stamp(parts[0]), float(parts[2]), float(parts[3]),
+                                 [n for n, v in zip(names, parts[6:10]) if v.lower().startswith("active")]))
                 except ValueError:
                     continue
-                for name, val in zip(names, parts[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
         os.unlink(self.path)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "samples": len(sm),
-                "reasons": sorted(reasons)}
+        lo, hi = (self.t_begin or 0.0) - 0.05, (self.t_end or time.time()) + 0.15
+        inside = [r for r in rows if r[0] is not None and lo <= r[0] <= hi]
+        scope = "timed window"
+        if not inside:  # clock skew or an unparsable stamp: fall back to everything the poller saw
+            inside, scope = rows, "whole run"
+        sm = sorted(r[1] for r in inside)
+        reasons = sorted({n for r in inside for n in r[3]})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": inside[-1][2] if inside else None,
+                "samples": len(sm), "scope": scope, "reasons": reasons}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -191,6 +218,9 @@ def run_b200(args) -> dict:
         raise SystemExit("bench.py --impl b200 needs a CUDA device: there is no CPU fallback")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    sampler = ClockSampler(local_rank)  # (polls from now on; only samples inside the timed window are reported)
+    if rank == 0:
+        sampler.start()
     bound_cores = None
     if world > 1:
         # several ranks share the host: each stays on the cores (and memory) next to its own GPU
@@ -335,14 +365,13 @@ def run_b200(args) -> dict:
         barrier()
         return e0.elapsed_time(e1)
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.begin()
     dev_ms, launches = timed_lanes(args.steps, args.warmup)
     dev_serial_ms, _ = timed(step_device, args.steps, args.warmup)
     e2e_single_ms, _ = timed(step_host, args.steps, max(3, args.warmup))
     e2e_ms = timed_pipeline(args.steps, max(3, args.warmup))
     e2e_pcm_ms = timed_pipeline(args.steps, max(3, args.warmup), pcm=True)
+    sampler.end()
     clocks = sampler.stop() if rank == 0 else None
     pipe.close()
 
