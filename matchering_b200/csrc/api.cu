@@ -14,6 +14,7 @@ namespace mgb {
 int g_use_tma = 1;
 int g_twiddle_chain = 1;
 int g_conv_fused = 1;
+int g_conv_wide = 0;
 int g_clip_ctas_per_sm = 3;
 int g_lookback_inclusive = 1;
 
@@ -236,6 +237,23 @@ int inverse_twiddle_count(int n) {
     if (!inverse_schedule(n, &npass, r)) return 0;
     return schedule_count(npass, r);
 }
+// the wide convolution kernel's two schedules, kept behind the fused inverse one
+template <int N>
+static int wide_counts(int* fwd, int* inv) {
+    if constexpr (WideRadices<N>::ok) {
+        *fwd = fft_schedule_twiddles<typename WideRadices<N>::Fwd>();
+        *inv = fft_schedule_twiddles<typename WideRadices<N>::Inv>();
+        return 1;
+    } else {
+        *fwd = *inv = 0;
+        return 0;
+    }
+}
+int wide_twiddle_count(int n) {
+    int f = 0, i = 0;
+    if (n == 8192) wide_counts<8192>(&f, &i);
+    return f + i;
+}
 int fill_twiddles(int n, int is_f64, void* table, cudaStream_t stream) {
     int npass, r[4];
     MGB_REQUIRE(radix_schedule(n, &npass, r), MGB_ERR_UNSUPPORTED, "fft: size %d has no radix schedule", n);
@@ -248,8 +266,18 @@ int fill_twiddles(int n, int is_f64, void* table, cudaStream_t stream) {
 int fill_inverse_twiddles(int n, cpx<float>* table, cudaStream_t stream) {
     int npass, r[4];
     if (!inverse_schedule(n, &npass, r)) return MGB_OK;
-    return launch("fft_twiddle_kernel", fft_twiddle_kernel<float>, dim3(16), dim3(256), 0, stream,
-                  table + twiddle_count(n), npass, r[0], r[1], r[2], r[3]);
+    MGB_TRY(launch("fft_twiddle_kernel", fft_twiddle_kernel<float>, dim3(16), dim3(256), 0, stream,
+                   table + twiddle_count(n), npass, r[0], r[1], r[2], r[3]));
+    if (n == 8192) {
+        using W = WideRadices<8192>;
+        cpx<float>* wide = table + twiddle_count(n) + inverse_twiddle_count(n);
+        MGB_TRY(launch("fft_twiddle_kernel", fft_twiddle_kernel<float>, dim3(16), dim3(256), 0, stream, wide, W::Fwd::n,
+                       W::Fwd::r[0], W::Fwd::r[1], W::Fwd::r[2], W::Fwd::r[3]));
+        MGB_TRY(launch("fft_twiddle_kernel", fft_twiddle_kernel<float>, dim3(16), dim3(256), 0, stream,
+                       wide + fft_schedule_twiddles<W::Fwd>(), W::Inv::n, W::Inv::r[0], W::Inv::r[1], W::Inv::r[2],
+                       W::Inv::r[3]));
+    }
+    return MGB_OK;
 }
 
 }  // namespace mgb
@@ -271,6 +299,10 @@ int mgb_set_option(const char* name, int value) {
     if (strcmp(name, "clip_ctas_per_sm") == 0) {
         MGB_REQUIRE(value >= 1 && value <= 16, MGB_ERR_INVALID, "clip_ctas_per_sm must be 1..16");
         g_clip_ctas_per_sm = value;
+        return MGB_OK;
+    }
+    if (strcmp(name, "conv_wide") == 0) {
+        g_conv_wide = value ? 1 : 0;
         return MGB_OK;
     }
     if (strcmp(name, "conv_fused") == 0) {
@@ -348,7 +380,7 @@ int mgb_plan_twiddle_bytes(int32_t fft_size, int64_t bytes_out[5]) {
     const int cf = twiddle_count(fft_size), c2 = twiddle_count(2 * fft_size);
     MGB_REQUIRE(cf > 0 && c2 > 0, MGB_ERR_UNSUPPORTED, "fft_size %d has no kernel", fft_size);
     bytes_out[0] = (int64_t)cf * 8;
-    bytes_out[1] = (int64_t)(c2 + inverse_twiddle_count(2 * fft_size)) * 8;
+    bytes_out[1] = (int64_t)(c2 + inverse_twiddle_count(2 * fft_size) + wide_twiddle_count(2 * fft_size)) * 8;
     bytes_out[2] = (int64_t)cf * 16;
     bytes_out[3] = (int64_t)c2 * 16;
     bytes_out[4] = (int64_t)align256(3 * sizeof(ScanPow));

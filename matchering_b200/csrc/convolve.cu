@@ -55,12 +55,12 @@ struct ConvBalance {
 // Loads the frame's 2F input samples (clipped to the signal) into the landing buffer, hands every thread
 // its 16 points z[r] = mid + i*g*side of index tid + r*THREADS.  On return every thread is past a
 // barrier that follows its last read of the landing buffer.
-template <int F>
+template <int F, int PTS = 16>
 __device__ __forceinline__ ConvBalance conv_load_frame(const float2* __restrict__ x, long long frames, long long origin,
                                                        float2* raw, TmaBarrier* bar, unsigned* red_u, int use_tma,
                                                        cpx<float>* z) {
     constexpr int N = 2 * F;
-    constexpr int THREADS = N / 16;
+    constexpr int THREADS = N / PTS;
     const int tid = threadIdx.x;
     const long long lo = origin < 0 ? 0 : origin;
     const long long hi = (origin + N < frames) ? origin + N : frames;  // exclusive
@@ -385,6 +385,107 @@ convolve_fused_kernel(const float2* __restrict__ x, long long frames, long long 
     ep.finish(sp.red_a, sp.red_b, sp.red_f, piece_sums, state);
 }
 
+// ---- wide kernel: 32 points per thread, three passes per transform -------------------------------------
+// Same structure as the fused kernel with radix 16 in the middle: forward 32*16*16, inverse 16*16*32.
+// A thread takes the radix-16 butterflies j and N/16 - j of the last forward pass (between them every
+// pair Z[k], Z[N-k]), applies the FIR spectra and runs the first inverse pass in registers; the last
+// inverse pass (radix 32 over j + r*N/32) feeds the epilogue: its outputs q = 16..31 are the output
+// samples j + 1 + (q-16)*N/32.  One twiddle stage and one trip through shared memory less per
+// transform than the fused kernel, at half the threads and twice the registers.
+template <int F, bool CHAIN>
+__global__ void __launch_bounds__(F / 16, 2)
+convolve_wide_kernel(const float2* __restrict__ x, long long frames, long long piece, int divisions,
+                     const cpx<float>* __restrict__ tw, const float2* __restrict__ h_mid,
+                     const float2* __restrict__ h_side, float2* __restrict__ result, float* __restrict__ mid_plane,
+                     double* __restrict__ piece_sums, mgb_track_state* __restrict__ state, int use_tma) {
+    constexpr int N = 2 * F;
+    constexpr int THREADS = N / 32;
+    constexpr int NB16 = N / 16, NB32 = N / 32;
+    using Fwd = typename WideRadices<N>::Fwd;
+    using Inv = typename WideRadices<N>::Inv;
+    static_assert(NB16 == 2 * THREADS && NB32 == THREADS, "schedule");
+    const cpx<float>* tw_fwd = tw + fft_schedule_twiddles<Radices<N>>() + fft_schedule_twiddles<InverseRadices<N>>();
+    const cpx<float>* tw_inv = tw_fwd + fft_schedule_twiddles<Fwd>();
+    MGB_DYN_SMEM(smem);
+    const ConvPointers<F> sp(smem);
+    const PackedPlanes planes = sp.planes;
+    const PlaneLoad<PackedPlanes> sl{planes};
+    const PlaneStore<PackedPlanes> ss{planes};
+    const int tid = threadIdx.x;
+    const long long n0 = (long long)blockIdx.x * F;
+
+    ConvBalance bal;
+    {
+        cpx<float> z[32];
+        bal = conv_load_frame<F, 32>(x, frames, n0 - F / 2, sp.raw, sp.bar, sp.red_u, use_tma, z);
+        Dft<32, +1, float>::run(z);  // first pass: points tid + r*THREADS, no twiddles
+#pragma unroll
+        for (int q = 0; q < 32; ++q) planes.store(tid * 32 + q, z[q]);
+    }
+    __syncthreads();
+    fft_pass<N, 16, 32, +1, THREADS, float, CHAIN>(tw_fwd, sl, ss, true);
+    __syncthreads();
+
+    // ---- last forward pass, FIR spectra, first inverse pass ----------------------------------------
+    {
+        const int ja = tid, jb = tid == 0 ? NB16 / 2 : NB16 - tid;
+        cpx<float> a[16], b[16];
+        fft_gather<16, NB16>(sl, ja, a);
+        fft_gather<16, NB16>(sl, jb, b);
+        __syncthreads();
+        const cpx<float>* tw_last = tw_fwd + fft_last_pass_twiddles<Fwd>();
+        fft_butterfly<16, NB16, +1, CHAIN>(tw_last, ja, a);  // a[q] = Z[ja + q*NB16]
+        fft_butterfly<16, NB16, +1, CHAIN>(tw_last, jb, b);  // b[q] = Z[jb + q*NB16]
+        if (tid != 0) {
+            // N - (ja + q*NB16) = jb + (15-q)*NB16
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                conv_apply_pair(a[q], b[15 - q], ja + q * NB16, h_mid, h_side, bal);
+                conv_apply_pair(b[q], a[15 - q], jb + q * NB16, h_mid, h_side, bal);
+            }
+        } else {
+            // butterflies 0 and N/32 pair with themselves: a[q] <-> a[16-q], b[q] <-> b[15-q]
+            cpx<float> t = a[0];
+            conv_apply_pair(a[0], t, 0, h_mid, h_side, bal);
+            t = a[8];
+            conv_apply_pair(a[8], t, F, h_mid, h_side, bal);
+#pragma unroll
+            for (int q = 1; q < 8; ++q) conv_apply_pair(a[q], a[16 - q], q * NB16, h_mid, h_side, bal);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) conv_apply_pair(b[q], b[15 - q], NB16 / 2 + q * NB16, h_mid, h_side, bal);
+        }
+        Dft<16, -1, float>::run(a);
+        Dft<16, -1, float>::run(b);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) planes.store(ja * 16 + q, a[q]);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) planes.store(jb * 16 + q, b[q]);
+    }
+    __syncthreads();
+    fft_pass<N, 16, 16, -1, THREADS, float, CHAIN>(tw_inv, sl, ss, true);
+    __syncthreads();
+
+    // ---- last inverse pass straight into the epilogue ------------------------------------------------
+    ConvEpilogue<F> ep(result, mid_plane, n0, frames, piece, divisions, bal);
+    {
+        const int j = tid;
+        cpx<float> v[32];
+        fft_gather<32, NB32>(sl, j, v);
+        fft_butterfly<32, NB32, -1, CHAIN>(tw_inv + fft_last_pass_twiddles<Inv>(), j, v);  // v[q] = y[j + q*NB32]
+        if (ep.full) {
+#pragma unroll
+            for (int q = 16; q < 31; ++q) ep.emit_full(j + 1 + (q - 16) * NB32, v[q]);
+            if (j != NB32 - 1) ep.emit_full(j + 1 + 15 * NB32, v[31]);  // (o = F for j = NB32-1: not an output)
+            else ep.emit_full(0, v[15]);
+        } else {
+#pragma unroll
+            for (int q = 16; q < 32; ++q) ep.emit(j + 1 + (q - 16) * NB32, v[q]);
+            if (j == NB32 - 1) ep.emit(0, v[15]);
+        }
+    }
+    ep.finish(sp.red_a, sp.red_b, sp.red_f, piece_sums, state);
+}
+
 template <int F>
 int launch_convolve_t(const mgb_plan& plan, const mgb_track_layout& layout, const float2* target, float2* result,
                       const Workspace& ws, mgb_track_state* state, cudaStream_t stream) {
@@ -394,7 +495,14 @@ int launch_convolve_t(const mgb_plan& plan, const mgb_track_layout& layout, cons
     if constexpr (InverseRadices<2 * F>::fused) {
         if (g_conv_fused) kernel = g_twiddle_chain ? convolve_fused_kernel<F, true> : convolve_fused_kernel<F, false>;
     }
-    return launch("convolve_kernel", kernel, dim3(nframes), dim3(F / 8), ConvSmem<F>::kBytes, stream, target, T,
+    int threads = F / 8;
+    if constexpr (WideRadices<2 * F>::ok) {
+        if (g_conv_wide) {
+            kernel = g_twiddle_chain ? convolve_wide_kernel<F, true> : convolve_wide_kernel<F, false>;
+            threads = F / 16;
+        }
+    }
+    return launch("convolve_kernel", kernel, dim3(nframes), dim3(threads), ConvSmem<F>::kBytes, stream, target, T,
                   (long long)layout.target_piece, layout.target_divisions, (const cpx<float>*)plan.d_tw_f32_2F,
                   (const float2*)ws.h_mid, (const float2*)ws.h_side, result, ws.mid_plane, ws.piece_sums, state,
                   g_use_tma);

@@ -19,7 +19,7 @@ __device__ __host__ __forceinline__ constexpr int fft_pad(int i) { return i + (i
 __device__ __host__ constexpr int fft_padded_size(int n) { return n + (n >> 5) + 1; }
 
 // ------------------------------------------------------------------------------------------------
-// compile-time roots of unity for the in-register butterflies (multiples of 2*pi/16)
+// compile-time roots of unity for the in-register butterflies (multiples of 2*pi/16, and of 2*pi/32)
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ constexpr T cos16(int k) {
@@ -36,24 +36,42 @@ __device__ __forceinline__ constexpr T sin16(int k) {
          : k == 6 ? T(0.70710678118654752440) : k == 7 ? T(0.38268343236508977173) : T(0);
 }
 
+// the odd 32nd roots (radix-32 butterflies of the wide convolution kernel); even ones are the 16th roots
+template <typename T>
+__device__ __forceinline__ constexpr T cos32(int k) {
+    // cos(2*pi*k/32), k = 0..16
+    return (k & 1) == 0 ? cos16<T>(k / 2)
+         : k == 1 ? T(0.98078528040323044913) : k == 3 ? T(0.83146961230254523708) : k == 5 ? T(0.55557023301960222474)
+         : k == 7 ? T(0.19509032201612826785) : k == 9 ? T(-0.19509032201612826785) : k == 11 ? T(-0.55557023301960222474)
+         : k == 13 ? T(-0.83146961230254523708) : T(-0.98078528040323044913);
+}
+template <typename T>
+__device__ __forceinline__ constexpr T sin32(int k) {
+    // sin(2*pi*k/32), k = 0..16
+    return (k & 1) == 0 ? sin16<T>(k / 2)
+         : k == 1 ? T(0.19509032201612826785) : k == 3 ? T(0.55557023301960222474) : k == 5 ? T(0.83146961230254523708)
+         : k == 7 ? T(0.98078528040323044913) : k == 9 ? T(0.98078528040323044913) : k == 11 ? T(0.83146961230254523708)
+         : k == 13 ? T(0.55557023301960222474) : T(0.19509032201612826785);
+}
+
 // multiply by exp(DIR * -2*pi*i * q / R), q < R/2, with the trivial cases folded away
 template <int R, int Q, int DIR, typename T>
 __device__ __forceinline__ cpx<T> mul_root(cpx<T> a) {
-    constexpr int K = Q * (16 / R);  // index into the 16th roots, 0..7
+    constexpr int K = Q * (32 / R);  // index into the 32nd roots, 0..15
     if constexpr (K == 0) {
         return a;
-    } else if constexpr (K == 4) {
+    } else if constexpr (K == 8) {
         // forward: * (-i) ; inverse: * (+i)
         return DIR > 0 ? cpx<T>{a.y, -a.x} : cpx<T>{-a.y, a.x};
-    } else if constexpr (K == 2) {
+    } else if constexpr (K == 4) {
         constexpr T c = cos16<T>(2);
         return DIR > 0 ? cpx<T>{c * (a.x + a.y), c * (a.y - a.x)} : cpx<T>{c * (a.x - a.y), c * (a.y + a.x)};
-    } else if constexpr (K == 6) {
+    } else if constexpr (K == 12) {
         constexpr T c = cos16<T>(2);
         return DIR > 0 ? cpx<T>{c * (a.y - a.x), -c * (a.x + a.y)} : cpx<T>{-c * (a.x + a.y), c * (a.x - a.y)};
     } else {
-        constexpr T wr = cos16<T>(K);
-        constexpr T wi = DIR > 0 ? -sin16<T>(K) : sin16<T>(K);
+        constexpr T wr = cos32<T>(K);
+        constexpr T wi = DIR > 0 ? -sin32<T>(K) : sin32<T>(K);
         return cpx<T>{a.x * wr - a.y * wi, a.x * wi + a.y * wr};
     }
 }
@@ -117,7 +135,7 @@ __device__ __forceinline__ void load_twiddles(const cpx<T>* __restrict__ tw, int
         w[2] = cmul(w[1], w[1]);
         w[3] = cmul(w[1], w[2]);
         if constexpr (R >= 8) {
-            if constexpr (R == 16) {
+            if constexpr (R >= 16) {
                 w[4] = tw[3 * NS + k];
                 if constexpr (DIR < 0) w[4].y = -w[4].y;
             } else {
@@ -127,10 +145,16 @@ __device__ __forceinline__ void load_twiddles(const cpx<T>* __restrict__ tw, int
             w[6] = cmul(w[4], w[2]);
             w[7] = cmul(w[4], w[3]);
         }
-        if constexpr (R == 16) {
+        if constexpr (R >= 16) {
             w[8] = cmul(w[4], w[4]);
 #pragma unroll
             for (int r = 9; r < 16; ++r) w[r] = cmul(w[8], w[r - 8]);
+        }
+        if constexpr (R == 32) {
+            w[16] = tw[15 * NS + k];
+            if constexpr (DIR < 0) w[16].y = -w[16].y;
+#pragma unroll
+            for (int r = 17; r < 32; ++r) w[r] = cmul(w[16], w[r - 16]);
         }
     }
 }
@@ -297,6 +321,15 @@ __device__ __forceinline__ void fft_remaining(Planes pl, const cpx<T>* __restric
 template <int N> struct InverseRadices { static constexpr bool fused = false; };
 template <> struct InverseRadices<8192>  { static constexpr bool fused = true; static constexpr int n = 4; static constexpr int r[4] = {8, 16, 8, 8}; };
 template <> struct InverseRadices<16384> { static constexpr bool fused = true; static constexpr int n = 4; static constexpr int r[4] = {8, 16, 16, 8}; };
+
+// Schedules of the wide convolution kernel (32 points per thread): three passes per transform instead of
+// four.  Forward 32*16*16 ends, inverse 16*16*32 starts with a radix-16 pass over the points j + r*N/16.
+template <int N> struct WideRadices { static constexpr bool ok = false; };
+template <> struct WideRadices<8192> {
+    static constexpr bool ok = true;
+    struct Fwd { static constexpr int n = 3; static constexpr int r[4] = {32, 16, 16, 1}; };
+    struct Inv { static constexpr int n = 3; static constexpr int r[4] = {16, 16, 32, 1}; };
+};
 
 template <typename Rd>
 __host__ __device__ constexpr int fft_schedule_twiddles() {

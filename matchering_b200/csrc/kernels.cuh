@@ -104,6 +104,7 @@ int twiddle_count(int n);
 extern int g_use_tma;
 extern int g_lookback_inclusive;  // limiter chunks publish their inclusive state (1, default) or aggregates only (0, tests)
 extern int g_clip_ctas_per_sm;  // grid of the correction passes, in CTAs per SM (tuning switch)
+extern int g_conv_wide;      // convolution: the 32-points-per-thread kernel (fft_size 4096; off by default)
 extern int g_conv_fused;     // convolution: ends of both transforms in registers where the schedule allows (1)
 extern int g_twiddle_chain;  // convolution FFTs: build twiddle powers in registers (1) or read them all (0)
 

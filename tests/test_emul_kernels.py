@@ -124,6 +124,18 @@ def test_generic_convolution_kernel_matches_golden(lib, golden):
     _compare(outs, (g["limited"], g["no_limiter"], g["normalized"]))
 
 
+def test_wide_convolution_kernel_matches_golden(lib, golden):
+    """The 32-points-per-thread convolution kernel (option conv_wide, fft_size 4096) against the golden vectors."""
+    g = golden("pipeline_small.npz")
+    cfg = port.OracleConfig(max_piece_size=float(g["max_piece_size_s"]))
+    lib.mgb_set_option(b"conv_wide", 1)
+    try:
+        outs, st, _, _, _ = run_pipeline(cfg, g["target"], g["reference"])
+    finally:
+        lib.mgb_set_option(b"conv_wide", 0)
+    _compare(outs, (g["limited"], g["no_limiter"], g["normalized"]))
+
+
 @pytest.mark.parametrize("fft_size,sr", [(1024, 44100), (2048, 22050), (4096, 96000), (8192, 44100)])
 def test_pipeline_other_configs(lib, fft_size, sr):
     cfg = port.OracleConfig(internal_sample_rate=sr, fft_size=fft_size, max_piece_size=0.4, rms_correction_steps=2)

@@ -527,3 +527,19 @@ def test_single_call_host_entry(torch_cuda, lib):
     for got, ref in zip(outs, want):
         assert np.abs(got.numpy() - ref).max() < 1e-6
     assert state.steps_done == 4 and state.limiter_engaged == 1
+
+
+def test_wide_convolution_kernel_against_oracle(torch_cuda, lib):
+    """The 32-points-per-thread convolution kernel (option conv_wide, fft_size 4096)."""
+    import port
+    from matchering_b200 import stages
+    cfg = _config(max_piece_size=1.0)
+    n = 44100 * 6 + 5
+    t, r = port.synth_target(n, 31), port.synth_reference(n - 999, 32)
+    lib.mgb_set_option(b"conv_wide", 1)
+    try:
+        got = stages.main(t, r, cfg, True, True, True)
+    finally:
+        lib.mgb_set_option(b"conv_wide", 0)
+    want = port.main(t.astype(np.float64), r.astype(np.float64), cfg, True, True, True)
+    _compare(got, want)
