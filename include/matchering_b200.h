@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MGB_VERSION 100 /* 0.1.0 */
+#define MGB_VERSION 200 /* 0.2.0 */
 
 typedef enum mgb_status {
     MGB_OK = 0,
@@ -220,6 +220,55 @@ int mgb_process_host(const mgb_plan* plan, const mgb_track_layout* layout, const
                      float* h_out_normalized, float* d_target_lr, float* d_reference_lr, float* d_result_lr,
                      float* d_out_lr, void* d_workspace, mgb_track_state* d_state, mgb_track_state* h_state_out,
                      void* stream);
+
+/* ---- the reference's own seam with the reference's own buffers ---------------------------------
+ * matchering/core.py:77-86 calls stages.main(target, reference, ...) with PAGEABLE float64 (frames, 2)
+ * numpy arrays and gets float64 arrays back; matchering/stages.py:202 calls limit() the same way.
+ * mgb_host_io moves such arrays at link speed without asking the caller to pin anything: a persistent
+ * pool of worker threads narrows float64 -> float32 (or copies float32) into a ring of pinned chunks
+ * while the calling thread issues one asynchronous copy per finished chunk; results come back either
+ * widened on the device and DMA'd straight into pinned memory from mgb_host_alloc (one copy, no host
+ * pass), or as float32 chunks through the same ring, widened by the workers, into any other memory.
+ * `*_width` = bytes per sample of the host arrays: 4 (float32) or 8 (float64).
+ * threads / chunk_samples / ring <= 0 pick defaults (half the host's hardware threads up to 16,
+ * 1 Mi samples, 6 chunks).  One transfer at a time per mgb_host_io. */
+typedef struct mgb_host_io mgb_host_io;
+int mgb_host_io_create(int32_t threads, int64_t chunk_samples, int32_t ring, mgb_host_io** out);
+int mgb_host_io_destroy(mgb_host_io* io);
+int mgb_host_io_threads(const mgb_host_io* io);
+/* pinned host memory for results (cudaHostAlloc); NULL on failure */
+void* mgb_host_alloc(int64_t bytes);
+void mgb_host_free(void* p);
+/* host array -> device float32; returns when the last chunk has left the staging ring */
+int mgb_host_upload(mgb_host_io* io, const void* h_src, int32_t src_width, float* d_dst, int64_t samples, void* stream);
+/* device float32 -> host array; d_wide (optional, `samples` doubles on the device) enables the direct
+ * float64 route into pinned memory.  Synchronises `stream`. */
+int mgb_host_download(mgb_host_io* io, const float* d_src, void* h_dst, int32_t dst_width, int64_t samples,
+                      double* d_wide, void* stream);
+
+/* device staging of one job, provided by the caller (PyTorch allocations on the Python side) */
+typedef struct mgb_host_buffers {
+    float* d_target_lr;    /* target_frames stereo frames */
+    float* d_reference_lr; /* reference_frames */
+    float* d_result_lr;    /* target_frames */
+    float* d_out_lr;       /* target_frames */
+    double* d_wide;        /* optional: 2 * target_frames doubles (direct float64 download) */
+    void* d_workspace;     /* layout->workspace_bytes */
+    mgb_track_state* d_state;
+} mgb_host_buffers;
+
+/* stages.main (matchering/stages.py:210-272) in ONE call on the caller's host arrays: upload, stages
+ * 1-4, download of every requested output (NULL = not needed, like the reference's need_* flags).
+ * Returns after the outputs and *h_state_out (optional) are in host memory. */
+int mgb_stages_main_host(mgb_host_io* io, const mgb_plan* plan, const mgb_track_layout* layout, const void* h_target,
+                         const void* h_reference, int32_t in_width, void* h_out_limited, void* h_out_no_limiter,
+                         void* h_out_normalized, int32_t out_width, const mgb_host_buffers* dev,
+                         mgb_track_state* h_state_out, void* stream);
+/* limiter.limit (matchering/limiter/hyrax.py:78-99) on a host array.  *h_engaged_out = 0 means the
+ * reference would return its input object untouched (hyrax.py:83-85): h_out is then NOT written. */
+int mgb_limit_host(mgb_host_io* io, const mgb_limiter_params* params, const void* h_in, int32_t in_width, void* h_out,
+                   int32_t out_width, int64_t frames, float* d_in_lr, float* d_out_lr, double* d_wide, void* d_workspace,
+                   int64_t workspace_bytes, int32_t* d_engaged, int32_t* h_engaged_out, void* stream);
 
 /* ---- batches of tracks with HOST buffers: `depth` tracks in flight ------------------------------
  * mgb_process_host serialises copies and kernels of one track; tracks are independent, so a

@@ -81,6 +81,13 @@ class TrackState(C.Structure):
     ]
 
 
+class HostBuffers(C.Structure):
+    _fields_ = [
+        ("d_target_lr", C.c_void_p), ("d_reference_lr", C.c_void_p), ("d_result_lr", C.c_void_p),
+        ("d_out_lr", C.c_void_p), ("d_wide", C.c_void_p), ("d_workspace", C.c_void_p), ("d_state", C.c_void_p),
+    ]
+
+
 class TrackLayout(C.Structure):
     _fields_ = [
         ("target_frames", C.c_int64), ("reference_frames", C.c_int64),
@@ -117,6 +124,19 @@ PROTOTYPES = {
     "mgb_process_host": (C.c_int, [C.POINTER(Plan), C.POINTER(TrackLayout), C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mgb_host_io_create": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.POINTER(C.c_void_p)]),
+    "mgb_host_io_destroy": (C.c_int, [C.c_void_p]),
+    "mgb_host_io_threads": (C.c_int, [C.c_void_p]),
+    "mgb_host_alloc": (C.c_void_p, [C.c_int64]),
+    "mgb_host_free": (None, [C.c_void_p]),
+    "mgb_host_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
+    "mgb_host_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
+    "mgb_stages_main_host": (C.c_int, [C.c_void_p, C.POINTER(Plan), C.POINTER(TrackLayout), C.c_void_p, C.c_void_p,
+                                       C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                       C.POINTER(HostBuffers), C.POINTER(TrackState), C.c_void_p]),
+    "mgb_limit_host": (C.c_int, [C.c_void_p, C.POINTER(LimiterParams), C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
+                                 C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                 C.POINTER(C.c_int32), C.c_void_p]),
     "mgb_pipeline_create": (C.c_int, [C.POINTER(Plan), C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_void_p)]),
     "mgb_pipeline_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                       C.POINTER(C.c_int32)]),
@@ -178,6 +198,6 @@ def load() -> C.CDLL:
                 f"{LIB_PATH} is missing: build it with `python -m matchering_b200.build` "
                 "(nvcc, sm_100a). matchering_b200 has no CPU fallback.")
         _LIB = bind(C.CDLL(LIB_PATH))
-        if _LIB.mgb_version() < 100:
+        if _LIB.mgb_version() < 200:
             raise ImportError("libmatchering_b200.so is older than this package")
     return _LIB

@@ -27,22 +27,30 @@ def _count_max_peaks(array):
     return peak, hits
 
 
+def peak_warning(peak: float, hits: int, config: Config):
+    """matchering/checker.py:75-87: nothing unless more than `clipping_samples_threshold` samples sit at
+    the peak; then CLIPPING when the peak is (close to) full scale, else LIMITER when there are more
+    than `limited_samples_threshold` of them.  -> the warning Code or None (shared by the host and the
+    device route)."""
+    if hits > config.clipping_samples_threshold:
+        if np.isclose(peak, 1.0):
+            return Code.WARNING_TARGET_IS_CLIPPING
+        if hits > config.limited_samples_threshold:
+            return Code.WARNING_TARGET_LIMITER_IS_APPLIED
+    return None
+
+
 def check(array: np.ndarray, sample_rate: int, config: Config, name: str):
+    """matchering/checker.py:90-137, in the reference's order: length at the SOURCE rate (minimum
+    scaled by the rate ratio, :99), channels, resampling, then (target only) clipping / limiter."""
     name = name.upper()
     is_target = name == "TARGET"
     frames, channels = array.shape[0], array.shape[1]
     debug(f"{name} audio length: {frames} samples ({time_str(frames, sample_rate)})")
-    if sample_rate != config.internal_sample_rate:
-        debug(f"Resampling {name} audio from {sample_rate} Hz to {config.internal_sample_rate} Hz...")
-        array = _resample(array, sample_rate, config.internal_sample_rate)
-        sample_rate = config.internal_sample_rate
-        frames = array.shape[0]
-        (warning if is_target else info)(
-            Code.WARNING_TARGET_IS_RESAMPLED if is_target else Code.INFO_REFERENCE_IS_RESAMPLED)
     if frames > config.max_length * sample_rate:
         raise ModuleError(Code.ERROR_TARGET_LENGTH_IS_EXCEEDED if is_target
                           else Code.ERROR_REFERENCE_LENGTH_LENGTH_IS_EXCEEDED)
-    if frames < config.fft_size:
+    if frames < config.fft_size * sample_rate // config.internal_sample_rate:
         raise ModuleError(Code.ERROR_TARGET_LENGTH_IS_TOO_SMALL if is_target
                           else Code.ERROR_REFERENCE_LENGTH_LENGTH_TOO_SMALL)
     if channels == 1:
@@ -51,12 +59,16 @@ def check(array: np.ndarray, sample_rate: int, config: Config, name: str):
     elif channels != 2:
         raise ModuleError(Code.ERROR_TARGET_NUM_OF_CHANNELS_IS_EXCEEDED if is_target
                           else Code.ERROR_REFERENCE_NUM_OF_CHANNELS_IS_EXCEEDED)
+    if sample_rate != config.internal_sample_rate:
+        debug(f"Resampling {name} audio from {sample_rate} Hz to {config.internal_sample_rate} Hz...")
+        array = _resample(array, sample_rate, config.internal_sample_rate)
+        sample_rate = config.internal_sample_rate
+        (warning if is_target else info)(
+            Code.WARNING_TARGET_IS_RESAMPLED if is_target else Code.INFO_REFERENCE_IS_RESAMPLED)
     if is_target:
-        peak, hits = _count_max_peaks(array)
-        if peak < 1.0 and hits > config.limited_samples_threshold:
-            warning(Code.WARNING_TARGET_LIMITER_IS_APPLIED)
-        elif peak >= 1.0 and hits > config.clipping_samples_threshold:
-            warning(Code.WARNING_TARGET_IS_CLIPPING)
+        code = peak_warning(*_count_max_peaks(array), config)
+        if code is not None:
+            warning(code)
     return array, sample_rate
 
 

@@ -104,9 +104,13 @@ Workspace carve_workspace(const mgb_plan& plan, const mgb_track_layout& L, void*
     w.mid_plane = (float*)take(L.target_frames * 4);
     w.zero_begin = base ? base + off : nullptr;
     w.piece_sums = (double*)take((int64_t)MGB_MAX_CORRECTION_STEPS * L.target_divisions * 8);
+    w.zero_end = base ? base + off : nullptr;
+    // zeroed by mgb_finalize right before every limiter launch (a second finalize on the same track
+    // must not find the first one's tickets and published carries)
+    const int64_t limiter_zero_from = off;
     w.tickets = (int*)take(256);
     w.lookback = take(limiter_lookback_bytes(L.target_frames));
-    w.zero_end = base ? base + off : nullptr;
+    w.limiter_zero_bytes = off - limiter_zero_from;
     w.total_bytes = off;
     return w;
 }
@@ -532,6 +536,11 @@ int mgb_finalize(const mgb_plan* plan, const mgb_track_layout* L, const float* d
     }
     if (d_out_limited) {
         MGB_TRY(check_aligned(d_out_limited, "d_out_limited"));
+#ifdef MGB_EMULATE
+        memset(ws.tickets, 0, ws.limiter_zero_bytes);
+#else
+        if (cudaMemsetAsync(ws.tickets, 0, ws.limiter_zero_bytes, st) != cudaSuccess) return cuda_status("memset");
+#endif
         MGB_TRY(launch_limiter(plan->limiter, res, (float2*)d_out_limited, L->target_frames, &d_state->gain,
                                &d_state->final_amplitude_coef, &d_state->limiter_engaged, ws.tickets,
                                (LookbackSlot*)ws.lookback, (const ScanPow*)plan->d_limiter_tables, st));

@@ -181,9 +181,12 @@ pcm24_decode_kernel(const unsigned char* __restrict__ in, float* __restrict__ ou
     }
 }
 
-__device__ __forceinline__ int quantize(float x, float top) {
-    const float q = rintf(x * top);  // round half to even, like lrint
-    return (int)fminf(top, fmaxf(-top - 1.0f, q));
+// In double, like libsndfile's d2s/d2bet writers the reference reaches with its float64 arrays: the
+// product x * top is exact in float64 (24 + 23 significant bits), so ties round exactly as lrint does
+// there; a float32 product would be rounded to 24 bits first and could land one LSB away.
+__device__ __forceinline__ int quantize(float x, double top) {
+    const double q = rint((double)x * top);  // round half to even, like lrint
+    return (int)fmin(top, fmax(-top - 1.0, q));
 }
 
 __global__ void __launch_bounds__(256)
@@ -195,19 +198,18 @@ pcm16_encode_kernel(const float* __restrict__ in, short* __restrict__ out, long 
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += stride) {
         const float2 v = in2[i];
         short2 q;
-        q.x = (short)quantize(v.x, 32767.0f);
-        q.y = (short)quantize(v.y, 32767.0f);
+        q.x = (short)quantize(v.x, 32767.0);
+        q.y = (short)quantize(v.y, 32767.0);
         out2[i] = q;
     }
-    if ((count & 1) && blockIdx.x == 0 && threadIdx.x == 0) out[count - 1] = (short)quantize(in[count - 1], 32767.0f);
+    if ((count & 1) && blockIdx.x == 0 && threadIdx.x == 0) out[count - 1] = (short)quantize(in[count - 1], 32767.0);
 }
 
 __global__ void __launch_bounds__(256)
 pcm24_encode_kernel(const float* __restrict__ in, unsigned char* __restrict__ out, long long count) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
-        // 8388607 is exactly representable in float32; the product is rounded once before rintf
-        const int q = quantize(in[i], 8388607.0f);
+        const int q = quantize(in[i], 8388607.0);
         unsigned char* p = out + 3 * i;
         p[0] = (unsigned char)(q & 0xff);
         p[1] = (unsigned char)((q >> 8) & 0xff);

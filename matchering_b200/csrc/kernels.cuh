@@ -21,9 +21,11 @@ struct Workspace {
     // ---- zeroed at the start of every job (one memset) ----
     unsigned char* zero_begin;
     double* piece_sums;     // [MGB_MAX_CORRECTION_STEPS][Dt] sums of clip(mid*gain)^2
+    unsigned char* zero_end;
+    // ---- zeroed before every limiter launch (limiter_zero_bytes from `tickets` on) ----
     int* tickets;           // [64] zeroed counters: 0 = limiter chunk ticket
     unsigned char* lookback;// [nchunks] LookbackSlot
-    unsigned char* zero_end;
+    int64_t limiter_zero_bytes;
     int64_t design_stride;  // doubles per channel in `design`
     int64_t total_bytes;
 };

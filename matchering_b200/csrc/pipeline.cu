@@ -8,6 +8,7 @@
 // mgb_pipeline_wait and the reuse of a slot whose previous result has not been collected.
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "kernels.cuh"
@@ -47,6 +48,25 @@ struct mgb_pipeline {
 };
 
 using namespace mgb;
+
+namespace {
+// A submit that fails after its copies were enqueued must not leave the slot looking free while the
+// device still reads or writes its buffers: drain the streams it used before reporting the error.
+struct SubmitGuard {
+    mgb_pipeline* p;
+    Slot* s;
+    bool ok = false;
+    ~SubmitGuard() {
+        if (ok) return;
+#ifndef MGB_EMULATE
+        cudaStreamSynchronize(p->s_h2d);
+        if (s->compute) cudaStreamSynchronize(s->compute);
+        cudaStreamSynchronize(p->s_d2h);
+#endif
+        s->busy = false;
+    }
+};
+}  // namespace
 
 #ifdef MGB_EMULATE
 #define MGB_CUDA_OK(call) (void)0
@@ -95,9 +115,17 @@ int mgb_pipeline_create(const mgb_plan* plan, int64_t max_target_frames, int64_t
     p->plan = *plan;
     p->max_target = max_target_frames;
     p->max_reference = max_reference_frames;
-    // the workspace grows with the frame counts and with the number of pieces; the largest track
-    // bounds both, plus a margin for slot counts that shrink as pieces get fewer
-    p->workspace_bytes = biggest.workspace_bytes + (8 << 20);
+    // the workspace grows with the frame counts and the number of pieces (both largest for the longest
+    // track) and with the analysis items = divisions x slots, which do NOT: slots = 3*SMs / divisions
+    // rounds down, so a shorter track with fewer pieces can have more items.  Items never exceed
+    // max(3*SMs, divisions); size for that.
+    {
+        mgb_track_layout worst = biggest;
+        const int64_t cap = 3LL * num_sms();
+        worst.target_slots = (int32_t)((std::max<int64_t>(cap, worst.target_divisions) + worst.target_divisions - 1) / worst.target_divisions);
+        worst.reference_slots = (int32_t)((std::max<int64_t>(cap, worst.reference_divisions) + worst.reference_divisions - 1) / worst.reference_divisions);
+        p->workspace_bytes = carve_workspace(*plan, worst, nullptr).total_bytes;
+    }
     p->slots.resize(depth);
 #ifndef MGB_EMULATE
     MGB_CUDA_OR_DESTROY(cudaStreamCreateWithFlags(&p->s_h2d, cudaStreamNonBlocking));
@@ -188,6 +216,7 @@ int mgb_pipeline_submit(mgb_pipeline* p, const float* h_target_lr, int64_t targe
     p->next = (p->next + 1) % (int)p->slots.size();
     Slot& s = p->slots[idx];
     MGB_TRY(mgb_pipeline_wait(p, idx, nullptr));  // the slot's previous result must have left the device
+    SubmitGuard guard{p, &s};
     MGB_TRY(mgb_track_layout_init(&p->plan, target_frames, reference_frames, &s.layout));
     MGB_REQUIRE(s.layout.workspace_bytes <= p->workspace_bytes, MGB_ERR_WORKSPACE, "pipeline: workspace too small");
     const size_t tb = (size_t)target_frames * 8, rb = (size_t)reference_frames * 8;
@@ -217,6 +246,7 @@ int mgb_pipeline_submit(mgb_pipeline* p, const float* h_target_lr, int64_t targe
     MGB_CUDA_OK(cudaEventRecord(s.d2h_done, p->s_d2h));
 #endif
     s.busy = true;
+    guard.ok = true;
     if (slot_out) *slot_out = idx;
     return MGB_OK;
 }
@@ -234,6 +264,7 @@ int mgb_pipeline_submit_pcm(mgb_pipeline* p, const void* h_target_pcm, int32_t t
     p->next = (p->next + 1) % (int)p->slots.size();
     Slot& s = p->slots[idx];
     MGB_TRY(mgb_pipeline_wait(p, idx, nullptr));
+    SubmitGuard guard{p, &s};
     MGB_TRY(mgb_track_layout_init(&p->plan, target_frames, reference_frames, &s.layout));
     MGB_REQUIRE(s.layout.workspace_bytes <= p->workspace_bytes, MGB_ERR_WORKSPACE, "pipeline: workspace too small");
     const size_t tb = (size_t)target_frames * 2 * (target_bits / 8), rb = (size_t)reference_frames * 2 * (reference_bits / 8);
@@ -269,6 +300,7 @@ int mgb_pipeline_submit_pcm(mgb_pipeline* p, const void* h_target_pcm, int32_t t
     MGB_CUDA_OK(cudaEventRecord(s.d2h_done, p->s_d2h));
 #endif
     s.busy = true;
+    guard.ok = true;
     if (slot_out) *slot_out = idx;
     return MGB_OK;
 }

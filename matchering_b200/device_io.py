@@ -10,6 +10,7 @@ import numpy as np
 import torch
 
 from . import _native, wavio
+from .checker import peak_warning
 from .defaults import Config
 from .engine import _require_cuda, _stream_ptr
 from .log import Code, ModuleError, debug, info, warning
@@ -67,10 +68,9 @@ def check_on_device(audio: torch.Tensor, config: Config, name: str) -> torch.Ten
         host = scratch.cpu().numpy()
         peak = float(host[:4].view(np.float32)[0])
         hits = int(host[8:16].view(np.uint64)[0])
-        if peak < 1.0 and hits > config.limited_samples_threshold:
-            warning(Code.WARNING_TARGET_LIMITER_IS_APPLIED)
-        elif peak >= 1.0 and hits > config.clipping_samples_threshold:
-            warning(Code.WARNING_TARGET_IS_CLIPPING)
+        code = peak_warning(peak, hits, config)  # matchering/checker.py:75-87
+        if code is not None:
+            warning(code)
     return audio
 
 

@@ -177,6 +177,144 @@ class TrackSession:
         return _native.TrackState.from_buffer_copy(raw)
 
 
+# ------------------------------------------------------------------------------------------------
+# host arrays in, host arrays out (the reference's seam: pageable float64 numpy, core.py:77-86)
+# ------------------------------------------------------------------------------------------------
+class PinnedBlock:
+    """A block of pinned host memory from `PinnedPool`, seen by numpy through __array_interface__:
+    np.asarray(block) (and every view of it) keeps the block alive, and the memory goes back to the
+    pool -- not to the OS -- when the last of them is dropped.  A result array therefore costs no page
+    faults and no cudaHostAlloc after the first call of its size, and the device can DMA float64
+    results straight into it."""
+
+    def __init__(self, pool, ptr: int, capacity: int, shape, dtype):
+        self._pool, self._ptr, self._capacity = pool, ptr, capacity
+        self.__array_interface__ = {"shape": tuple(shape), "typestr": np.dtype(dtype).str, "data": (ptr, False),
+                                    "version": 3}
+
+    def __del__(self):
+        pool, self._pool = self._pool, None
+        if pool is not None:
+            pool.release(self._ptr, self._capacity)
+
+
+class PinnedPool:
+    GRANULE = 2 << 20
+
+    def __init__(self, lib, keep_bytes: int):
+        self.lib, self.keep_bytes = lib, keep_bytes
+        self.free: dict = {}
+        self.cached = 0
+
+    def array(self, shape, dtype) -> np.ndarray:
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        capacity = max(self.GRANULE, (nbytes + self.GRANULE - 1) // self.GRANULE * self.GRANULE)
+        stack = self.free.get(capacity)
+        if stack:
+            ptr = stack.pop()
+            self.cached -= capacity
+        else:
+            ptr = self.lib.mgb_host_alloc(capacity)
+            if not ptr:
+                self.trim(0)
+                ptr = self.lib.mgb_host_alloc(capacity)
+            if not ptr:
+                raise MemoryError(f"cannot pin {capacity} bytes of host memory for a result array")
+        return np.asarray(PinnedBlock(self, ptr, capacity, shape, dtype))
+
+    def release(self, ptr: int, capacity: int) -> None:
+        if self.cached + capacity > self.keep_bytes:
+            self.lib.mgb_host_free(ptr)
+            return
+        self.free.setdefault(capacity, []).append(ptr)
+        self.cached += capacity
+
+    def trim(self, keep_bytes: int) -> None:
+        for capacity, stack in self.free.items():
+            while stack and self.cached > keep_bytes:
+                self.lib.mgb_host_free(stack.pop())
+                self.cached -= capacity
+
+
+class HostIO:
+    """The library's host transport (mgb_host_io: worker threads + pinned staging ring) and the pool of
+    pinned result arrays; one per process."""
+    _instance = None
+
+    def __init__(self):
+        import os
+        self.lib = _native.load()
+        handle = C.c_void_p()
+        threads = int(os.environ.get("MGB_HOST_THREADS", "0"))
+        _native.check(self.lib, self.lib.mgb_host_io_create(threads, 0, 0, C.byref(handle)))
+        self.handle = handle
+        self.pool = PinnedPool(self.lib, int(float(os.environ.get("MGB_PINNED_CACHE_GB", "4")) * (1 << 30)))
+
+    @classmethod
+    def get(cls) -> "HostIO":
+        if cls._instance is None:
+            _require_cuda()
+            cls._instance = HostIO()
+        return cls._instance
+
+    @property
+    def threads(self) -> int:
+        return int(self.lib.mgb_host_io_threads(self.handle))
+
+
+def host_array_ok(a) -> bool:
+    """numpy arrays the host transport takes as they are: (frames, 2), float32/float64, C-contiguous."""
+    return (isinstance(a, np.ndarray) and a.ndim == 2 and a.shape[1] == 2 and a.dtype in (np.float32, np.float64)
+            and a.flags["C_CONTIGUOUS"])
+
+
+_SESSION_CACHE: dict = {}
+_SESSION_CACHE_MAX = 2
+
+
+def host_session(plan: DevicePlan, target_frames: int, reference_frames: int) -> "TrackSession":
+    """TrackSession with the device staging of the single-call host entry, cached per (plan, sizes):
+    mastering the next track of the same length allocates nothing."""
+    key = (id(plan), target_frames, reference_frames)
+    sess = _SESSION_CACHE.pop(key, None)
+    if sess is None:
+        sess = TrackSession(plan, target_frames, reference_frames)
+        dev = plan.device
+        sess.d_target = torch.empty((target_frames, 2), dtype=torch.float32, device=dev)
+        sess.d_reference = torch.empty((reference_frames, 2), dtype=torch.float32, device=dev)
+        sess.d_out = torch.empty((target_frames, 2), dtype=torch.float32, device=dev)
+        sess.d_wide = torch.empty((target_frames, 2), dtype=torch.float64, device=dev)
+        b = _native.HostBuffers()
+        b.d_target_lr, b.d_reference_lr = sess.d_target.data_ptr(), sess.d_reference.data_ptr()
+        b.d_result_lr, b.d_out_lr, b.d_wide = sess.result.data_ptr(), sess.d_out.data_ptr(), sess.d_wide.data_ptr()
+        b.d_workspace, b.d_state = sess.workspace.data_ptr(), sess.state.data_ptr()
+        sess.host_buffers = b
+    _SESSION_CACHE[key] = sess  # most recently used last
+    while len(_SESSION_CACHE) > _SESSION_CACHE_MAX:
+        _SESSION_CACHE.pop(next(iter(_SESSION_CACHE)))
+    return sess
+
+
+def stages_main_host(plan: DevicePlan, target: np.ndarray, reference: np.ndarray, need_default: bool,
+                     need_no_limiter: bool, need_no_limiter_normalized: bool):
+    """stages.main on host numpy arrays through mgb_stages_main_host: one native call, results in pinned
+    arrays of the target's dtype.  -> ((limited, plain, normalized), TrackState)"""
+    io = HostIO.get()
+    if reference.dtype != target.dtype:
+        reference = reference.astype(target.dtype)
+    sess = host_session(plan, target.shape[0], reference.shape[0])
+    width = target.dtype.itemsize
+    outs = [io.pool.array(target.shape, target.dtype) if need else None
+            for need in (need_default, need_no_limiter, need_no_limiter_normalized)]
+    state = _native.TrackState()
+    ptr = lambda a: a.ctypes.data if a is not None else None
+    _native.check(io.lib, io.lib.mgb_stages_main_host(
+        io.handle, C.byref(plan.struct), C.byref(sess.layout), target.ctypes.data, reference.ctypes.data, width,
+        ptr(outs[0]), ptr(outs[1]), ptr(outs[2]), width, C.byref(sess.host_buffers), C.byref(state),
+        _stream_ptr(plan.device)))
+    return tuple(outs), state
+
+
 def encode_pcm(t: torch.Tensor, bits: int):
     """float32 CUDA (frames, 2) -> host numpy PCM: int16 (frames, 2) or packed 24-bit uint8 (frames, 6),
     quantised on the device (lrint(x * (2^(bits-1) - 1)), clipped: libsndfile's float -> int write)."""

@@ -370,6 +370,15 @@ def synth_limiter_input(n: int, seed: int) -> np.ndarray:
     return np.ascontiguousarray(x.astype(np.float32))
 
 
+def synth_limiter_input_prefix(n: int, m: int, seed: int) -> np.ndarray:
+    """The first m frames of synth_limiter_input(n, seed) without synthesising the other n - m (the
+    generator fills row-major, and linspace(0, 500, n)[k] = k * 500 / (n - 1))."""
+    rng = np.random.default_rng(seed)
+    env = 0.3 + 0.7 * np.abs(np.sin(np.linspace(0, 500, n)[:m] if n < (1 << 22) else np.arange(m) * (500.0 / (n - 1))))
+    x = (rng.uniform(0, 1, (m, 2)) * 3 - 1.5) * env[:, None]
+    return np.ascontiguousarray(x.astype(np.float32))
+
+
 def synth_tonal(n: int, seed: int, sample_rate: int = 44100) -> np.ndarray:
     """Decaying harmonic notes with random panning between stretches of exact digital silence
     (head and tail): pieces and frames with zero energy, strongly coloured spectra."""

@@ -28,7 +28,8 @@ def test_cuda_library_loads_and_exports_every_symbol():
     for name in header_symbols():
         assert hasattr(lib, name), name
     lib.mgb_version.restype = C.c_int
-    assert lib.mgb_version() == 100
+    assert lib.mgb_version() == 200
+    assert C.sizeof(_native.HostBuffers) == 7 * 8
     # struct layouts the binding assumes (sizes of the C structs, computed from the header's fields)
     assert C.sizeof(_native.LimiterParams) == 8 + 4 * 4 + 7 * 8
     assert C.sizeof(_native.TrackLayout) == 4 * 8 + 4 * 4 + 8

@@ -255,11 +255,11 @@ def test_pcm_conversions_are_bit_exact(lib):
     xin = aligned_copy(x)
     q16 = aligned((5001, 2), np.int16)
     _native.check(lib, lib.mgb_pcm_encode(ptr(xin), 16, ptr(q16), x.size, None))
-    want16 = np.clip(np.rint(x * np.float32(32767.0)), -32768, 32767).astype(np.int16)
+    want16 = np.clip(np.rint(x.astype(np.float64) * 32767.0), -32768, 32767).astype(np.int16)  # in float64, like wavio.write
     assert np.array_equal(q16, want16)
     q24 = aligned((5001, 6), np.uint8)
     _native.check(lib, lib.mgb_pcm_encode(ptr(xin), 24, ptr(q24), x.size, None))
-    want24 = np.clip(np.rint(x * np.float32(8388607.0)), -8388608, 8388607).astype(np.int64)
+    want24 = np.clip(np.rint(x.astype(np.float64) * 8388607.0), -8388608, 8388607).astype(np.int64)
     got24 = (_from_pcm24(q24) * 8388608.0).astype(np.int64)
     assert np.array_equal(got24, want24)
     back = aligned((5001, 2), np.float32)
@@ -428,3 +428,28 @@ def test_tonal_material_with_digital_silence(lib, one_sided):
     outs, st, _, _, _ = run_pipeline(cfg, t, r)
     want = port.main(t.astype(np.float64), r.astype(np.float64), cfg, True, True, True)
     _compare(outs, want)
+
+
+def test_finalize_twice_on_one_track(lib):
+    """mgb_finalize is re-entrant on a mastered track: the second call must find fresh limiter
+    tickets and look-back slots (it used to return MGB_OK and write nothing)."""
+    from emul_harness import get_emul_plan
+    cfg = port.OracleConfig(fft_size=1024, max_piece_size=0.3)
+    t, r = port.synth_target(30000, 1), port.synth_reference(28000, 2)
+    outs, state, fir, result, L = run_pipeline(cfg, t, r, need=(True, False, False))
+    ep = get_emul_plan(cfg, False)
+    # run_pipeline's workspace is gone; redo the stages on one we keep and finalize twice
+    ws = aligned((L.workspace_bytes,), np.uint8)
+    tgt, ref = aligned_copy(t, np.float32), aligned_copy(r, np.float32)
+    res = aligned((len(t), 2), np.float32)
+    st = _native.TrackState()
+    P, LL = C.byref(ep.struct), C.byref(L)
+    _native.check(lib, lib.mgb_match_levels(P, LL, ptr(tgt), ptr(ref), ptr(ws), C.byref(st), None))
+    _native.check(lib, lib.mgb_match_frequencies(P, LL, ptr(tgt), ptr(res), None, ptr(ws), C.byref(st), None))
+    _native.check(lib, lib.mgb_correct_levels(P, LL, ptr(ws), C.byref(st), None))
+    first, second = aligned((len(t), 2), np.float32), aligned((len(t), 2), np.float32)
+    second[...] = 7.0
+    _native.check(lib, lib.mgb_finalize(P, LL, ptr(res), ptr(first), None, None, ptr(ws), C.byref(st), None))
+    _native.check(lib, lib.mgb_finalize(P, LL, ptr(res), ptr(second), None, None, ptr(ws), C.byref(st), None))
+    assert st.limiter_engaged == 1
+    assert np.array_equal(first, second) and np.array_equal(first, outs[0])

@@ -210,25 +210,56 @@ def test_limiter_three_minutes_against_oracle(torch_cuda):
     assert abs(np.abs(got).max() - _config().threshold) < 1e-6
 
 
-def test_limiter_one_hour_properties(torch_cuda):
-    """BASELINE config 5 at full size (158.76 M frames; the oracle needs 13.7 GB and a minute for
-    it, so size-independent properties instead): the peak sits at the threshold, the gain never
-    exceeds 1, and -- the limiter being causal up to its short look-ahead -- the first three
-    minutes of the hour equal a three-minute run."""
+def _compare_decimated(y, g, prefix, tol):
+    """y: (frames, 2) CUDA tensor; g: a golden file of oracle/make_golden_full.py (decimated output of the
+    UNMODIFIED reference at full size).  -> the largest error seen anywhere."""
+    import torch
+    every, window = int(g[prefix + "every"]), int(g[prefix + "window"])
+    assert y.shape[0] == int(g[prefix + "frames"])
+    worst = float(np.abs(y[::every].cpu().numpy().astype(np.float64) - g[prefix + "rows"]).max())
+    for start, want in zip(g[prefix + "window_starts"], g[prefix + "windows"]):
+        got = y[int(start):int(start) + window].cpu().numpy().astype(np.float64)
+        worst = max(worst, float(np.abs(got - want).max()))
+    assert worst < tol, f"decimated rows / windows differ by {worst}"
+    # 64 block sums of the output and of its square: every frame of the buffer takes part
+    edges = g[prefix + "block_edges"]
+    y64 = y.to(torch.float64)
+    csum = torch.cat([torch.zeros((1, 2), dtype=torch.float64, device=y.device), torch.cumsum(y64, 0)])
+    csq = torch.cat([torch.zeros((1, 2), dtype=torch.float64, device=y.device), torch.cumsum(y64 * y64, 0)])
+    idx = torch.from_numpy(edges).to(y.device)
+    block_sum = (csum[idx[1:]] - csum[idx[:-1]]).cpu().numpy()
+    block_sq = (csq[idx[1:]] - csq[idx[:-1]]).cpu().numpy()
+    frames_per_block = np.diff(edges)[:, None]
+    # a per-sample error e moves a block's mean by at most e and its mean square by at most 2*peak*e
+    assert np.abs(block_sum - g[prefix + "block_sum"]).max() / frames_per_block.min() < tol
+    peak = float(g[prefix + "peak"])
+    assert (np.abs(block_sq - g[prefix + "block_sumsq"]) / frames_per_block).max() < 2 * max(peak, 1.0) * tol
+    mono = y.abs().amax(dim=1)
+    assert abs(float(mono.max()) - peak) < tol
+    assert abs(float(mono[int(g[prefix + "peak_at"])]) - peak) < tol
+    return worst
+
+
+def test_config5_limiter_one_hour_against_reference_golden(torch_cuda, golden):
+    """BASELINE config 5 AT FULL SIZE: limit() on one hour of 44.1 kHz stereo (158.76 M frames, 34 454
+    chunks chained by look-back) against the unmodified reference's output, decimated
+    (tests/golden/c5_limiter_hour.npz: every 997th frame, 12 windows across chunk boundaries up to the
+    buffer's end, 64 block sums, the peak).  Tolerance 3e-7 like the short limiter tests."""
     torch = torch_cuda
     import port
     from matchering_b200.limiter import limit
-    n3 = 44100 * 180
-    x3 = port.synth_limiter_input(n3, seed=0)
-    reps = 20
-    x = torch.from_numpy(x3).cuda().repeat(reps, 1)
-    y = limit(x, _config())
-    assert y.shape == (n3 * reps, 2)
+    g = golden("c5_limiter_hour.npz")
+    n = int(g["frames"])
+    x = port.synth_limiter_input(n, seed=int(g["seed"]))
+    assert abs(float(x.astype(np.float64).sum()) - float(g["input_sum"])) < 1e-3, "synthetic input differs from the golden's"
+    xd = torch.from_numpy(x).cuda()
+    del x
+    y = limit(xd, _config())
+    worst = _compare_decimated(y, g, "", 3e-7)
+    print("config-5 (1 h limiter) max-abs error vs the reference at the golden points:", worst)
     thr = _config().threshold
     assert abs(float(y.abs().max()) - thr) < 1e-6
-    assert bool((y.abs() <= x.abs() + 1e-7).all())
-    y3 = limit(torch.from_numpy(x3).cuda(), _config())
-    assert float((y[: n3 - 4096] - y3[: n3 - 4096]).abs().max()) < 1e-7
+    assert bool((y.abs() <= xd.abs() + 1e-7).all())
 
 
 def test_full_size_config2_against_oracle(torch_cuda):
@@ -364,30 +395,27 @@ def test_direct_smoothing_path_matches_operator_path(torch_cuda, lib, golden):
     assert np.abs(firs[0][0] - g["fir_mid"]).max() < 1e-7
 
 
-def test_config3_shape_96k(torch_cuda):
-    """BASELINE config 3 (10-min 96 kHz): parity against the oracle on one minute (the oracle needs
-    ~50 s for the full ten), then the full-size run through properties that do not need the oracle:
-    finite, and its peak sits at the threshold (levels and FIR depend on the whole track, so only
-    invariants are compared at full size)."""
+def test_config3_ten_minutes_96k_against_reference_golden(torch_cuda, golden):
+    """BASELINE config 3 AT FULL SIZE: stages.main on 10 minutes of 96 kHz stereo (57.6 M frames, 41
+    pieces x 342 STFT frames, limiter windows 193 / 96) against the unmodified reference's outputs,
+    decimated (tests/golden/c3_pipeline_96k.npz).  Tolerance: the north star's 1e-5."""
     torch = torch_cuda
     import port
     from matchering_b200 import stages
-    cfg = _config(internal_sample_rate=96000)
-    n1 = 96000 * 60
-    t, r = port.synth_target(n1, 7), port.synth_reference(n1, 8)
-    got = stages.main(t, r, cfg, True, True, False)
-    want = port.main(t.astype(np.float64), r.astype(np.float64), port.config_from(cfg), True, True, False)
-    _compare(got, want)
-    # full size: 57.6 M frames, tiled from the minute so that no 10-minute noise has to be synthesised
-    tt = torch.from_numpy(t).cuda().repeat(10, 1)
-    rr = torch.from_numpy(r).cuda().repeat(10, 1)
-    full = stages.main(tt, rr, cfg, True, False, False)[0]
-    assert full.shape == (n1 * 10, 2) and bool(torch.isfinite(full).all())
-    # the limiter pins the peak at the threshold; the reference peaks at tanh(3) < threshold, so the
-    # result is scaled by the same final amplitude coefficient as the one-minute run
-    peak = float(full.abs().max())
-    assert abs(peak - float(np.abs(want[0]).max())) < 1e-5
-    assert peak <= cfg.threshold
+    g = golden("c3_pipeline_96k.npz")
+    n = int(g["limited_frames"])
+    t = port.synth_target(n, int(g["target_seed"]))
+    r = port.synth_reference(n, int(g["reference_seed"]))
+    got_sum = float(t.astype(np.float64).sum() + r.astype(np.float64).sum())
+    assert abs(got_sum - float(g["input_sum"])) < 1e-3, "synthetic inputs differ from the golden's"
+    cfg = _config(internal_sample_rate=int(g["sample_rate"]))
+    td, rd = torch.from_numpy(t).cuda(), torch.from_numpy(r).cuda()
+    del t, r
+    limited, plain, _ = stages.main(td, rd, cfg, True, True, False)
+    e_lim = _compare_decimated(limited, g, "limited_", TOL)
+    e_plain = _compare_decimated(plain, g, "no_limiter_", TOL)
+    print("config-3 (10 min @ 96 kHz) max-abs errors vs the reference at the golden points (limited, no limiter):", e_lim, e_plain)
+    assert float(limited.abs().max()) <= cfg.threshold + 1e-6
 
 
 def test_config4_shape_batch_of_tracks(torch_cuda):
@@ -543,3 +571,94 @@ def test_wide_convolution_kernel_against_oracle(torch_cuda, lib):
         lib.mgb_set_option(b"conv_wide", 0)
     want = port.main(t.astype(np.float64), r.astype(np.float64), cfg, True, True, True)
     _compare(got, want)
+
+
+def test_host_seam_results_are_owned_by_the_caller(torch_cuda):
+    """stages.main(numpy) returns arrays in pooled pinned memory: two live results never share memory,
+    a dropped result's block is reused, and the inputs are not touched (SURVEY.md 8b ownership)."""
+    import gc
+    import port
+    from matchering_b200 import stages
+    from matchering_b200.engine import HostIO
+    cfg = _config(max_piece_size=2.0)
+    t, r = port.synth_target(150000, 71).astype(np.float64), port.synth_reference(140000, 72).astype(np.float64)
+    t0, r0 = t.copy(), r.copy()
+    a = stages.main(t, r, cfg)[0]
+    a_copy = a.copy()
+    b = stages.main(t * 0.5, r, cfg)[0]
+    assert a.dtype == np.float64 and a.flags["WRITEABLE"] and not np.shares_memory(a, b)
+    assert np.array_equal(a, a_copy) and np.array_equal(t, t0) and np.array_equal(r, r0)
+    addr = a.ctypes.data
+    view = a[::2]  # a view keeps the block alive after `a` is gone
+    del a
+    gc.collect()
+    c = stages.main(t, r, cfg)[0]
+    assert c.ctypes.data != addr and np.array_equal(view, a_copy[::2])
+    del view, c
+    gc.collect()
+    pool = HostIO.get().pool
+    assert pool.cached > 0
+    d = stages.main(t, r, cfg)[0]
+    assert np.abs(d - a_copy).max() < 1e-6
+    want = port.main(t, r, cfg)[0]
+    assert np.abs(d - want).max() < TOL
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_host_seam_matches_device_path(torch_cuda, dtype):
+    """numpy in (one native call, worker-thread upload, pinned results) == torch in (staged calls)."""
+    torch = torch_cuda
+    import port
+    from matchering_b200 import stages
+    from matchering_b200.limiter import limit
+    cfg = _config(max_piece_size=3.0)
+    # several ring wraps: 1.3 M samples per signal against 1 Mi-sample chunks x 6
+    t, r = port.synth_target(660000 + 123, 81), port.synth_reference(600000, 82)
+    dev = stages.main(torch.from_numpy(t).cuda(), torch.from_numpy(r).cuda(), cfg, True, True, True)
+    host = stages.main(t.astype(dtype), r.astype(dtype), cfg, True, True, True)
+    for h, d in zip(host, dev):
+        assert h.dtype == dtype and np.abs(h - d.cpu().numpy()).max() < 1e-6
+    x = port.synth_limiter_input(500000, 3)
+    yd = limit(torch.from_numpy(x).cuda(), cfg).cpu().numpy()
+    yh = limit(x.astype(dtype), cfg)
+    assert yh.dtype == dtype and np.array_equal(yh.astype(np.float32), yd)
+    quiet = (0.1 * x).astype(dtype)
+    assert limit(quiet, cfg) is quiet
+
+
+def test_checker_rule_on_the_device(torch_cuda):
+    """matchering/checker.py:75-87 through device_io.check_on_device (mgb_check_peaks): the same cases and
+    expected warnings as tests/test_checker_parity.py, which pins them to the live reference."""
+    torch = torch_cuda
+    import matchering_b200 as mg
+    from matchering_b200.device_io import check_on_device
+    from matchering_b200.log import Code
+    from matchering_b200.log.explanations import explain
+    from test_checker_parity import CASES
+    for label, array, expected in CASES:
+        seen = []
+        mg.log(warning_handler=seen.append)
+        try:
+            check_on_device(torch.from_numpy(array.astype(np.float32)).cuda(), mg.Config(), "target")
+        finally:
+            mg.log()
+        assert seen == [explain(Code(c), False) for c in expected], label
+
+
+def test_device_pcm_quantiser_is_bit_identical_to_the_host_writer(torch_cuda):
+    """encode_pcm (device) == wavio.write's quantiser (host, float64 like libsndfile's double writers),
+    including ties and values near full scale."""
+    torch = torch_cuda
+    from matchering_b200.engine import encode_pcm
+    rng = np.random.default_rng(5)
+    x = rng.uniform(-1.05, 1.05, (200000, 2)).astype(np.float32)
+    for bits, top in ((16, 32767.0), (24, 8388607.0)):
+        ties = ((rng.integers(-int(top), int(top), 4096) + 0.5) / top).astype(np.float32)
+        x[:2048, 0], x[:2048, 1] = ties[:2048], ties[2048:]
+        want = np.clip(np.rint(x.astype(np.float64) * top), -top - 1, top).astype(np.int64)
+        got = encode_pcm(torch.from_numpy(x).cuda(), bits)
+        if bits == 24:
+            b = got.astype(np.int64).reshape(-1, 2, 3)
+            val = b[..., 0] | (b[..., 1] << 8) | (b[..., 2] << 16)
+            got = np.where(val >= 1 << 23, val - (1 << 24), val)
+        assert np.array_equal(got.astype(np.int64), want)

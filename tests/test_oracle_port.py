@@ -110,3 +110,18 @@ def test_preview_pieces_against_reference(reference_package, monkeypatch, n, who
     assert (len(r_piece) == n) == whole
     if not whole:
         assert r_piece[0].tolist() == [0.0, 0.0] and r_piece[-1].tolist() == [0.0, 0.0]
+
+
+def test_port_limiter_against_full_size_reference_golden(golden):
+    """The first 40 s of BASELINE config 5's hour against the unmodified reference's decimated output
+    (tests/golden/c5_limiter_hour.npz): the limiter is causal apart from its 88-sample look-ahead, so
+    a prefix run equals the hour's prefix away from its own end."""
+    g = golden("c5_limiter_hour.npz")
+    n, every = int(g["frames"]), int(g["every"])
+    m = 44100 * 40
+    x = port.synth_limiter_input_prefix(n, m, int(g["seed"]))
+    small = port.synth_limiter_input(5000, 3)
+    assert np.array_equal(port.synth_limiter_input_prefix(5000, 1200, 3), small[:1200])
+    y = port.limit(x.astype(np.float64), port.OracleConfig())
+    keep = (m - 8192) // every
+    assert np.abs(y[::every][:keep] - g["rows"][:keep]).max() < 1e-12
