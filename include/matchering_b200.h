@@ -136,8 +136,9 @@ const char* mgb_last_error_string(void);
  * 0 = plain coalesced loads.  "twiddle_chain": convolution FFTs build twiddle powers in registers
  * (1, default) or read them all from the table (0).  "conv_fused": the convolution keeps the last
  * forward pass, the spectral product, the first inverse pass and the epilogue in registers (1, default,
- * fft_size 4096 and 8192) or sends every pass through shared memory (0).  "conv_wide": the
- * 32-points-per-thread convolution kernel (fft_size 4096 only; 0, default: off).  "clip_ctas_per_sm": grid of
+ * fft_size 4096 and 8192) or sends every pass through shared memory (0).  "conv_frame": overlap-save
+ * frame of the convolution in FIR lengths, 4 (default: a 4F-point transform pair yields 3F outputs; fft_size
+ * 2048 and 4096 with pieces of at least 3F samples) or 2 (2F-point pair, F outputs).  "clip_ctas_per_sm": grid of
  * the RMS-correction passes in CTAs per SM (1..16, default 3).  "design_direct": mgb_test_design_fir runs the
  * spline/LOWESS chain directly even when the plan has a smoothing operator.  "lookback_inclusive":
  * 0 makes limiter chunks publish aggregates only, so every look-back walks to its cut-off.

@@ -14,7 +14,7 @@ namespace mgb {
 int g_use_tma = 1;
 int g_twiddle_chain = 1;
 int g_conv_fused = 1;
-int g_conv_wide = 0;
+int g_conv_ovs = 4;
 int g_clip_ctas_per_sm = 3;
 int g_lookback_inclusive = 1;
 
@@ -98,9 +98,9 @@ Workspace carve_workspace(const mgb_plan& plan, const mgb_track_layout& L, void*
     w.mask_t = take(L.target_divisions);
     w.mask_r = take(L.reference_divisions);
     w.design_stride = (design_doubles_per_channel(plan) + 31) / 32 * 32;
-    w.design = (double*)take(4 * w.design_stride * 8);
-    w.h_mid = (float2*)take((F + 1) * 8);
-    w.h_side = (float2*)take((F + 1) * 8);
+    w.design = (double*)take(8 * w.design_stride * 8);  // 2 channels x up to 4 design CTAs
+    w.h_mid = (float2*)take((2 * F + 1) * 8);           // FIR spectrum bins 0..N/2 of the N = 2F or 4F grid
+    w.h_side = (float2*)take((2 * F + 1) * 8);
     w.mid_plane = (float*)take(L.target_frames * 4);
     w.zero_begin = base ? base + off : nullptr;
     w.piece_sums = (double*)take((int64_t)MGB_MAX_CORRECTION_STEPS * L.target_divisions * 8);
@@ -241,22 +241,12 @@ int inverse_twiddle_count(int n) {
     if (!inverse_schedule(n, &npass, r)) return 0;
     return schedule_count(npass, r);
 }
-// the wide convolution kernel's two schedules, kept behind the fused inverse one
-template <int N>
-static int wide_counts(int* fwd, int* inv) {
-    if constexpr (WideRadices<N>::ok) {
-        *fwd = fft_schedule_twiddles<typename WideRadices<N>::Fwd>();
-        *inv = fft_schedule_twiddles<typename WideRadices<N>::Inv>();
-        return 1;
-    } else {
-        *fwd = *inv = 0;
-        return 0;
-    }
-}
-int wide_twiddle_count(int n) {
-    int f = 0, i = 0;
-    if (n == 8192) wide_counts<8192>(&f, &i);
-    return f + i;
+// the 4F-point transform pair of the long-frame convolution (conv_frame_ovs == 4), kept behind the 2F tables
+int long_frame_twiddle_count(int fft_size) {
+    const int n4 = 4 * fft_size;
+    int npass, r[4];
+    if (!inverse_schedule(n4, &npass, r)) return 0;
+    return twiddle_count(n4) + inverse_twiddle_count(n4);
 }
 int fill_twiddles(int n, int is_f64, void* table, cudaStream_t stream) {
     int npass, r[4];
@@ -270,18 +260,8 @@ int fill_twiddles(int n, int is_f64, void* table, cudaStream_t stream) {
 int fill_inverse_twiddles(int n, cpx<float>* table, cudaStream_t stream) {
     int npass, r[4];
     if (!inverse_schedule(n, &npass, r)) return MGB_OK;
-    MGB_TRY(launch("fft_twiddle_kernel", fft_twiddle_kernel<float>, dim3(16), dim3(256), 0, stream,
-                   table + twiddle_count(n), npass, r[0], r[1], r[2], r[3]));
-    if (n == 8192) {
-        using W = WideRadices<8192>;
-        cpx<float>* wide = table + twiddle_count(n) + inverse_twiddle_count(n);
-        MGB_TRY(launch("fft_twiddle_kernel", fft_twiddle_kernel<float>, dim3(16), dim3(256), 0, stream, wide, W::Fwd::n,
-                       W::Fwd::r[0], W::Fwd::r[1], W::Fwd::r[2], W::Fwd::r[3]));
-        MGB_TRY(launch("fft_twiddle_kernel", fft_twiddle_kernel<float>, dim3(16), dim3(256), 0, stream,
-                       wide + fft_schedule_twiddles<W::Fwd>(), W::Inv::n, W::Inv::r[0], W::Inv::r[1], W::Inv::r[2],
-                       W::Inv::r[3]));
-    }
-    return MGB_OK;
+    return launch("fft_twiddle_kernel", fft_twiddle_kernel<float>, dim3(16), dim3(256), 0, stream, table + twiddle_count(n),
+                  npass, r[0], r[1], r[2], r[3]);
 }
 
 }  // namespace mgb
@@ -305,8 +285,9 @@ int mgb_set_option(const char* name, int value) {
         g_clip_ctas_per_sm = value;
         return MGB_OK;
     }
-    if (strcmp(name, "conv_wide") == 0) {
-        g_conv_wide = value ? 1 : 0;
+    if (strcmp(name, "conv_frame") == 0) {
+        MGB_REQUIRE(value == 2 || value == 4, MGB_ERR_INVALID, "conv_frame must be 2 or 4 (FIR lengths per overlap-save frame)");
+        g_conv_ovs = value;
         return MGB_OK;
     }
     if (strcmp(name, "conv_fused") == 0) {
@@ -384,7 +365,7 @@ int mgb_plan_twiddle_bytes(int32_t fft_size, int64_t bytes_out[5]) {
     const int cf = twiddle_count(fft_size), c2 = twiddle_count(2 * fft_size);
     MGB_REQUIRE(cf > 0 && c2 > 0, MGB_ERR_UNSUPPORTED, "fft_size %d has no kernel", fft_size);
     bytes_out[0] = (int64_t)cf * 8;
-    bytes_out[1] = (int64_t)(c2 + inverse_twiddle_count(2 * fft_size) + wide_twiddle_count(2 * fft_size)) * 8;
+    bytes_out[1] = (int64_t)(c2 + inverse_twiddle_count(2 * fft_size) + long_frame_twiddle_count(fft_size)) * 8;
     bytes_out[2] = (int64_t)cf * 16;
     bytes_out[3] = (int64_t)c2 * 16;
     bytes_out[4] = (int64_t)align256(3 * sizeof(ScanPow));
@@ -400,6 +381,11 @@ int mgb_plan_fill_twiddles(const mgb_plan* plan, void* stream) {
     MGB_TRY(fill_twiddles(plan->fft_size, 0, plan->d_tw_f32_F, st));
     MGB_TRY(fill_twiddles(2 * plan->fft_size, 0, plan->d_tw_f32_2F, st));
     MGB_TRY(fill_inverse_twiddles(2 * plan->fft_size, (cpx<float>*)plan->d_tw_f32_2F, st));
+    if (long_frame_twiddle_count(plan->fft_size)) {
+        cpx<float>* tw4 = (cpx<float>*)plan->d_tw_f32_2F + twiddle_count(2 * plan->fft_size) + inverse_twiddle_count(2 * plan->fft_size);
+        MGB_TRY(fill_twiddles(4 * plan->fft_size, 0, tw4, st));
+        MGB_TRY(fill_inverse_twiddles(4 * plan->fft_size, tw4, st));
+    }
     MGB_TRY(fill_twiddles(plan->fft_size, 1, plan->d_tw_f64_F, st));
     if (plan->d_tw_f64_2F && plan->fft_size <= 4096) MGB_TRY(fill_twiddles(2 * plan->fft_size, 1, plan->d_tw_f64_2F, st));
     if (!plan->d_limiter_tables) return MGB_OK;  // FFT-only plans (tests); mgb_finalize insists on the tables
@@ -699,13 +685,13 @@ int mgb_test_design_fir(const mgb_plan* plan, const double* d_avg, double* d_fir
     MGB_TRY(check_plan(plan));
     MGB_REQUIRE(d_avg && d_fir_out, MGB_ERR_INVALID, "test_design_fir: NULL argument");
     MGB_TRY(check_aligned(d_workspace, "d_workspace"));
-    // workspace: [2][stride] doubles then two (F+1) float2 spectra
+    // workspace: [8][stride] doubles then two (2F+1) float2 spectra
     Workspace ws;
     memset(&ws, 0, sizeof(ws));
     ws.design_stride = (design_doubles_per_channel(*plan) + 31) / 32 * 32;
     ws.design = (double*)d_workspace;
-    ws.h_mid = (float2*)((unsigned char*)d_workspace + align256(4 * ws.design_stride * 8));
-    ws.h_side = ws.h_mid + (plan->fft_size + 1 + 31) / 32 * 32;
+    ws.h_mid = (float2*)((unsigned char*)d_workspace + align256(8 * ws.design_stride * 8));
+    ws.h_side = ws.h_mid + (2 * plan->fft_size + 1 + 31) / 32 * 32;
     mgb_track_layout L;
     memset(&L, 0, sizeof(L));
     L.target_piece = L.reference_piece = plan->fft_size;

@@ -24,9 +24,8 @@ namespace mgb {
 
 namespace {
 
-template <int F>
+template <int N>
 struct ConvSmem {
-    static constexpr int N = 2 * F;
     static constexpr int kPlaneBytes = (int)((PackedPlanes::bytes(N) + 15) / 16 * 16);
     static constexpr int kBytes = kPlaneBytes + 16 + 32 * 8 + 32 * 8 + 64 * 4 + 32;
 };
@@ -52,14 +51,13 @@ struct ConvBalance {
     bool mid_silent, side_silent, any_silent;
 };
 
-// Loads the frame's 2F input samples (clipped to the signal) into the landing buffer, hands every thread
+// Loads the frame's N input samples (clipped to the signal) into the landing buffer, hands every thread
 // its 16 points z[r] = mid + i*g*side of index tid + r*THREADS.  On return every thread is past a
 // barrier that follows its last read of the landing buffer.
-template <int F, int PTS = 16>
+template <int N, int PTS = 16>
 __device__ __forceinline__ ConvBalance conv_load_frame(const float2* __restrict__ x, long long frames, long long origin,
                                                        float2* raw, TmaBarrier* bar, unsigned* red_u, int use_tma,
                                                        cpx<float>* z) {
-    constexpr int N = 2 * F;
     constexpr int THREADS = N / PTS;
     const int tid = threadIdx.x;
     const long long lo = origin < 0 ? 0 : origin;
@@ -134,9 +132,9 @@ __device__ __forceinline__ void conv_apply_pair(cpx<float>& zk, cpx<float>& zn, 
     zn = cpx<float>{pmr + psi, psr - pmi};
 }
 
-// Output side of a frame: circular index F-1+o of the inverse transform is output sample n0+o.
+// Output side of a frame of OUT outputs: circular index F-1+o of the inverse transform is output sample n0+o.
 // mid/side -> L/R (dsp.ms_to_lr), the first RMS-correction step's sum of clip(mid)^2 per piece, the peak.
-template <int F>
+template <int OUT>
 struct ConvEpilogue {
     float2* res;
     float* midp;
@@ -151,17 +149,17 @@ struct ConvEpilogue {
                                             long long piece, int divisions_, const ConvBalance& bal) {
         res = result + n0;
         midp = mid_plane + n0;
-        valid = (int)((frames - n0 < F) ? frames - n0 : F);
+        valid = (int)((frames - n0 < OUT) ? frames - n0 : OUT);
         const long long counted = piece * divisions_;  // samples that enter the piece RMS (dsp.unfold)
         pa = n0 / piece;
         const long long brel = (pa + 1) * piece - n0;  // first output of the next piece
-        boundary = (int)(brel < F ? brel : F);
-        count_to = (int)((counted - n0 < 0) ? 0 : (counted - n0 < F ? counted - n0 : F));
+        boundary = (int)(brel < OUT ? brel : OUT);
+        count_to = (int)((counted - n0 < 0) ? 0 : (counted - n0 < OUT ? counted - n0 : OUT));
         divisions = divisions_;
         mid_silent = bal.mid_silent;
         side_silent = bal.side_silent;
         any_silent = bal.any_silent;
-        full = valid == F && boundary == F && count_to == F && !any_silent;
+        full = valid == OUT && boundary == OUT && count_to == OUT && !any_silent;
     }
     __device__ __forceinline__ void emit_full(int o, cpx<float> y) {  // emit() when `full` (which implies: no silent channel)
         const float m = y.x, sd = y.y;
@@ -213,7 +211,7 @@ struct ConvEpilogue {
     }
 };
 
-template <int F>
+template <int N>
 struct ConvPointers {
     PackedPlanes planes;
     float2* raw;
@@ -225,7 +223,7 @@ struct ConvPointers {
         planes = PackedPlanes{reinterpret_cast<float2*>(smem)};
         raw = reinterpret_cast<float2*>(smem);  // the landing buffer IS the frame's storage: unpadded
                                                 // until the first pass has gathered it, padded after
-        unsigned char* tail = smem + ConvSmem<F>::kPlaneBytes;
+        unsigned char* tail = smem + ConvSmem<N>::kPlaneBytes;
         tail += (16 - (reinterpret_cast<uintptr_t>(tail) & 15)) & 15;
         bar = reinterpret_cast<TmaBarrier*>(tail);
         red_a = reinterpret_cast<double*>(tail + 16);
@@ -245,13 +243,13 @@ convolve_kernel(const float2* __restrict__ x, long long frames, long long piece,
     constexpr int N = 2 * F;
     constexpr int THREADS = N / 16;
     MGB_DYN_SMEM(smem);
-    const ConvPointers<F> sp(smem);
+    const ConvPointers<N> sp(smem);
     const PackedPlanes planes = sp.planes;
     const int tid = threadIdx.x;
     const long long n0 = (long long)blockIdx.x * F;
 
     cpx<float> z[N / THREADS];
-    const ConvBalance bal = conv_load_frame<F>(x, frames, n0 - F / 2, sp.raw, sp.bar, sp.red_u, use_tma, z);
+    const ConvBalance bal = conv_load_frame<N>(x, frames, n0 - F / 2, sp.raw, sp.bar, sp.red_u, use_tma, z);
 
     // ---- forward transform of z = mid + i*g*side ---------------------------------------------------
     fft_first_pass_regs<N, +1, THREADS, float>(planes, z, /*barrier_before_store=*/false);
@@ -290,35 +288,42 @@ convolve_kernel(const float2* __restrict__ x, long long frames, long long piece,
 // N/8 = 2*THREADS butterflies, butterfly j touching the points j + r*N/8 in both.  A thread takes the
 // butterflies j and N/8 - j: between them they hold every pair Z[k], Z[N-k] the FIR spectra need, so
 // the last forward pass, the spectral product and the first inverse pass happen in registers.  The
-// inverse schedule also ends with a radix-8 pass over j + r*N/8: outputs q = 4..7 of butterfly j are
-// the circular indices F + j + (q-4)*N/8, i.e. output samples j + 1 + (q-4)*N/8 -- contiguous across
-// the block, so the epilogue runs straight from registers (outputs q < 4 are never formed, except
-// index F-1 = output 0).
-template <int F, bool CHAIN>
-__global__ void __launch_bounds__(F / 8, (F <= 4096 ? 2 : 1))
+// inverse schedule also ends with a radix-8 pass over j + r*N/8: its outputs q >= Q0 = 8F/N are the
+// circular indices >= F, i.e. output samples j + 1 + (q-Q0)*N/8 -- contiguous across the block, so the
+// epilogue runs straight from registers (outputs q < Q0 are never formed, except index F-1 = output 0).
+//
+// OVS = N/F is the overlap-save frame length in FIR lengths.  OVS = 2 spends a 2F-point transform pair
+// on F outputs; OVS = 4 spends a 4F-point pair on 3F outputs: 5*4F*log2(4F)*2 / 3F = 187 flop per output
+// frame for F = 4096 against 260 (-28 %), at one 139 KB CTA of 1024 threads per SM instead of two
+// 70 KB CTAs of 512.
+template <int F, int OVS, bool CHAIN>
+__global__ void __launch_bounds__(OVS * F / 16, (OVS * F <= 8192 ? 2 : 1))
 convolve_fused_kernel(const float2* __restrict__ x, long long frames, long long piece, int divisions,
                       const cpx<float>* __restrict__ tw, const float2* __restrict__ h_mid,
                       const float2* __restrict__ h_side, float2* __restrict__ result, float* __restrict__ mid_plane,
                       double* __restrict__ piece_sums, mgb_track_state* __restrict__ state, int use_tma) {
-    constexpr int N = 2 * F;
+    constexpr int N = OVS * F;
+    constexpr int OUT = N - F;  // outputs per frame
     constexpr int THREADS = N / 16;
     constexpr int NB8 = N / 8;
+    constexpr int Q0 = F / NB8;  // first output q of the last inverse pass that is an output sample
     using Fwd = Radices<N>;
     using Inv = InverseRadices<N>;
     static_assert(Inv::fused && Fwd::r[Fwd::n - 1] == 8 && Inv::r[0] == 8 && Inv::r[Inv::n - 1] == 8, "schedule");
     static_assert(fft_last_pass_ns<Fwd>() == NB8 && fft_last_pass_ns<Inv>() == NB8 && NB8 == 2 * THREADS, "schedule");
+    static_assert(Q0 * NB8 == F && Q0 >= 1 && Q0 < 8, "frame length");
     const cpx<float>* tw_inv = tw + fft_schedule_twiddles<Fwd>();
     MGB_DYN_SMEM(smem);
-    const ConvPointers<F> sp(smem);
+    const ConvPointers<N> sp(smem);
     const PackedPlanes planes = sp.planes;
     const PlaneLoad<PackedPlanes> sl{planes};
     const int tid = threadIdx.x;
-    const long long n0 = (long long)blockIdx.x * F;
+    const long long n0 = (long long)blockIdx.x * OUT;
 
     ConvBalance bal;
     {
         cpx<float> z[N / THREADS];
-        bal = conv_load_frame<F>(x, frames, n0 - F / 2, sp.raw, sp.bar, sp.red_u, use_tma, z);
+        bal = conv_load_frame<N>(x, frames, n0 - F / 2, sp.raw, sp.bar, sp.red_u, use_tma, z);
         fft_first_pass_regs<N, +1, THREADS, float>(planes, z, /*barrier_before_store=*/false);
     }
     __syncthreads();
@@ -346,7 +351,7 @@ convolve_fused_kernel(const float2* __restrict__ x, long long frames, long long 
             cpx<float> t = a[0];
             conv_apply_pair(a[0], t, 0, h_mid, h_side, bal);
             t = a[4];
-            conv_apply_pair(a[4], t, F, h_mid, h_side, bal);
+            conv_apply_pair(a[4], t, N / 2, h_mid, h_side, bal);
 #pragma unroll
             for (int q = 1; q < 4; ++q) conv_apply_pair(a[q], a[8 - q], q * NB8, h_mid, h_side, bal);
 #pragma unroll
@@ -363,7 +368,7 @@ convolve_fused_kernel(const float2* __restrict__ x, long long frames, long long 
     fft_middle<N, -1, THREADS, float, CHAIN, Inv>(planes, tw_inv);
 
     // ---- last inverse pass straight into the epilogue ------------------------------------------------
-    ConvEpilogue<F> ep(result, mid_plane, n0, frames, piece, divisions, bal);
+    ConvEpilogue<OUT> ep(result, mid_plane, n0, frames, piece, divisions, bal);
     const cpx<float>* tw_last = tw_inv + fft_last_pass_twiddles<Inv>();
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
@@ -373,114 +378,13 @@ convolve_fused_kernel(const float2* __restrict__ x, long long frames, long long 
         fft_butterfly<8, NB8, -1, CHAIN>(tw_last, j, v);  // v[q] = y[j + q*NB8]
         if (ep.full) {
 #pragma unroll
-            for (int q = 4; q < 7; ++q) ep.emit_full(j + 1 + (q - 4) * NB8, v[q]);
-            if (j != NB8 - 1) ep.emit_full(j + 1 + 3 * NB8, v[7]);  // (o = F for j = NB8-1: not an output)
-            else ep.emit_full(0, v[3]);
+            for (int q = Q0; q < 7; ++q) ep.emit_full(j + 1 + (q - Q0) * NB8, v[q]);
+            if (j != NB8 - 1) ep.emit_full(j + 1 + (7 - Q0) * NB8, v[7]);  // (o = OUT for j = NB8-1: not an output)
+            else ep.emit_full(0, v[Q0 - 1]);
         } else {
 #pragma unroll
-            for (int q = 4; q < 8; ++q) ep.emit(j + 1 + (q - 4) * NB8, v[q]);  // (o = F for j = NB8-1, q = 7: not valid)
-            if (j == NB8 - 1) ep.emit(0, v[3]);
-        }
-    }
-    ep.finish(sp.red_a, sp.red_b, sp.red_f, piece_sums, state);
-}
-
-// ---- wide kernel: 32 points per thread, three passes per transform -------------------------------------
-// Same structure as the fused kernel with radix 16 in the middle: forward 32*16*16, inverse 16*16*32.
-// A thread takes the radix-16 butterflies j and N/16 - j of the last forward pass (between them every
-// pair Z[k], Z[N-k]), applies the FIR spectra and runs the first inverse pass in registers; the last
-// inverse pass (radix 32 over j + r*N/32) feeds the epilogue: its outputs q = 16..31 are the output
-// samples j + 1 + (q-16)*N/32.  One twiddle stage and one trip through shared memory less per
-// transform than the fused kernel, at half the threads and twice the registers.
-template <int F, bool CHAIN>
-__global__ void __launch_bounds__(F / 16, 2)
-convolve_wide_kernel(const float2* __restrict__ x, long long frames, long long piece, int divisions,
-                     const cpx<float>* __restrict__ tw, const float2* __restrict__ h_mid,
-                     const float2* __restrict__ h_side, float2* __restrict__ result, float* __restrict__ mid_plane,
-                     double* __restrict__ piece_sums, mgb_track_state* __restrict__ state, int use_tma) {
-    constexpr int N = 2 * F;
-    constexpr int THREADS = N / 32;
-    constexpr int NB16 = N / 16, NB32 = N / 32;
-    using Fwd = typename WideRadices<N>::Fwd;
-    using Inv = typename WideRadices<N>::Inv;
-    static_assert(NB16 == 2 * THREADS && NB32 == THREADS, "schedule");
-    const cpx<float>* tw_fwd = tw + fft_schedule_twiddles<Radices<N>>() + fft_schedule_twiddles<InverseRadices<N>>();
-    const cpx<float>* tw_inv = tw_fwd + fft_schedule_twiddles<Fwd>();
-    MGB_DYN_SMEM(smem);
-    const ConvPointers<F> sp(smem);
-    const PackedPlanes planes = sp.planes;
-    const PlaneLoad<PackedPlanes> sl{planes};
-    const PlaneStore<PackedPlanes> ss{planes};
-    const int tid = threadIdx.x;
-    const long long n0 = (long long)blockIdx.x * F;
-
-    ConvBalance bal;
-    {
-        cpx<float> z[32];
-        bal = conv_load_frame<F, 32>(x, frames, n0 - F / 2, sp.raw, sp.bar, sp.red_u, use_tma, z);
-        Dft<32, +1, float>::run(z);  // first pass: points tid + r*THREADS, no twiddles
-#pragma unroll
-        for (int q = 0; q < 32; ++q) planes.store(tid * 32 + q, z[q]);
-    }
-    __syncthreads();
-    fft_pass<N, 16, 32, +1, THREADS, float, CHAIN>(tw_fwd, sl, ss, true);
-    __syncthreads();
-
-    // ---- last forward pass, FIR spectra, first inverse pass ----------------------------------------
-    {
-        const int ja = tid, jb = tid == 0 ? NB16 / 2 : NB16 - tid;
-        cpx<float> a[16], b[16];
-        fft_gather<16, NB16>(sl, ja, a);
-        fft_gather<16, NB16>(sl, jb, b);
-        __syncthreads();
-        const cpx<float>* tw_last = tw_fwd + fft_last_pass_twiddles<Fwd>();
-        fft_butterfly<16, NB16, +1, CHAIN>(tw_last, ja, a);  // a[q] = Z[ja + q*NB16]
-        fft_butterfly<16, NB16, +1, CHAIN>(tw_last, jb, b);  // b[q] = Z[jb + q*NB16]
-        if (tid != 0) {
-            // N - (ja + q*NB16) = jb + (15-q)*NB16
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                conv_apply_pair(a[q], b[15 - q], ja + q * NB16, h_mid, h_side, bal);
-                conv_apply_pair(b[q], a[15 - q], jb + q * NB16, h_mid, h_side, bal);
-            }
-        } else {
-            // butterflies 0 and N/32 pair with themselves: a[q] <-> a[16-q], b[q] <-> b[15-q]
-            cpx<float> t = a[0];
-            conv_apply_pair(a[0], t, 0, h_mid, h_side, bal);
-            t = a[8];
-            conv_apply_pair(a[8], t, F, h_mid, h_side, bal);
-#pragma unroll
-            for (int q = 1; q < 8; ++q) conv_apply_pair(a[q], a[16 - q], q * NB16, h_mid, h_side, bal);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) conv_apply_pair(b[q], b[15 - q], NB16 / 2 + q * NB16, h_mid, h_side, bal);
-        }
-        Dft<16, -1, float>::run(a);
-        Dft<16, -1, float>::run(b);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) planes.store(ja * 16 + q, a[q]);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) planes.store(jb * 16 + q, b[q]);
-    }
-    __syncthreads();
-    fft_pass<N, 16, 16, -1, THREADS, float, CHAIN>(tw_inv, sl, ss, true);
-    __syncthreads();
-
-    // ---- last inverse pass straight into the epilogue ------------------------------------------------
-    ConvEpilogue<F> ep(result, mid_plane, n0, frames, piece, divisions, bal);
-    {
-        const int j = tid;
-        cpx<float> v[32];
-        fft_gather<32, NB32>(sl, j, v);
-        fft_butterfly<32, NB32, -1, CHAIN>(tw_inv + fft_last_pass_twiddles<Inv>(), j, v);  // v[q] = y[j + q*NB32]
-        if (ep.full) {
-#pragma unroll
-            for (int q = 16; q < 31; ++q) ep.emit_full(j + 1 + (q - 16) * NB32, v[q]);
-            if (j != NB32 - 1) ep.emit_full(j + 1 + 15 * NB32, v[31]);  // (o = F for j = NB32-1: not an output)
-            else ep.emit_full(0, v[15]);
-        } else {
-#pragma unroll
-            for (int q = 16; q < 32; ++q) ep.emit(j + 1 + (q - 16) * NB32, v[q]);
-            if (j == NB32 - 1) ep.emit(0, v[15]);
+            for (int q = Q0; q < 8; ++q) ep.emit(j + 1 + (q - Q0) * NB8, v[q]);  // (o = OUT for j = NB8-1, q = 7: not valid)
+            if (j == NB8 - 1) ep.emit(0, v[Q0 - 1]);
         }
     }
     ep.finish(sp.red_a, sp.red_b, sp.red_f, piece_sums, state);
@@ -490,25 +394,42 @@ template <int F>
 int launch_convolve_t(const mgb_plan& plan, const mgb_track_layout& layout, const float2* target, float2* result,
                       const Workspace& ws, mgb_track_state* state, cudaStream_t stream) {
     const long long T = layout.target_frames;
-    const unsigned nframes = (unsigned)((T + F - 1) / F);
-    auto kernel = g_twiddle_chain ? convolve_kernel<F, true> : convolve_kernel<F, false>;
-    if constexpr (InverseRadices<2 * F>::fused) {
-        if (g_conv_fused) kernel = g_twiddle_chain ? convolve_fused_kernel<F, true> : convolve_fused_kernel<F, false>;
-    }
-    int threads = F / 8;
-    if constexpr (WideRadices<2 * F>::ok) {
-        if (g_conv_wide) {
-            kernel = g_twiddle_chain ? convolve_wide_kernel<F, true> : convolve_wide_kernel<F, false>;
-            threads = F / 16;
+    const int ovs = conv_frame_ovs(plan.fft_size, layout.target_piece);
+    auto args = [&](auto kernel, int out, int threads, size_t smem) {
+        const unsigned nframes = (unsigned)((T + out - 1) / out);
+        return launch("convolve_kernel", kernel, dim3(nframes), dim3(threads), smem, stream, target, T,
+                      (long long)layout.target_piece, layout.target_divisions, (const cpx<float>*)plan.d_tw_f32_2F,
+                      (const float2*)ws.h_mid, (const float2*)ws.h_side, result, ws.mid_plane, ws.piece_sums, state,
+                      g_use_tma);
+    };
+    if constexpr (InverseRadices<4 * F>::fused) {
+        if (ovs == 4) {
+            // twiddles of the 4F transform live behind the 2F tables (mgb_plan_twiddle_bytes)
+            const cpx<float>* tw4 = (const cpx<float>*)plan.d_tw_f32_2F + twiddle_count(2 * F) + inverse_twiddle_count(2 * F);
+            const unsigned nframes = (unsigned)((T + 3 * F - 1) / (3 * F));
+            auto kernel = g_twiddle_chain ? convolve_fused_kernel<F, 4, true> : convolve_fused_kernel<F, 4, false>;
+            return launch("convolve_kernel", kernel, dim3(nframes), dim3(4 * F / 16), ConvSmem<4 * F>::kBytes, stream, target, T,
+                          (long long)layout.target_piece, layout.target_divisions, tw4, (const float2*)ws.h_mid,
+                          (const float2*)ws.h_side, result, ws.mid_plane, ws.piece_sums, state, g_use_tma);
         }
     }
-    return launch("convolve_kernel", kernel, dim3(nframes), dim3(threads), ConvSmem<F>::kBytes, stream, target, T,
-                  (long long)layout.target_piece, layout.target_divisions, (const cpx<float>*)plan.d_tw_f32_2F,
-                  (const float2*)ws.h_mid, (const float2*)ws.h_side, result, ws.mid_plane, ws.piece_sums, state,
-                  g_use_tma);
+    if constexpr (InverseRadices<2 * F>::fused) {
+        if (g_conv_fused)
+            return args(g_twiddle_chain ? convolve_fused_kernel<F, 2, true> : convolve_fused_kernel<F, 2, false>, F, F / 8,
+                        ConvSmem<2 * F>::kBytes);
+    }
+    return args(g_twiddle_chain ? convolve_kernel<F, true> : convolve_kernel<F, false>, F, F / 8, ConvSmem<2 * F>::kBytes);
 }
 
 }  // namespace
+
+// Overlap-save frame length, in FIR lengths, of the convolution (and therefore the grid the design kernel
+// must put the FIR spectra on): 4 where the 4F-point fused kernel exists, is switched on and every output
+// frame of 3F samples touches at most two pieces; 2 otherwise.
+int conv_frame_ovs(int fft_size, long long target_piece) {
+    if (g_conv_ovs == 4 && g_conv_fused && (fft_size == 4096 || fft_size == 2048) && target_piece >= 3LL * fft_size) return 4;
+    return 2;
+}
 
 int launch_convolve(const mgb_plan& plan, const mgb_track_layout& layout, const float2* target, float2* result,
                     const Workspace& ws, mgb_track_state* state, cudaStream_t stream) {

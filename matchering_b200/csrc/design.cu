@@ -25,6 +25,7 @@ namespace {
 constexpr int kDesignThreads = 512;
 constexpr int kWarm = 48;
 constexpr int kBatch = 16;  // rows fetched together in the substitution sweeps
+constexpr int kDesignBlocks = 4;  // scratch blocks per channel: one per design CTA (up to 4 residue classes)
 
 // ------------------------------------------------------------------------------------------------
 struct SplineTables {
@@ -195,6 +196,7 @@ struct DesignArgs {
     float2* h_side;
     mgb_track_state* state;        // null with avg_override: c0 = 1, coef = 1
     int s_ready;                   // the smoothed curve is already in the scratch (operator path)
+    int ovs;                       // FIR spectra on the ovs*F-point grid of the convolution (2 or 4): ovs CTAs per channel
 };
 
 // Matching curve m[k] = mean|rfft(reference)| / max(eps, mean|rfft(target)|) from the per-(piece,
@@ -270,7 +272,7 @@ spectrum_mean_kernel(DesignArgs a, int n_lin, int fft_size, double eps, Prefetch
         // normalisation 1/coef are applied to the means instead of to the samples
         const double norm_t = lv.c0 / ((double)lv.loud_t * (double)a.frames_per_piece_t * (double)fft_size);
         const double norm_r = 1.0 / (lv.coef * (double)lv.loud_r * (double)a.frames_per_piece_r * (double)fft_size);
-        a.scratch[(long long)(2 * ch) * a.stride + k] = (sr * norm_r) / fmax(eps, st * norm_t);
+        a.scratch[(long long)(kDesignBlocks * ch) * a.stride + k] = (sr * norm_r) / fmax(eps, st * norm_t);
     }
 }
 
@@ -289,14 +291,14 @@ design_kernel(mgb_plan plan, DesignArgs a) {
     double* im = re + DesignSmem<F>::kPlane;
     const SplitPlanes<double> planes{re, im};
     const int tid = threadIdx.x, nthr = blockDim.x;
-    const int ch = blockIdx.x >> 1;
-    const int parity = blockIdx.x & 1;  // which half of the FIR spectrum this CTA produces (step G)
+    const int ch = blockIdx.x / a.ovs;
+    const int parity = blockIdx.x % a.ovs;  // which residue class of the FIR spectrum's bins this CTA produces (step G)
     const int NL = plan.n_log;
     const cpx<double>* tw = (const cpx<double>*)plan.d_tw_f64_F;
 
     // scratch blocks: [channel][parity]; the matching curve m (and, on the operator path, the smoothed
     // curve s) are produced into the parity-0 block by the kernels that ran before
-    double* base0 = a.scratch + (long long)(2 * ch) * a.stride;
+    double* base0 = a.scratch + (long long)(kDesignBlocks * ch) * a.stride;
     double* base = base0 + (long long)parity * a.stride;
     double* m = base;                       // [HB] matching curve
     double* s = (a.s_ready ? base0 : base) + 2 * HB;  // [HB] smoothed curve on the linear grid
@@ -316,7 +318,7 @@ design_kernel(mgb_plan plan, DesignArgs a) {
             const double ar = a.avg_override[(long long)(2 + ch) * HB + k];
             m[k] = ar / fmax(eps, at);
         }
-    } else if (parity == 1 && !a.s_ready) {
+    } else if (parity != 0 && !a.s_ready) {
         for (int k = tid; k < HB; k += nthr) m[k] = base0[k];  // own copy: the direct chain works in place
     }  // otherwise spectrum_mean_kernel / ratio_kernel has already written m into the parity-0 block
     __syncthreads();
@@ -339,37 +341,34 @@ design_kernel(mgb_plan plan, DesignArgs a) {
         __syncthreads();
     }
 
-    // ---- G: spectrum of the FIR on the 2F grid, bins 0..F ---------------------------------------
-    // even bins 2j = FFT_F(fir)[j]; odd bins 2j+1 = FFT_F(fir[n] * exp(-i*pi*n/F))[j].  Two CTAs per
-    // channel: both have just designed the same FIR (steps A-F are cheap and deterministic), one
-    // transforms it for the even bins, the other for the odd bins.
+    // ---- G: spectrum of the FIR on the ovs*F grid, bins 0..ovs*F/2 --------------------------------
+    // bin ovs*j + r = FFT_F(fir[n] * exp(-2*pi*i*r*n/(ovs*F)))[j].  ovs CTAs per channel: all have just designed
+    // the same FIR (steps A-F are cheap and deterministic), CTA r transforms it for the bins of residue r.
     {
         float2* H = ch == 0 ? a.h_mid : a.h_side;
-        const double scale = c0 / (2.0 * (double)F);
+        const int ovs = a.ovs;
+        const double scale = c0 / ((double)ovs * (double)F);
         float hpeak = 0.0f;  // max |H| of this CTA's bins: the convolution compares the two channels' peaks
         if (parity == 0) {
             auto first_even = [&](int i) { return cpx<double>{fir[i], 0.0}; };
             fft_run<F, +1, kDesignThreads, double>(planes, tw, first_even, PlaneStore<SplitPlanes<double>>{planes}, false, true);
-            __syncthreads();
-            for (int j = tid; j <= F / 2; j += nthr) {
-                const int jj = j & (F - 1);
-                const float2 h = make_float2((float)(re[fft_pad(jj)] * scale), (float)(im[fft_pad(jj)] * scale));
-                H[2 * j] = h;
-                hpeak = fmaxf(hpeak, sqrtf(h.x * h.x + h.y * h.y));
-            }
         } else {
-            auto first_odd = [&](int i) {
+            const double step = -2.0 * (double)parity / ((double)ovs * (double)F);
+            auto first_mod = [&](int i) {
                 double sn, cs;
-                sincospi(-(double)i / (double)F, &sn, &cs);
+                sincospi(step * (double)i, &sn, &cs);
                 return cpx<double>{fir[i] * cs, fir[i] * sn};
             };
-            fft_run<F, +1, kDesignThreads, double>(planes, tw, first_odd, PlaneStore<SplitPlanes<double>>{planes}, false, true);
-            __syncthreads();
-            for (int j = tid; j < F / 2; j += nthr) {
-                const float2 h = make_float2((float)(re[fft_pad(j)] * scale), (float)(im[fft_pad(j)] * scale));
-                H[2 * j + 1] = h;
-                hpeak = fmaxf(hpeak, sqrtf(h.x * h.x + h.y * h.y));
-            }
+            fft_run<F, +1, kDesignThreads, double>(planes, tw, first_mod, PlaneStore<SplitPlanes<double>>{planes}, false, true);
+        }
+        __syncthreads();
+        // bins ovs*j + parity <= ovs*F/2  (j = F/2 only for parity 0, where it wraps to the real bin F/2 of FFT_F)
+        const int jmax = (ovs * F / 2 - parity) / ovs;
+        for (int j = tid; j <= jmax; j += nthr) {
+            const int jj = j & (F - 1);
+            const float2 h = make_float2((float)(re[fft_pad(jj)] * scale), (float)(im[fft_pad(jj)] * scale));
+            H[ovs * j + parity] = h;
+            hpeak = fmaxf(hpeak, sqrtf(h.x * h.x + h.y * h.y));
         }
         __shared__ float red_peak[32];
         hpeak = block_max(hpeak, red_peak);
@@ -380,7 +379,7 @@ design_kernel(mgb_plan plan, DesignArgs a) {
 __global__ void ratio_kernel(const double* __restrict__ avg, double* __restrict__ scratch, long long stride, int n_lin,
                              double eps) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x, ch = blockIdx.y;
-    if (k < n_lin) scratch[(long long)(2 * ch) * stride + k] = avg[(long long)(2 + ch) * n_lin + k] / fmax(eps, avg[(long long)ch * n_lin + k]);
+    if (k < n_lin) scratch[(long long)(kDesignBlocks * ch) * stride + k] = avg[(long long)(2 + ch) * n_lin + k] / fmax(eps, avg[(long long)ch * n_lin + k]);
 }
 
 // ---- the smoothing as a Config-only matrix ------------------------------------------------------
@@ -424,7 +423,7 @@ smooth_operator_kernel(const double* __restrict__ S, double* __restrict__ scratc
     if (r >= n_lin) return;
     const double* row = S + (long long)r * n_lin;
     const double* m0 = scratch;               // channel 0, parity-0 block
-    const double* m1 = scratch + 2 * stride;  // channel 1, parity-0 block
+    const double* m1 = scratch + kDesignBlocks * stride;  // channel 1, parity-0 block
     double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
     // rows start at r*n_lin doubles: 16-byte aligned only for even r*n_lin, so peel to alignment
     int c0 = ((reinterpret_cast<uintptr_t>(row) & 15) != 0) ? 1 : 0;
@@ -464,13 +463,13 @@ smooth_operator_kernel(const double* __restrict__ S, double* __restrict__ scratc
     const double sa = warp_sum(a0 + a1), sb = warp_sum(b0 + b1);
     if (lane == 0) {
         scratch[2LL * n_lin + r] = sa;
-        scratch[2 * stride + 2LL * n_lin + r] = sb;
+        scratch[kDesignBlocks * stride + 2LL * n_lin + r] = sb;
     }
 }
 
 template <int F>
 int launch_design_t(const mgb_plan& plan, const DesignArgs& a, cudaStream_t stream) {
-    return launch("design_kernel", design_kernel<F>, dim3(4), dim3(kDesignThreads), DesignSmem<F>::kBytes, stream, plan, a);
+    return launch("design_kernel", design_kernel<F>, dim3(2 * a.ovs), dim3(kDesignThreads), DesignSmem<F>::kBytes, stream, plan, a);
 }
 
 }  // namespace
@@ -531,6 +530,7 @@ int launch_design(const mgb_plan& plan, const mgb_track_layout& layout, const Wo
     a.h_side = ws.h_side;
     a.state = avg_override ? nullptr : state;
     a.s_ready = 0;
+    a.ovs = conv_frame_ovs(plan.fft_size, layout.target_piece);
     if (!avg_override) {
         PrefetchList pf;
         pf.count = 0;

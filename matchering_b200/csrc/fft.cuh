@@ -322,15 +322,6 @@ template <int N> struct InverseRadices { static constexpr bool fused = false; };
 template <> struct InverseRadices<8192>  { static constexpr bool fused = true; static constexpr int n = 4; static constexpr int r[4] = {8, 16, 8, 8}; };
 template <> struct InverseRadices<16384> { static constexpr bool fused = true; static constexpr int n = 4; static constexpr int r[4] = {8, 16, 16, 8}; };
 
-// Schedules of the wide convolution kernel (32 points per thread): three passes per transform instead of
-// four.  Forward 32*16*16 ends, inverse 16*16*32 starts with a radix-16 pass over the points j + r*N/16.
-template <int N> struct WideRadices { static constexpr bool ok = false; };
-template <> struct WideRadices<8192> {
-    static constexpr bool ok = true;
-    struct Fwd { static constexpr int n = 3; static constexpr int r[4] = {32, 16, 16, 1}; };
-    struct Inv { static constexpr int n = 3; static constexpr int r[4] = {16, 16, 32, 1}; };
-};
-
 template <typename Rd>
 __host__ __device__ constexpr int fft_schedule_twiddles() {
     int total = 0, ns = Rd::r[0];

@@ -14,9 +14,9 @@ struct Workspace {
     float* absmax_part_r;   // [Dr*Sr + 1]
     unsigned char* mask_t;  // [Dt] loudest-piece mask of the target
     unsigned char* mask_r;  // [Dr]
-    double* design;         // [2 channels][2 CTAs][design_stride] float64 vectors of the FIR design
-    float2* h_mid;          // [F+1] spectrum of the mid FIR on the 2F grid (bins 0..F), c0/(2F) folded in
-    float2* h_side;         // [F+1]
+    double* design;         // [2 channels][4 CTAs][design_stride] float64 vectors of the FIR design
+    float2* h_mid;          // [2F+1] spectrum of the mid FIR on the convolution's N = 2F or 4F grid (bins 0..N/2), c0/N folded in
+    float2* h_side;         // [2F+1]
     float* mid_plane;       // [T] mid channel of the convolution result
     // ---- zeroed at the start of every job (one memset) ----
     unsigned char* zero_begin;
@@ -69,6 +69,7 @@ int build_operator(const mgb_plan& plan, double* op_out, void* workspace, cudaSt
 extern int g_design_direct;  // tests: force the direct (non-operator) smoothing in mgb_test_design_fir
 
 // convolve.cu -----------------------------------------------------------------------------------
+int conv_frame_ovs(int fft_size, long long target_piece);  // 2 or 4: transform length of the convolution in FIR lengths
 int launch_convolve(const mgb_plan& plan, const mgb_track_layout& layout, const float2* target, float2* result,
                     const Workspace& ws, mgb_track_state* state, cudaStream_t stream);
 
@@ -102,11 +103,12 @@ int launch_test_fft(int n, int is_f64, int dir, const void* in, void* out, int b
                     cudaStream_t stream);
 int fill_twiddles(int n, int is_f64, void* table, cudaStream_t stream);
 int twiddle_count(int n);
+int inverse_twiddle_count(int n);
 
 extern int g_use_tma;
 extern int g_lookback_inclusive;  // limiter chunks publish their inclusive state (1, default) or aggregates only (0, tests)
 extern int g_clip_ctas_per_sm;  // grid of the correction passes, in CTAs per SM (tuning switch)
-extern int g_conv_wide;      // convolution: the 32-points-per-thread kernel (fft_size 4096; off by default)
+extern int g_conv_ovs;       // convolution: FIR lengths per overlap-save frame where the long-frame kernel exists (4, default) or 2
 extern int g_conv_fused;     // convolution: ends of both transforms in registers where the schedule allows (1)
 extern int g_twiddle_chain;  // convolution FFTs: build twiddle powers in registers (1) or read them all (0)
 

@@ -124,16 +124,25 @@ def test_generic_convolution_kernel_matches_golden(lib, golden):
     _compare(outs, (g["limited"], g["no_limiter"], g["normalized"]))
 
 
-def test_wide_convolution_kernel_matches_golden(lib, golden):
-    """The 32-points-per-thread convolution kernel (option conv_wide, fft_size 4096) against the golden vectors."""
-    g = golden("pipeline_small.npz")
-    cfg = port.OracleConfig(max_piece_size=float(g["max_piece_size_s"]))
-    lib.mgb_set_option(b"conv_wide", 1)
+@pytest.mark.parametrize("fft_size,n,piece_s", [(4096, 60011, 0.5), (2048, 30011, 0.25)])
+def test_long_frame_convolution_against_oracle(lib, fft_size, n, piece_s):
+    """Overlap-save frames of 4 FIR lengths (3F outputs per 4F-point transform pair; default where pieces are at
+    least 3F long) against the oracle and against the 2-FIR-length frames: ragged last frame, piece boundaries
+    inside frames, samples beyond piece*divisions."""
+    cfg = port.OracleConfig(fft_size=fft_size, max_piece_size=piece_s)
+    t, r = port.synth_target(n, 3), port.synth_reference(n - 777, 4)
+    want = port.main(t.astype(np.float64), r.astype(np.float64), cfg, True, True, True)
+    got = {}
     try:
-        outs, st, _, _, _ = run_pipeline(cfg, g["target"], g["reference"])
+        for frame in (4, 2):
+            assert lib.mgb_set_option(b"conv_frame", frame) == 0
+            outs, st, fir, _, L = run_pipeline(cfg, t, r)
+            assert L.target_piece >= 3 * fft_size
+            _compare(outs, want)
+            got[frame] = outs
     finally:
-        lib.mgb_set_option(b"conv_wide", 0)
-    _compare(outs, (g["limited"], g["no_limiter"], g["normalized"]))
+        lib.mgb_set_option(b"conv_frame", 4)
+    assert np.abs(got[2][1] - got[4][1]).max() < 2e-6
 
 
 @pytest.mark.parametrize("fft_size,sr", [(1024, 44100), (2048, 22050), (4096, 96000), (8192, 44100)])

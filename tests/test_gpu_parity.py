@@ -557,20 +557,26 @@ def test_single_call_host_entry(torch_cuda, lib):
     assert state.steps_done == 4 and state.limiter_engaged == 1
 
 
-def test_wide_convolution_kernel_against_oracle(torch_cuda, lib):
-    """The 32-points-per-thread convolution kernel (option conv_wide, fft_size 4096)."""
+@pytest.mark.parametrize("fft_size", [2048, 4096])
+def test_both_convolution_frame_lengths_against_oracle(torch_cuda, lib, fft_size):
+    """Overlap-save frames of 4 FIR lengths (default where the kernel exists) and of 2, ragged ends, piece
+    boundaries inside frames."""
     import port
     from matchering_b200 import stages
-    cfg = _config(max_piece_size=1.0)
+    cfg = _config(fft_size=fft_size, max_piece_size=1.0)
     n = 44100 * 6 + 5
     t, r = port.synth_target(n, 31), port.synth_reference(n - 999, 32)
-    lib.mgb_set_option(b"conv_wide", 1)
-    try:
-        got = stages.main(t, r, cfg, True, True, True)
-    finally:
-        lib.mgb_set_option(b"conv_wide", 0)
     want = port.main(t.astype(np.float64), r.astype(np.float64), cfg, True, True, True)
-    _compare(got, want)
+    got = {}
+    try:
+        for frame in (2, 4):
+            assert lib.mgb_set_option(b"conv_frame", frame) == 0
+            got[frame] = stages.main(t, r, cfg, True, True, True)
+            _compare(got[frame], want)
+    finally:
+        lib.mgb_set_option(b"conv_frame", 4)
+    assert np.abs(got[2][1] - got[4][1]).max() < 2e-6
+    assert lib.mgb_set_option(b"conv_frame", 3) != 0
 
 
 def test_host_seam_results_are_owned_by_the_caller(torch_cuda):
