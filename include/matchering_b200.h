@@ -92,10 +92,15 @@ typedef struct mgb_plan {
     void* d_tw_f64_F;    /* double2 table of the F-point transform  */
     void* d_tw_f64_2F;   /* double2 table of the 2F-point transform */
     void* d_limiter_tables; /* powers of the limiter's three poles (blocked-scan carries) */
-    /* optional: the whole smoothing chain (spline, LOWESS, spline, overrides) as one matrix,
-     * s = S m, S row-major [n_lin][n_lin], built on the device by mgb_plan_build_operator.  NULL =
-     * run the chain directly per track (slower: two latency-bound CTAs). */
+    /* optional: the whole smoothing chain (spline, LOWESS, spline, overrides) as one Config-only matrix,
+     * s = S m, S [n_lin][n_lin].  mgb_plan_build_operator builds it densely on the device; it is numerically
+     * BANDED (LOWESS window 307 of 8193 log-grid points, spline influence decaying 0.27^n), so the plan keeps
+     * only each row's band: row r = `count` entries of d_smooth_op from `offset` on, multiplying m[first ..]
+     * (offsets even: 16-byte aligned rows; 4.8 MB instead of 33.6 MB at the default Config; what lies outside
+     * the bands is below 1e-18 of the largest entry).  NULL = run the chain directly per track (slower:
+     * latency-bound CTAs). */
     const double* d_smooth_op;
+    const int32_t* d_smooth_op_rows; /* [n_lin][4]: offset, first column, count, 0 */
 } mgb_plan;
 
 /* Per-track scalars, resident in device memory (one struct per track in flight). */
@@ -159,8 +164,9 @@ int mgb_plan_twiddle_bytes(int32_t fft_size, int64_t bytes_out[5]);
 /* Fill plan->d_tw_* and plan->d_limiter_tables (device buffers of the sizes above) on `stream`. */
 int mgb_plan_fill_twiddles(const mgb_plan* plan, void* stream);
 
-/* Build the smoothing operator of `plan` (plan->d_smooth_op may be NULL in the plan passed here)
- * into d_operator_out [n_lin*n_lin doubles] using d_workspace of mgb_plan_operator_workspace_bytes. */
+/* Build the DENSE smoothing operator of `plan` (plan->d_smooth_op may be NULL in the plan passed here)
+ * into d_operator_out [n_lin*n_lin doubles, row-major]; the host keeps each row's band (matchering_b200/plan.py
+ * band_operator) and uploads that as plan->d_smooth_op / _ptr / _lo using d_workspace of mgb_plan_operator_workspace_bytes. */
 int64_t mgb_plan_operator_workspace_bytes(const mgb_plan* plan);
 int mgb_plan_build_operator(const mgb_plan* plan, double* d_operator_out, void* d_workspace, int64_t workspace_bytes,
                             void* stream);

@@ -55,7 +55,7 @@ class Plan(C.Structure):
         ("d_tw_f32_F", C.c_void_p), ("d_tw_f32_2F", C.c_void_p),
         ("d_tw_f64_F", C.c_void_p), ("d_tw_f64_2F", C.c_void_p),
         ("d_limiter_tables", C.c_void_p),
-        ("d_smooth_op", C.c_void_p),
+        ("d_smooth_op", C.c_void_p), ("d_smooth_op_rows", C.c_void_p),
     ]
 
 

@@ -413,52 +413,43 @@ transpose_kernel(const double* __restrict__ in, double* __restrict__ out, int n)
         if (bx + r < n && by + tx < n) out[(long long)(bx + r) * n + by + tx] = tile[tx][r];
 }
 
-// s[ch] = S m[ch] for both channels; one warp per row, four rows per CTA.  Each lane streams its
-// share of the row with 16-byte loads, four of them in flight, so the 33.6 MB matrix moves at HBM
-// speed instead of at one-load-latency per iteration.
+// s[ch] = S m[ch] for both channels from the row bands of S; one warp per row, four rows per CTA.  A row is
+// ~300 doubles (at most ~530) at the default Config: each lane takes pairs with 16-byte loads, all of a
+// lane's loads (at most 9 pairs) issued before the first use.
 __global__ void __launch_bounds__(128)
-smooth_operator_kernel(const double* __restrict__ S, double* __restrict__ scratch, long long stride, int n_lin) {
+smooth_operator_kernel(const double* __restrict__ S, const int4* __restrict__ rows, double* __restrict__ scratch,
+                       long long stride, int n_lin) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r = blockIdx.x * 4 + warp;
     if (r >= n_lin) return;
-    const double* row = S + (long long)r * n_lin;
-    const double* m0 = scratch;               // channel 0, parity-0 block
-    const double* m1 = scratch + kDesignBlocks * stride;  // channel 1, parity-0 block
+    const int4 row = rows[r];  // offset (even), first column, count
+    const double2* vals = reinterpret_cast<const double2*>(S + row.x);
+    const double* m0 = scratch + row.y;                           // channel 0, parity-0 block
+    const double* m1 = scratch + kDesignBlocks * stride + row.y;  // channel 1, parity-0 block
+    const int pairs = row.z >> 1;
     double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-    // rows start at r*n_lin doubles: 16-byte aligned only for even r*n_lin, so peel to alignment
-    int c0 = ((reinterpret_cast<uintptr_t>(row) & 15) != 0) ? 1 : 0;
-    if (c0 && lane == 0) {
-        a0 += row[0] * m0[0];
-        b0 += row[0] * m1[0];
-    }
-    const int pairs = (n_lin - c0) >> 1;
-    const double2* row2 = reinterpret_cast<const double2*>(row + c0);
-    int p = lane;
-    for (; p + 96 < pairs; p += 128) {
+    for (int base = 0; base < pairs; base += 32 * 4) {
         double2 w[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) w[u] = row2[p + 32 * u];
+        for (int u = 0; u < 4; ++u) {
+            const int p = base + lane + 32 * u;
+            w[u] = p < pairs ? vals[p] : make_double2(0.0, 0.0);
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int c = c0 + 2 * (p + 32 * u);
-            a0 += w[u].x * m0[c];
-            a1 += w[u].y * m0[c + 1];
-            b0 += w[u].x * m1[c];
-            b1 += w[u].y * m1[c + 1];
+            const int p = base + lane + 32 * u;
+            if (p < pairs) {
+                a0 += w[u].x * m0[2 * p];
+                a1 += w[u].y * m0[2 * p + 1];
+                b0 += w[u].x * m1[2 * p];
+                b1 += w[u].y * m1[2 * p + 1];
+            }
         }
     }
-    for (; p < pairs; p += 32) {
-        const double2 w = row2[p];
-        const int c = c0 + 2 * p;
-        a0 += w.x * m0[c];
-        a1 += w.y * m0[c + 1];
-        b0 += w.x * m1[c];
-        b1 += w.y * m1[c + 1];
-    }
-    const int tail = c0 + 2 * pairs;  // at most one element left
-    if (tail < n_lin && lane == 0) {
-        a0 += row[tail] * m0[tail];
-        b0 += row[tail] * m1[tail];
+    if ((row.z & 1) && lane == 0) {
+        const double w = S[row.x + row.z - 1];
+        a0 += w * m0[row.z - 1];
+        b0 += w * m1[row.z - 1];
     }
     const double sa = warp_sum(a0 + a1), sb = warp_sum(b0 + b1);
     if (lane == 0) {
@@ -560,7 +551,7 @@ int launch_design(const mgb_plan& plan, const mgb_track_layout& layout, const Wo
                        (size_t)(layout.target_divisions + layout.reference_divisions + 16), stream, a, plan.n_lin,
                        plan.fft_size, plan.min_value, pf));
     }
-    if (plan.d_smooth_op && !(avg_override && g_design_direct)) {
+    if (plan.d_smooth_op && plan.d_smooth_op_rows && !(avg_override && g_design_direct)) {
         if (avg_override) {
             // test entry: the matching curve has to exist before the GEMV
             MGB_TRY(launch("ratio_kernel", ratio_kernel, dim3((plan.n_lin + 255) / 256, 2), dim3(256), 0, stream, avg_override,
@@ -568,7 +559,7 @@ int launch_design(const mgb_plan& plan, const mgb_track_layout& layout, const Wo
             a.avg_override = nullptr;
         }
         MGB_TRY(launch("smooth_operator_kernel", smooth_operator_kernel, dim3((plan.n_lin + 3) / 4), dim3(128), 0, stream,
-                       plan.d_smooth_op, a.scratch, a.stride, plan.n_lin));
+                       plan.d_smooth_op, (const int4*)plan.d_smooth_op_rows, a.scratch, a.stride, plan.n_lin));
         a.s_ready = 1;
     }
     switch (plan.fft_size) {

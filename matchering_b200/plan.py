@@ -170,6 +170,31 @@ def lowess_tables(n: int, frac: float, delta: float):
 
 
 # ------------------------------------------------------------------------------------------------
+# the smoothing operator's band
+# ------------------------------------------------------------------------------------------------
+def band_operator(dense: np.ndarray, relative_floor: float = 1e-18):
+    """Row bands of the dense smoothing operator S (mgb_plan_build_operator): spline -> LOWESS -> spline
+    has finite reach (a 307-point LOWESS window on the log grid, spline influence decaying 0.27^n), so
+    each row is non-negligible only on a contiguous stretch of columns.  Entries outside the stretch
+    are below `relative_floor` * max|S| (2e-15 of the largest matching-curve value in the worst case,
+    less than the float64 rounding of the row sums themselves).
+    -> (values float64 [total], rows int32 [n][4] = (offset into values, even; first column; count; 0))"""
+    n = dense.shape[0]
+    keep = np.abs(dense) > relative_floor * np.abs(dense).max()
+    any_ = keep.any(axis=1)
+    lo = np.where(any_, keep.argmax(axis=1), 0).astype(np.int64)
+    hi = np.where(any_, n - keep[:, ::-1].argmax(axis=1), 0).astype(np.int64)
+    width = hi - lo
+    start = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum((width + 1) // 2 * 2, out=start[1:])   # every row starts on a 16-byte boundary
+    values = np.zeros(max(2, int(start[-1])), dtype=np.float64)
+    for r in range(n):
+        values[start[r]:start[r] + width[r]] = dense[r, lo[r]:hi[r]]
+    rows = np.stack([start[:-1], lo, width, np.zeros(n, dtype=np.int64)], axis=1).astype(np.int32)
+    return values, np.ascontiguousarray(rows)
+
+
+# ------------------------------------------------------------------------------------------------
 # limiter constants
 # ------------------------------------------------------------------------------------------------
 @dataclass

@@ -47,6 +47,7 @@ struct alignas(8) float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
 struct alignas(16) double2 { double x, y; };
 struct alignas(8) int2 { int x, y; };
+struct alignas(16) int4 { int x, y, z, w; };
 struct alignas(4) short2 { short x, y; };
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }

@@ -84,8 +84,10 @@ class EmulPlan:
             ws = aligned((ws_bytes,), np.uint8)
             op = aligned((t.n_lin, t.n_lin), np.float64)
             _native.check(self.lib, self.lib.mgb_plan_build_operator(C.byref(s), ptr(op), ptr(ws), ws_bytes, None))
-            self.keep["smooth_op"] = op
-            s.d_smooth_op = op.ctypes.data
+            values, rows = plan_mod.band_operator(np.array(op))
+            self.keep["smooth_op"], self.keep["smooth_op_rows"] = aligned_copy(values), aligned_copy(rows)
+            s.d_smooth_op = self.keep["smooth_op"].ctypes.data
+            s.d_smooth_op_rows = self.keep["smooth_op_rows"].ctypes.data
 
     def layout(self, target_frames, reference_frames):
         L = _native.TrackLayout()
