@@ -61,6 +61,10 @@ typedef struct mgb_plan {
     int32_t lowess_k;          /* neighbourhood size int(frac*n_log + 1e-10) */
     int32_t lowess_nfit;       /* number of regression points */
     int32_t lowess_nrows;      /* distinct coefficient rows in d_lw_rows */
+    int32_t lowess_it;         /* robustness iterations (dsp.py:103-106 `it`; 0 at the reference defaults).  > 0 makes
+                                * LOWESS non-linear in the data: no smoothing operator, the direct chain re-weights the
+                                * regressions with bisquare weights of the residuals (6 * median scale) */
+    int32_t reserved0;
     double max_piece_size;     /* samples, as Config stores it (defaults.py:109) */
     double threshold;
     double min_value;

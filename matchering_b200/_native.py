@@ -41,6 +41,8 @@ class Plan(C.Structure):
         ("lowess_k", C.c_int32),
         ("lowess_nfit", C.c_int32),
         ("lowess_nrows", C.c_int32),
+        ("lowess_it", C.c_int32),
+        ("reserved0", C.c_int32),
         ("max_piece_size", C.c_double),
         ("threshold", C.c_double),
         ("min_value", C.c_double),

@@ -112,6 +112,130 @@ __device__ __forceinline__ double spline_eval(const double* __restrict__ y, cons
     return w[0] * y[idx] + w[1] * y[idx + 1] + w[2] * M[idx] + w[3] * M[idx + 1];
 }
 
+// ---- LOWESS pieces (statsmodels nonparametric/_smoothers_lowess.pyx semantics, dsp.py:103-106) --------
+// abscissa j of numpy.linspace(0, 1, n)
+__device__ __forceinline__ double lowess_x(int j, int n) { return j == n - 1 ? 1.0 : (double)j * (1.0 / (double)(n - 1)); }
+
+// fitted values at the regression points (fit[f]) -> all n abscissae by the `delta` interpolation
+// (update_indices / interpolate_skipped_fits).  Ends with a barrier.
+__device__ __forceinline__ void lowess_interpolate(const mgb_plan& plan, const double* __restrict__ fit, double* __restrict__ out) {
+    const int last = plan.lowess_nfit - 1;
+    for (int j = threadIdx.x; j < plan.n_log; j += blockDim.x) {
+        const int sg = plan.d_lw_seg[j];
+        const double al = plan.d_lw_alpha[j];  // 0 at a regression point
+        out[j] = al * fit[min(sg + 1, last)] + (1.0 - al) * fit[sg];
+    }
+    __syncthreads();
+}
+
+// One local regression per warp with weights tricube(distance / radius) * resid_w (calculate_weights,
+// calculate_y_fit): fit = sum_j w_j (1 + (x_i - xbar)(x_j - xbar)/sqdev) y_j with w normalised; "not ok"
+// (sum w <= 0 or a single non-zero weight) -> fit = y_i.  No trailing barrier.
+__device__ void lowess_weighted_fits(const mgb_plan& plan, const double* __restrict__ y, const double* __restrict__ resid_w,
+                                     double* __restrict__ fit) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int k = plan.lowess_k, n = plan.n_log;
+    for (int f = warp; f < plan.lowess_nfit; f += nwarps) {
+        const int i = plan.d_lw_fit_idx[f], left = plan.d_lw_fit_left[f];
+        const double xi = lowess_x(i, n);
+        const double radius = fmax(xi - lowess_x(left, n), lowess_x(left + k - 1, n) - xi);
+        double sw = 0.0, swx = 0.0, nz = 0.0;
+        for (int j = lane; j < k; j += 32) {
+            const double xj = lowess_x(left + j, n);
+            const double d = fabs(xj - xi);
+            double w = d / radius;
+            w = 1.0 - w * w * w;
+            w = w * w * w;
+            if (d >= radius) w = 0.0;
+            w *= resid_w[left + j];
+            sw += w;
+            swx += w * xj;
+            nz += w != 0.0 ? 1.0 : 0.0;
+        }
+        sw = warp_sum(sw);
+        swx = warp_sum(swx);
+        nz = warp_sum(nz);
+        double value = y[i];
+        if (sw > 0.0 && nz != 1.0) {
+            const double xbar = swx / sw;
+            double sqdev = 0.0, swy = 0.0, swdy = 0.0;
+            for (int j = lane; j < k; j += 32) {
+                const double xj = lowess_x(left + j, n);
+                const double d = fabs(xj - xi);
+                double w = d / radius;
+                w = 1.0 - w * w * w;
+                w = w * w * w;
+                if (d >= radius) w = 0.0;
+                w = w * resid_w[left + j] / sw;
+                const double dx = xj - xbar;
+                sqdev += w * dx * dx;
+                swy += w * y[left + j];
+                swdy += w * dx * y[left + j];
+            }
+            sqdev = warp_sum(sqdev);
+            swy = warp_sum(swy);
+            swdy = warp_sum(swdy);
+            value = swy + (xi - xbar) / sqdev * swdy;
+        }
+        if (lane == 0) fit[f] = value;
+    }
+}
+
+// k-th smallest (0-based) of n NON-NEGATIVE doubles: radix select on the bit patterns, one byte per pass.
+// Every thread of the block calls and gets the value; barriers inside.
+__device__ double block_kth_smallest(const double* __restrict__ v, int n, int k) {
+    __shared__ unsigned hist[256];
+    __shared__ unsigned long long sel_prefix;
+    __shared__ int sel_rank;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    if (tid == 0) {
+        sel_prefix = 0ull;
+        sel_rank = k;
+    }
+    unsigned long long mask = 0ull;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        for (int b = tid; b < 256; b += nthr) hist[b] = 0u;
+        __syncthreads();
+        const unsigned long long prefix = sel_prefix;
+        for (int j = tid; j < n; j += nthr) {
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(v[j]);
+            if ((bits & mask) == prefix) atomicAdd(&hist[(unsigned)(bits >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int rank = sel_rank, b = 0;
+            while (b < 255 && rank >= (int)hist[b]) {
+                rank -= (int)hist[b];
+                ++b;
+            }
+            sel_rank = rank;
+            sel_prefix = prefix | ((unsigned long long)b << shift);
+        }
+        mask |= 0xffull << shift;
+        __syncthreads();
+    }
+    return __longlong_as_double((long long)sel_prefix);
+}
+
+// bisquare weights of the residuals (calculate_residual_weights): scale 6 * median|y - fit|; a zero median
+// leaves weight 1 on the exact fits and 0 elsewhere.  `absres` is scratch [n].  Ends with a barrier.
+__device__ void lowess_residual_weights(const double* __restrict__ y, const double* __restrict__ fitted, int n,
+                                        double* __restrict__ absres, double* __restrict__ resid_w) {
+    for (int j = threadIdx.x; j < n; j += blockDim.x) absres[j] = fabs(y[j] - fitted[j]);
+    __syncthreads();
+    double median = block_kth_smallest(absres, n, n / 2);
+    if (!(n & 1)) median = 0.5 * (median + block_kth_smallest(absres, n, n / 2 - 1));
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        double u = absres[j];
+        if (median == 0.0) u = u > 0.0 ? 1.0 : 0.0;
+        else u /= 6.0 * median;
+        if (u >= 1.0) u = 1.0;
+        const double t = 1.0 - u * u;
+        resid_w[j] = t * t;
+    }
+    __syncthreads();
+}
+
 // Scratch layout of one channel's design vectors (doubles): m, M1, s [n_lin each], then
 // mlog, slog, zz, M2 [n_log each], then fir [F].
 // smooth_curve: m -> s, match_frequencies.__smooth_exponentially (:45-75): cubic spline to the
@@ -134,8 +258,9 @@ __device__ void smooth_curve(const mgb_plan& plan, double* __restrict__ base) {
     for (int j = tid; j < NL; j += nthr) mlog[j] = spline_eval(m, M1, plan.d_sa_eval_idx[j], plan.d_sa_eval_w + 4LL * j);
     __syncthreads();
 
-    // ---- D: LOWESS (dsp.py:103-106): each regression is a Config-only row of k coefficients ------
-    {
+    // ---- D: LOWESS (dsp.py:103-106) -----------------------------------------------------------
+    if (plan.lowess_it == 0) {
+        // no robustness iterations: each regression is a Config-only row of k coefficients
         const int k = plan.lowess_k;
         const int nfit = plan.lowess_nfit;
         for (int f = warp; f < nfit; f += 2 * nwarps) {  // two regressions per pass: twice the loads in flight
@@ -157,13 +282,20 @@ __device__ void smooth_curve(const mgb_plan& plan, double* __restrict__ base) {
             }
         }
         __syncthreads();
-        const int last = plan.lowess_nfit - 1;
-        for (int j = tid; j < NL; j += nthr) {
-            const int sg = plan.d_lw_seg[j];
-            const double al = plan.d_lw_alpha[j];  // 0 at a regression point
-            slog[j] = al * zz[min(sg + 1, last)] + (1.0 - al) * zz[sg];
-        }
+        lowess_interpolate(plan, zz, slog);
+    } else {
+        // lowess_it > 0: every pass after the first multiplies the tricube weights by the bisquare weights of
+        // the previous pass's residuals, so the regressions depend on the data.  M2 (free until step E) holds
+        // the residual weights.
+        double* resid_w = M2;
+        for (int j = tid; j < NL; j += nthr) resid_w[j] = 1.0;
         __syncthreads();
+        for (int pass = 0; pass <= plan.lowess_it; ++pass) {
+            lowess_weighted_fits(plan, mlog, resid_w, zz);
+            __syncthreads();
+            lowess_interpolate(plan, zz, slog);
+            if (pass < plan.lowess_it) lowess_residual_weights(mlog, slog, NL, zz, resid_w);
+        }
     }
 
     // ---- E: cubic spline log grid -> linear grid, then the two overrides (:67-73) -------------

@@ -23,8 +23,10 @@ def load_to_device(file: str, file_type: str, config: Config):
     eligible for the device route (the caller then uses loader.load + checker.check)."""
     if real_soundfile() is not None or not file.lower().endswith(".wav"):
         return None
+    from .engine import HostIO
+    _require_cuda()
     try:
-        got = wavio.read_pcm(file)
+        got = wavio.read_pcm(file, HostIO.get().pool.array)  # into pinned memory: the upload below is one DMA
     except OSError:
         return None
     if got is None:
@@ -32,11 +34,10 @@ def load_to_device(file: str, file_type: str, config: Config):
     raw, rate, channels, bits = got
     if rate != config.internal_sample_rate or channels > 2:
         return None
-    _require_cuda()
     debug(f"Loading the {file_type.upper()} file: '{file}'... ({bits}-bit PCM, decoded on the device)")
     lib = _native.load()
     device = torch.device("cuda", torch.cuda.current_device())
-    d_raw = torch.from_numpy(np.ascontiguousarray(raw)).to(device)
+    d_raw = torch.from_numpy(raw).to(device)
     frames = raw.shape[0]
     out = torch.empty((frames, channels), dtype=torch.float32, device=device)
     _native.check(lib, lib.mgb_pcm_decode(d_raw.data_ptr(), bits, out.data_ptr(), frames * channels, _stream_ptr(device)))

@@ -38,6 +38,7 @@ class DevicePlan:
         s.rms_correction_steps, s.lowess_k = t.rms_correction_steps, t.lowess_k
         s.lowess_nfit = len(t.arrays["lw_fit_idx"])
         s.lowess_nrows = len(t.arrays["lw_rows"])
+        s.lowess_it = t.lowess_it
         s.max_piece_size, s.threshold, s.min_value = t.max_piece_size, t.threshold, t.min_value
         s.limiter = limiter_params(t.limiter)
         self._keep = {}
@@ -54,6 +55,8 @@ class DevicePlan:
         self.struct = s
         with torch.cuda.device(device):
             _native.check(self.lib, self.lib.mgb_plan_fill_twiddles(C.byref(s), _stream_ptr(device)))
+            if t.lowess_it > 0:
+                return  # robustness iterations make the smoothing non-linear in the data: direct chain per track
             # the smoothing chain as one Config-only matrix, built on the device from the direct kernels
             ws_bytes = int(self.lib.mgb_plan_operator_workspace_bytes(C.byref(s)))
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
@@ -321,7 +324,8 @@ def stages_main_host(plan: DevicePlan, target: np.ndarray, reference: np.ndarray
 
 def encode_pcm(t: torch.Tensor, bits: int):
     """float32 CUDA (frames, 2) -> host numpy PCM: int16 (frames, 2) or packed 24-bit uint8 (frames, 6),
-    quantised on the device (lrint(x * (2^(bits-1) - 1)), clipped: libsndfile's float -> int write)."""
+    quantised on the device (lrint(x * (2^(bits-1) - 1)), clipped: libsndfile's float -> int write) and
+    copied into pooled pinned memory."""
     lib = _native.load()
     frames = t.shape[0]
     if bits == 16:
@@ -331,4 +335,6 @@ def encode_pcm(t: torch.Tensor, bits: int):
     else:
         raise ValueError("PCM width must be 16 or 24")
     _native.check(lib, lib.mgb_pcm_encode(t.data_ptr(), bits, out.data_ptr(), frames * 2, _stream_ptr(t.device)))
-    return out.cpu().numpy()
+    host = HostIO.get().pool.array(tuple(out.shape), np.int16 if bits == 16 else np.uint8)
+    torch.from_numpy(host).copy_(out)
+    return host

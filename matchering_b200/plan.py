@@ -249,6 +249,7 @@ class PlanTables:
     n_log: int
     rms_correction_steps: int
     lowess_k: int
+    lowess_it: int
     max_piece_size: float
     threshold: float
     min_value: float
@@ -269,8 +270,8 @@ def build_tables(config) -> PlanTables:
     F = config.fft_size
     if F not in SUPPORTED_FFT_SIZES:
         raise UnsupportedConfig(f"fft_size={F}: kernels exist for {SUPPORTED_FFT_SIZES}")
-    if config.lowess_it != 0:
-        raise UnsupportedConfig("lowess_it > 0 (robustness iterations) has no kernel; the reference default is 0")
+    if config.lowess_it > 8:
+        raise UnsupportedConfig("lowess_it > 8")
     if config.rms_correction_steps > 16:
         raise UnsupportedConfig("rms_correction_steps > 16")
     sr = config.internal_sample_rate
@@ -292,5 +293,5 @@ def build_tables(config) -> PlanTables:
     for name, arr in arrays.items():
         want = np.int32 if arr.dtype.kind == "i" else np.float64
         arrays[name] = np.ascontiguousarray(arr, dtype=want)
-    return PlanTables(sr, F, n_lin, n_log, config.rms_correction_steps, k, float(config.max_piece_size),
+    return PlanTables(sr, F, n_lin, n_log, config.rms_correction_steps, k, int(config.lowess_it), float(config.max_piece_size),
                       config.threshold, config.min_value, limiter_constants(config), arrays)

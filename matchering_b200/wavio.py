@@ -4,6 +4,7 @@ The reference delegates file I/O to libsndfile (matchering/loader.py:35, saver.p
 not in this image; file I/O is outside the accelerated hot path."""
 from __future__ import annotations
 
+import os
 import struct
 
 import numpy as np
@@ -87,41 +88,71 @@ def write(path: str, array: np.ndarray, sample_rate: int, subtype: str) -> None:
 
 
 def write_pcm(path: str, pcm: np.ndarray, sample_rate: int, bits: int, channels: int = 2) -> None:
-    """Already-quantised samples (int16 (frames, ch) or packed 24-bit uint8 (frames, 3*ch)) -> WAV."""
-    payload = np.ascontiguousarray(pcm).tobytes()
+    """Already-quantised samples (int16 (frames, ch) or packed 24-bit uint8 (frames, 3*ch)) -> WAV.  The
+    samples go from the caller's buffer (pinned, when they come from the device) straight into the file."""
+    pcm = np.ascontiguousarray(pcm)
+    nbytes = pcm.nbytes
     block = channels * bits // 8
     fmt = struct.pack("<HHIIHH", _PCM, channels, int(sample_rate), int(sample_rate) * block, block, bits)
-    body = b"WAVE" + b"fmt " + struct.pack("<I", len(fmt)) + fmt + b"data" + struct.pack("<I", len(payload)) + payload
-    if len(payload) & 1:
-        body += b"\x00"
-    with open(path, "wb") as f:
-        f.write(b"RIFF" + struct.pack("<I", len(body)) + body)
+    head = b"WAVE" + b"fmt " + struct.pack("<I", len(fmt)) + fmt + b"data" + struct.pack("<I", nbytes)
+    with open(path, "wb", buffering=0) as f:
+        f.write(b"RIFF" + struct.pack("<I", len(head) + nbytes + (nbytes & 1)) + head)
+        f.write(memoryview(pcm).cast("B"))
+        if nbytes & 1:
+            f.write(b"\x00")
 
 
-def read_pcm(path: str):
-    """Raw 16- or 24-bit PCM of a WAV file without converting it on the host:
-    -> (samples, sample_rate, channels, bits) with samples int16 (frames, ch) or packed 24-bit uint8
-    (frames, 3*ch); None when the file is not 16/24-bit PCM WAV."""
-    with open(path, "rb") as f:
-        data = f.read()
-    if len(data) < 12 or data[:4] != b"RIFF" or data[8:12] != b"WAVE":
+def _pcm_layout(f):
+    """Walk the RIFF chunks of an open file without reading the samples.
+    -> (data offset, data bytes, sample_rate, channels, bits) or None when it is not 16/24-bit PCM WAV."""
+    head = f.read(12)
+    if len(head) < 12 or head[:4] != b"RIFF" or head[8:12] != b"WAVE":
         return None
-    pos, fmt, payload = 12, None, None
-    while pos + 8 <= len(data):
-        cid, size = data[pos:pos + 4], struct.unpack("<I", data[pos + 4:pos + 8])[0]
+    fmt, data_at, data_size = None, None, None
+    pos = 12
+    while True:
+        f.seek(pos)
+        hdr = f.read(8)
+        if len(hdr) < 8:
+            break
+        cid, size = hdr[:4], struct.unpack("<I", hdr[4:8])[0]
         if cid == b"fmt ":
-            fmt = data[pos + 8:pos + 8 + size]
+            fmt = f.read(size)
         elif cid == b"data":
-            payload = memoryview(data)[pos + 8:pos + 8 + size]
+            data_at, data_size = pos + 8, size
         pos += 8 + size + (size & 1)
-    if fmt is None or payload is None or len(fmt) < 16:
+    if fmt is None or data_at is None or len(fmt) < 16:
         return None
     tag, channels, rate, _, _, bits = struct.unpack("<HHIIHH", fmt[:16])
     if tag == _EXTENSIBLE and len(fmt) >= 26:
         tag = struct.unpack("<H", fmt[24:26])[0]
     if tag != _PCM or bits not in (16, 24) or channels < 1:
         return None
-    block = channels * bits // 8
-    frames = len(payload) // block
-    raw = np.frombuffer(payload[: frames * block], dtype=np.int16 if bits == 16 else np.uint8)
-    return raw.reshape(frames, channels if bits == 16 else 3 * channels), int(rate), int(channels), int(bits)
+    return data_at, data_size, int(rate), int(channels), int(bits)
+
+
+def read_pcm(path: str, allocate=None):
+    """Raw 16- or 24-bit PCM of a WAV file without converting it on the host:
+    -> (samples, sample_rate, channels, bits) with samples int16 (frames, ch) or packed 24-bit uint8
+    (frames, 3*ch); None when the file is not 16/24-bit PCM WAV.  `allocate(shape, dtype)` supplies the
+    buffer the samples are read into (pinned memory, so that the device can DMA from it); default numpy."""
+    with open(path, "rb", buffering=0) as f:
+        layout = _pcm_layout(f)
+        if layout is None:
+            return None
+        data_at, data_size, rate, channels, bits = layout
+        block = channels * bits // 8
+        size = os.fstat(f.fileno()).st_size
+        frames = max(0, min(data_size, size - data_at)) // block
+        shape = (frames, channels if bits == 16 else 3 * channels)
+        dtype = np.int16 if bits == 16 else np.uint8
+        raw = allocate(shape, dtype) if allocate is not None else np.empty(shape, dtype=dtype)
+        f.seek(data_at)
+        view = memoryview(raw).cast("B")
+        got = 0
+        while got < len(view):
+            k = f.readinto(view[got:])
+            if not k:
+                raise OSError("short read")
+            got += k
+    return raw, rate, channels, bits

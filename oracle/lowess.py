@@ -95,8 +95,11 @@ def lowess(y: np.ndarray, x: np.ndarray, frac: float, it: int, delta: float) -> 
                 y_fit[last + 1:i] = a * y_fit[i] + (1.0 - a) * y_fit[last]
             last = i
         if robust_iter < it:
-            resid = y - y_fit
-            s = np.median(np.abs(resid))
-            u = resid / (6.0 * s) if s > 0 else np.zeros(n)
-            resid_w = np.where(np.abs(u) < 1.0, (1.0 - u * u) ** 2, 0.0)
+            # calculate_residual_weights: |residual| / (6 * median), trimmed at 1, through the bisquare;
+            # a zero median keeps weight 1 on the exact fits and 0 elsewhere
+            u = np.abs(y - y_fit)
+            s = np.median(u)
+            u = np.where(u > 0, 1.0, 0.0) if s == 0 else u / (6.0 * s)
+            u = np.minimum(u, 1.0)
+            resid_w = (1.0 - u * u) ** 2
     return y_fit

@@ -65,6 +65,7 @@ class EmulPlan:
         s.rms_correction_steps, s.lowess_k = t.rms_correction_steps, t.lowess_k
         s.lowess_nfit = len(t.arrays["lw_fit_idx"])
         s.lowess_nrows = len(t.arrays["lw_rows"])
+        s.lowess_it = t.lowess_it
         s.max_piece_size, s.threshold, s.min_value = t.max_piece_size, t.threshold, t.min_value
         s.limiter = limiter_params(t.limiter)
         for name, arr in t.arrays.items():

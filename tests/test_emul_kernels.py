@@ -462,3 +462,35 @@ def test_finalize_twice_on_one_track(lib):
     _native.check(lib, lib.mgb_finalize(P, LL, ptr(res), ptr(second), None, None, ptr(ws), C.byref(st), None))
     assert st.limiter_engaged == 1
     assert np.array_equal(first, second) and np.array_equal(first, outs[0])
+
+
+@pytest.mark.parametrize("it", [1, 3])
+def test_fir_design_with_lowess_robustness_iterations(lib, it):
+    """Config.lowess_it > 0 (legal, matchering/defaults.py:135; dsp.py:103-106): LOWESS re-weights its
+    regressions with bisquare weights of the residuals, the smoothing is no longer a Config-only matrix and
+    the design kernel runs the chain directly.  A curve with outliers, so that the weights matter."""
+    cfg = port.OracleConfig(lowess_it=it)
+    ep = EmulPlan(cfg)
+    assert ep.struct.lowess_it == it and not ep.struct.d_smooth_op
+    rng = np.random.default_rng(30 + it)
+    k = np.arange(2049)
+    at = 1e-3 * (1 + 0.3 * rng.standard_normal(2049)) ** 2 + 1e-5
+    ar = 3e-3 / np.sqrt(1 + k / 20.0) * (1 + 0.3 * rng.standard_normal(2049)) ** 2 + 1e-6
+    ar[rng.choice(2049, 40, replace=False)] *= 30.0  # outliers: what the robustness iterations are for
+    avg = aligned_copy(np.stack([at, 0.5 * at, ar, 0.7 * ar]))
+    fir = aligned((2, 4096), np.float64)
+    ws = aligned((4 << 20,), np.uint8)
+    _native.check(lib, lib.mgb_test_design_fir(C.byref(ep.struct), ptr(avg), ptr(fir), ptr(ws), None))
+    want = port.design_fir(at.copy(), ar.copy(), cfg)
+    plain = port.design_fir(at.copy(), ar.copy(), port.OracleConfig())
+    assert np.abs(want - plain).max() > 1e-4  # the iterations change the FIR visibly
+    assert np.abs(fir[0] - want).max() < 1e-12
+    assert np.abs(fir[1] - port.design_fir(0.5 * at, 0.7 * ar, cfg)).max() < 1e-12
+
+
+def test_pipeline_with_lowess_robustness_iterations(lib):
+    cfg = port.OracleConfig(fft_size=1024, max_piece_size=0.3, lowess_it=2)
+    t, r = port.synth_target(30000, 1), port.synth_reference(28000, 2)
+    outs, st, fir, _, _ = run_pipeline(cfg, t, r)
+    want = port.main(t.astype(np.float64), r.astype(np.float64), cfg, True, True, True)
+    _compare(outs, want)

@@ -363,7 +363,7 @@ def test_unsupported_configs_fail_loudly(torch_cuda):
     from matchering_b200.plan import UnsupportedConfig
     import matchering_b200 as mg
     x = np.zeros((20000, 2), dtype=np.float32)
-    for cfg in (_config(fft_size=512), _config(lowess_it=1), _config(limiter=mg.LimiterConfig(release_filter_order=2)),
+    for cfg in (_config(fft_size=512), _config(limiter=mg.LimiterConfig(release_filter_order=2)),
                 _config(fft_size=4096, max_piece_size=0.1)):
         with pytest.raises(UnsupportedConfig):
             stages.main(x[:5000], x[:5000], cfg)
@@ -668,3 +668,18 @@ def test_device_pcm_quantiser_is_bit_identical_to_the_host_writer(torch_cuda):
             val = b[..., 0] | (b[..., 1] << 8) | (b[..., 2] << 16)
             got = np.where(val >= 1 << 23, val - (1 << 24), val)
         assert np.array_equal(got.astype(np.int64), want)
+
+
+@pytest.mark.parametrize("it", [1, 2])
+def test_lowess_robustness_iterations_against_oracle(torch_cuda, it):
+    """Config.lowess_it > 0: the design kernel runs spline / LOWESS with bisquare re-weighting / spline itself."""
+    import port
+    from matchering_b200 import stages
+    cfg = _config(max_piece_size=1.0, lowess_it=it)
+    n = 44100 * 4 + 5
+    t, r = port.synth_target(n, 21), port.synth_reference(n - 999, 22)
+    got = stages.main(t, r, cfg, True, True, True)
+    want = port.main(t.astype(np.float64), r.astype(np.float64), cfg, True, True, True)
+    _compare(got, want)
+    plain = stages.main(t, r, _config(max_piece_size=1.0), False, True, False)[1]
+    assert np.abs(plain - got[1]).max() > 1e-6  # not the it = 0 result
