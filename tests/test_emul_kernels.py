@@ -211,7 +211,7 @@ def test_unsupported_configs_fail_loudly():
     with pytest.raises(plan_mod.UnsupportedConfig):
         plan_mod.build_tables(port.OracleConfig(fft_size=512))
     with pytest.raises(plan_mod.UnsupportedConfig):
-        plan_mod.build_tables(port.OracleConfig(lowess_it=2))
+        plan_mod.build_tables(port.OracleConfig(lowess_it=9))
     lim = port.OracleLimiterConfig(hold_filter_order=2)
     with pytest.raises(plan_mod.UnsupportedConfig):
         plan_mod.build_tables(port.OracleConfig(limiter=lim))
