@@ -333,12 +333,15 @@ def run_b200(args) -> dict:
     sampler = ClockSampler(local_rank)  # (polls from now on; only samples inside the timed window are reported)
     if rank == 0:
         sampler.start()
-    bound_cores = None
+    # every rank stays on the cores (and memory) next to its own GPU; the host transport's worker threads are
+    # created later and inherit the mask.  Ranks that share a socket share its cores: divide the workers.
+    from matchering_b200.sharding import bind_host_thread_near_gpu
+    bound_cores = bind_host_thread_near_gpu(local_rank)
+    if world > 1 and "MGB_HOST_THREADS" not in os.environ:
+        sockets = 2 if (bound_cores or 0) < (os.cpu_count() or 1) else 1
+        per_socket = max(1, (world + sockets - 1) // sockets)
+        os.environ["MGB_HOST_THREADS"] = str(max(4, min(32, (bound_cores or os.cpu_count() or 8) // (2 * per_socket))))
     if world > 1:
-        # several ranks share the host: each stays on the cores (and memory) next to its own GPU; the host
-        # transport's worker threads are created later and inherit the mask
-        from matchering_b200.sharding import bind_host_thread_near_gpu
-        bound_cores = bind_host_thread_near_gpu(local_rank)
         # keep stdout for the one JSON line: NCCL prints its version banner there at VERSION level
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"

@@ -241,8 +241,8 @@ int mgb_process_host(const mgb_plan* plan, const mgb_track_layout* layout, const
  * widened on the device and DMA'd straight into pinned memory from mgb_host_alloc (one copy, no host
  * pass), or as float32 chunks through the same ring, widened by the workers, into any other memory.
  * `*_width` = bytes per sample of the host arrays: 4 (float32) or 8 (float64).
- * threads / chunk_samples / ring <= 0 pick defaults (half the host's hardware threads up to 16,
- * 1 Mi samples, 6 chunks).  One transfer at a time per mgb_host_io. */
+ * threads / chunk_samples / ring <= 0 pick defaults (half the hardware threads the process may run on, at
+ * most 32; 256 Ki samples; 12 chunks).  One transfer at a time per mgb_host_io. */
 typedef struct mgb_host_io mgb_host_io;
 int mgb_host_io_create(int32_t threads, int64_t chunk_samples, int32_t ring, mgb_host_io** out);
 int mgb_host_io_destroy(mgb_host_io* io);
@@ -252,8 +252,9 @@ void* mgb_host_alloc(int64_t bytes);
 void mgb_host_free(void* p);
 /* host array -> device float32; returns when the last chunk has left the staging ring */
 int mgb_host_upload(mgb_host_io* io, const void* h_src, int32_t src_width, float* d_dst, int64_t samples, void* stream);
-/* device float32 -> host array; d_wide (optional, `samples` doubles on the device) enables the direct
- * float64 route into pinned memory.  Synchronises `stream`. */
+/* device float32 -> host array.  float64 destinations are filled by the worker threads from float32 chunks
+ * (half the bytes on the link); d_wide (optional, `samples` doubles on the device) is only used by a pool
+ * of one thread with a pinned destination: widen on the device, one DMA.  Synchronises `stream`. */
 int mgb_host_download(mgb_host_io* io, const float* d_src, void* h_dst, int32_t dst_width, int64_t samples,
                       double* d_wide, void* stream);
 

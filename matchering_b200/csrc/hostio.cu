@@ -15,6 +15,7 @@
 // The worker pool is persistent (threads sleep on a condition variable between transfers and spin on
 // atomics inside one).  Nothing here touches sample VALUES except the float64 <-> float32 conversion
 // the reference's caller would otherwise pay for on the device.
+#include <sched.h>
 #include <string.h>
 
 #include <atomic>
@@ -243,7 +244,12 @@ int download(mgb_host_io* io, const float* d_src, void* h_dst, int dst_width, in
              cudaStream_t st) {
     MGB_REQUIRE(dst_width == 4 || dst_width == 8, MGB_ERR_INVALID, "host array must be float32 or float64");
     if (samples == 0) return MGB_OK;
-    if (is_pinned(h_dst) && (dst_width == 4 || d_wide)) {
+    // float64 results: measured on the B200 box (tools/seam_sweep.py), float32 chunks through the ring widened by
+    // the workers (63.5 MB over the link, 1.5 ms for a 3-minute track) beat widening on the device and one DMA of
+    // 127 MB (2.4 ms) even into pinned memory; the direct DMA is kept for d_wide callers that ask for it with
+    // a pinned float64 destination AND no worker threads to spare (pool of one)
+    const bool direct = is_pinned(h_dst) && (dst_width == 4 || (d_wide && io->pool->size() <= 1));
+    if (direct) {
         const void* src = d_src;
         if (dst_width == 8) {
             MGB_TRY(launch_convert_f32_f64(d_src, d_wide, samples, st));
@@ -311,12 +317,19 @@ extern "C" {
 int mgb_host_io_create(int32_t threads, int64_t chunk_samples, int32_t ring, mgb_host_io** out) {
     MGB_REQUIRE(out != nullptr, MGB_ERR_INVALID, "host_io: NULL argument");
     if (threads <= 0) {
-        // enough threads to saturate one socket's memory controllers without fighting the caller's own
-        unsigned hw = std::thread::hardware_concurrency();
-        threads = hw >= 32 ? 16 : (hw >= 8 ? (int)hw / 2 : (hw > 1 ? (int)hw - 1 : 1));
+        // half of the hardware threads this process may run on, at most 32: on the 128-thread B200 host the
+        // float64 -> float32 upload goes from 42 GB/s with 8 workers to 69 GB/s with 32 and flattens after that
+        int usable = (int)std::thread::hardware_concurrency();
+#if defined(__linux__) && !defined(MGB_EMULATE)
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof(set), &set) == 0) usable = CPU_COUNT(&set);
+#endif
+        threads = usable >= 64 ? 32 : (usable >= 4 ? usable / 2 : 1);
     }
-    if (chunk_samples <= 0) chunk_samples = 1 << 20;  // 4 MB of float32 per chunk
-    if (ring <= 0) ring = 6;
+    // 1 MB float32 chunks: small enough that the link starts after 1/60 of a 3-minute track has been narrowed
+    // (4 MB chunks cost a third of the upload rate), large enough that a chunk's DMA (20 us) hides its bookkeeping
+    if (chunk_samples <= 0) chunk_samples = 1 << 18;
+    if (ring <= 0) ring = 12;
     MGB_REQUIRE(threads <= 256 && ring <= 64 && chunk_samples % 16 == 0, MGB_ERR_INVALID, "host_io: bad geometry");
     mgb_host_io* io = new mgb_host_io();
     io->chunk = chunk_samples;
