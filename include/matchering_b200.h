@@ -38,17 +38,26 @@ typedef enum mgb_status {
 } mgb_status;
 
 /* Limiter constants derived from Config (matchering/defaults.py:25-58, limiter/hyrax.py:44-72,
- * utils.py:50-55).  First-order sections only (the reference defaults); higher Butterworth
- * orders are rejected with MGB_ERR_UNSUPPORTED by the host before they get here. */
+ * utils.py:50-55).  The hold and release low-passes are Butterworth sections of order 1 (the reference
+ * default) or 2, as scipy.signal.butter returns them (transfer-function form, a[0] = 1), zero-padded above
+ * the order.  Orders above 2 are rejected with MGB_ERR_UNSUPPORTED: at the limiter's cut-offs (7 Hz and 0.27 Hz
+ * against 44.1 kHz) the transfer-function form the reference runs (scipy lfilter) is itself ill-conditioned
+ * there -- measured in the build container, its float64 output differs from an extended-precision run of the
+ * same coefficients by 5e-5 (release, order 3) to 2e-4 (hold, order 4), above the 1e-5 parity bound, and the
+ * order-4 release filter's rounded coefficients are unstable (output 7e7) -- so there is no reference result
+ * to be faithful to. */
+#define MGB_MAX_FILTER_ORDER 2
 typedef struct mgb_limiter_params {
     double threshold;   /* Config.threshold */
     int32_t reach;      /* make_odd(attack_samples) - 1 : half width of the centred max */
     int32_t hold;       /* hold_samples : length of the trailing max */
     int32_t warmup;     /* samples after which attack_c^n < 1e-10 (halo of the attack filter) */
+    int32_t hold_order;    /* LimiterConfig.hold_filter_order    (defaults.py:48-50) */
+    int32_t release_order; /* LimiterConfig.release_filter_order (defaults.py:54-56) */
     int32_t reserved;
     double attack_c;    /* exp(attack_filter_coefficient / attack_samples) */
-    double hold_b0, hold_b1, hold_a1;       /* butter(1, hold_filter_coefficient, fs) */
-    double release_b0, release_b1, release_a1; /* butter(1, release_filter_coefficient/release, fs) */
+    double hold_b[MGB_MAX_FILTER_ORDER + 1], hold_a[MGB_MAX_FILTER_ORDER + 1];       /* butter(order, hold_filter_coefficient, fs) */
+    double release_b[MGB_MAX_FILTER_ORDER + 1], release_a[MGB_MAX_FILTER_ORDER + 1]; /* butter(order, release_filter_coefficient/release, fs) */
 } mgb_limiter_params;
 
 /* Config-only device tables (all double unless noted).  n_lin = fft_size/2+1,
@@ -252,9 +261,9 @@ void* mgb_host_alloc(int64_t bytes);
 void mgb_host_free(void* p);
 /* host array -> device float32; returns when the last chunk has left the staging ring */
 int mgb_host_upload(mgb_host_io* io, const void* h_src, int32_t src_width, float* d_dst, int64_t samples, void* stream);
-/* device float32 -> host array.  float64 destinations are filled by the worker threads from float32 chunks
- * (half the bytes on the link); d_wide (optional, `samples` doubles on the device) is only used by a pool
- * of one thread with a pinned destination: widen on the device, one DMA.  Synchronises `stream`. */
+/* device float32 -> host array.  Pinned destinations (mgb_host_alloc) are written by ONE DMA: float32 as it is,
+ * float64 after widening on the device into d_wide (`samples` doubles; NULL = no such route).  Anything else is
+ * filled by the worker threads from float32 chunks that come through the ring.  Synchronises `stream`. */
 int mgb_host_download(mgb_host_io* io, const float* d_src, void* h_dst, int32_t dst_width, int64_t samples,
                       double* d_wide, void* stream);
 

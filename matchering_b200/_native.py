@@ -19,17 +19,36 @@ MGB_ERR_CUDA = -4
 MGB_MAX_CORRECTION_STEPS = 16
 
 
+MGB_MAX_FILTER_ORDER = 2
+
+
 class LimiterParams(C.Structure):
     _fields_ = [
         ("threshold", C.c_double),
         ("reach", C.c_int32),
         ("hold", C.c_int32),
         ("warmup", C.c_int32),
+        ("hold_order", C.c_int32),
+        ("release_order", C.c_int32),
         ("reserved", C.c_int32),
         ("attack_c", C.c_double),
-        ("hold_b0", C.c_double), ("hold_b1", C.c_double), ("hold_a1", C.c_double),
-        ("release_b0", C.c_double), ("release_b1", C.c_double), ("release_a1", C.c_double),
+        ("hold_b", C.c_double * (MGB_MAX_FILTER_ORDER + 1)), ("hold_a", C.c_double * (MGB_MAX_FILTER_ORDER + 1)),
+        ("release_b", C.c_double * (MGB_MAX_FILTER_ORDER + 1)), ("release_a", C.c_double * (MGB_MAX_FILTER_ORDER + 1)),
     ]
+
+    @classmethod
+    def from_constants(cls, lc) -> "LimiterParams":
+        """plan.LimiterConstants -> the C struct (coefficients zero-padded above the filter's order)."""
+        p = cls()
+        p.threshold = lc.threshold
+        p.reach, p.hold, p.warmup = lc.reach, lc.hold, lc.warmup
+        p.attack_c = lc.attack_c
+        p.hold_order, p.release_order = len(lc.hold_a) - 1, len(lc.release_a) - 1
+        for name in ("hold_b", "hold_a", "release_b", "release_a"):
+            dst = getattr(p, name)
+            for i, v in enumerate(getattr(lc, name)):
+                dst[i] = float(v)
+        return p
 
 
 class Plan(C.Structure):

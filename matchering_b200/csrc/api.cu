@@ -109,7 +109,7 @@ Workspace carve_workspace(const mgb_plan& plan, const mgb_track_layout& L, void*
     // must not find the first one's tickets and published carries)
     const int64_t limiter_zero_from = off;
     w.tickets = (int*)take(256);
-    w.lookback = take(limiter_lookback_bytes(L.target_frames));
+    w.lookback = take(limiter_lookback_bytes(plan.limiter, L.target_frames));
     w.limiter_zero_bytes = off - limiter_zero_from;
     w.total_bytes = off;
     return w;
@@ -368,7 +368,7 @@ int mgb_plan_twiddle_bytes(int32_t fft_size, int64_t bytes_out[5]) {
     bytes_out[1] = (int64_t)(c2 + inverse_twiddle_count(2 * fft_size) + long_frame_twiddle_count(fft_size)) * 8;
     bytes_out[2] = (int64_t)cf * 16;
     bytes_out[3] = (int64_t)c2 * 16;
-    bytes_out[4] = (int64_t)align256(3 * sizeof(ScanPow));
+    bytes_out[4] = limiter_tables_bytes();
     return MGB_OK;
 }
 
@@ -390,7 +390,7 @@ int mgb_plan_fill_twiddles(const mgb_plan* plan, void* stream) {
     if (plan->d_tw_f64_2F && plan->fft_size <= 4096) MGB_TRY(fill_twiddles(2 * plan->fft_size, 1, plan->d_tw_f64_2F, st));
     if (!plan->d_limiter_tables) return MGB_OK;  // FFT-only plans (tests); mgb_finalize insists on the tables
     MGB_TRY(check_aligned(plan->d_limiter_tables, "d_limiter_tables"));
-    return launch_limiter_tables(plan->limiter, (ScanPow*)plan->d_limiter_tables, st);
+    return launch_limiter_tables(plan->limiter, plan->d_limiter_tables, st);
 }
 
 int64_t mgb_plan_operator_workspace_bytes(const mgb_plan* plan) {
@@ -529,15 +529,18 @@ int mgb_finalize(const mgb_plan* plan, const mgb_track_layout* L, const float* d
 #endif
         MGB_TRY(launch_limiter(plan->limiter, res, (float2*)d_out_limited, L->target_frames, &d_state->gain,
                                &d_state->final_amplitude_coef, &d_state->limiter_engaged, ws.tickets,
-                               (LookbackSlot*)ws.lookback, (const ScanPow*)plan->d_limiter_tables, st));
+                               ws.lookback, plan->d_limiter_tables, st));
     }
     return MGB_OK;
 }
 
+// standalone limiter workspace: [0,4): peak bits  [16,20): ticket  [256, kLimitHeader): pole tables  [kLimitHeader, ...): look-back words
+static const int64_t kLimitHeader = 256 + 32768;
+
 int64_t mgb_limiter_workspace_bytes(const mgb_limiter_params* params, int64_t frames) {
-    (void)params;
-    if (frames <= 0) return 4096;
-    return 4096 + limiter_lookback_bytes(frames);
+    if (!params) return -1;
+    if (frames <= 0) return kLimitHeader;
+    return kLimitHeader + limiter_lookback_bytes(*params, frames);
 }
 
 int mgb_limit(const mgb_limiter_params* params, const float* d_in_lr, float* d_out_lr, int64_t frames,
@@ -548,25 +551,26 @@ int mgb_limit(const mgb_limiter_params* params, const float* d_in_lr, float* d_o
     MGB_TRY(check_aligned(d_workspace, "d_workspace"));
     MGB_REQUIRE(d_engaged != nullptr, MGB_ERR_INVALID, "d_engaged is NULL");
     MGB_REQUIRE(frames > 6, MGB_ERR_INVALID, "limit: the input must be longer than filtfilt's padlen (6)");
+    MGB_REQUIRE(limiter_tables_bytes() <= 32768, MGB_ERR_WORKSPACE, "limit: pole tables outgrew the workspace header");
     MGB_REQUIRE(workspace_bytes >= mgb_limiter_workspace_bytes(params, frames), MGB_ERR_WORKSPACE,
                 "limit: workspace of %lld bytes, need %lld", (long long)workspace_bytes,
                 (long long)mgb_limiter_workspace_bytes(params, frames));
     cudaStream_t st = (cudaStream_t)stream;
     unsigned char* base = (unsigned char*)d_workspace;
-    // [0,4): peak bits  [16,20): ticket  [256, 4096): pole tables  [4096, ...): look-back slots
+    const int64_t zero_bytes = kLimitHeader + limiter_lookback_bytes(*params, frames);
 #ifdef MGB_EMULATE
-    memset(base, 0, 4096 + limiter_lookback_bytes(frames));
+    memset(base, 0, zero_bytes);
 #else
-    if (cudaMemsetAsync(base, 0, 4096 + limiter_lookback_bytes(frames), st) != cudaSuccess) return cuda_status("memset");
+    if (cudaMemsetAsync(base, 0, zero_bytes, st) != cudaSuccess) return cuda_status("memset");
 #endif
-    ScanPow* tables = (ScanPow*)(base + 256);
+    void* tables = base + 256;
     MGB_TRY(launch_limiter_tables(*params, tables, st));
     float* peak = (float*)base;
     int* ticket = (int*)(base + 16);
     MGB_TRY(launch_absmax((const float2*)d_in_lr, frames, peak, st));
     MGB_TRY(launch_limiter_engaged(peak, nullptr, params->threshold, d_engaged, st));
     return launch_limiter(*params, (const float2*)d_in_lr, (float2*)d_out_lr, frames, nullptr, nullptr, d_engaged, ticket,
-                          (LookbackSlot*)(base + 4096), tables, st);
+                          base + kLimitHeader, tables, st);
 }
 
 int mgb_process_host(const mgb_plan* plan, const mgb_track_layout* L, const float* h_target_lr,

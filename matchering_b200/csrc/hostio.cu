@@ -16,6 +16,7 @@
 // atomics inside one).  Nothing here touches sample VALUES except the float64 <-> float32 conversion
 // the reference's caller would otherwise pay for on the device.
 #include <sched.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -244,11 +245,13 @@ int download(mgb_host_io* io, const float* d_src, void* h_dst, int dst_width, in
              cudaStream_t st) {
     MGB_REQUIRE(dst_width == 4 || dst_width == 8, MGB_ERR_INVALID, "host array must be float32 or float64");
     if (samples == 0) return MGB_OK;
-    // float64 results: measured on the B200 box (tools/seam_sweep.py), float32 chunks through the ring widened by
-    // the workers (63.5 MB over the link, 1.5 ms for a 3-minute track) beat widening on the device and one DMA of
-    // 127 MB (2.4 ms) even into pinned memory; the direct DMA is kept for d_wide callers that ask for it with
-    // a pinned float64 destination AND no worker threads to spare (pool of one)
-    const bool direct = is_pinned(h_dst) && (dst_width == 4 || (d_wide && io->pool->size() <= 1));
+    // float64 results into pinned memory: widened on the device and copied by ONE DMA (2.4 ms for a 3-minute
+    // track at 54 GB/s).  Float32 chunks through the ring, widened by the workers, move half the bytes over the
+    // link and measured 1.5-1.8 ms for that track when the host was otherwise idle -- but 50 % SLOWER on the
+    // one-hour limiter buffer (2.5 GB: the widening competes with itself for the socket's memory bandwidth), so
+    // the DMA route, which does not depend on host threads at all, is the default; MGB_DOWNLOAD_RING=1 switches.
+    static const bool prefer_ring = getenv("MGB_DOWNLOAD_RING") && atoi(getenv("MGB_DOWNLOAD_RING")) != 0;
+    const bool direct = is_pinned(h_dst) && (dst_width == 4 || (d_wide && !prefer_ring));
     if (direct) {
         const void* src = d_src;
         if (dst_width == 8) {

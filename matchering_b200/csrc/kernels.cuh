@@ -36,9 +36,7 @@ struct alignas(16) LookbackWord {
     double value;         // status 1: the chunk's zero-carry aggregate; status 2: its inclusive end state
     long long status;     // 0 = nothing yet
 };
-struct LookbackSlot {
-    LookbackWord hold, rel;
-};
+// (a chunk's words: the hold section's `order capacity` state components, then the release section's)
 
 // powers of a pole for a blocked scan with `ept` elements per thread (limiter.cu)
 struct ScanPow {
@@ -48,13 +46,24 @@ struct ScanPow {
     double pc[33];  // P^k, P = p^kLimiterCore: weight of a chunk k chunks back (look-back)
 };
 
+// Powers of the companion matrix C of an order-N recursive section (hold / release low-pass) for the same blocked
+// scan over its state (y[n-1], ..., y[n-N]); N = 1 is a scalar pole.
+template <int N>
+struct SectionTab {
+    double pe[9][N];      // row 0 of C^(e+1): what the state before the thread's first element adds to element e
+    double ql[33][N][N];  // C^(ept*k)
+    double qw[17][N][N];  // C^(ept*32*k)
+    double pc[33][N][N];  // C^(kLimiterCore*k): a chunk k chunks back (look-back)
+};
+
 constexpr int kLimiterThreads = 512;
 constexpr int kLimiterCoreEpt = 9;                                   // core samples per thread
 constexpr int kLimiterCore = kLimiterThreads * kLimiterCoreEpt;      // 4608 samples per chunk
 constexpr int kLimiterSpanEptMax = 17;                               // span samples per thread (odd)
 
 Workspace carve_workspace(const mgb_plan& plan, const mgb_track_layout& layout, void* base);
-int64_t limiter_lookback_bytes(int64_t frames);
+int64_t limiter_lookback_bytes(const mgb_limiter_params& lp, int64_t frames);
+int64_t limiter_tables_bytes();
 
 // analyze.cu ------------------------------------------------------------------------------------
 int launch_analyze(const mgb_plan& plan, const float2* x, int64_t frames, int64_t piece, int divisions, int slots,
@@ -92,9 +101,9 @@ int launch_convert_f32_f64(const float* in, double* out, int64_t count, cudaStre
 
 // limiter.cu ------------------------------------------------------------------------------------
 int launch_limiter(const mgb_limiter_params& lp, const float2* in, float2* out, int64_t frames, const double* pre_gain,
-                   const double* post_gain, const int* engaged, int* ticket, LookbackSlot* lookback,
-                   const ScanPow* tables, cudaStream_t stream);
-int launch_limiter_tables(const mgb_limiter_params& lp, ScanPow* tables, cudaStream_t stream);
+                   const double* post_gain, const int* engaged, int* ticket, void* lookback, const void* tables,
+                   cudaStream_t stream);
+int launch_limiter_tables(const mgb_limiter_params& lp, void* tables, cudaStream_t stream);
 int launch_limiter_engaged(const float* peak_bits, const double* pre_gain, double threshold, int* engaged,
                            cudaStream_t stream);
 

@@ -16,8 +16,10 @@
 //   g_att  = backward(forward(A)) one-pole, float64 state   (blocked scan; the pole is fast, so a
 //            `warmup`-sample halo on both sides replaces cross-chunk carries to < 1e-10)
 //   H      = trailing running max of A over `hold`
-//   hold   = IIR1(H), rel = IIR1(max(H, hold))              (float64 blocked scans whose carries
-//            cross chunks by decoupled look-back: aggregate first, inclusive when known)
+//   hold   = IIR(H), rel = IIR(max(H, hold))                (Butterworth low-passes of order 1..2 as
+//            scipy.signal.lfilter runs them; float64 blocked scans over the filter's state vector --
+//            the last `order` outputs -- whose carries cross chunks by decoupled look-back: aggregate
+//            first, inclusive when known.  Order 1, the reference default, is a scalar scan.)
 //   out    = x * (1 - max(g, g_att, hold, rel)) * post_gain
 // HBM traffic: 8 B/frame read (+ the halo, which hits L2) and 8 B/frame written.
 #include "kernels.cuh"
@@ -89,6 +91,97 @@ __device__ __forceinline__ double scan_carry_rev(double B, const ScanPow* t, con
     return prev + t->ql[rl] * ((rw > 0 ? warp_carry : 0.0) + t->qw[rw] * (*c0));
 }
 
+// ------------------------------------------------------------------------------------------------
+// Recursive sections of order N (hold and release low-passes).  lfilter(b, a, x) is
+//     y[n] = sum_{i=0..N} b[i] x[n-i] - sum_{i=1..N} a[i] y[n-i]          (a[0] = 1, zero initial state)
+// The feed-forward sum is formed per sample from the thread's own inputs; the recursion is a linear
+// recurrence over the STATE s = (y[n-1], ..., y[n-N]) with the companion matrix C (row 0 = -a[1..N], row i =
+// e_{i-1}): a segment maps s -> C^len s + (its zero-state end state), which is what the blocked scan and the
+// look-back combine.  N = 1 is the scalar scan of a single pole; every loop below unrolls away there.
+// ------------------------------------------------------------------------------------------------
+template <int N>
+struct StVec {
+    double v[N];
+};
+template <int N>
+__device__ __forceinline__ StVec<N> st_zero() {
+    StVec<N> z;
+#pragma unroll
+    for (int i = 0; i < N; ++i) z.v[i] = 0.0;
+    return z;
+}
+template <int N>
+__device__ __forceinline__ StVec<N> st_shfl_up(StVec<N> a, int d) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) a.v[i] = __shfl_up_sync(0xffffffffu, a.v[i], d);
+    return a;
+}
+template <int N>
+__device__ __forceinline__ StVec<N> st_shfl(StVec<N> a, int src) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) a.v[i] = __shfl_sync(0xffffffffu, a.v[i], src);
+    return a;
+}
+// y += M x
+template <int N>
+__device__ __forceinline__ void st_addmul(StVec<N>& y, const double (*M)[N], const StVec<N>& x) {
+#pragma unroll
+    for (int r = 0; r < N; ++r)
+#pragma unroll
+        for (int c = 0; c < N; ++c) y.v[r] += M[r][c] * x.v[c];
+}
+template <int N>
+__device__ __forceinline__ StVec<N> st_mul(const double (*M)[N], const StVec<N>& x) {
+    StVec<N> y = st_zero<N>();
+    st_addmul<N>(y, M, x);
+    return y;
+}
+
+// Exclusive carry of the section's state across the block: given each thread's zero-state end state B, returns
+// the state just before the thread's first element when the state before the block's first element is zero
+// (the chunk's carry-in is added later, section_lead).  Same structure and the same single barrier as
+// scan_carry; scratch: >= 32*N doubles, alternate between two buffers.  Every thread of the block must call.
+template <int N>
+__device__ __forceinline__ StVec<N> section_scan(StVec<N> B, const SectionTab<N>* t, double* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    StVec<N> v = B;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const StVec<N> up = st_shfl_up<N>(v, d);
+        if (lane >= d) st_addmul<N>(v, t->ql[d], up);
+    }
+    if (lane == 31) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) scratch[warp * N + i] = v.v[i];
+    }
+    __syncthreads();
+    StVec<N> w = st_zero<N>();
+    if (lane < NT / 32) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) w.v[i] = scratch[lane * N + i];
+    }
+#pragma unroll
+    for (int d = 1; d < NT / 32; d <<= 1) {
+        const StVec<N> up = st_shfl_up<N>(w, d);
+        if (lane >= d) st_addmul<N>(w, t->qw[d], up);
+    }
+    // state at the end of the previous warp: inclusive total of warps 0..warp-1
+    StVec<N> warp_carry = st_shfl<N>(w, (warp + 31) & 31);
+    if (warp == 0) warp_carry = st_zero<N>();
+    StVec<N> prev = st_shfl_up<N>(v, 1);
+    if (lane == 0) prev = st_zero<N>();
+    st_addmul<N>(prev, t->ql[lane], warp_carry);
+    return prev;
+}
+
+// C^(tid * CORE_EPT) applied to the chunk's carry-in: what the carry-in contributes to the state just before
+// the thread's first element.
+template <int N>
+__device__ __forceinline__ StVec<N> section_lead(const SectionTab<N>* t, const StVec<N>& cin) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    return st_mul<N>(t->ql[lane], st_mul<N>(t->qw[warp], cin));
+}
+
 // 16-byte publish / poll of a LookbackWord through L2 (st.cg / ld.cg: coherent device-wide).
 __device__ __forceinline__ void publish(LookbackWord* w, double v, int status) {
 #ifdef MGB_EMULATE
@@ -110,30 +203,73 @@ __device__ __forceinline__ int poll(const LookbackWord* w, double* v) {
 #endif
 }
 
-// Carry into chunk `chunk` of a first-order recurrence whose per-chunk multiplier is P = pc[1]
-// (decoupled look-back).  One warp inspects 32 predecessors at a time: every lane polls one
-// predecessor's word, the window is cut at the nearest predecessor whose INCLUSIVE state is known,
-// each lane weighs its value by P^distance, and one warp reduction at the very end adds them up.
-// The walk stops when whatever lies further back weighs less than 1e-9 (all values are gains in
-// [0, 1], so that bounds the absolute error of the carry).  Called by all 32 lanes of one warp.
-__device__ __forceinline__ double lookback(LookbackSlot* slots, int chunk, bool release, const double* pc) {
+// Carry into chunk `chunk` of a section whose per-chunk transition is P = pc[1] (decoupled look-back).  One warp
+// inspects 32 predecessors at a time: every lane polls one predecessor's words, the window is cut at the nearest
+// predecessor whose INCLUSIVE state is known, each lane weighs its state by P^distance, and one warp reduction
+// at the very end adds them up.  The walk stops when whatever lies further back weighs less than 1e-9 (all
+// states are gains in [0, 1], so that bounds the absolute error of the carry).  A state of N doubles travels as
+// N words that each carry the status: a reader that catches the writer between two words sees different
+// statuses and polls again.  Called by all 32 lanes of one warp.
+template <int N>
+__device__ __forceinline__ StVec<N> lookback(const LookbackWord* words /* this section's words of chunk 0 */, int chunk,
+                                             const SectionTab<N>* t) {
+    constexpr int STRIDE = 2 * N;  // words per chunk: hold[N] then release[N]
     const int lane = threadIdx.x & 31;
-    double acc = 0.0, mult = 1.0;
-    for (int base = chunk - 1; base >= 0 && mult > 1e-9; base -= 32) {
+    StVec<N> acc = st_zero<N>();
+    double mult[N][N];
+#pragma unroll
+    for (int r = 0; r < N; ++r)
+#pragma unroll
+        for (int c = 0; c < N; ++c) mult[r][c] = r == c ? 1.0 : 0.0;
+    double bound = 1.0;
+    for (int base = chunk - 1; base >= 0 && bound > 1e-9; base -= 32) {
         const int j = base - lane;
         int st = 2;  // before the first chunk: inclusive state 0 (lfilter starts from rest)
-        double val = 0.0;
+        StVec<N> val = st_zero<N>();
         if (j >= 0) {
-            const LookbackWord* w = release ? &slots[j].rel : &slots[j].hold;
-            while ((st = poll(w, &val)) == 0) __nanosleep(20);
+            const LookbackWord* w = words + (long long)j * STRIDE;
+            for (;;) {
+                st = poll(w, &val.v[0]);
+                bool same = st != 0;
+#pragma unroll
+                for (int i = 1; i < N; ++i) same = same && poll(w + i, &val.v[i]) == st;
+                if (same) break;
+                __nanosleep(20);
+            }
         }
         const unsigned inclusive = __ballot_sync(0xffffffffu, st == 2);
         const int first = inclusive ? __ffs((int)inclusive) - 1 : 32;
-        if (lane <= first) acc += mult * pc[lane] * val;
+        if (lane <= first) st_addmul<N>(acc, mult, st_mul<N>(t->pc[lane], val));
         if (inclusive) break;
-        mult *= pc[32];
+        // mult <- mult * P^32, and its infinity norm as the bound on what lies further back
+        double next[N][N];
+        bound = 0.0;
+#pragma unroll
+        for (int r = 0; r < N; ++r) {
+            double rowsum = 0.0;
+#pragma unroll
+            for (int c = 0; c < N; ++c) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < N; ++k) s += mult[r][k] * t->pc[32][k][c];
+                next[r][c] = s;
+                rowsum += fabs(s);
+            }
+            bound = fmax(bound, rowsum);
+        }
+#pragma unroll
+        for (int r = 0; r < N; ++r)
+#pragma unroll
+            for (int c = 0; c < N; ++c) mult[r][c] = next[r][c];
     }
-    return warp_sum(acc);
+#pragma unroll
+    for (int i = 0; i < N; ++i) acc.v[i] = warp_sum(acc.v[i]);
+    return acc;
+}
+template <int N>
+__device__ __forceinline__ void publish_state(LookbackWord* words, const StVec<N>& s, int status) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) publish(words + i, s.v[i], status);
 }
 
 struct LimiterGeom {
@@ -146,26 +282,79 @@ struct LimiterGeom {
     int margin;                   // zeros kept on both sides of G so that window reads need no bounds test (multiple of 4)
 };
 
-// powers of the three poles, computed once per parameter set (not per CTA: pow() is slow)
-__global__ void limiter_tables_kernel(mgb_limiter_params lp, int span_ept, ScanPow* tables) {
+// Config-only tables, computed once per parameter set (not per CTA: pow() is slow): powers of the attack pole
+// (ScanPow) and, for the hold and release sections, powers of their companion matrices (SectionTab), by binary
+// exponentiation, one thread per table entry.
+template <int N>
+__device__ void companion_power(const double* a /* a[1..N] at a[1].. */, long long k, double (*out)[N]) {
+    double base[N][N], acc[N][N], tmp[N][N];
+    for (int r = 0; r < N; ++r)
+        for (int c = 0; c < N; ++c) {
+            base[r][c] = r == 0 ? -a[c + 1] : (r - 1 == c ? 1.0 : 0.0);
+            acc[r][c] = r == c ? 1.0 : 0.0;
+        }
+    while (k > 0) {
+        if (k & 1) {
+            for (int r = 0; r < N; ++r)
+                for (int c = 0; c < N; ++c) {
+                    double sum = 0.0;
+                    for (int m = 0; m < N; ++m) sum += acc[r][m] * base[m][c];
+                    tmp[r][c] = sum;
+                }
+            for (int r = 0; r < N; ++r)
+                for (int c = 0; c < N; ++c) acc[r][c] = tmp[r][c];
+        }
+        k >>= 1;
+        if (k) {
+            for (int r = 0; r < N; ++r)
+                for (int c = 0; c < N; ++c) {
+                    double sum = 0.0;
+                    for (int m = 0; m < N; ++m) sum += base[r][m] * base[m][c];
+                    tmp[r][c] = sum;
+                }
+            for (int r = 0; r < N; ++r)
+                for (int c = 0; c < N; ++c) base[r][c] = tmp[r][c];
+        }
+    }
+    for (int r = 0; r < N; ++r)
+        for (int c = 0; c < N; ++c) out[r][c] = acc[r][c];
+}
+
+template <int N>
+__global__ void limiter_tables_kernel(mgb_limiter_params lp, int span_ept, unsigned char* tables) {
     const int i = threadIdx.x;
-    for (int f = 0; f < 3; ++f) {
-        const double p = f == 0 ? lp.attack_c : (f == 1 ? -lp.hold_a1 : -lp.release_a1);
-        const int ept = f == 0 ? span_ept : CORE_EPT;
-        ScanPow* t = tables + f;
-        if (i < SPAN_EPT_MAX + 2) t->pe[i] = pow(p, (double)i);
-        if (i < 33) t->ql[i] = pow(p, (double)(ept * i));
-        if (i < 17) t->qw[i] = pow(p, (double)(ept * 32 * i));
-        if (i < 33) t->pc[i] = pow(p, (double)LC * (double)i);
+    ScanPow* att = reinterpret_cast<ScanPow*>(tables);
+    {
+        const double p = lp.attack_c;
+        if (i < SPAN_EPT_MAX + 2) att->pe[i] = pow(p, (double)i);
+        if (i < 33) att->ql[i] = pow(p, (double)(span_ept * i));
+        if (i < 17) att->qw[i] = pow(p, (double)(span_ept * 32 * i));
+        if (i < 33) att->pc[i] = pow(p, (double)LC * (double)i);
+    }
+    SectionTab<N>* sec = reinterpret_cast<SectionTab<N>*>(tables + sizeof(ScanPow));
+    for (int f = 0; f < 2; ++f) {
+        const double* a = f == 0 ? lp.hold_a : lp.release_a;  // a[0] = 1; entries above the order are zero
+        SectionTab<N>* t = sec + f;
+        if (i < CORE_EPT) {
+            double m[N][N];
+            companion_power<N>(a, i + 1, m);
+            for (int c = 0; c < N; ++c) t->pe[i][c] = m[0][c];
+        }
+        if (i < 33) companion_power<N>(a, (long long)CORE_EPT * i, t->ql[i]);
+        if (i < 17) companion_power<N>(a, (long long)CORE_EPT * 32 * i, t->qw[i]);
+        if (i < 33) companion_power<N>(a, (long long)LC * i, t->pc[i]);
     }
 }
 
-template <int EPT>
-__global__ void __launch_bounds__(NT, 2)
+// NO = order capacity of the hold and release sections: 1 (the reference defaults: scalar scans, tables in shared
+// memory) or MGB_MAX_FILTER_ORDER = 2 (orders 1..2 zero-padded to 2; tables read through L1).
+template <int EPT, int NO>
+__global__ void __launch_bounds__(NT, NO == 1 ? 2 : 1)
 limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__ in, float2* __restrict__ out,
                long long frames, const double* __restrict__ pre_gain, const double* __restrict__ post_gain,
-               const int* __restrict__ engaged, int* __restrict__ ticket, LookbackSlot* __restrict__ slots,
-               const ScanPow* __restrict__ tables) {
+               const int* __restrict__ engaged, int* __restrict__ ticket, LookbackWord* __restrict__ slots,
+               const unsigned char* __restrict__ tables) {
+    constexpr int HC = CORE_EPT + NO;  // H samples a thread needs: its core and the NO before it
     constexpr int CAP = EPT * NT;
     MGB_DYN_SMEM(smem);
     double* Fd = reinterpret_cast<double*>(smem);                 // [CAP] float64 work plane
@@ -174,14 +363,15 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
     float* G = reinterpret_cast<float*>(smem + (size_t)CAP * 8) + gm.margin;
     float* Wk = G + CAP + gm.margin;                              // [CAP] suffix maxima, later the hold envelope
     __shared__ float blockmax[NT];
-    __shared__ ScanPow pw3[3];
-    __shared__ double scratch_a[32], scratch_b[32];  // scan_carry alternates between them
-    __shared__ double bcast[2];
-    __shared__ double warp_edge[NT / 32];
+    __shared__ ScanPow pw_att;
+    __shared__ SectionTab<1> pw_sec[2];  // (order capacity 1 only: the two sections' tables)
+    __shared__ double scratch_a[32 * NO], scratch_b[32 * NO];  // the block scans alternate between them
+    __shared__ double bcast[2 + 2 * NO];
     __shared__ int chunk_s;
-    const ScanPow* pow_att = &pw3[0];
-    const ScanPow* pow_hold = &pw3[1];
-    const ScanPow* pow_rel = &pw3[2];
+    const ScanPow* pow_att = &pw_att;
+    const SectionTab<NO>* sec_global = reinterpret_cast<const SectionTab<NO>*>(tables + sizeof(ScanPow));
+    const SectionTab<NO>* tab_hold = NO == 1 ? reinterpret_cast<const SectionTab<NO>*>(&pw_sec[0]) : sec_global;
+    const SectionTab<NO>* tab_rel = NO == 1 ? reinterpret_cast<const SectionTab<NO>*>(&pw_sec[1]) : sec_global + 1;
 
     const int tid = threadIdx.x;
     const double pre = pre_gain ? *pre_gain : 1.0;
@@ -191,8 +381,13 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
     if (tid == 0) chunk_s = atomicAdd(ticket, 1);
     {
         const double* src = reinterpret_cast<const double*>(tables);
-        double* dst = reinterpret_cast<double*>(pw3);
-        for (int i = tid; i < (int)(3 * sizeof(ScanPow) / sizeof(double)); i += NT) dst[i] = src[i];
+        double* dst = reinterpret_cast<double*>(&pw_att);
+        for (int i = tid; i < (int)(sizeof(ScanPow) / sizeof(double)); i += NT) dst[i] = src[i];
+        if (NO == 1) {
+            src += sizeof(ScanPow) / sizeof(double);
+            dst = reinterpret_cast<double*>(pw_sec);
+            for (int i = tid; i < (int)(2 * sizeof(SectionTab<1>) / sizeof(double)); i += NT) dst[i] = src[i];
+        }
     }
     __syncthreads();
     const int chunk = chunk_s;
@@ -246,7 +441,7 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
     //   H[n] = max A[n-hold+1 .. n] = max g[n-hold+1-reach .. n+reach]   (hyrax.py:38-40)
     // Every thread owns EPT consecutive samples: their prefix and suffix maxima inside the block
     // (PF, SF) and the block maximum.  A window [l, r] is max(SF[l], whole blocks between, PF[r]).
-    float hc[CORE_EPT + 1];  // H at span indices cidx + tid*CORE_EPT - 1 + e
+    float hc[HC];  // H at span indices cidx + tid*CORE_EPT - NO + e
     {
         float* PF = reinterpret_cast<float*>(smem);  // [CAP] lower half of Fd's bytes (Aenv is the upper half)
         float* SF = Wk;                              // [CAP]
@@ -313,63 +508,69 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
                 Aenv[i] = window(max(i - reach, 0), r, r / EPT, PF[r]);
             }
         }
-        // H for the thread's own CORE_EPT core samples and the one before them (the filters below run
+        // H for the thread's own CORE_EPT core samples and the NO before them (the filters below run
         // over the core in this very mapping, so H never goes through shared memory for another thread):
-        // windows [bh+e-reach-hold+1, bh+e+reach], e = 0..CORE_EPT
-        const int bh = cidx + tid * CORE_EPT - 1;
+        // windows [bh+e-reach-hold+1, bh+e+reach], e = 0..HC-1
+        const int bh = cidx + tid * CORE_EPT - NO;
         if (gm.shared_core) {
-            float lh[CORE_EPT + 1], rh[CORE_EPT + 1];
+            float lh[HC], rh[HC];
 #pragma unroll
-            for (int e = 0; e < CORE_EPT; ++e) {
+            for (int e = 0; e < HC - 1; ++e) {
                 lh[e] = gat(bh - reach - hold + 1 + e);
                 rh[e + 1] = gat(bh + reach + 1 + e);
             }
-            lh[CORE_EPT] = rh[0] = 0.0f;
+            lh[HC - 1] = rh[0] = 0.0f;
 #pragma unroll
-            for (int e = CORE_EPT - 1; e >= 0; --e) lh[e] = fmaxf(lh[e], lh[e + 1]);
+            for (int e = HC - 2; e >= 0; --e) lh[e] = fmaxf(lh[e], lh[e + 1]);
 #pragma unroll
-            for (int e = 1; e <= CORE_EPT; ++e) rh[e] = fmaxf(rh[e], rh[e - 1]);
+            for (int e = 1; e < HC; ++e) rh[e] = fmaxf(rh[e], rh[e - 1]);
             const int r = min(bh + reach, CAP - 1);
-            const float core = window(max(bh + CORE_EPT + 1 - reach - hold, 0), r, r / EPT, PF[r]);
+            const float core = window(max(bh + HC - reach - hold, 0), r, r / EPT, PF[r]);
 #pragma unroll
-            for (int e = 0; e <= CORE_EPT; ++e) hc[e] = fmaxf(core, fmaxf(lh[e], rh[e]));
+            for (int e = 0; e < HC; ++e) hc[e] = fmaxf(core, fmaxf(lh[e], rh[e]));
         } else {
 #pragma unroll
-            for (int e = 0; e <= CORE_EPT; ++e) {
+            for (int e = 0; e < HC; ++e) {
                 const int r = min(bh + e + reach, CAP - 1);
                 hc[e] = window(max(bh + e - reach - hold + 1, 0), r, r / EPT, PF[r]);
             }
         }
         // lfilter starts from rest: the envelope before the first sample is 0, not a window maximum
 #pragma unroll
-        for (int e = 0; e <= CORE_EPT; ++e)
+        for (int e = 0; e < HC; ++e)
             if (bh + e < vlo) hc[e] = 0.0f;
     }
 
-    // ---- P3: hold_out = lfilter(butter(1, f_hold), H), zero-carry pass (hyrax.py:61-66) -------------
+    // ---- P3: hold_out = lfilter(butter(order, f_hold), H), zero-state pass (hyrax.py:61-66) ---------
     // The chunk's aggregate is published now; the carry from the previous chunks is only needed after
     // the attack filter below, which gives the predecessors time to publish theirs.
-    LookbackSlot* slot = slots + chunk;
+    LookbackWord* slot_hold = slots + (long long)chunk * (2 * NO);
+    LookbackWord* slot_rel = slot_hold + NO;
     double hold_y[CORE_EPT];
-    double prev_last;  // the previous thread's last hold sample (zero carry into the chunk)
-    float* Hown = Wk + tid * (CORE_EPT + 1);  // the thread's own H samples, parked until the release filter
+    StVec<NO> hold_carry;  // hold_out just before the thread's first sample, zero carry into the chunk
+    float* Hown = Wk + tid * HC;  // the thread's own H samples, parked until the release filter
     {
-        double acc = 0.0;
 #pragma unroll
         for (int e = 0; e < CORE_EPT; ++e) {
-            const double u = lp.hold_b0 * (double)hc[e + 1] + lp.hold_b1 * (double)hc[e];
-            acc = u - lp.hold_a1 * acc;
+            double acc = lp.hold_b[0] * (double)hc[e + NO];
+#pragma unroll
+            for (int i = 1; i <= NO; ++i) acc += lp.hold_b[i] * (double)hc[e + NO - i];
+#pragma unroll
+            for (int i = 1; i <= NO; ++i)
+                if (e - i >= 0) acc -= lp.hold_a[i] * hold_y[e - i];
             hold_y[e] = acc;
         }
+        StVec<NO> end;
+#pragma unroll
+        for (int i = 0; i < NO; ++i) end.v[i] = hold_y[CORE_EPT - 1 - i];
         // (the barrier inside also ends P2: every thread is done with PF, SF and the sparse table)
-        const double carry = scan_carry(acc, pow_hold, 0.0, scratch_a);
+        hold_carry = section_scan<NO>(end, tab_hold, scratch_a);
+        if (tid == NT - 1) {  // the chunk's zero-carry end state
+            st_addmul<NO>(end, tab_hold->ql[1], hold_carry);
+            publish_state<NO>(slot_hold, end, 1);
+        }
 #pragma unroll
-        for (int e = 0; e < CORE_EPT; ++e) hold_y[e] += pow_hold->pe[e + 1] * carry;
-        if (tid == NT - 1) publish(&slot->hold, hold_y[CORE_EPT - 1], 1);
-        prev_last = __shfl_up_sync(0xffffffffu, hold_y[CORE_EPT - 1], 1);
-        if ((tid & 31) == 31) warp_edge[tid >> 5] = hold_y[CORE_EPT - 1];  // read by the next warp's lane 0 in P5
-#pragma unroll
-        for (int e = 0; e <= CORE_EPT; ++e) Hown[e] = hc[e];  // SF (= Wk) is free now; only this thread reads these back
+        for (int e = 0; e < HC; ++e) Hown[e] = hc[e];  // SF (= Wk) is free now; only this thread reads these back
     }
 
     // ---- P4: g_att = filtfilt one-pole over A (hyrax.py:48-51) -------------------------------------
@@ -445,48 +646,79 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
 
     // ---- P5: hold carry from the previous chunks (decoupled look-back), finish hold_out -------------
     if (tid < 32) {
-        const double cin = lookback(slots, chunk, false, pow_hold->pc);
-        if (tid == 0) bcast[0] = cin;
+        const StVec<NO> cin = lookback<NO>(slots, chunk, tab_hold);
+        if (tid == 0) {
+#pragma unroll
+            for (int i = 0; i < NO; ++i) bcast[2 + i] = cin.v[i];
+        }
     }
     __syncthreads();  // also: every thread is done reading Fd as the attack filter's plane
-    const double hold_cin = bcast[0];
-    double hold_prev;  // hold_out just before the thread's first sample
+    StVec<NO> hold_prev;  // hold_out at the NO samples before the thread's first one
     {
-        const double lead = pow_hold->ql[tid & 31] * pow_hold->qw[tid >> 5];  // pole^(tid*CORE_EPT)
-        if ((tid & 31) == 0 && tid > 0) prev_last = warp_edge[(tid >> 5) - 1];
-        hold_prev = tid == 0 ? hold_cin : prev_last + lead * hold_cin;
+        StVec<NO> cin;
 #pragma unroll
-        for (int e = 0; e < CORE_EPT; ++e) hold_y[e] += pow_hold->pe[e + 1] * lead * hold_cin;
-        if (tid == NT - 1 && gm.publish_inclusive) publish(&slot->hold, hold_y[CORE_EPT - 1], 2);
+        for (int i = 0; i < NO; ++i) cin.v[i] = bcast[2 + i];
+        hold_prev = section_lead<NO>(tab_hold, cin);
+#pragma unroll
+        for (int i = 0; i < NO; ++i) hold_prev.v[i] += hold_carry.v[i];
+#pragma unroll
+        for (int e = 0; e < CORE_EPT; ++e)
+#pragma unroll
+            for (int i = 0; i < NO; ++i) hold_y[e] += tab_hold->pe[e][i] * hold_prev.v[i];
+        if (tid == NT - 1 && gm.publish_inclusive) {
+            StVec<NO> end;
+#pragma unroll
+            for (int i = 0; i < NO; ++i) end.v[i] = hold_y[CORE_EPT - 1 - i];
+            publish_state<NO>(slot_hold, end, 2);
+        }
     }
 
-    // ---- P6: release_out = lfilter(butter(1, f_rel), max(H, hold_out)) (hyrax.py:68-73) -------------
+    // ---- P6: release_out = lfilter(butter(order, f_rel), max(H, hold_out)) (hyrax.py:68-73) ----------
     {
         double rel_y[CORE_EPT];
-        double acc = 0.0;
-        double prev_in = fmax((double)Hown[0], hold_prev);
+        double win[HC];  // the section's input max(H, hold_out) at the NO samples before the core and on it
+#pragma unroll
+        for (int i = 0; i < NO; ++i) win[i] = fmax((double)Hown[i], hold_prev.v[NO - 1 - i]);
+#pragma unroll
+        for (int e = 0; e < CORE_EPT; ++e) win[NO + e] = fmax((double)Hown[NO + e], hold_y[e]);
 #pragma unroll
         for (int e = 0; e < CORE_EPT; ++e) {
-            const double cur = fmax((double)Hown[e + 1], hold_y[e]);
-            const double u = lp.release_b0 * cur + lp.release_b1 * prev_in;
-            prev_in = cur;
-            acc = u - lp.release_a1 * acc;
+            double acc = lp.release_b[0] * win[e + NO];
+#pragma unroll
+            for (int i = 1; i <= NO; ++i) acc += lp.release_b[i] * win[e + NO - i];
+#pragma unroll
+            for (int i = 1; i <= NO; ++i)
+                if (e - i >= 0) acc -= lp.release_a[i] * rel_y[e - i];
             rel_y[e] = acc;
         }
-        const double carry = scan_carry(acc, pow_rel, 0.0, scratch_b);
+        StVec<NO> end;
 #pragma unroll
-        for (int e = 0; e < CORE_EPT; ++e) rel_y[e] += pow_rel->pe[e + 1] * carry;
-        if (tid == NT - 1) publish(&slot->rel, rel_y[CORE_EPT - 1], 1);
+        for (int i = 0; i < NO; ++i) end.v[i] = rel_y[CORE_EPT - 1 - i];
+        StVec<NO> rel_prev = section_scan<NO>(end, tab_rel, scratch_b);
+        if (tid == NT - 1) {
+            st_addmul<NO>(end, tab_rel->ql[1], rel_prev);
+            publish_state<NO>(slot_rel, end, 1);
+        }
         if (tid < 32) {
-            const double cr = lookback(slots, chunk, true, pow_rel->pc);
-            if (tid == 0) bcast[1] = cr;
+            const StVec<NO> cr = lookback<NO>(slots + NO, chunk, tab_rel);
+            if (tid == 0) {
+#pragma unroll
+                for (int i = 0; i < NO; ++i) bcast[2 + NO + i] = cr.v[i];
+            }
         }
         __syncthreads();
-        const double cin = bcast[1];
-        const double lead = pow_rel->ql[tid & 31] * pow_rel->qw[tid >> 5];
+        {
+            StVec<NO> cin;
+#pragma unroll
+            for (int i = 0; i < NO; ++i) cin.v[i] = bcast[2 + NO + i];
+            const StVec<NO> lead = section_lead<NO>(tab_rel, cin);
+#pragma unroll
+            for (int i = 0; i < NO; ++i) rel_prev.v[i] += lead.v[i];
+        }
 #pragma unroll
         for (int e = 0; e < CORE_EPT; ++e) {
-            rel_y[e] += pow_rel->pe[e + 1] * lead * cin;
+#pragma unroll
+            for (int i = 0; i < NO; ++i) rel_y[e] += tab_rel->pe[e][i] * rel_prev.v[i];
             const int i = cidx + tid * CORE_EPT + e;
             const double g_rel = fmax(hold_y[e], rel_y[e]);            // hyrax.py:75
 #ifdef MGB_LIM_DEBUG
@@ -496,7 +728,11 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
             Fd[tid * CORE_EPT + e] = 1.0 - fmax((double)G[i], g_rel);  // hyrax.py:97
 #endif
         }
-        if (tid == NT - 1 && gm.publish_inclusive) publish(&slot->rel, rel_y[CORE_EPT - 1], 2);
+        if (tid == NT - 1 && gm.publish_inclusive) {
+#pragma unroll
+            for (int i = 0; i < NO; ++i) end.v[i] = rel_y[CORE_EPT - 1 - i];
+            publish_state<NO>(slot_rel, end, 2);
+        }
     }
 #ifdef MGB_LIM_DEBUG
     __syncthreads();
@@ -539,24 +775,35 @@ __global__ void limiter_engaged_kernel(const float* peak_bits, const double* pre
     *engaged = (fabs(r - 1.0) <= 1e-8 + 1e-5 * 1.0) ? 0 : 1;
 }
 
+// order capacity of the kernel that serves these parameters: 1 (scalar sections) or MGB_MAX_FILTER_ORDER
+int limiter_order_capacity(const mgb_limiter_params& lp) {
+    return (lp.hold_order <= 1 && lp.release_order <= 1) ? 1 : MGB_MAX_FILTER_ORDER;
+}
+
 int limiter_geometry(const mgb_limiter_params& lp, LimiterGeom* g) {
     MGB_REQUIRE(lp.reach >= 1 && lp.hold >= 3 && lp.warmup >= 8, MGB_ERR_INVALID, "limiter: bad window sizes");
+    MGB_REQUIRE(lp.hold_order >= 1 && lp.hold_order <= MGB_MAX_FILTER_ORDER && lp.release_order >= 1 &&
+                    lp.release_order <= MGB_MAX_FILTER_ORDER,
+                MGB_ERR_UNSUPPORTED, "limiter: hold / release filter orders %d / %d, kernels exist for 1..%d", lp.hold_order,
+                lp.release_order, MGB_MAX_FILTER_ORDER);
+    const int no = limiter_order_capacity(lp);
     MGB_REQUIRE(lp.attack_c > 0.0 && lp.attack_c < 1.0, MGB_ERR_INVALID, "limiter: attack pole out of (0,1)");
     MGB_REQUIRE(lp.threshold > 0.0, MGB_ERR_INVALID, "limiter: threshold must be positive");
     g->reach = lp.reach;
     g->hold = lp.hold;
     g->warm = lp.warmup;
-    g->left = lp.warmup > lp.hold ? lp.warmup : lp.hold;
+    g->left = lp.warmup > lp.hold + no - 1 ? lp.warmup : lp.hold + no - 1;  // H is needed `no` samples before the core
     g->filt = LC + g->left + g->warm;
     g->span = g->filt + 2 * g->reach;
     int ept = (g->span + NT - 1) / NT;
     if (!(ept & 1)) ept += 1;  // odd stride: the blocked scans read shared memory conflict-free
     if (ept < 11) ept = 11;
+    if (ept < CORE_EPT + no) ept = (CORE_EPT + no) | 1;  // every thread parks its CORE_EPT + no samples of H in one plane
     g->ept = ept;
     g->publish_inclusive = g_lookback_inclusive;
     // the cores [b+ept-1-reach, b+reach] and [b+ept-reach-hold, b+reach] must not be empty
-    g->shared_core = (2 * lp.reach >= ept - 1 && 2 * lp.reach + lp.hold >= ept) ? 1 : 0;
-    g->margin = (lp.reach + lp.hold + ept + 3) / 4 * 4;  // the furthest a window part reaches outside [0, CAP)
+    g->shared_core = (2 * lp.reach >= ept - 1 && 2 * lp.reach + lp.hold >= CORE_EPT + no) ? 1 : 0;
+    g->margin = (lp.reach + lp.hold + ept + no + 3) / 4 * 4;  // the furthest a window part reaches outside [0, CAP)
     MGB_REQUIRE(ept <= SPAN_EPT_MAX, MGB_ERR_UNSUPPORTED,
                 "limiter: halo of %d samples exceeds the kernel's span", g->span - LC);
     return MGB_OK;
@@ -564,30 +811,45 @@ int limiter_geometry(const mgb_limiter_params& lp, LimiterGeom* g) {
 
 }  // namespace
 
-int64_t limiter_lookback_bytes(int64_t frames) {
+int64_t limiter_lookback_bytes(int64_t frames, int order_capacity) {
     const int64_t chunks = (frames + LC - 1) / LC;
-    return (chunks * (int64_t)sizeof(LookbackSlot) + 255) / 256 * 256;
+    return (chunks * 2 * order_capacity * (int64_t)sizeof(LookbackWord) + 255) / 256 * 256;
+}
+int64_t limiter_lookback_bytes(const mgb_limiter_params& lp, int64_t frames) {
+    return limiter_lookback_bytes(frames, limiter_order_capacity(lp));
 }
 
-int launch_limiter_tables(const mgb_limiter_params& lp, ScanPow* tables, cudaStream_t stream) {
+int64_t limiter_tables_bytes() { return (int64_t)(sizeof(ScanPow) + 2 * sizeof(SectionTab<MGB_MAX_FILTER_ORDER>) + 255) / 256 * 256; }
+
+int launch_limiter_tables(const mgb_limiter_params& lp, void* tables, cudaStream_t stream) {
     LimiterGeom g;
     MGB_TRY(limiter_geometry(lp, &g));
-    return launch("limiter_tables_kernel", limiter_tables_kernel, dim3(1), dim3(64), 0, stream, lp, g.ept, tables);
+    if (limiter_order_capacity(lp) == 1)
+        return launch("limiter_tables_kernel", limiter_tables_kernel<1>, dim3(1), dim3(64), 0, stream, lp, g.ept,
+                      (unsigned char*)tables);
+    return launch("limiter_tables_kernel", limiter_tables_kernel<MGB_MAX_FILTER_ORDER>, dim3(1), dim3(64), 0, stream, lp, g.ept,
+                  (unsigned char*)tables);
 }
 
 int launch_limiter(const mgb_limiter_params& lp, const float2* in, float2* out, int64_t frames, const double* pre_gain,
-                   const double* post_gain, const int* engaged, int* ticket, LookbackSlot* lookback,
-                   const ScanPow* tables, cudaStream_t stream) {
+                   const double* post_gain, const int* engaged, int* ticket, void* lookback, const void* tables,
+                   cudaStream_t stream) {
     LimiterGeom g;
     MGB_TRY(limiter_geometry(lp, &g));
     MGB_REQUIRE(frames > 6, MGB_ERR_INVALID, "limiter: the input must be longer than filtfilt's padlen (6)");
     MGB_REQUIRE(tables != nullptr, MGB_ERR_INVALID, "limiter: pole tables missing");
     const int64_t chunks = (frames + LC - 1) / LC;
     const size_t smem = (size_t)g.ept * NT * 16 + (size_t)g.margin * 8;
-#define MGB_LIMITER_CASE(E)                                                                                       \
-    case E:                                                                                                       \
-        return launch("limiter_kernel", limiter_kernel<E>, dim3((unsigned)chunks), dim3(NT), smem, stream, lp, g, in, \
-                      out, (long long)frames, pre_gain, post_gain, engaged, ticket, lookback, tables);
+    const int no = limiter_order_capacity(lp);
+#define MGB_LIMITER_CASE(E)                                                                                           \
+    case E:                                                                                                           \
+        if (no == 1)                                                                                                  \
+            return launch("limiter_kernel", limiter_kernel<E, 1>, dim3((unsigned)chunks), dim3(NT), smem, stream, lp, g, in, \
+                          out, (long long)frames, pre_gain, post_gain, engaged, ticket, (LookbackWord*)lookback,     \
+                          (const unsigned char*)tables);                                                             \
+        return launch("limiter_kernel", limiter_kernel<E, MGB_MAX_FILTER_ORDER>, dim3((unsigned)chunks), dim3(NT), smem, \
+                      stream, lp, g, in, out, (long long)frames, pre_gain, post_gain, engaged, ticket,               \
+                      (LookbackWord*)lookback, (const unsigned char*)tables);
     switch (g.ept) {
         MGB_LIMITER_CASE(11)
         MGB_LIMITER_CASE(13)

@@ -80,14 +80,7 @@ class DevicePlan:
 
 
 def limiter_params(lc: _plan.LimiterConstants) -> _native.LimiterParams:
-    p = _native.LimiterParams()
-    p.threshold = lc.threshold
-    p.reach, p.hold, p.warmup = lc.reach, lc.hold, lc.warmup
-    p.attack_c = lc.attack_c
-    p.hold_b0, p.hold_b1, p.hold_a1 = float(lc.hold_b[0]), float(lc.hold_b[1]), float(lc.hold_a[1])
-    p.release_b0, p.release_b1, p.release_a1 = (float(lc.release_b[0]), float(lc.release_b[1]),
-                                                float(lc.release_a[1]))
-    return p
+    return _native.LimiterParams.from_constants(lc)
 
 
 def get_plan(config, device=None) -> DevicePlan:
@@ -253,7 +246,8 @@ class HostIO:
         self.lib = _native.load()
         handle = C.c_void_p()
         threads = int(os.environ.get("MGB_HOST_THREADS", "0"))
-        _native.check(self.lib, self.lib.mgb_host_io_create(threads, 0, 0, C.byref(handle)))
+        chunk = int(os.environ.get("MGB_HOST_CHUNK", "0"))  # samples per ring chunk (tuning)
+        _native.check(self.lib, self.lib.mgb_host_io_create(threads, chunk, 0, C.byref(handle)))
         self.handle = handle
         self.pool = PinnedPool(self.lib, int(float(os.environ.get("MGB_PINNED_CACHE_GB", "4")) * (1 << 30)))
 

@@ -210,6 +210,7 @@ class LimiterConstants:
     release_a: np.ndarray
 
 
+MAX_FILTER_ORDER = 2   # MGB_MAX_FILTER_ORDER
 MAX_LIMITER_HALO = 4096  # left + right halo the limiter kernel's shared-memory span can hold
 
 
@@ -223,8 +224,11 @@ def limiter_constants(config) -> LimiterConstants:
     if hold < 3:
         # hyrax.py:38-40 slices with [:-0] when (hold-1)//2 == 0 and returns an empty array
         raise UnsupportedConfig("limiter hold shorter than 3 samples breaks the reference itself")
-    if lim.hold_filter_order != 1 or lim.release_filter_order != 1:
-        raise UnsupportedConfig("only first-order hold/release filters (the reference defaults) have a kernel")
+    if lim.hold_filter_order > MAX_FILTER_ORDER or lim.release_filter_order > MAX_FILTER_ORDER:
+        raise UnsupportedConfig(
+            f"hold / release filter orders above {MAX_FILTER_ORDER} have no kernel: at the limiter's cut-offs scipy's "
+            "transfer-function form (what the reference runs) is ill-conditioned from order 3 on -- its own rounding "
+            "noise exceeds the parity bound, order 4 release is unstable -- so there is no reference result to match")
     reach = (attack + 1 if not attack & 1 else attack) - 1  # make_odd(attack) - 1, utils.py:54-55
     c = math.exp(lim.attack_filter_coefficient / attack)
     if not 0.0 < c < 1.0:

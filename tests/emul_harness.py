@@ -43,13 +43,7 @@ def aligned_copy(a, dtype=None):
 
 
 def limiter_params(lc: plan_mod.LimiterConstants) -> _native.LimiterParams:
-    p = _native.LimiterParams()
-    p.threshold = lc.threshold
-    p.reach, p.hold, p.warmup = lc.reach, lc.hold, lc.warmup
-    p.attack_c = lc.attack_c
-    p.hold_b0, p.hold_b1, p.hold_a1 = float(lc.hold_b[0]), float(lc.hold_b[1]), float(lc.hold_a[1])
-    p.release_b0, p.release_b1, p.release_a1 = float(lc.release_b[0]), float(lc.release_b[1]), float(lc.release_a[1])
-    return p
+    return _native.LimiterParams.from_constants(lc)
 
 
 class EmulPlan:

@@ -31,7 +31,7 @@ def test_cuda_library_loads_and_exports_every_symbol():
     assert lib.mgb_version() == 200
     assert C.sizeof(_native.HostBuffers) == 7 * 8
     # struct layouts the binding assumes (sizes of the C structs, computed from the header's fields)
-    assert C.sizeof(_native.LimiterParams) == 8 + 4 * 4 + 7 * 8
+    assert C.sizeof(_native.LimiterParams) == 8 + 6 * 4 + 8 + 4 * (_native.MGB_MAX_FILTER_ORDER + 1) * 8
     assert C.sizeof(_native.TrackLayout) == 4 * 8 + 4 * 4 + 8
     assert C.sizeof(_native.TrackState) == 6 * 8 + 16 * 8 + 2 * 8 + 4 + 4 * 4 + 3 * 4  # the last three: fir peaks + reserved
 

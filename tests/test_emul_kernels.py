@@ -196,6 +196,39 @@ def test_limiter_narrow_and_wide_windows(lib, sr, attack):
     assert engaged == 1 and np.abs(out - want).max() < 3e-7
 
 
+@pytest.mark.parametrize("hold_order,release_order,sr", [(2, 1, 44100), (1, 2, 44100), (2, 2, 44100), (2, 2, 96000),
+                                                         (2, 2, 8000)])
+def test_limiter_higher_filter_orders(lib, hold_order, release_order, sr):
+    """LimiterConfig.hold_filter_order / release_filter_order > 1 (legal, matchering/defaults.py:48-56): the hold
+    and release low-passes become order-N Butterworth sections, run as blocked scans over the filter's state
+    vector with matrix-valued carries across threads, warps and chunks (five chunks here, so the look-back
+    carries states, too)."""
+    # (a release of 20 ms instead of 3 s: in half a second of signal the default release filter never rises above
+    # the hold filter, and its order would not show in the output)
+    lim = port.OracleLimiterConfig(hold_filter_order=hold_order, release_filter_order=release_order, release=20.0)
+    cfg = port.OracleConfig(internal_sample_rate=sr, limiter=lim)
+    x = port.synth_limiter_input(22000, seed=10 * hold_order + release_order)
+    x[9000:15000] *= 0.05  # a quiet stretch: the gain recovers along the release curve
+    want = port.limit(x.astype(np.float64), cfg)
+    out, engaged = _limit(lib, x, cfg)
+    assert engaged == 1
+    # not the order-1 result, and neither section alone explains the difference
+    for other in (port.OracleLimiterConfig(release=20.0),
+                  port.OracleLimiterConfig(hold_filter_order=hold_order, release=20.0),
+                  port.OracleLimiterConfig(release_filter_order=release_order, release=20.0)):
+        if (other.hold_filter_order, other.release_filter_order) != (hold_order, release_order):
+            plain = port.limit(x.astype(np.float64), port.OracleConfig(internal_sample_rate=sr, limiter=other))
+            assert np.abs(plain - want).max() > 1e-4
+    assert np.abs(out - want).max() < 1e-6
+    for inclusive in (0,):  # aggregates only: every look-back walks its whole window
+        lib.mgb_set_option(b"lookback_inclusive", inclusive)
+        try:
+            again, _ = _limit(lib, x, cfg)
+        finally:
+            lib.mgb_set_option(b"lookback_inclusive", 1)
+        assert np.abs(again - want).max() < 1e-6
+
+
 def test_limiter_not_engaged_copies_input(lib):
     x = (0.2 * port.synth_limiter_input(6000, 2)).astype(np.float32)
     out, engaged = _limit(lib, x, port.OracleConfig())
@@ -212,7 +245,7 @@ def test_unsupported_configs_fail_loudly():
         plan_mod.build_tables(port.OracleConfig(fft_size=512))
     with pytest.raises(plan_mod.UnsupportedConfig):
         plan_mod.build_tables(port.OracleConfig(lowess_it=9))
-    lim = port.OracleLimiterConfig(hold_filter_order=2)
+    lim = port.OracleLimiterConfig(hold_filter_order=3)
     with pytest.raises(plan_mod.UnsupportedConfig):
         plan_mod.build_tables(port.OracleConfig(limiter=lim))
 
@@ -494,3 +527,15 @@ def test_pipeline_with_lowess_robustness_iterations(lib):
     outs, st, fir, _, _ = run_pipeline(cfg, t, r)
     want = port.main(t.astype(np.float64), r.astype(np.float64), cfg, True, True, True)
     _compare(outs, want)
+
+
+def test_pipeline_with_second_order_limiter_filters(lib):
+    """The whole pipeline with LimiterConfig(hold_filter_order=2, release_filter_order=2): mgb_finalize sizes the
+    look-back words and picks the limiter kernel from the plan's filter orders."""
+    lim = port.OracleLimiterConfig(hold_filter_order=2, release_filter_order=2, release=30.0)
+    cfg = port.OracleConfig(fft_size=1024, max_piece_size=0.3, limiter=lim)
+    t, r = port.synth_target(30000, 1), port.synth_reference(28000, 2)
+    outs, st, _, _, _ = run_pipeline(cfg, t, r)
+    want = port.main(t.astype(np.float64), r.astype(np.float64), cfg, True, True, True)
+    _compare(outs, want)
+    assert st.limiter_engaged == 1

@@ -363,7 +363,7 @@ def test_unsupported_configs_fail_loudly(torch_cuda):
     from matchering_b200.plan import UnsupportedConfig
     import matchering_b200 as mg
     x = np.zeros((20000, 2), dtype=np.float32)
-    for cfg in (_config(fft_size=512), _config(limiter=mg.LimiterConfig(release_filter_order=2)),
+    for cfg in (_config(fft_size=512), _config(limiter=mg.LimiterConfig(release_filter_order=3)),
                 _config(fft_size=4096, max_piece_size=0.1)):
         with pytest.raises(UnsupportedConfig):
             stages.main(x[:5000], x[:5000], cfg)
@@ -683,3 +683,39 @@ def test_lowess_robustness_iterations_against_oracle(torch_cuda, it):
     _compare(got, want)
     plain = stages.main(t, r, _config(max_piece_size=1.0), False, True, False)[1]
     assert np.abs(plain - got[1]).max() > 1e-6  # not the it = 0 result
+
+
+@pytest.mark.parametrize("hold_order,release_order,sr", [(2, 1, 44100), (1, 2, 44100), (2, 2, 96000)])
+def test_limiter_second_order_filters_against_oracle(torch_cuda, hold_order, release_order, sr):
+    """LimiterConfig.hold_filter_order / release_filter_order = 2 (legal, matchering/defaults.py:48-56): blocked
+    scans over the filters' state vectors, 2x2 matrix carries across threads, warps and (by look-back) 130
+    chunks; a short release so that the release filter shows in the output, and the default one."""
+    import matchering_b200 as mg
+    import port
+    from matchering_b200.limiter import limit
+    x = port.synth_limiter_input(600000, seed=hold_order * 10 + release_order)
+    x[200000:330000] *= 0.05
+    for release in (25.0, 3000.0):
+        kw = dict(hold_filter_order=hold_order, release_filter_order=release_order, release=release)
+        cfg = _config(internal_sample_rate=sr, limiter=mg.LimiterConfig(**kw))
+        want = port.limit(x.astype(np.float64), port.OracleConfig(internal_sample_rate=sr, limiter=port.OracleLimiterConfig(**kw)))
+        got = limit(x, cfg)
+        assert np.abs(got - want).max() < 1e-6
+    plain = limit(x, _config(internal_sample_rate=sr, limiter=mg.LimiterConfig(release=25.0)))
+    second = limit(x, _config(internal_sample_rate=sr, limiter=mg.LimiterConfig(
+        release=25.0, hold_filter_order=hold_order, release_filter_order=release_order)))
+    assert np.abs(plain - second).max() > 1e-4
+
+
+def test_pipeline_with_second_order_limiter_filters(torch_cuda):
+    import matchering_b200 as mg
+    import port
+    from matchering_b200 import stages
+    kw = dict(hold_filter_order=2, release_filter_order=2, release=40.0)
+    cfg = _config(max_piece_size=1.0, limiter=mg.LimiterConfig(**kw))
+    n = 44100 * 4 + 5
+    t, r = port.synth_target(n, 21), port.synth_reference(n - 999, 22)
+    got = stages.main(t, r, cfg, True, True, True)
+    want = port.main(t.astype(np.float64), r.astype(np.float64),
+                     port.OracleConfig(max_piece_size=1.0, limiter=port.OracleLimiterConfig(**kw)), True, True, True)
+    _compare(got, want)
