@@ -213,6 +213,7 @@ int launch_analyze_t(const mgb_plan& plan, const float2* x, int64_t frames, int6
 int launch_analyze(const mgb_plan& plan, const float2* x, int64_t frames, int64_t piece, int divisions, int slots,
                    float* spec_part, double* sumsq_part, float* absmax_part, cudaStream_t stream) {
     switch (plan.fft_size) {
+        case 512: return launch_analyze_t<512>(plan, x, frames, piece, divisions, slots, spec_part, sumsq_part, absmax_part, stream);
         case 1024: return launch_analyze_t<1024>(plan, x, frames, piece, divisions, slots, spec_part, sumsq_part, absmax_part, stream);
         case 2048: return launch_analyze_t<2048>(plan, x, frames, piece, divisions, slots, spec_part, sumsq_part, absmax_part, stream);
         case 4096: return launch_analyze_t<4096>(plan, x, frames, piece, divisions, slots, spec_part, sumsq_part, absmax_part, stream);

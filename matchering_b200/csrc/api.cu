@@ -118,8 +118,8 @@ Workspace carve_workspace(const mgb_plan& plan, const mgb_track_layout& L, void*
 static int check_plan(const mgb_plan* plan) {
     MGB_REQUIRE(plan != nullptr, MGB_ERR_INVALID, "plan is NULL");
     const int F = plan->fft_size;
-    MGB_REQUIRE(F == 1024 || F == 2048 || F == 4096 || F == 8192, MGB_ERR_UNSUPPORTED,
-                "fft_size %d: kernels exist for 1024, 2048, 4096, 8192", F);
+    MGB_REQUIRE(F == 512 || F == 1024 || F == 2048 || F == 4096 || F == 8192, MGB_ERR_UNSUPPORTED,
+                "fft_size %d: kernels exist for 512, 1024, 2048, 4096, 8192", F);
     MGB_REQUIRE(plan->n_lin == F / 2 + 1 && plan->n_log >= 4, MGB_ERR_INVALID, "plan grid sizes inconsistent");
     MGB_REQUIRE(plan->rms_correction_steps >= 0 && plan->rms_correction_steps <= MGB_MAX_CORRECTION_STEPS,
                 MGB_ERR_UNSUPPORTED, "rms_correction_steps %d > %d", plan->rms_correction_steps, MGB_MAX_CORRECTION_STEPS);
@@ -176,6 +176,7 @@ int launch_test_fft(int n, int is_f64, int dir, const void* in, void* out, int b
         return is_f64 ? launch_test_fft_t<NN, double, 512>(dir, in, out, batch, tw, stream)                   \
                       : launch_test_fft_t<NN, float, NN / 16>(dir, in, out, batch, tw, stream);
     switch (n) {
+        MGB_FFT_CASE(512)
         MGB_FFT_CASE(1024)
         MGB_FFT_CASE(2048)
         MGB_FFT_CASE(4096)
@@ -197,6 +198,7 @@ static void radices_of(int* npass, int r[4]) {
 }
 static bool radix_schedule(int n, int* npass, int r[4]) {
     switch (n) {
+        case 512: radices_of<512>(npass, r); return true;
         case 1024: radices_of<1024>(npass, r); return true;
         case 2048: radices_of<2048>(npass, r); return true;
         case 4096: radices_of<4096>(npass, r); return true;

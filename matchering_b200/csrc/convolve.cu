@@ -438,6 +438,7 @@ int launch_convolve(const mgb_plan& plan, const mgb_track_layout& layout, const 
         return MGB_ERR_UNSUPPORTED;
     }
     switch (plan.fft_size) {
+        case 512: return launch_convolve_t<512>(plan, layout, target, result, ws, state, stream);
         case 1024: return launch_convolve_t<1024>(plan, layout, target, result, ws, state, stream);
         case 2048: return launch_convolve_t<2048>(plan, layout, target, result, ws, state, stream);
         case 4096: return launch_convolve_t<4096>(plan, layout, target, result, ws, state, stream);

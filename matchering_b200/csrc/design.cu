@@ -695,6 +695,7 @@ int launch_design(const mgb_plan& plan, const mgb_track_layout& layout, const Wo
         a.s_ready = 1;
     }
     switch (plan.fft_size) {
+        case 512: return launch_design_t<512>(plan, a, stream);
         case 1024: return launch_design_t<1024>(plan, a, stream);
         case 2048: return launch_design_t<2048>(plan, a, stream);
         case 4096: return launch_design_t<4096>(plan, a, stream);

@@ -253,7 +253,7 @@ struct PlaneStore {
 // Radix schedule of an N-point transform.  Sizes outside this list are rejected by the C ABI.
 template <int N> struct Radices;
 template <> struct Radices<256>   { static constexpr int n = 2; static constexpr int r[4] = {16, 16, 1, 1}; };
-template <> struct Radices<512>   { static constexpr int n = 3; static constexpr int r[4] = {8, 8, 8, 1}; };
+template <> struct Radices<512>   { static constexpr int n = 3; static constexpr int r[4] = {16, 8, 4, 1}; };  // radix 16 first: 16 points per thread, like every other size
 template <> struct Radices<1024>  { static constexpr int n = 3; static constexpr int r[4] = {16, 8, 8, 1}; };
 template <> struct Radices<2048>  { static constexpr int n = 3; static constexpr int r[4] = {16, 16, 8, 1}; };
 template <> struct Radices<4096>  { static constexpr int n = 3; static constexpr int r[4] = {16, 16, 16, 1}; };

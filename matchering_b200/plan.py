@@ -23,7 +23,7 @@ from dataclasses import dataclass, field
 import numpy as np
 from scipy import signal as _signal
 
-SUPPORTED_FFT_SIZES = (1024, 2048, 4096, 8192)
+SUPPORTED_FFT_SIZES = (512, 1024, 2048, 4096, 8192)
 
 
 class UnsupportedConfig(NotImplementedError):

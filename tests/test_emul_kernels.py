@@ -18,7 +18,7 @@ def lib():
     return emul_lib()
 
 
-@pytest.mark.parametrize("n,f64", [(1024, 0), (4096, 0), (8192, 0), (16384, 0), (2048, 1), (8192, 1)])
+@pytest.mark.parametrize("n,f64", [(512, 0), (512, 1), (1024, 0), (4096, 0), (8192, 0), (16384, 0), (2048, 1), (8192, 1)])
 def test_fft_matches_numpy(lib, n, f64):
     rng = np.random.default_rng(n + f64)
     dt = np.complex128 if f64 else np.complex64
@@ -145,7 +145,7 @@ def test_long_frame_convolution_against_oracle(lib, fft_size, n, piece_s):
     assert np.abs(got[2][1] - got[4][1]).max() < 2e-6
 
 
-@pytest.mark.parametrize("fft_size,sr", [(1024, 44100), (2048, 22050), (4096, 96000), (8192, 44100)])
+@pytest.mark.parametrize("fft_size,sr", [(512, 44100), (512, 8000), (1024, 44100), (2048, 22050), (4096, 96000), (8192, 44100)])
 def test_pipeline_other_configs(lib, fft_size, sr):
     cfg = port.OracleConfig(internal_sample_rate=sr, fft_size=fft_size, max_piece_size=0.4, rms_correction_steps=2)
     n = int(sr * 1.1) + 13
@@ -241,8 +241,9 @@ def test_limiter_rejects_too_short_input(lib):
 
 
 def test_unsupported_configs_fail_loudly():
-    with pytest.raises(plan_mod.UnsupportedConfig):
-        plan_mod.build_tables(port.OracleConfig(fft_size=512))
+    for fft_size in (256, 16384):
+        with pytest.raises(plan_mod.UnsupportedConfig):
+            plan_mod.build_tables(port.OracleConfig(fft_size=fft_size))
     with pytest.raises(plan_mod.UnsupportedConfig):
         plan_mod.build_tables(port.OracleConfig(lowess_it=9))
     lim = port.OracleLimiterConfig(hold_filter_order=3)

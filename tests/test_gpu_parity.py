@@ -38,7 +38,7 @@ def test_native_library_is_the_cuda_build(lib):
     assert n.LIB_PATH.endswith("libmatchering_b200.so") and lib.mgb_version() >= 100
 
 
-@pytest.mark.parametrize("n,f64", [(1024, 0), (2048, 0), (4096, 0), (8192, 0), (16384, 0), (4096, 1), (8192, 1)])
+@pytest.mark.parametrize("n,f64", [(512, 0), (512, 1), (1024, 0), (2048, 0), (4096, 0), (8192, 0), (16384, 0), (4096, 1), (8192, 1)])
 def test_fft_matches_numpy(torch_cuda, lib, n, f64):
     torch = torch_cuda
     from matchering_b200 import _native
@@ -115,7 +115,7 @@ def test_fir_and_scalars_match_golden(torch_cuda, golden):
     assert st.steps_done == 4 and st.limiter_engaged == 1
 
 
-@pytest.mark.parametrize("fft_size,sr,seconds", [(1024, 44100, 1.5), (2048, 22050, 2.0), (4096, 96000, 1.2), (8192, 44100, 2.5)])
+@pytest.mark.parametrize("fft_size,sr,seconds", [(512, 44100, 1.0), (1024, 44100, 1.5), (2048, 22050, 2.0), (4096, 96000, 1.2), (8192, 44100, 2.5)])
 def test_pipeline_other_configs_against_oracle(torch_cuda, fft_size, sr, seconds):
     import port
     from matchering_b200 import stages
@@ -363,7 +363,7 @@ def test_unsupported_configs_fail_loudly(torch_cuda):
     from matchering_b200.plan import UnsupportedConfig
     import matchering_b200 as mg
     x = np.zeros((20000, 2), dtype=np.float32)
-    for cfg in (_config(fft_size=512), _config(limiter=mg.LimiterConfig(release_filter_order=3)),
+    for cfg in (_config(fft_size=256), _config(fft_size=16384), _config(limiter=mg.LimiterConfig(release_filter_order=3)),
                 _config(fft_size=4096, max_piece_size=0.1)):
         with pytest.raises(UnsupportedConfig):
             stages.main(x[:5000], x[:5000], cfg)
