@@ -343,6 +343,16 @@ int mgb_window_energy(const float* d_lr, int64_t frames, int64_t window, int64_t
 int mgb_preview_piece(const float* d_in_lr, float* d_out_lr, int64_t frames, double clip_to, int64_t fade_frames,
                       void* stream);
 
+/* Resampling to Config.internal_sample_rate (matchering/checker.py:30-44 = resampy.resample(array, rate_in,
+ * rate_out, axis=0), filter "kaiser_best"; resampy/core.py, resampy/interpn.py).  d_win_delta: nwin pairs of
+ * doubles (table entry, forward difference to the next entry; the last difference is 0) -- half of the
+ * Kaiser-windowed sinc at num_table entries per zero crossing, already scaled by rate_out/rate_in when that is
+ * below 1 (built by matchering_b200/resample.py).  frames_out must equal mgb_resample_frames(): resampy's
+ * int(frames_in * rate_out / rate_in). */
+int64_t mgb_resample_frames(int64_t frames_in, int32_t rate_in, int32_t rate_out);
+int mgb_resample(const float* d_in_lr, int64_t frames_in, int32_t rate_in, float* d_out_lr, int64_t frames_out,
+                 int32_t rate_out, const double* d_win_delta, int32_t nwin, int32_t num_table, void* stream);
+
 /* ---- building blocks exported for the parity tests (tests/ only) ------------------------------ */
 /* forward or inverse (dir = +1 / -1) complex FFT of `batch` frames of n points through the same
  * shared-memory kernel the pipeline uses; is_f64 selects the double variant (n in {F, 2F}). */

@@ -12,7 +12,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 SRC_DIR = os.path.join(PKG_DIR, "csrc")
 OBJ_DIR = os.path.join(PKG_DIR, "_build")
 LIB_PATH = os.path.join(PKG_DIR, "libmatchering_b200.so")
-SOURCES = ["api.cu", "analyze.cu", "design.cu", "convolve.cu", "correct.cu", "limiter.cu", "pipeline.cu", "hostio.cu"]
+SOURCES = ["api.cu", "analyze.cu", "design.cu", "convolve.cu", "correct.cu", "limiter.cu", "pipeline.cu", "hostio.cu", "resample.cu"]
 HEADERS = sorted(f for f in os.listdir(SRC_DIR) if f.endswith(".cuh")) + [os.path.join("..", "..", "include", "matchering_b200.h")]
 
 NVCC_FLAGS = [

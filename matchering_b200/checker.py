@@ -1,5 +1,6 @@
-"""mg.check (reference: matchering/checker.py:30-142): input validation in front of the hot path.
-Host-side numpy; SURVEY.md section 8(f) lists it as a later candidate for the device."""
+"""mg.check (reference: matchering/checker.py:30-142): input validation in front of the hot path, for arrays
+that are on the host (device_io.check_on_device is the same for signals already on the device); resampling
+runs on the device either way."""
 import numpy as np
 
 from .defaults import Config
@@ -8,17 +9,10 @@ from .utils import time_str
 
 
 def _resample(array, old_rate: int, new_rate: int):
-    try:
-        import resampy
-    except ImportError:
-        resampy = None
-    if resampy is not None and getattr(resampy, "__version__", None):  # a real install, not a test stand-in
-        return resampy.resample(array, old_rate, new_rate, axis=0)
-    # resampy absent: polyphase Kaiser-windowed sinc from scipy instead
-    from math import gcd
-    from scipy.signal import resample_poly
-    g = gcd(int(old_rate), int(new_rate))
-    return resample_poly(array, new_rate // g, old_rate // g, axis=0)
+    """matchering/checker.py:42: resampy.resample(array, old_rate, new_rate, axis=0) -- here the device kernel
+    (csrc/resample.cu) with resampy's kaiser_best table rebuilt from its documented parameters."""
+    from .resample import resample
+    return resample(array, int(old_rate), int(new_rate))
 
 
 def _count_max_peaks(array):

@@ -76,7 +76,8 @@ def _load_and_check(file: str, name: str, temp_folder: str, config: Config):
     from .device_io import check_on_device, load_to_device
     on_device = load_to_device(file, name, config)
     if on_device is not None:
-        return check_on_device(on_device, config, name), config.internal_sample_rate
+        audio, rate = on_device
+        return check_on_device(audio, config, name, rate), config.internal_sample_rate
     audio, rate = load(file, name, temp_folder)
     return check(audio, rate, config, name)
 

@@ -1,8 +1,9 @@
-"""File boundary on the device (SURVEY.md section 8f, items 1-2): when a WAV file holds 16/24-bit PCM
-at the internal sample rate, its raw samples go to the GPU as they are, are decoded there
-(mgb_pcm_decode), checked there (mgb_check_peaks / mgb_check_equality, the reductions of
-matchering/checker.py) and never exist as a float array on the host.  Anything else (other formats,
-other sample rates, more than two channels) takes the reference's host route through loader/checker.
+"""File boundary on the device (SURVEY.md section 8f, items 1, 2 and 4): when a WAV file holds 16/24-bit PCM
+(at any sample rate), its raw samples go to the GPU as they are, are decoded there (mgb_pcm_decode),
+resampled to the internal rate there if need be (mgb_resample), checked there (mgb_check_peaks /
+mgb_check_equality, the reductions of matchering/checker.py) and never exist as a float array on the
+host.  Anything else (other formats, more than two channels) takes the reference's host route through
+loader/checker.
 """
 from __future__ import annotations
 
@@ -32,7 +33,7 @@ def load_to_device(file: str, file_type: str, config: Config):
     if got is None:
         return None
     raw, rate, channels, bits = got
-    if rate != config.internal_sample_rate or channels > 2:
+    if channels > 2:
         return None
     debug(f"Loading the {file_type.upper()} file: '{file}'... ({bits}-bit PCM, decoded on the device)")
     lib = _native.load()
@@ -42,26 +43,34 @@ def load_to_device(file: str, file_type: str, config: Config):
     out = torch.empty((frames, channels), dtype=torch.float32, device=device)
     _native.check(lib, lib.mgb_pcm_decode(d_raw.data_ptr(), bits, out.data_ptr(), frames * channels, _stream_ptr(device)))
     debug(f"The {file_type.upper()} file is loaded")
-    return out
+    return out, rate
 
 
-def check_on_device(audio: torch.Tensor, config: Config, name: str) -> torch.Tensor:
-    """matchering/checker.py:90-137 for a signal that is already on the device at the internal rate:
-    length limits, mono -> stereo, and (target only) the clipping / limiter detection."""
+def check_on_device(audio: torch.Tensor, config: Config, name: str, sample_rate: int = None) -> torch.Tensor:
+    """matchering/checker.py:90-137 for a signal that is already on the device, in the reference's order: length
+    limits at the SOURCE rate, mono -> stereo, resampling to the internal rate (csrc/resample.cu), and (target
+    only) the clipping / limiter detection."""
     name = name.upper()
     is_target = name == "TARGET"
     frames, channels = audio.shape
     sr = config.internal_sample_rate
-    debug(f"{name} audio length: {frames} samples ({time_str(frames, sr)})")
-    if frames > config.max_length * sr:
+    sample_rate = sr if sample_rate is None else int(sample_rate)
+    debug(f"{name} audio length: {frames} samples ({time_str(frames, sample_rate)})")
+    if frames > config.max_length * sample_rate:
         raise ModuleError(Code.ERROR_TARGET_LENGTH_IS_EXCEEDED if is_target
                           else Code.ERROR_REFERENCE_LENGTH_LENGTH_IS_EXCEEDED)
-    if frames < config.fft_size:
+    if frames < config.fft_size * sample_rate // sr:
         raise ModuleError(Code.ERROR_TARGET_LENGTH_IS_TOO_SMALL if is_target
                           else Code.ERROR_REFERENCE_LENGTH_LENGTH_TOO_SMALL)
     if channels == 1:
         info(Code.INFO_TARGET_IS_MONO if is_target else Code.INFO_REFERENCE_IS_MONO)
         audio = audio.repeat(1, 2).contiguous()
+    if sample_rate != sr:
+        from .resample import resample_on_device
+        debug(f"Resampling {name} audio from {sample_rate} Hz to {sr} Hz...")
+        audio = resample_on_device(audio, sample_rate, sr)
+        frames = audio.shape[0]
+        (warning if is_target else info)(Code.WARNING_TARGET_IS_RESAMPLED if is_target else Code.INFO_REFERENCE_IS_RESAMPLED)
     if is_target:
         lib = _native.load()
         scratch = torch.zeros(16, dtype=torch.uint8, device=audio.device)

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 SRC_DIR = os.path.join(ROOT, "matchering_b200", "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 LIB_PATH = os.path.join(OUT_DIR, "libmatchering_b200_emul.so")
-SOURCES = ["api.cu", "analyze.cu", "design.cu", "convolve.cu", "correct.cu", "limiter.cu", "pipeline.cu", "hostio.cu"]
+SOURCES = ["api.cu", "analyze.cu", "design.cu", "convolve.cu", "correct.cu", "limiter.cu", "pipeline.cu", "hostio.cu", "resample.cu"]
 FLAGS = ["-O2", "-std=c++17", "-fPIC", "-DMGB_EMULATE", "-include", os.path.join(HERE, "cuda_emul.h"),
          "-Wno-unused-function", "-Wno-unknown-pragmas", "-fno-strict-aliasing"]
 

@@ -540,3 +540,33 @@ def test_pipeline_with_second_order_limiter_filters(lib):
     want = port.main(t.astype(np.float64), r.astype(np.float64), cfg, True, True, True)
     _compare(outs, want)
     assert st.limiter_engaged == 1
+
+
+@pytest.mark.parametrize("rate_in,rate_out,n", [(48000, 44100, 20011), (22050, 44100, 9000), (96000, 44100, 30000),
+                                                (44100, 48000, 7001), (8000, 44100, 700)])
+def test_resampler_matches_oracle(lib, rate_in, rate_out, n):
+    """mgb_resample (csrc/resample.cu) against the oracle's restatement of resampy's kaiser_best resampler:
+    same table, same index arithmetic, float64 accumulation; down- and up-sampling, edges included."""
+    import resample as oracle_resample
+    from matchering_b200 import resample as product
+    rng = np.random.default_rng(n)
+    x = rng.uniform(-0.9, 0.9, (n, 2)).astype(np.float32)
+    want = oracle_resample.resample(x.astype(np.float64), rate_in, rate_out)
+    frames_out = int(lib.mgb_resample_frames(n, rate_in, rate_out))
+    assert frames_out == want.shape[0]
+    # the product's own table (built without the oracle) must be the oracle's table
+    ratio = float(rate_out) / rate_in
+    product._TABLES.clear()
+    num_bits = 2 ** product.PRECISION
+    m = num_bits * product.NUM_ZEROS
+    from scipy.signal.windows import kaiser
+    win = product.ROLLOFF * np.sinc(product.ROLLOFF * np.linspace(0, product.NUM_ZEROS, num=m + 1)) * kaiser(2 * m + 1, product.BETA)[m:]
+    ref_win, ref_bits = oracle_resample.kaiser_best_filter()
+    assert np.array_equal(win, ref_win) and num_bits == ref_bits
+    if ratio < 1:
+        win = ratio * win
+    pairs = aligned_copy(np.stack([win, np.diff(win, append=win[-1])], axis=1))
+    xin, out = aligned_copy(x), aligned((frames_out, 2), np.float32)
+    _native.check(lib, lib.mgb_resample(ptr(xin), n, rate_in, ptr(out), frames_out, rate_out, ptr(pairs), len(win), num_bits, None))
+    assert np.abs(out - want).max() < 2e-7
+    assert lib.mgb_resample(ptr(xin), n, rate_in, ptr(out), frames_out + 1, rate_out, ptr(pairs), len(win), num_bits, None) == _native.MGB_ERR_INVALID

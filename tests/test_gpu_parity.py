@@ -719,3 +719,45 @@ def test_pipeline_with_second_order_limiter_filters(torch_cuda):
     want = port.main(t.astype(np.float64), r.astype(np.float64),
                      port.OracleConfig(max_piece_size=1.0, limiter=port.OracleLimiterConfig(**kw)), True, True, True)
     _compare(got, want)
+
+
+@pytest.mark.parametrize("rate_in", [48000, 22050, 96000])
+def test_device_resampler_against_oracle(torch_cuda, rate_in):
+    """matchering_b200.resample (mgb_resample) against the oracle's restatement of resampy.resample (kaiser_best)."""
+    torch = torch_cuda
+    import resample as oracle_resample
+    from matchering_b200.resample import resample_on_device
+    rng = np.random.default_rng(rate_in)
+    x = rng.uniform(-0.9, 0.9, (rate_in * 2 + 17, 2)).astype(np.float32)
+    want = oracle_resample.resample(x.astype(np.float64), rate_in, 44100)
+    got = resample_on_device(torch.from_numpy(x).cuda(), rate_in, 44100).cpu().numpy()
+    assert got.shape == want.shape and np.abs(got - want).max() < 2e-7
+
+
+def test_process_resamples_files_on_the_device(torch_cuda, tmp_path):
+    """mg.process with a 48 kHz 24-bit target and a 22.05 kHz 16-bit reference: both are resampled to the internal
+    44.1 kHz on the device (the reference resamples with resampy on the host, matchering/checker.py:30-44), the
+    target's resampling is announced as a warning, the reference's as an info, like in the reference."""
+    import matchering_b200 as mg
+    import port
+    import resample as oracle_resample
+    from matchering_b200 import wavio
+    t48 = port.synth_target(48000 * 5, 3)
+    r22 = port.synth_reference(22050 * 6, 4)
+    wavio.write(str(tmp_path / "t.wav"), t48, 48000, "PCM_24")
+    wavio.write(str(tmp_path / "r.wav"), r22, 22050, "PCM_16")
+    warnings_seen, infos_seen = [], []
+    mg.log(warning_handler=warnings_seen.append, info_handler=infos_seen.append)
+    try:
+        mg.process(str(tmp_path / "t.wav"), str(tmp_path / "r.wav"), [mg.Result(str(tmp_path / "o.wav"), "FLOAT", use_limiter=False)],
+                   config=mg.Config(max_piece_size=2.0))
+    finally:
+        mg.log()
+    assert any("resampl" in w.lower() for w in warnings_seen) and any("resampl" in i.lower() for i in infos_seen)
+    t_dec, _ = wavio.read(str(tmp_path / "t.wav"))
+    r_dec, _ = wavio.read(str(tmp_path / "r.wav"))
+    t44 = oracle_resample.resample(t_dec, 48000, 44100).astype(np.float32).astype(np.float64)
+    r44 = oracle_resample.resample(r_dec, 22050, 44100).astype(np.float32).astype(np.float64)
+    want = port.main(t44, r44, port.OracleConfig(max_piece_size=2.0), False, True, False)[1]
+    got, sr = wavio.read(str(tmp_path / "o.wav"))
+    assert sr == 44100 and got.shape == want.shape and np.abs(got - want).max() < 2e-5
