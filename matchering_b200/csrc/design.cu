@@ -333,7 +333,8 @@ struct DesignArgs {
 
 // Matching curve m[k] = mean|rfft(reference)| / max(eps, mean|rfft(target)|) from the per-(piece,
 // slot) partial sums of analyze.cu, over the loudest pieces only (match_frequencies.py:42,93-94).
-// grid = (ceil(n_lin/16), 2 channels); block = 16 bins x 16 slices of the (piece, slot) items.
+// grid = (ceil(n_lin/32), 2 channels); block = 32 bins x 32 slices of the (piece, slot) items, four loads of a
+// slice in flight at a time (the partial spectra sit in L2: the sums are bound by load latency, not bandwidth).
 struct PrefetchList {
     const void* ptr[14];
     long long bytes[14];
@@ -348,9 +349,11 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 #endif
 }
 
-__global__ void __launch_bounds__(256)
+constexpr int kMeanBins = 32, kMeanSlices = 32;
+
+__global__ void __launch_bounds__(kMeanBins * kMeanSlices)
 spectrum_mean_kernel(DesignArgs a, int n_lin, int fft_size, double eps, PrefetchList pf) {
-    constexpr int BINS = 16, SLICES = 16;
+    constexpr int BINS = kMeanBins, SLICES = kMeanSlices;
     __shared__ double part_t[SLICES][BINS + 1], part_r[SLICES][BINS + 1];
     __shared__ double red_d[32];
     __shared__ float red_f[32];
@@ -386,11 +389,21 @@ spectrum_mean_kernel(DesignArgs a, int n_lin, int fft_size, double eps, Prefetch
     const int ch = blockIdx.y;
     double st = 0.0, sr = 0.0;
     if (k < n_lin) {
-        const int items_t = a.div_t * a.slots_t, items_r = a.div_r * a.slots_r;
-        for (int it = sy; it < items_t; it += SLICES)
-            if (mask_t[it / a.slots_t]) st += (double)a.spec_part_t[((long long)it * 2 + ch) * n_lin + k];
-        for (int it = sy; it < items_r; it += SLICES)
-            if (mask_r[it / a.slots_r]) sr += (double)a.spec_part_r[((long long)it * 2 + ch) * n_lin + k];
+        auto masked_sum = [&](const float* part, const unsigned char* mask, int items, int slots) {
+            double total = 0.0;
+            for (int it = sy; it < items; it += 4 * SLICES) {
+                float v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int iu = it + u * SLICES;
+                    v[u] = (iu < items && mask[iu / slots]) ? part[((long long)iu * 2 + ch) * n_lin + k] : 0.0f;
+                }
+                total += ((double)v[0] + (double)v[1]) + ((double)v[2] + (double)v[3]);
+            }
+            return total;
+        };
+        st = masked_sum(a.spec_part_t, mask_t, a.div_t * a.slots_t, a.slots_t);
+        sr = masked_sum(a.spec_part_r, mask_r, a.div_r * a.slots_r, a.slots_r);
     }
     part_t[sy][bx] = st;
     part_r[sy][bx] = sr;
@@ -679,7 +692,8 @@ int launch_design(const mgb_plan& plan, const mgb_track_layout& layout, const Wo
         add(plan.d_lw_alpha, ng * 8);
         add(plan.d_lw_rows, (long long)plan.lowess_nrows * plan.lowess_k * 8);
         add(plan.d_hann, F * 8);
-        MGB_TRY(launch("spectrum_mean_kernel", spectrum_mean_kernel, dim3((plan.n_lin + 15) / 16, 2), dim3(256),
+        MGB_TRY(launch("spectrum_mean_kernel", spectrum_mean_kernel, dim3((plan.n_lin + kMeanBins - 1) / kMeanBins, 2),
+                       dim3(kMeanBins * kMeanSlices),
                        (size_t)(layout.target_divisions + layout.reference_divisions + 16), stream, a, plan.n_lin,
                        plan.fft_size, plan.min_value, pf));
     }

@@ -22,6 +22,9 @@
 //            first, inclusive when known.  Order 1, the reference default, is a scalar scan.)
 //   out    = x * (1 - max(g, g_att, hold, rel)) * post_gain
 // HBM traffic: 8 B/frame read (+ the halo, which hits L2) and 8 B/frame written.
+#include <math.h>
+#include <string.h>
+
 #include "kernels.cuh"
 
 namespace mgb {
@@ -282,45 +285,8 @@ struct LimiterGeom {
     int margin;                   // zeros kept on both sides of G so that window reads need no bounds test (multiple of 4)
 };
 
-// Config-only tables, computed once per parameter set (not per CTA: pow() is slow): powers of the attack pole
-// (ScanPow) and, for the hold and release sections, powers of their companion matrices (SectionTab), by binary
-// exponentiation, one thread per table entry.
-template <int N>
-__device__ void companion_power(const double* a /* a[1..N] at a[1].. */, long long k, double (*out)[N]) {
-    double base[N][N], acc[N][N], tmp[N][N];
-    for (int r = 0; r < N; ++r)
-        for (int c = 0; c < N; ++c) {
-            base[r][c] = r == 0 ? -a[c + 1] : (r - 1 == c ? 1.0 : 0.0);
-            acc[r][c] = r == c ? 1.0 : 0.0;
-        }
-    while (k > 0) {
-        if (k & 1) {
-            for (int r = 0; r < N; ++r)
-                for (int c = 0; c < N; ++c) {
-                    double sum = 0.0;
-                    for (int m = 0; m < N; ++m) sum += acc[r][m] * base[m][c];
-                    tmp[r][c] = sum;
-                }
-            for (int r = 0; r < N; ++r)
-                for (int c = 0; c < N; ++c) acc[r][c] = tmp[r][c];
-        }
-        k >>= 1;
-        if (k) {
-            for (int r = 0; r < N; ++r)
-                for (int c = 0; c < N; ++c) {
-                    double sum = 0.0;
-                    for (int m = 0; m < N; ++m) sum += base[r][m] * base[m][c];
-                    tmp[r][c] = sum;
-                }
-            for (int r = 0; r < N; ++r)
-                for (int c = 0; c < N; ++c) base[r][c] = tmp[r][c];
-        }
-    }
-    for (int r = 0; r < N; ++r)
-        for (int c = 0; c < N; ++c) out[r][c] = acc[r][c];
-}
-
-template <int N>
+// Config-only tables, computed once per parameter set (not per CTA: pow() is slow).  Order capacity 1: powers of
+// the three poles, on the device.
 __global__ void limiter_tables_kernel(mgb_limiter_params lp, int span_ept, unsigned char* tables) {
     const int i = threadIdx.x;
     ScanPow* att = reinterpret_cast<ScanPow*>(tables);
@@ -331,18 +297,14 @@ __global__ void limiter_tables_kernel(mgb_limiter_params lp, int span_ept, unsig
         if (i < 17) att->qw[i] = pow(p, (double)(span_ept * 32 * i));
         if (i < 33) att->pc[i] = pow(p, (double)LC * (double)i);
     }
-    SectionTab<N>* sec = reinterpret_cast<SectionTab<N>*>(tables + sizeof(ScanPow));
+    SectionTab<1>* sec = reinterpret_cast<SectionTab<1>*>(tables + sizeof(ScanPow));
     for (int f = 0; f < 2; ++f) {
-        const double* a = f == 0 ? lp.hold_a : lp.release_a;  // a[0] = 1; entries above the order are zero
-        SectionTab<N>* t = sec + f;
-        if (i < CORE_EPT) {
-            double m[N][N];
-            companion_power<N>(a, i + 1, m);
-            for (int c = 0; c < N; ++c) t->pe[i][c] = m[0][c];
-        }
-        if (i < 33) companion_power<N>(a, (long long)CORE_EPT * i, t->ql[i]);
-        if (i < 17) companion_power<N>(a, (long long)CORE_EPT * 32 * i, t->qw[i]);
-        if (i < 33) companion_power<N>(a, (long long)LC * i, t->pc[i]);
+        const double p = f == 0 ? -lp.hold_a[1] : -lp.release_a[1];
+        SectionTab<1>* t = sec + f;
+        if (i < CORE_EPT) t->pe[i][0] = pow(p, (double)(i + 1));
+        if (i < 33) t->ql[i][0][0] = pow(p, (double)(CORE_EPT * i));
+        if (i < 17) t->qw[i][0][0] = pow(p, (double)(CORE_EPT * 32 * i));
+        if (i < 33) t->pc[i][0][0] = pow(p, (double)LC * (double)i);
     }
 }
 
@@ -811,6 +773,87 @@ int limiter_geometry(const mgb_limiter_params& lp, LimiterGeom* g) {
 
 }  // namespace
 
+// ---- order capacity 2: powers of the sections' companion matrices, on the HOST in extended precision -------
+// C = [[-a1, -a2], [1, 0]] has its two eigenvalues 3e-5 apart (a Butterworth pair at 0.27 Hz against 44.1 kHz):
+// powers by repeated squaring in float64 lose a digit per squaring (measured: relative error 2e-8 at C^4608,
+// 3e-3 at C^147456), and the blocked scan weighs whole chunks with exactly those powers.  In closed form,
+//     C^m = [[U_m, -a2 U_(m-1)], [U_(m-1), -a2 U_(m-2)]],   U_m = r^m sin((m+1) theta) / sin(theta)
+// for the pole pair r exp(+-i theta) of the ROUNDED coefficients the reference's lfilter runs with -- the
+// discriminant a1^2 - 4 a2 formed exactly (fma) and everything after it in long double.
+struct SectionPowers {
+    long double A, B;       // z^2 - A z + B
+    int kind;               // 0: B == 0 (an order-1 section padded to 2); 1: complex pair; 2: real pair; 3: double root
+    long double r_log, theta, sin_theta;  // kind 1
+    long double p1, p2;                   // kind 2 (p1 alone for kinds 0 and 3)
+    explicit SectionPowers(const double* a) {
+        A = -(long double)a[1];
+        B = (long double)a[2];
+        if (a[2] == 0.0) {
+            kind = 0;
+            p1 = A;
+            return;
+        }
+        const double hi = a[1] * a[1];
+        const double lo = fma(a[1], a[1], -hi);                       // a1^2 = hi + lo exactly
+        const long double disc = ((long double)hi - 4.0L * B) + (long double)lo;  // (hi - 4 a2 is exact in double range)
+        if (disc < 0) {
+            kind = 1;
+            r_log = 0.5L * log1pl(B - 1.0L);
+            theta = atan2l(sqrtl(-disc), A);
+            sin_theta = sinl(theta);
+        } else if (disc > 0) {
+            kind = 2;
+            const long double q = sqrtl(disc);
+            p1 = 0.5L * (A + q);
+            p2 = 0.5L * (A - q);
+        } else {
+            kind = 3;
+            p1 = 0.5L * A;
+        }
+    }
+    long double U(long long m) const {  // m >= -1
+        if (m < 0) return 0.0L;
+        switch (kind) {
+            case 0: return powl(p1, (long double)m);
+            case 1: return expl((long double)m * r_log) * sinl((long double)(m + 1) * theta) / sin_theta;
+            case 2: return (powl(p1, (long double)(m + 1)) - powl(p2, (long double)(m + 1))) / (p1 - p2);
+            default: return (long double)(m + 1) * powl(p1, (long double)m);
+        }
+    }
+    void power(long long m, double (*out)[2]) const {
+        if (m == 0) {
+            out[0][0] = out[1][1] = 1.0;
+            out[0][1] = out[1][0] = 0.0;
+            return;
+        }
+        const long double u0 = U(m), u1 = U(m - 1), u2 = U(m - 2);
+        out[0][0] = (double)u0;
+        out[0][1] = (double)(-B * u1);
+        out[1][0] = (double)u1;
+        out[1][1] = (double)(-B * u2);
+    }
+};
+
+static void fill_section_tables(const double* a, SectionTab<2>* t) {
+    const SectionPowers sp(a);
+    double m[2][2];
+    for (int e = 0; e < CORE_EPT; ++e) {
+        sp.power(e + 1, m);
+        t->pe[e][0] = m[0][0];
+        t->pe[e][1] = m[0][1];
+    }
+    for (int k = 0; k < 33; ++k) sp.power((long long)CORE_EPT * k, t->ql[k]);
+    for (int k = 0; k < 17; ++k) sp.power((long long)CORE_EPT * 32 * k, t->qw[k]);
+    for (int k = 0; k < 33; ++k) sp.power((long long)LC * k, t->pc[k]);
+}
+
+static void fill_attack_tables(double p, int span_ept, ScanPow* t) {
+    for (int i = 0; i < SPAN_EPT_MAX + 2; ++i) t->pe[i] = (double)powl((long double)p, (long double)i);
+    for (int i = 0; i < 33; ++i) t->ql[i] = (double)powl((long double)p, (long double)(span_ept * i));
+    for (int i = 0; i < 17; ++i) t->qw[i] = (double)powl((long double)p, (long double)(span_ept * 32 * i));
+    for (int i = 0; i < 33; ++i) t->pc[i] = (double)powl((long double)p, (long double)LC * (long double)i);
+}
+
 int64_t limiter_lookback_bytes(int64_t frames, int order_capacity) {
     const int64_t chunks = (frames + LC - 1) / LC;
     return (chunks * 2 * order_capacity * (int64_t)sizeof(LookbackWord) + 255) / 256 * 256;
@@ -825,10 +868,25 @@ int launch_limiter_tables(const mgb_limiter_params& lp, void* tables, cudaStream
     LimiterGeom g;
     MGB_TRY(limiter_geometry(lp, &g));
     if (limiter_order_capacity(lp) == 1)
-        return launch("limiter_tables_kernel", limiter_tables_kernel<1>, dim3(1), dim3(64), 0, stream, lp, g.ept,
+        return launch("limiter_tables_kernel", limiter_tables_kernel, dim3(1), dim3(64), 0, stream, lp, g.ept,
                       (unsigned char*)tables);
-    return launch("limiter_tables_kernel", limiter_tables_kernel<MGB_MAX_FILTER_ORDER>, dim3(1), dim3(64), 0, stream, lp, g.ept,
-                  (unsigned char*)tables);
+    // order 2: host tables (see SectionPowers), one small upload; the copy from pageable memory is staged before
+    // the call returns, so the local buffer may go out of scope
+    struct Block {
+        ScanPow attack;
+        SectionTab<2> section[2];
+    } block;
+    static_assert(sizeof(Block) == sizeof(ScanPow) + 2 * sizeof(SectionTab<2>), "table layout");
+    fill_attack_tables(lp.attack_c, g.ept, &block.attack);
+    fill_section_tables(lp.hold_a, &block.section[0]);
+    fill_section_tables(lp.release_a, &block.section[1]);
+#ifdef MGB_EMULATE
+    (void)stream;
+    memcpy(tables, &block, sizeof(block));
+#else
+    if (cudaMemcpyAsync(tables, &block, sizeof(block), cudaMemcpyHostToDevice, stream) != cudaSuccess) return cuda_status("limiter tables");
+#endif
+    return MGB_OK;
 }
 
 int launch_limiter(const mgb_limiter_params& lp, const float2* in, float2* out, int64_t frames, const double* pre_gain,

@@ -570,3 +570,21 @@ def test_resampler_matches_oracle(lib, rate_in, rate_out, n):
     _native.check(lib, lib.mgb_resample(ptr(xin), n, rate_in, ptr(out), frames_out, rate_out, ptr(pairs), len(win), num_bits, None))
     assert np.abs(out - want).max() < 2e-7
     assert lib.mgb_resample(ptr(xin), n, rate_in, ptr(out), frames_out + 1, rate_out, ptr(pairs), len(win), num_bits, None) == _native.MGB_ERR_INVALID
+
+
+def test_second_order_release_filter_over_many_chunks(lib):
+    """The default 3-second release as an order-2 section: its pole pair sits 3e-5 apart, and weights of whole chunks
+    (companion-matrix powers up to C^147456) must be exact -- repeated squaring in float64 was off by 3e-3 there and
+    cost 2e-5 in the output; the tables come from the closed form in extended precision (limiter.cu SectionPowers)."""
+    lim = port.OracleLimiterConfig(release_filter_order=2)
+    cfg = port.OracleConfig(limiter=lim)
+    x = port.synth_limiter_input(115000, seed=12)
+    x[40000:70000] *= 0.05
+    want = port.limit(x.astype(np.float64), cfg)
+    for inclusive in (1, 0):
+        lib.mgb_set_option(b"lookback_inclusive", inclusive)
+        try:
+            out, _ = _limit(lib, x, cfg)
+        finally:
+            lib.mgb_set_option(b"lookback_inclusive", 1)
+        assert np.abs(out - want).max() < 3e-7
