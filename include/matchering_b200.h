@@ -358,6 +358,11 @@ int mgb_resample(const float* d_in_lr, int64_t frames_in, int32_t rate_in, float
  * shared-memory kernel the pipeline uses; is_f64 selects the double variant (n in {F, 2F}). */
 int mgb_test_fft(int32_t n, int32_t is_f64, int32_t dir, const void* d_in, void* d_out, int32_t batch,
                  const void* d_twiddles, void* stream);
+/* the limiter's two scanned gain envelopes instead of its output: d_gains_out[n] = (attack gain g_att[n]
+ * (hyrax.py:48-51, the filtfilt result), release gain max(hold_out, release_out)[n] (hyrax.py:56-75)).  Same
+ * arguments as mgb_limit; kernels exist for the 44.1 / 96 kHz default windows. */
+int mgb_test_limiter_gains(const mgb_limiter_params* params, const float* d_in_lr, float* d_gains_out, int64_t frames,
+                           void* d_workspace, int64_t workspace_bytes, int32_t* d_engaged, void* stream);
 /* the FIR design alone from given average spectra: d_avg = [4][n_lin] doubles
  * (target mid, target side, reference mid, reference side), already scaled. d_fir_out [2][F]. */
 int mgb_test_design_fir(const mgb_plan* plan, const double* d_avg, double* d_fir_out, void* d_workspace,

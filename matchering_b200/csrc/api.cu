@@ -545,8 +545,8 @@ int64_t mgb_limiter_workspace_bytes(const mgb_limiter_params* params, int64_t fr
     return kLimitHeader + limiter_lookback_bytes(*params, frames);
 }
 
-int mgb_limit(const mgb_limiter_params* params, const float* d_in_lr, float* d_out_lr, int64_t frames,
-              void* d_workspace, int64_t workspace_bytes, int32_t* d_engaged, void* stream) {
+static int limit_impl(const mgb_limiter_params* params, const float* d_in_lr, float* d_out_lr, int64_t frames,
+                      void* d_workspace, int64_t workspace_bytes, int32_t* d_engaged, void* stream, bool gains_only) {
     MGB_REQUIRE(params != nullptr, MGB_ERR_INVALID, "params is NULL");
     MGB_TRY(check_aligned(d_in_lr, "d_in_lr"));
     MGB_TRY(check_aligned(d_out_lr, "d_out_lr"));
@@ -572,7 +572,17 @@ int mgb_limit(const mgb_limiter_params* params, const float* d_in_lr, float* d_o
     MGB_TRY(launch_absmax((const float2*)d_in_lr, frames, peak, st));
     MGB_TRY(launch_limiter_engaged(peak, nullptr, params->threshold, d_engaged, st));
     return launch_limiter(*params, (const float2*)d_in_lr, (float2*)d_out_lr, frames, nullptr, nullptr, d_engaged, ticket,
-                          base + kLimitHeader, tables, st);
+                          base + kLimitHeader, tables, st, gains_only);
+}
+
+int mgb_limit(const mgb_limiter_params* params, const float* d_in_lr, float* d_out_lr, int64_t frames,
+              void* d_workspace, int64_t workspace_bytes, int32_t* d_engaged, void* stream) {
+    return limit_impl(params, d_in_lr, d_out_lr, frames, d_workspace, workspace_bytes, d_engaged, stream, false);
+}
+
+int mgb_test_limiter_gains(const mgb_limiter_params* params, const float* d_in_lr, float* d_gains_out, int64_t frames,
+                           void* d_workspace, int64_t workspace_bytes, int32_t* d_engaged, void* stream) {
+    return limit_impl(params, d_in_lr, d_gains_out, frames, d_workspace, workspace_bytes, d_engaged, stream, true);
 }
 
 int mgb_process_host(const mgb_plan* plan, const mgb_track_layout* L, const float* h_target_lr,

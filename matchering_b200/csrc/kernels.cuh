@@ -102,7 +102,7 @@ int launch_convert_f32_f64(const float* in, double* out, int64_t count, cudaStre
 // limiter.cu ------------------------------------------------------------------------------------
 int launch_limiter(const mgb_limiter_params& lp, const float2* in, float2* out, int64_t frames, const double* pre_gain,
                    const double* post_gain, const int* engaged, int* ticket, void* lookback, const void* tables,
-                   cudaStream_t stream);
+                   cudaStream_t stream, bool gains_only = false);
 int launch_limiter_tables(const mgb_limiter_params& lp, void* tables, cudaStream_t stream);
 int launch_limiter_engaged(const float* peak_bits, const double* pre_gain, double threshold, int* engaged,
                            cudaStream_t stream);

@@ -310,7 +310,9 @@ __global__ void limiter_tables_kernel(mgb_limiter_params lp, int span_ept, unsig
 
 // NO = order capacity of the hold and release sections: 1 (the reference defaults: scalar scans, tables in shared
 // memory) or MGB_MAX_FILTER_ORDER = 2 (orders 1..2 zero-padded to 2; tables read through L1).
-template <int EPT, int NO>
+// GAINS (tests only, mgb_test_limiter_gains): instead of the limited samples, write the two float64-scan results
+// per frame: (g_att, the attack filter's gain; max(hold_out, release_out), the release gain).
+template <int EPT, int NO, bool GAINS = false>
 __global__ void __launch_bounds__(NT, NO == 1 ? 2 : 1)
 limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__ in, float2* __restrict__ out,
                long long frames, const double* __restrict__ pre_gain, const double* __restrict__ post_gain,
@@ -602,7 +604,10 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
             const int i = tid * EPT + e;
-            if (i >= cidx && i < cidx + LC) G[i] = fmaxf(G[i], (float)(y[e] + pow_att->pe[EPT - e] * back));
+            if (i >= cidx && i < cidx + LC) {
+                const float att = (float)(y[e] + pow_att->pe[EPT - e] * back);
+                G[i] = GAINS ? att : fmaxf(G[i], att);
+            }
         }
     }
 
@@ -683,12 +688,7 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
             for (int i = 0; i < NO; ++i) rel_y[e] += tab_rel->pe[e][i] * rel_prev.v[i];
             const int i = cidx + tid * CORE_EPT + e;
             const double g_rel = fmax(hold_y[e], rel_y[e]);            // hyrax.py:75
-#ifdef MGB_LIM_DEBUG
-            Fd[tid * CORE_EPT + e] = hold_y[e];
-            G[i] = (float)rel_y[e];
-#else
-            Fd[tid * CORE_EPT + e] = 1.0 - fmax((double)G[i], g_rel);  // hyrax.py:97
-#endif
+            Fd[tid * CORE_EPT + e] = GAINS ? g_rel : 1.0 - fmax((double)G[i], g_rel);  // hyrax.py:97
         }
         if (tid == NT - 1 && gm.publish_inclusive) {
 #pragma unroll
@@ -696,11 +696,8 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
             publish_state<NO>(slot_rel, end, 2);
         }
     }
-#ifdef MGB_LIM_DEBUG
-    __syncthreads();
-#else
-    __syncwarp();  // a warp applies the gains of its own 32*CORE_EPT consecutive samples: no block barrier
-#endif
+    if (GAINS) __syncthreads();  // (the attack gains in G were written in another mapping)
+    else __syncwarp();           // a warp applies the gains of its own 32*CORE_EPT consecutive samples: no block barrier
 
     // ---- P7: apply (hyrax.py:99, stages.py:203) -----------------------------------------------------
     // The gains sit in shared memory in the filters' mapping (thread t: samples t*CORE_EPT ..); lane l of
@@ -717,13 +714,13 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
         for (int q = 0; q < CORE_EPT; ++q) {
             const int k = wbase + q * 32;
             if (k < core_n) {
-#ifdef MGB_LIM_DEBUG
-                out[s0 + k] = make_float2((float)Fd[k], G[cidx + k]);
-#else
-                // (in float64 to the end: a frame the hard clip brings to the threshold must round to it exactly)
-                const double gain = Fd[k] * scale;
-                out[s0 + k] = make_float2((float)((double)v[q].x * gain), (float)((double)v[q].y * gain));
-#endif
+                if (GAINS) {
+                    out[s0 + k] = make_float2(G[cidx + k], (float)Fd[k]);
+                } else {
+                    // (in float64 to the end: a frame the hard clip brings to the threshold must round to it exactly)
+                    const double gain = Fd[k] * scale;
+                    out[s0 + k] = make_float2((float)((double)v[q].x * gain), (float)((double)v[q].y * gain));
+                }
             }
         }
     }
@@ -891,7 +888,7 @@ int launch_limiter_tables(const mgb_limiter_params& lp, void* tables, cudaStream
 
 int launch_limiter(const mgb_limiter_params& lp, const float2* in, float2* out, int64_t frames, const double* pre_gain,
                    const double* post_gain, const int* engaged, int* ticket, void* lookback, const void* tables,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, bool gains_only) {
     LimiterGeom g;
     MGB_TRY(limiter_geometry(lp, &g));
     MGB_REQUIRE(frames > 6, MGB_ERR_INVALID, "limiter: the input must be longer than filtfilt's padlen (6)");
@@ -899,6 +896,18 @@ int launch_limiter(const mgb_limiter_params& lp, const float2* in, float2* out, 
     const int64_t chunks = (frames + LC - 1) / LC;
     const size_t smem = (size_t)g.ept * NT * 16 + (size_t)g.margin * 8;
     const int no = limiter_order_capacity(lp);
+    if (gains_only) {  // test entry: the sample rates of the golden vectors (44.1 and 96 kHz windows), both capacities
+        auto go = [&](auto kernel) {
+            return launch("limiter_kernel", kernel, dim3((unsigned)chunks), dim3(NT), smem, stream, lp, g, in, out,
+                          (long long)frames, pre_gain, post_gain, engaged, ticket, (LookbackWord*)lookback,
+                          (const unsigned char*)tables);
+        };
+        if (no == 1 && g.ept == 11) return go(limiter_kernel<11, 1, true>);
+        if (no == 1 && g.ept == 13) return go(limiter_kernel<13, 1, true>);
+        if (no == MGB_MAX_FILTER_ORDER && g.ept == 11) return go(limiter_kernel<11, MGB_MAX_FILTER_ORDER, true>);
+        set_error("limiter gains (test entry): no kernel for %d span samples per thread at order capacity %d", g.ept, no);
+        return MGB_ERR_UNSUPPORTED;
+    }
 #define MGB_LIMITER_CASE(E)                                                                                           \
     case E:                                                                                                           \
         if (no == 1)                                                                                                  \

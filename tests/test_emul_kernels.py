@@ -588,3 +588,32 @@ def test_second_order_release_filter_over_many_chunks(lib):
         finally:
             lib.mgb_set_option(b"lookback_inclusive", 1)
         assert np.abs(out - want).max() < 3e-7
+
+
+def _limiter_gains(lib, x, cfg):
+    params = limiter_params(plan_mod.limiter_constants(cfg))
+    n = len(x)
+    ws_bytes = int(lib.mgb_limiter_workspace_bytes(C.byref(params), n))
+    ws = aligned((ws_bytes,), np.uint8)
+    xin, out = aligned_copy(x, np.float32), aligned((n, 2), np.float32)
+    engaged = aligned((4,), np.int32)
+    _native.check(lib, lib.mgb_test_limiter_gains(C.byref(params), ptr(xin), ptr(out), n, ptr(ws), ws_bytes, ptr(engaged), None))
+    return out
+
+
+def test_limiter_gain_envelopes_match_golden(lib, golden):
+    """The limiter's two scanned envelopes themselves -- the attack gain (filtfilt, hyrax.py:43-53) and the release
+    gain (hold / release low-passes, hyrax.py:56-75) -- against the UNMODIFIED reference's private helpers
+    (tests/golden/limiter.npz), not just the samples they end up scaling."""
+    g = golden("limiter.npz")
+    gains = _limiter_gains(lib, g["x"], port.OracleConfig())
+    assert np.abs(gains[:, 0] - g["gain_attack"]).max() < 2e-7
+    assert np.abs(gains[:, 1] - g["gain_release"]).max() < 2e-7
+    # and with second-order sections (golden from the oracle's trace)
+    lim = port.OracleLimiterConfig(hold_filter_order=2, release_filter_order=2, release=30.0)
+    cfg = port.OracleConfig(limiter=lim)
+    trace = {}
+    port.limit(g["x"].astype(np.float64), cfg, trace)
+    gains2 = _limiter_gains(lib, g["x"], cfg)
+    assert np.abs(gains2[:, 0] - trace["g_att"]).max() < 2e-7
+    assert np.abs(gains2[:, 1] - np.maximum(trace["hold_out"], trace["rel_out"])).max() < 2e-7

@@ -761,3 +761,36 @@ def test_process_resamples_files_on_the_device(torch_cuda, tmp_path):
     want = port.main(t44, r44, port.OracleConfig(max_piece_size=2.0), False, True, False)[1]
     got, sr = wavio.read(str(tmp_path / "o.wav"))
     assert sr == 44100 and got.shape == want.shape and np.abs(got - want).max() < 2e-5
+
+
+def test_limiter_gain_envelopes_match_golden(torch_cuda, lib, golden):
+    """The limiter's two scanned envelopes on the device (mgb_test_limiter_gains) against the unmodified reference's
+    private helpers: attack gain (filtfilt) and release gain (hold / release low-passes), at 44.1 and 96 kHz windows."""
+    torch = torch_cuda
+    import port
+    from matchering_b200 import _native
+    from matchering_b200.engine import limiter_params
+    from matchering_b200.plan import limiter_constants
+    g = golden("limiter.npz")
+    x = torch.from_numpy(g["x"]).cuda()
+    n = x.shape[0]
+
+    def gains(cfg):
+        params = limiter_params(limiter_constants(cfg))
+        ws_bytes = int(lib.mgb_limiter_workspace_bytes(C.byref(params), n))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+        out = torch.empty((n, 2), dtype=torch.float32, device="cuda")
+        flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+        _native.check(lib, lib.mgb_test_limiter_gains(C.byref(params), x.data_ptr(), out.data_ptr(), n, ws.data_ptr(), ws_bytes,
+                                                      flag.data_ptr(), None))
+        return out.cpu().numpy()
+
+    got = gains(_config())
+    assert np.abs(got[:, 0] - g["gain_attack"]).max() < 2e-7
+    assert np.abs(got[:, 1] - g["gain_release"]).max() < 2e-7
+    for sr in (44100, 96000):
+        trace = {}
+        port.limit(g["x"].astype(np.float64), port.OracleConfig(internal_sample_rate=sr), trace)
+        got = gains(_config(internal_sample_rate=sr))
+        assert np.abs(got[:, 0] - trace["g_att"]).max() < 2e-7
+        assert np.abs(got[:, 1] - np.maximum(trace["hold_out"], trace["rel_out"])).max() < 2e-7
