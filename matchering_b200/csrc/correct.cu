@@ -68,7 +68,7 @@ clip_sumsq_kernel(const float* __restrict__ mid, long long piece, int divisions,
 
     // prologue, identical in every CTA: the previous step's coefficient from its per-piece sums, and
     // the gain accumulated so far (stages.py:161-168 applied lazily)
-    const double c_prev = correction_coefficient(prev_sums, divisions, piece, eps, state->reference_match_rms, red);
+    const double c_prev = correction_coefficient(prev_sums, divisions, piece, eps, state->reference_match_rms);  // per warp, no barrier
     double gain = c_prev;
     for (int j = 0; j < step - 1; ++j) gain *= state->correction[j];
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
@@ -92,13 +92,12 @@ clip_sumsq_kernel(const float* __restrict__ mid, long long piece, int divisions,
 
 // after the last step: its coefficient, the total gain, the result's peak, the limiter's early-out
 // flag (hyrax.py:83-85) and the normalisation coefficient (stages.py:186-191); one CTA
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32)
 correction_final_kernel(const double* __restrict__ last_sums, int divisions, long long piece, int steps, double eps,
                         double threshold, mgb_track_state* __restrict__ state) {
-    __shared__ double red[32];
     double gain = 1.0;
     if (steps > 0) {
-        const double c_last = correction_coefficient(last_sums, divisions, piece, eps, state->reference_match_rms, red);
+        const double c_last = correction_coefficient(last_sums, divisions, piece, eps, state->reference_match_rms);
         gain = c_last;
         for (int j = 0; j < steps - 1; ++j) gain *= state->correction[j];
         if (threadIdx.x == 0) state->correction[steps - 1] = c_last;
@@ -316,7 +315,7 @@ int launch_correction_final(const mgb_plan& plan, const mgb_track_layout& layout
                             mgb_track_state* state, cudaStream_t stream) {
     const int steps = plan.rms_correction_steps, div = layout.target_divisions;
     const double* last = ws.piece_sums + (long long)(steps > 0 ? steps - 1 : 0) * div;
-    return launch("correction_final_kernel", correction_final_kernel, dim3(1), dim3(256), 0, stream, last, div,
+    return launch("correction_final_kernel", correction_final_kernel, dim3(1), dim3(32), 0, stream, last, div,
                   (long long)layout.target_piece, steps, plan.min_value, plan.threshold, state);
 }
 

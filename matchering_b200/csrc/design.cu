@@ -355,8 +355,6 @@ __global__ void __launch_bounds__(kMeanBins * kMeanSlices)
 spectrum_mean_kernel(DesignArgs a, int n_lin, int fft_size, double eps, PrefetchList pf) {
     constexpr int BINS = kMeanBins, SLICES = kMeanSlices;
     __shared__ double part_t[SLICES][BINS + 1], part_r[SLICES][BINS + 1];
-    __shared__ double red_d[32];
-    __shared__ float red_f[32];
     MGB_DYN_SMEM(smem);  // loudest-piece masks: [div_t] then [div_r] bytes
     unsigned char* mask_t = smem;
     unsigned char* mask_r = smem + a.div_t;
@@ -369,10 +367,16 @@ spectrum_mean_kernel(DesignArgs a, int n_lin, int fft_size, double eps, Prefetch
             for (long long off = gtid * 128; off < pf.bytes[t]; off += gsize * 128)
                 prefetch_l2(reinterpret_cast<const char*>(pf.ptr[t]) + off);
     }
-    // Level statistics (match_levels.py:29-131), recomputed identically by every CTA from the
-    // analysis pass's partial sums; CTA (0,0) records them in the track state.
-    const LevelsResult lv = levels_compute(a.levels, mask_t, mask_r, red_d, red_f);
+    // Level statistics (match_levels.py:29-131), recomputed identically by every CTA from the analysis pass's
+    // partial sums: warp 0 does it with shuffles and leaves the masks and the scalars in shared memory (one
+    // barrier); CTA (0,0) records them in the track state.
+    __shared__ LevelsResult lv_s;
+    if (threadIdx.x < 32) {
+        const LevelsResult mine = levels_compute_warp(a.levels, mask_t, mask_r);
+        if (threadIdx.x == 0) lv_s = mine;
+    }
     __syncthreads();
+    const LevelsResult lv = lv_s;
     if (blockIdx.x == 0 && blockIdx.y == 0) {
         if (threadIdx.x == 0) {
             levels_store(lv, a.state);

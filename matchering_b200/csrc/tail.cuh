@@ -3,6 +3,9 @@
 // recomputes them in its prologue from the previous kernel's partial sums -- deterministic, so all
 // CTAs agree bit for bit -- instead of paying a single-CTA kernel launch or a last-block handshake
 // per step on a pipeline whose whole device time is a few hundred microseconds.
+// They run per WARP (lanes stride over the pieces, shuffles reduce): a dozen or so pieces do not fill a
+// block, and block-wide reductions cost three barriers each -- 21 barriers for the level statistics,
+// 9 per correction coefficient, which was most of the 25 us / 14 us their kernels took.
 #pragma once
 #include "common.cuh"
 
@@ -33,16 +36,20 @@ __device__ __forceinline__ double piece_rms(const double* part, int p, int slots
     return sqrt(s / piece);  // dsp.py:86
 }
 
-// Every thread of the block calls (barriers inside); mask_t[div_t] / mask_r[div_r] live in shared
-// memory and are valid after the call.
-__device__ __forceinline__ LevelsResult levels_compute(const LevelsArgs& a, unsigned char* mask_t, unsigned char* mask_r,
-                                                       double* red_d, float* red_f) {
-    const int tid = threadIdx.x, nthr = blockDim.x;
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// All 32 lanes of ONE warp call (no block barrier inside); every lane gets the result.  If `mask_t` /
+// `mask_r` (shared or global, [div_t] / [div_r]) are not null the warp writes the loudest-piece masks there.
+__device__ __forceinline__ LevelsResult levels_compute_warp(const LevelsArgs& a, unsigned char* mask_t, unsigned char* mask_r) {
+    const int lane = threadIdx.x & 31;
     LevelsResult out;
     float pk = 0.0f;
-    for (int i = tid; i < a.div_r * a.slots_r + 1; i += nthr) pk = fmaxf(pk, a.absmax_r[i]);
-    pk = block_max(pk, red_f);
-    out.peak = (double)pk;
+    for (int i = lane; i < a.div_r * a.slots_r + 1; i += 32) pk = fmaxf(pk, a.absmax_r[i]);
+    out.peak = (double)warp_max_f(pk);
     out.coef = 1.0;
     if (out.peak < a.threshold) out.coef = fmax(a.eps, out.peak / a.threshold);  // dsp.py:96-99
 
@@ -55,24 +62,23 @@ __device__ __forceinline__ LevelsResult levels_compute(const LevelsArgs& a, unsi
         const double piece = (double)(sig == 0 ? a.piece_t : a.piece_r);
         unsigned char* mask = sig == 0 ? mask_t : mask_r;
         double acc = 0.0;
-        for (int p = tid; p < div; p += nthr) {
+        for (int p = lane; p < div; p += 32) {
             const double r = piece_rms(part, p, slots, piece);
             acc += r * r;
         }
-        const double total = block_sum(acc, red_d);
-        const double avg = sqrt(total / (double)div);  // rms(rmses), match_levels.py:101
+        const double avg = sqrt(warp_sum(acc) / (double)div);  // rms(rmses), match_levels.py:101
         double accm = 0.0, cnt = 0.0;
-        for (int p = tid; p < div; p += nthr) {
+        for (int p = lane; p < div; p += 32) {
             const double r = piece_rms(part, p, slots, piece);
             const bool m = r >= avg;  // match_levels.py:65
-            mask[p] = m ? 1 : 0;
+            if (mask) mask[p] = m ? 1 : 0;
             if (m) {
                 accm += r * r;
                 cnt += 1.0;
             }
         }
-        const double tm = block_sum(accm, red_d);
-        const double tc = block_sum(cnt, red_d);
+        const double tm = warp_sum(accm);
+        const double tc = warp_sum(cnt);
         match[sig] = sqrt(tm / tc);
         loud[sig] = (int)tc;
     }
@@ -101,23 +107,24 @@ __device__ __forceinline__ void levels_store(const LevelsResult& r, mgb_track_st
 }
 
 // ---- one RMS-correction step's coefficient from its per-piece sums (stages.py:153-168) -------------
-// Every thread of the block calls (barriers inside); all get the coefficient.
+// All 32 lanes of a warp call (no block barrier); every lane -- and, the arithmetic being the same in every
+// warp, every warp of every CTA -- gets the same coefficient.
 __device__ __forceinline__ double correction_coefficient(const double* sums, int divisions, long long piece, double eps,
-                                                         double reference_match_rms, double* red) {
-    const int tid = threadIdx.x, nthr = blockDim.x;
+                                                         double reference_match_rms) {
+    const int lane = threadIdx.x & 31;
     double acc = 0.0;
-    for (int p = tid; p < divisions; p += nthr) acc += sums[p] / (double)piece;  // rms^2
-    const double avg = sqrt(block_sum(acc, red) / (double)divisions);
+    for (int p = lane; p < divisions; p += 32) acc += sums[p] / (double)piece;  // rms^2
+    const double avg = sqrt(warp_sum(acc) / (double)divisions);
     double accm = 0.0, cnt = 0.0;
-    for (int p = tid; p < divisions; p += nthr) {
+    for (int p = lane; p < divisions; p += 32) {
         const double r = sqrt(sums[p] / (double)piece);
         if (r >= avg) {
             accm += r * r;
             cnt += 1.0;
         }
     }
-    const double tm = block_sum(accm, red);
-    const double tc = block_sum(cnt, red);
+    const double tm = warp_sum(accm);
+    const double tc = warp_sum(cnt);
     return reference_match_rms / fmax(eps, sqrt(tm / tc));
 }
 
