@@ -368,12 +368,43 @@ spectrum_mean_kernel(DesignArgs a, int n_lin, int fft_size, double eps, Prefetch
                 prefetch_l2(reinterpret_cast<const char*>(pf.ptr[t]) + off);
     }
     // Level statistics (match_levels.py:29-131), recomputed identically by every CTA from the analysis pass's
-    // partial sums: warp 0 does it with shuffles and leaves the masks and the scalars in shared memory (one
-    // barrier); CTA (0,0) records them in the track state.
+    // partial sums.  The partial sums are folded per piece by the whole block first -- one warp per piece, lanes
+    // over its slots, so every load is in flight at once (a lane walking a piece's 34 slots alone was 25 us of
+    // serial L2 latency) -- then warp 0 derives the statistics from the per-piece sums with shuffles and leaves
+    // the masks and the scalars in shared memory; CTA (0,0) records them in the track state.
     __shared__ LevelsResult lv_s;
-    if (threadIdx.x < 32) {
-        const LevelsResult mine = levels_compute_warp(a.levels, mask_t, mask_r);
-        if (threadIdx.x == 0) lv_s = mine;
+    __shared__ unsigned peak_bits_s;
+    double* piece_sum = reinterpret_cast<double*>(smem + ((a.div_t + a.div_r + 15) / 16) * 16);  // [div_t + div_r]
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        if (threadIdx.x == 0) peak_bits_s = 0u;
+        __syncthreads();
+        float pk = 0.0f;
+        for (int i = threadIdx.x; i < a.div_r * a.slots_r + 1; i += blockDim.x) pk = fmaxf(pk, a.levels.absmax_r[i]);
+        pk = warp_max_f(pk);
+        if (lane == 0 && pk > 0.0f) atomicMax(&peak_bits_s, __float_as_uint(pk));  // non-negative floats order like their bits
+        for (int p = warp; p < a.div_t + a.div_r; p += nwarps) {
+            const bool is_t = p < a.div_t;
+            const double* part = is_t ? a.levels.sumsq_t + (long long)p * a.slots_t
+                                      : a.levels.sumsq_r + (long long)(p - a.div_t) * a.slots_r;
+            const int slots = is_t ? a.slots_t : a.slots_r;
+            double sum = 0.0;
+            for (int k = lane; k < slots; k += 32) sum += part[k];
+            sum = warp_sum(sum);
+            if (lane == 0) piece_sum[p] = sum;
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            LevelsArgs folded = a.levels;
+            folded.sumsq_t = piece_sum;
+            folded.sumsq_r = piece_sum + a.div_t;
+            folded.slots_t = folded.slots_r = 1;
+            const float peak = __uint_as_float(peak_bits_s);
+            folded.absmax_r = &peak;
+            folded.div_r_items_override = 1;
+            const LevelsResult mine = levels_compute_warp(folded, mask_t, mask_r);
+            if (threadIdx.x == 0) lv_s = mine;
+        }
     }
     __syncthreads();
     const LevelsResult lv = lv_s;
@@ -656,6 +687,7 @@ int launch_design(const mgb_plan& plan, const mgb_track_layout& layout, const Wo
     a.levels.slots_r = layout.reference_slots;
     a.levels.threshold = plan.threshold;
     a.levels.eps = plan.min_value;
+    a.levels.div_r_items_override = 0;
     a.div_t = layout.target_divisions;
     a.slots_t = layout.target_slots;
     a.div_r = layout.reference_divisions;
@@ -698,7 +730,9 @@ int launch_design(const mgb_plan& plan, const mgb_track_layout& layout, const Wo
         add(plan.d_hann, F * 8);
         MGB_TRY(launch("spectrum_mean_kernel", spectrum_mean_kernel, dim3((plan.n_lin + kMeanBins - 1) / kMeanBins, 2),
                        dim3(kMeanBins * kMeanSlices),
-                       (size_t)(layout.target_divisions + layout.reference_divisions + 16), stream, a, plan.n_lin,
+                       (size_t)((layout.target_divisions + layout.reference_divisions + 15) / 16 * 16 +
+                                (layout.target_divisions + layout.reference_divisions) * 8 + 16),
+                       stream, a, plan.n_lin,
                        plan.fft_size, plan.min_value, pf));
     }
     if (plan.d_smooth_op && plan.d_smooth_op_rows && !(avg_override && g_design_direct)) {

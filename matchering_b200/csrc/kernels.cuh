@@ -46,6 +46,8 @@ struct ScanPow {
     double pc[33];  // P^k, P = p^kLimiterCore: weight of a chunk k chunks back (look-back)
 };
 
+constexpr int kLookbackJumps = 64;  // look-back windows with tabulated weights: 2048 chunks = 9.4 M samples back
+
 // Powers of the companion matrix C of an order-N recursive section (hold / release low-pass) for the same blocked
 // scan over its state (y[n-1], ..., y[n-N]); N = 1 is a scalar pole.
 template <int N>
@@ -54,6 +56,8 @@ struct SectionTab {
     double ql[33][N][N];  // C^(ept*k)
     double qw[17][N][N];  // C^(ept*32*k)
     double pc[33][N][N];  // C^(kLimiterCore*k): a chunk k chunks back (look-back)
+    double pj[kLookbackJumps][N][N];  // C^(kLimiterCore*32*j): the look-back's j-th window of 32 chunks, tabulated
+                                      // directly (a running product of pc[32] loses a digit per step for a pole pair)
 };
 
 constexpr int kLimiterThreads = 512;

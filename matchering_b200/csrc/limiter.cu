@@ -218,14 +218,71 @@ __device__ __forceinline__ StVec<N> lookback(const LookbackWord* words /* this s
                                              const SectionTab<N>* t) {
     constexpr int STRIDE = 2 * N;  // words per chunk: hold[N] then release[N]
     const int lane = threadIdx.x & 31;
+    if constexpr (N == 1) {
+        // a single pole: scalar weights, the running product P^32, P^64, ... is exact enough (no table)
+        double acc1 = 0.0, m1 = 1.0;
+        for (int base = chunk - 1; base >= 0 && m1 > 1e-9; base -= 32) {
+            const int j = base - lane;
+            int st = 2;  // before the first chunk: inclusive state 0 (lfilter starts from rest)
+            double val = 0.0;
+            if (j >= 0) {
+                const LookbackWord* w = words + (long long)j * STRIDE;
+                while ((st = poll(w, &val)) == 0) __nanosleep(20);
+            }
+            const unsigned inclusive = __ballot_sync(0xffffffffu, st == 2);
+            const int first = inclusive ? __ffs((int)inclusive) - 1 : 32;
+            if (lane <= first) acc1 += m1 * t->pc[lane][0][0] * val;
+            if (inclusive) break;
+            m1 *= t->pc[32][0][0];
+        }
+        StVec<N> out;
+        out.v[0] = warp_sum(acc1);
+        return out;
+    }
     StVec<N> acc = st_zero<N>();
-    double mult[N][N];
+    double mult[N][N];  // C^(LC*32*jump): weight of this window's nearest chunk
+    int jump = 0;       // windows of 32 chunks already behind us
+    for (int base = chunk - 1; base >= 0; base -= 32, ++jump) {
+        // From the table (a running product would cost a digit per multiplication for a pole pair); beyond
+        // the table -- 2048 chunks back, where the weights of any ordinary release are long below the cut-off
+        // -- the product of what is left is good enough.
+        if (N > 1 && jump < kLookbackJumps) {
 #pragma unroll
-    for (int r = 0; r < N; ++r)
+            for (int r = 0; r < N; ++r)
 #pragma unroll
-        for (int c = 0; c < N; ++c) mult[r][c] = r == c ? 1.0 : 0.0;
-    double bound = 1.0;
-    for (int base = chunk - 1; base >= 0 && bound > 1e-9; base -= 32) {
+                for (int c = 0; c < N; ++c) mult[r][c] = t->pj[jump][r][c];
+        } else if (jump == 0) {
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int c = 0; c < N; ++c) mult[r][c] = r == c ? 1.0 : 0.0;
+        } else {  // (a single pole: the running product is exact enough, no table)
+            double next[N][N];
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int c = 0; c < N; ++c) {
+                    double sum = 0.0;
+#pragma unroll
+                    for (int k = 0; k < N; ++k) sum += mult[r][k] * t->pc[32][k][c];
+                    next[r][c] = sum;
+                }
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int c = 0; c < N; ++c) mult[r][c] = next[r][c];
+        }
+        // (past its peak at 1/(1-|p|) samples the norm of C^m only falls: once this window's nearest chunk
+        // weighs less than 1e-9, so does everything behind it)
+        double bound = 0.0;
+#pragma unroll
+        for (int r = 0; r < N; ++r) {
+            double rowsum = 0.0;
+#pragma unroll
+            for (int c = 0; c < N; ++c) rowsum += fabs(mult[r][c]);
+            bound = fmax(bound, rowsum);
+        }
+        if (bound <= 1e-9) break;
         const int j = base - lane;
         int st = 2;  // before the first chunk: inclusive state 0 (lfilter starts from rest)
         StVec<N> val = st_zero<N>();
@@ -244,26 +301,6 @@ __device__ __forceinline__ StVec<N> lookback(const LookbackWord* words /* this s
         const int first = inclusive ? __ffs((int)inclusive) - 1 : 32;
         if (lane <= first) st_addmul<N>(acc, mult, st_mul<N>(t->pc[lane], val));
         if (inclusive) break;
-        // mult <- mult * P^32, and its infinity norm as the bound on what lies further back
-        double next[N][N];
-        bound = 0.0;
-#pragma unroll
-        for (int r = 0; r < N; ++r) {
-            double rowsum = 0.0;
-#pragma unroll
-            for (int c = 0; c < N; ++c) {
-                double s = 0.0;
-#pragma unroll
-                for (int k = 0; k < N; ++k) s += mult[r][k] * t->pc[32][k][c];
-                next[r][c] = s;
-                rowsum += fabs(s);
-            }
-            bound = fmax(bound, rowsum);
-        }
-#pragma unroll
-        for (int r = 0; r < N; ++r)
-#pragma unroll
-            for (int c = 0; c < N; ++c) mult[r][c] = next[r][c];
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) acc.v[i] = warp_sum(acc.v[i]);
@@ -305,6 +342,7 @@ __global__ void limiter_tables_kernel(mgb_limiter_params lp, int span_ept, unsig
         if (i < 33) t->ql[i][0][0] = pow(p, (double)(CORE_EPT * i));
         if (i < 17) t->qw[i][0][0] = pow(p, (double)(CORE_EPT * 32 * i));
         if (i < 33) t->pc[i][0][0] = pow(p, (double)LC * (double)i);
+        for (int j = i; j < kLookbackJumps; j += blockDim.x) t->pj[j][0][0] = pow(p, (double)LC * 32.0 * (double)j);
     }
 }
 
@@ -842,6 +880,7 @@ static void fill_section_tables(const double* a, SectionTab<2>* t) {
     for (int k = 0; k < 33; ++k) sp.power((long long)CORE_EPT * k, t->ql[k]);
     for (int k = 0; k < 17; ++k) sp.power((long long)CORE_EPT * 32 * k, t->qw[k]);
     for (int k = 0; k < 33; ++k) sp.power((long long)LC * k, t->pc[k]);
+    for (int j = 0; j < kLookbackJumps; ++j) sp.power((long long)LC * 32 * j, t->pj[j]);
 }
 
 static void fill_attack_tables(double p, int span_ept, ScanPow* t) {

@@ -19,6 +19,7 @@ struct LevelsArgs {
     long long piece_t, piece_r;
     int div_t, slots_t, div_r, slots_r;
     double threshold, eps;
+    int div_r_items_override;  // > 0: absmax_r holds this many entries (already folded), not div_r*slots_r + 1
 };
 
 struct LevelsResult {
@@ -48,7 +49,8 @@ __device__ __forceinline__ LevelsResult levels_compute_warp(const LevelsArgs& a,
     const int lane = threadIdx.x & 31;
     LevelsResult out;
     float pk = 0.0f;
-    for (int i = lane; i < a.div_r * a.slots_r + 1; i += 32) pk = fmaxf(pk, a.absmax_r[i]);
+    const int peaks = a.div_r_items_override > 0 ? a.div_r_items_override : a.div_r * a.slots_r + 1;
+    for (int i = lane; i < peaks; i += 32) pk = fmaxf(pk, a.absmax_r[i]);
     out.peak = (double)warp_max_f(pk);
     out.coef = 1.0;
     if (out.peak < a.threshold) out.coef = fmax(a.eps, out.peak / a.threshold);  // dsp.py:96-99

@@ -195,25 +195,31 @@ class PinnedBlock:
     def __del__(self):
         pool, self._pool = self._pool, None
         if pool is not None:
-            pool.release(self._ptr, self._capacity)
+            try:
+                pool.release(self._ptr, self._capacity)
+            except Exception:  # interpreter shutdown: the library may already be gone
+                pass
 
 
 class PinnedPool:
     GRANULE = 2 << 20
 
     def __init__(self, lib, keep_bytes: int):
+        import threading
         self.lib, self.keep_bytes = lib, keep_bytes
         self.free: dict = {}
         self.cached = 0
+        self._lock = threading.Lock()  # arrays are dropped (and blocks released) from whatever thread holds the last reference
 
     def array(self, shape, dtype) -> np.ndarray:
         nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
         capacity = max(self.GRANULE, (nbytes + self.GRANULE - 1) // self.GRANULE * self.GRANULE)
-        stack = self.free.get(capacity)
-        if stack:
-            ptr = stack.pop()
-            self.cached -= capacity
-        else:
+        with self._lock:
+            stack = self.free.get(capacity)
+            ptr = stack.pop() if stack else None
+            if ptr is not None:
+                self.cached -= capacity
+        if ptr is None:
             ptr = self.lib.mgb_host_alloc(capacity)
             if not ptr:
                 self.trim(0)
@@ -223,17 +229,23 @@ class PinnedPool:
         return np.asarray(PinnedBlock(self, ptr, capacity, shape, dtype))
 
     def release(self, ptr: int, capacity: int) -> None:
-        if self.cached + capacity > self.keep_bytes:
+        with self._lock:
+            keep = self.cached + capacity <= self.keep_bytes
+            if keep:
+                self.free.setdefault(capacity, []).append(ptr)
+                self.cached += capacity
+        if not keep:
             self.lib.mgb_host_free(ptr)
-            return
-        self.free.setdefault(capacity, []).append(ptr)
-        self.cached += capacity
 
     def trim(self, keep_bytes: int) -> None:
-        for capacity, stack in self.free.items():
-            while stack and self.cached > keep_bytes:
-                self.lib.mgb_host_free(stack.pop())
-                self.cached -= capacity
+        drop = []
+        with self._lock:
+            for capacity, stack in self.free.items():
+                while stack and self.cached > keep_bytes:
+                    drop.append(stack.pop())
+                    self.cached -= capacity
+        for ptr in drop:
+            self.lib.mgb_host_free(ptr)
 
 
 class HostIO:
@@ -249,6 +261,8 @@ class HostIO:
         chunk = int(os.environ.get("MGB_HOST_CHUNK", "0"))  # samples per ring chunk (tuning)
         _native.check(self.lib, self.lib.mgb_host_io_create(threads, chunk, 0, C.byref(handle)))
         self.handle = handle
+        import threading
+        self.lock = threading.Lock()  # one transfer at a time per mgb_host_io (ctypes drops the GIL during a call)
         self.pool = PinnedPool(self.lib, int(float(os.environ.get("MGB_PINNED_CACHE_GB", "4")) * (1 << 30)))
 
     @classmethod
@@ -309,10 +323,12 @@ def stages_main_host(plan: DevicePlan, target: np.ndarray, reference: np.ndarray
             for need in (need_default, need_no_limiter, need_no_limiter_normalized)]
     state = _native.TrackState()
     ptr = lambda a: a.ctypes.data if a is not None else None
-    _native.check(io.lib, io.lib.mgb_stages_main_host(
-        io.handle, C.byref(plan.struct), C.byref(sess.layout), target.ctypes.data, reference.ctypes.data, width,
-        ptr(outs[0]), ptr(outs[1]), ptr(outs[2]), width, C.byref(sess.host_buffers), C.byref(state),
-        _stream_ptr(plan.device)))
+    with io.lock:
+        status = io.lib.mgb_stages_main_host(
+            io.handle, C.byref(plan.struct), C.byref(sess.layout), target.ctypes.data, reference.ctypes.data, width,
+            ptr(outs[0]), ptr(outs[1]), ptr(outs[2]), width, C.byref(sess.host_buffers), C.byref(state),
+            _stream_ptr(plan.device))
+    _native.check(io.lib, status)
     return tuple(outs), state
 
 

@@ -52,7 +52,7 @@ def _limit_host(array: np.ndarray, params, device, lib):
         raise ValueError("The length of the input vector x must be greater than padlen, which is 6.")
     io = HostIO.get()
     with torch.cuda.device(device):
-        key = (device.index, frames)
+        key = (device.index, frames, params.hold_order, params.release_order)  # (the workspace depends on the orders)
         bufs = _LIMIT_BUFFERS.get(key)
         if bufs is None:
             _LIMIT_BUFFERS.clear()  # one size cached: an hour of audio is 1.3 GB per buffer
@@ -68,10 +68,12 @@ def _limit_host(array: np.ndarray, params, device, lib):
         out = io.pool.array(array.shape, array.dtype)
         engaged = C.c_int32(0)
         width = array.dtype.itemsize
-        _native.check(lib, lib.mgb_limit_host(
-            io.handle, C.byref(params), array.ctypes.data, width, out.ctypes.data, width, frames, bufs["x"].data_ptr(),
-            bufs["y"].data_ptr(), bufs["wide"].data_ptr() if bufs["wide"] is not None else None, bufs["ws"].data_ptr(),
-            bufs["ws_bytes"], bufs["engaged"].data_ptr(), C.byref(engaged), _stream_ptr(device)))
+        with io.lock:
+            status = lib.mgb_limit_host(
+                io.handle, C.byref(params), array.ctypes.data, width, out.ctypes.data, width, frames, bufs["x"].data_ptr(),
+                bufs["y"].data_ptr(), bufs["wide"].data_ptr() if bufs["wide"] is not None else None, bufs["ws"].data_ptr(),
+                bufs["ws_bytes"], bufs["engaged"].data_ptr(), C.byref(engaged), _stream_ptr(device))
+        _native.check(lib, status)
     if engaged.value == 0:
         debug("The limiter is not needed!")
         return array

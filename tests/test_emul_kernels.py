@@ -575,19 +575,21 @@ def test_resampler_matches_oracle(lib, rate_in, rate_out, n):
 def test_second_order_release_filter_over_many_chunks(lib):
     """The default 3-second release as an order-2 section: its pole pair sits 3e-5 apart, and weights of whole chunks
     (companion-matrix powers up to C^147456) must be exact -- repeated squaring in float64 was off by 3e-3 there and
-    cost 2e-5 in the output; the tables come from the closed form in extended precision (limiter.cu SectionPowers)."""
-    lim = port.OracleLimiterConfig(release_filter_order=2)
-    cfg = port.OracleConfig(limiter=lim)
-    x = port.synth_limiter_input(115000, seed=12)
-    x[40000:70000] *= 0.05
-    want = port.limit(x.astype(np.float64), cfg)
-    for inclusive in (1, 0):
-        lib.mgb_set_option(b"lookback_inclusive", inclusive)
-        try:
-            out, _ = _limit(lib, x, cfg)
-        finally:
-            lib.mgb_set_option(b"lookback_inclusive", 1)
-        assert np.abs(out - want).max() < 3e-7
+    cost 2e-5 in the output; the tables come from the closed form in extended precision (limiter.cu SectionPowers),
+    including the weights of whole look-back windows (a running product of C^147456 cost 5e-6 at 96 kHz)."""
+    for sr, n in ((44100, 115000), (96000, 330000)):  # 25 chunks; 72 chunks = three look-back windows of 32
+        lim = port.OracleLimiterConfig(release_filter_order=2, hold_filter_order=2 if sr == 96000 else 1)
+        cfg = port.OracleConfig(internal_sample_rate=sr, limiter=lim)
+        x = port.synth_limiter_input(n, seed=12)
+        x[n // 3:n // 2] *= 0.05
+        want = port.limit(x.astype(np.float64), cfg)
+        for inclusive in (1, 0):  # 0: aggregates only, every look-back walks all its predecessors (on the device a
+            lib.mgb_set_option(b"lookback_inclusive", inclusive)  # chunk often finds only aggregates for a while)
+            try:
+                out, _ = _limit(lib, x, cfg)
+            finally:
+                lib.mgb_set_option(b"lookback_inclusive", 1)
+            assert np.abs(out - want).max() < 3e-7
 
 
 def _limiter_gains(lib, x, cfg):
