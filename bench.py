@@ -60,9 +60,9 @@ def parse_args():
     ap.add_argument("--seconds", type=float, default=None, help="override the workload's track length (tuning runs only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-files", action="store_true", help="skip the mg.process-on-WAV-files leg")
-    ap.add_argument("--reference-budget-s", type=float, default=300.0,
+    ap.add_argument("--reference-budget-s", type=float, default=360.0,
                     help="reference arm: wall-clock budget for all steps; the per-step sample shrinks to fit")
-    ap.add_argument("--lanes", type=int, default=3, help="tracks in flight per GPU for the device-resident number")
+    ap.add_argument("--lanes", type=int, default=6, help="tracks in flight per GPU for the device-resident number")
     ap.add_argument("--opt", action="append", default=[], help="library switch name=value (A/B measurements)")
     return ap.parse_args()
 
