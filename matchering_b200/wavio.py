@@ -87,6 +87,39 @@ def write(path: str, array: np.ndarray, sample_rate: int, subtype: str) -> None:
         f.write(b"RIFF" + struct.pack("<I", len(body)) + body)
 
 
+_IO_POOL = None
+_IO_SLICE = 4 << 20
+
+
+def _sliced_io(fd: int, view: memoryview, offset: int, write: bool) -> None:
+    """pread / pwrite of a large buffer in 4 MB slices on a few threads (the calls release the GIL): the copy between
+    the page cache and the (pinned) buffer is a single-threaded memcpy per call, 5 GB/s; eight of them in parallel move
+    a 32 MB track in a couple of milliseconds instead of seven."""
+    global _IO_POOL
+    n = len(view)
+    if n <= _IO_SLICE:
+        done = 0
+        while done < n:
+            k = os.pwrite(fd, view[done:], offset + done) if write else os.preadv(fd, [view[done:]], offset + done)
+            if k <= 0:
+                raise OSError("short read" if not write else "short write")
+            done += k
+        return
+    if _IO_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _IO_POOL = ThreadPoolExecutor(max_workers=8, thread_name_prefix="mgb-io")
+
+    def one(lo: int) -> None:
+        hi = min(n, lo + _IO_SLICE)
+        while lo < hi:
+            k = os.pwrite(fd, view[lo:hi], offset + lo) if write else os.preadv(fd, [view[lo:hi]], offset + lo)
+            if k <= 0:
+                raise OSError("short read" if not write else "short write")
+            lo += k
+
+    list(_IO_POOL.map(one, range(0, n, _IO_SLICE)))
+
+
 def write_pcm(path: str, pcm: np.ndarray, sample_rate: int, bits: int, channels: int = 2) -> None:
     """Already-quantised samples (int16 (frames, ch) or packed 24-bit uint8 (frames, 3*ch)) -> WAV.  The
     samples go from the caller's buffer (pinned, when they come from the device) straight into the file."""
@@ -95,11 +128,12 @@ def write_pcm(path: str, pcm: np.ndarray, sample_rate: int, bits: int, channels:
     block = channels * bits // 8
     fmt = struct.pack("<HHIIHH", _PCM, channels, int(sample_rate), int(sample_rate) * block, block, bits)
     head = b"WAVE" + b"fmt " + struct.pack("<I", len(fmt)) + fmt + b"data" + struct.pack("<I", nbytes)
+    prefix = b"RIFF" + struct.pack("<I", len(head) + nbytes + (nbytes & 1)) + head
     with open(path, "wb", buffering=0) as f:
-        f.write(b"RIFF" + struct.pack("<I", len(head) + nbytes + (nbytes & 1)) + head)
-        f.write(memoryview(pcm).cast("B"))
+        f.write(prefix)
+        _sliced_io(f.fileno(), memoryview(pcm).cast("B"), len(prefix), write=True)
         if nbytes & 1:
-            f.write(b"\x00")
+            os.pwrite(f.fileno(), b"\x00", len(prefix) + nbytes)
 
 
 def _pcm_layout(f):
@@ -147,12 +181,5 @@ def read_pcm(path: str, allocate=None):
         shape = (frames, channels if bits == 16 else 3 * channels)
         dtype = np.int16 if bits == 16 else np.uint8
         raw = allocate(shape, dtype) if allocate is not None else np.empty(shape, dtype=dtype)
-        f.seek(data_at)
-        view = memoryview(raw).cast("B")
-        got = 0
-        while got < len(view):
-            k = f.readinto(view[got:])
-            if not k:
-                raise OSError("short read")
-            got += k
+        _sliced_io(f.fileno(), memoryview(raw).cast("B"), data_at, write=False)
     return raw, rate, channels, bits
