@@ -426,7 +426,7 @@ int mgb_track_layout_init(const mgb_plan* plan, int64_t target_frames, int64_t r
         const int64_t n = sig == 0 ? target_frames : reference_frames;
         // match_levels.py:47-59: float division, then int() truncation
         const double q = (double)n / plan->max_piece_size;
-        MGB_REQUIRE(q < 16000.0, MGB_ERR_UNSUPPORTED, "more than 16000 pieces");
+        MGB_REQUIRE(q < 8000.0, MGB_ERR_UNSUPPORTED, "more than 8000 pieces (their statistics live in one CTA's shared memory)");
         const int32_t divisions = (int32_t)q + 1;
         const int64_t piece = (int64_t)((double)n / (double)divisions);
         MGB_REQUIRE(piece >= plan->fft_size, MGB_ERR_UNSUPPORTED,
