@@ -93,8 +93,8 @@ _IO_SLICE = 4 << 20
 
 def _sliced_io(fd: int, view: memoryview, offset: int, write: bool) -> None:
     """pread / pwrite of a large buffer in 4 MB slices on a few threads (the calls release the GIL): the copy between
-    the page cache and the (pinned) buffer is a single-threaded memcpy per call, 5 GB/s; eight of them in parallel move
-    a 32 MB track in a couple of milliseconds instead of seven."""
+    the page cache and the (pinned) buffer is a single-threaded memcpy per call, 5 GB/s; eight of them in parallel read
+    a 32 MB track in 1.5 ms instead of 6.5 (measured on the B200 host; writes of new files did not gain)."""
     global _IO_POOL
     n = len(view)
     if n <= _IO_SLICE:
@@ -131,9 +131,9 @@ def write_pcm(path: str, pcm: np.ndarray, sample_rate: int, bits: int, channels:
     prefix = b"RIFF" + struct.pack("<I", len(head) + nbytes + (nbytes & 1)) + head
     with open(path, "wb", buffering=0) as f:
         f.write(prefix)
-        _sliced_io(f.fileno(), memoryview(pcm).cast("B"), len(prefix), write=True)
+        f.write(memoryview(pcm).cast("B"))  # (parallel slices measured slower here: a new file's pages are allocated under one lock)
         if nbytes & 1:
-            os.pwrite(f.fileno(), b"\x00", len(prefix) + nbytes)
+            f.write(b"\x00")
 
 
 def _pcm_layout(f):
