@@ -159,7 +159,8 @@ const char* mgb_last_error_string(void);
  * 2048 and 4096 with pieces of at least 3F samples) or 2 (2F-point pair, F outputs).  "clip_ctas_per_sm": grid of
  * the RMS-correction passes in CTAs per SM (1..16, default 3).  "design_direct": mgb_test_design_fir runs the
  * spline/LOWESS chain directly even when the plan has a smoothing operator.  "lookback_inclusive":
- * 0 makes limiter chunks publish aggregates only, so every look-back walks to its cut-off.
+ * 0 makes limiter chunks publish aggregates only, so every look-back walks to its cut-off.  "limiter_ticket":
+ * 1 hands the limiter's chunks out by an atomic ticket instead of the block index (0, default).
  * Returns MGB_ERR_INVALID for an unknown name. */
 int mgb_set_option(const char* name, int value);
 

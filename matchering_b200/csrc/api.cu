@@ -17,6 +17,7 @@ int g_conv_fused = 1;
 int g_conv_ovs = 4;
 int g_clip_ctas_per_sm = 3;
 int g_lookback_inclusive = 1;
+int g_limiter_ticket = 0;
 
 #ifndef MGB_EMULATE
 long long g_launch_count = 0;
@@ -302,6 +303,10 @@ int mgb_set_option(const char* name, int value) {
     }
     if (strcmp(name, "lookback_inclusive") == 0) {
         g_lookback_inclusive = value ? 1 : 0;
+        return MGB_OK;
+    }
+    if (strcmp(name, "limiter_ticket") == 0) {
+        g_limiter_ticket = value ? 1 : 0;
         return MGB_OK;
     }
     if (strcmp(name, "design_direct") == 0) {

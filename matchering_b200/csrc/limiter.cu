@@ -320,6 +320,7 @@ struct LimiterGeom {
     int publish_inclusive;        // 0: chunks publish aggregates only (test switch: every look-back then walks to the cut-off)
     int shared_core;              // both windows are wide enough for the per-thread shared-core evaluation
     int margin;                   // zeros kept on both sides of G so that window reads need no bounds test (multiple of 4)
+    int use_ticket;               // chunks handed out by an atomic ticket instead of the block index
 };
 
 // Config-only tables, computed once per parameter set (not per CTA: pow() is slow).  Order capacity 1: powers of
@@ -376,11 +377,43 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
     const SectionTab<NO>* tab_rel = NO == 1 ? reinterpret_cast<const SectionTab<NO>*>(&pw_sec[1]) : sec_global + 1;
 
     const int tid = threadIdx.x;
+    // Which chunk: the block index (default) or an atomic ticket (option "limiter_ticket").  The look-back only ever
+    // waits for LOWER chunks; with the block index that is safe as long as blocks start in index order -- what the
+    // hardware does for a one-dimensional grid and what every decoupled-look-back scan relies on -- and it saves the
+    // ticket's round trip through L2 plus a barrier in front of the chunk's first loads (12 % of this kernel's
+    // stall samples sat there).  The ticket makes the order explicit instead.
+    int chunk = blockIdx.x;
+    if (gm.use_ticket) {
+        if (tid == 0) chunk_s = atomicAdd(ticket, 1);
+        __syncthreads();
+        chunk = chunk_s;
+    }
+    const long long s0 = (long long)chunk * LC;
+    const int core_n = (int)((s0 + LC < frames) ? LC : frames - s0);
+    const int reach = gm.reach, hold = gm.hold, HL = gm.left, FL = gm.filt;
+    const long long ga = s0 - HL - reach;  // sample at span index 0
+    const int cidx = HL + reach;           // span index of the chunk's first sample
+    // span indices that fall inside the signal: [vlo, vhi)
+    const int vlo = ga < 0 ? (int)(-ga) : 0;
+    const int vhi = (frames - ga < (long long)gm.span) ? (int)(frames - ga) : gm.span;
+    const double thr = lp.threshold;
+
+    // ---- P1: hard-clip gain g = 1 - thr/max(|L|,|R|,thr) over the span (dsp.py:117-121, hyrax.py:87)
+    // All of the thread's loads go out first (one DRAM latency, not EPT), then the scalars and the tables: the
+    // kernel's first use of anything it loaded comes after everything has been requested.
+    float2 v[EPT];
+    {
+        const float2* base = in + ga;
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+            const int i = tid + k * NT;
+            v[k] = (i >= vlo && i < vhi) ? __ldg(base + i) : make_float2(0.0f, 0.0f);
+        }
+    }
     const double pre = pre_gain ? *pre_gain : 1.0;
     const double post = post_gain ? *post_gain : 1.0;
     const double scale = pre * post;
-
-    if (tid == 0) chunk_s = atomicAdd(ticket, 1);
+    const bool bypass = engaged && *engaged == 0;
     {
         const double* src = reinterpret_cast<const double*>(tables);
         double* dst = reinterpret_cast<double*>(&pw_att);
@@ -391,52 +424,28 @@ limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__
             for (int i = tid; i < (int)(2 * sizeof(SectionTab<1>) / sizeof(double)); i += NT) dst[i] = src[i];
         }
     }
-    __syncthreads();
-    const int chunk = chunk_s;
-    const long long s0 = (long long)chunk * LC;
-    const int core_n = (int)((s0 + LC < frames) ? LC : frames - s0);
-
-    if (engaged && *engaged == 0) {  // hyrax.py:83-85: the limiter is not needed
+    if (bypass) {  // hyrax.py:83-85: the limiter is not needed
         for (int k = tid; k < core_n; k += NT) {
-            const float2 v = in[s0 + k];
-            out[s0 + k] = make_float2((float)((double)v.x * pre * post), (float)((double)v.y * pre * post));
+            const float2 w = in[s0 + k];
+            out[s0 + k] = make_float2((float)((double)w.x * pre * post), (float)((double)w.y * pre * post));
         }
         return;
     }
-
-    const int reach = gm.reach, hold = gm.hold, HL = gm.left, FL = gm.filt;
-    const long long ga = s0 - HL - reach;  // sample at span index 0
-    const int cidx = HL + reach;           // span index of the chunk's first sample
-    // span indices that fall inside the signal: [vlo, vhi)
-    const int vlo = ga < 0 ? (int)(-ga) : 0;
-    const int vhi = (frames - ga < (long long)gm.span) ? (int)(frames - ga) : gm.span;
-    const double thr = lp.threshold;
-
-    // ---- P1: hard-clip gain g = 1 - thr/max(|L|,|R|,thr) over the span (dsp.py:117-121, hyrax.py:87)
     for (int i = tid; i < gm.margin; i += NT) {
         G[-1 - i] = 0.0f;
         G[CAP + i] = 0.0f;
     }
-    {
-        const float2* base = in + ga;
-        float2 v[EPT];  // all of the thread's loads are issued before the first use: one DRAM latency, not EPT
 #pragma unroll
-        for (int k = 0; k < EPT; ++k) {
-            const int i = tid + k * NT;
-            v[k] = (i >= vlo && i < vhi) ? __ldg(base + i) : make_float2(0.0f, 0.0f);
-        }
-#pragma unroll
-        for (int k = 0; k < EPT; ++k) {
-            // g = 1 - thr/a = (a - thr)/a: the difference in float64 (it decides which frames are touched at
-            // all, and cancels when a is close to thr), the quotient in float32 -- g is kept as float32 anyway
-            const double a = (double)fmaxf(fabsf(v[k].x), fabsf(v[k].y)) * pre;
-            const double over = a - thr;
-            float g = 0.0f;
-            if (over > 0.0) g = __fdiv_rn((float)over, (float)a);
-            G[tid + k * NT] = g;
-        }
+    for (int k = 0; k < EPT; ++k) {
+        // g = 1 - thr/a = (a - thr)/a: the difference in float64 (it decides which frames are touched at
+        // all, and cancels when a is close to thr), the quotient in float32 -- g is kept as float32 anyway
+        const double a = (double)fmaxf(fabsf(v[k].x), fabsf(v[k].y)) * pre;
+        const double over = a - thr;
+        float g = 0.0f;
+        if (over > 0.0) g = __fdiv_rn((float)over, (float)a);
+        G[tid + k * NT] = g;
     }
-    __syncthreads();
+    __syncthreads();  // (also: the pole tables are in shared memory)
 
     // ---- P2: both running maxima of g ----------------------------------------------------------------
     //   A[n] = max g[n-reach .. n+reach]                                 (hyrax.py:35-37)
@@ -798,6 +807,7 @@ int limiter_geometry(const mgb_limiter_params& lp, LimiterGeom* g) {
     if (ept < CORE_EPT + no) ept = (CORE_EPT + no) | 1;  // every thread parks its CORE_EPT + no samples of H in one plane
     g->ept = ept;
     g->publish_inclusive = g_lookback_inclusive;
+    g->use_ticket = g_limiter_ticket;
     // the cores [b+ept-1-reach, b+reach] and [b+ept-reach-hold, b+reach] must not be empty
     g->shared_core = (2 * lp.reach >= ept - 1 && 2 * lp.reach + lp.hold >= CORE_EPT + no) ? 1 : 0;
     g->margin = (lp.reach + lp.hold + ept + no + 3) / 4 * 4;  // the furthest a window part reaches outside [0, CAP)

@@ -258,8 +258,9 @@ class HostIO:
         self.lib = _native.load()
         handle = C.c_void_p()
         threads = int(os.environ.get("MGB_HOST_THREADS", "0"))
-        chunk = int(os.environ.get("MGB_HOST_CHUNK", "0"))  # samples per ring chunk (tuning)
-        _native.check(self.lib, self.lib.mgb_host_io_create(threads, chunk, 0, C.byref(handle)))
+        chunk = int(os.environ.get("MGB_HOST_CHUNK", "0"))  # samples per ring chunk, chunks in the ring (tuning)
+        ring = int(os.environ.get("MGB_HOST_RING", "0"))
+        _native.check(self.lib, self.lib.mgb_host_io_create(threads, chunk, ring, C.byref(handle)))
         self.handle = handle
         import threading
         self.lock = threading.Lock()  # one transfer at a time per mgb_host_io (ctypes drops the GIL during a call)

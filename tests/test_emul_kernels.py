@@ -172,6 +172,12 @@ def test_limiter_matches_golden_several_chunks(lib, golden):
     out, engaged = _limit(lib, g["x"], port.OracleConfig())
     assert engaged == 1
     assert np.abs(out - g["y_44100"]).max() < 3e-7
+    lib.mgb_set_option(b"limiter_ticket", 1)  # chunks by atomic ticket instead of by block index
+    try:
+        ticketed, _ = _limit(lib, g["x"], port.OracleConfig())
+    finally:
+        lib.mgb_set_option(b"limiter_ticket", 0)
+    assert np.array_equal(ticketed, out)
     out96, _ = _limit(lib, g["x"], port.OracleConfig(internal_sample_rate=96000))
     assert np.abs(out96 - g["y_96000"]).max() < 3e-7
 
