@@ -356,10 +356,12 @@ int mgb_host_io_create(int32_t threads, int64_t chunk_samples, int32_t ring, mgb
 #endif
         threads = usable >= 64 ? 32 : (usable >= 4 ? usable / 2 : 1);
     }
-    // 1 MB float32 chunks: small enough that the link starts after 1/60 of a 3-minute track has been narrowed
-    // (4 MB chunks cost a third of the upload rate), large enough that a chunk's DMA (20 us) hides its bookkeeping
-    if (chunk_samples <= 0) chunk_samples = 1 << 18;
-    if (ring <= 0) ring = 12;
+    // A ring of 16 chunks of 256 KB: small enough to stay in the cores' caches between the workers' stores and the
+    // DMA engine's reads.  Measured with four ranks on one socket (tools/gpu_n4_sweep.sh): 7.8 ms per
+    // stages.main call against 14.3 ms with twelve 1 MB chunks, whose stores and re-reads went through DRAM and
+    // took a third of the socket's memory bandwidth; chunks of 64 KB cost more in copy launches than they save.
+    if (chunk_samples <= 0) chunk_samples = 1 << 16;
+    if (ring <= 0) ring = 16;
     MGB_REQUIRE(threads <= 256 && ring <= 64 && chunk_samples % 16 == 0, MGB_ERR_INVALID, "host_io: bad geometry");
     mgb_host_io* io = new mgb_host_io();
     io->chunk = chunk_samples;
