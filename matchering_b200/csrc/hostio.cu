@@ -242,20 +242,27 @@ int upload(mgb_host_io* io, const void* h_src, int src_width, float* d_dst, int6
     int rc = MGB_OK;
     auto lead = [&]() {
         int64_t issued = 0, freed = 0;
+        std::vector<int64_t> group_end(nchunks);  // chunk k left the ring when the copy that ends with chunk group_end[k] has
         while (issued < nchunks) {
             if (ready[issued].load(std::memory_order_acquire) == P) {
+                // every finished chunk that follows in the ring without wrapping goes into the same copy: when the workers
+                // are ahead of this thread (large transfers) one launch moves several chunks
+                int64_t last = issued;
+                while (last + 1 < nchunks && (last + 1) % ring != 0 && ready[last + 1].load(std::memory_order_acquire) == P) ++last;
                 const int64_t base = issued * chunk;
-                const int64_t len = (samples - base < chunk) ? samples - base : chunk;
+                const int64_t end = (last + 1) * chunk < samples ? (last + 1) * chunk : samples;
                 const int slot = (int)(issued % ring);
-                if (cudaMemcpyAsync(d_dst + base, io->staging + slot * chunk, (size_t)len * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
-                    cudaEventRecord(io->events[slot], st) != cudaSuccess) {
+                if (cudaMemcpyAsync(d_dst + base, io->staging + slot * chunk, (size_t)(end - base) * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+                    cudaEventRecord(io->events[last % ring], st) != cudaSuccess) {
                     rc = cuda_status("H2D chunk");
                     failed.store(1);
                     return;
                 }
-                ++issued;
-            } else if (freed < issued && cudaEventQuery(io->events[freed % ring]) == cudaSuccess) {
-                released.store(++freed, std::memory_order_release);
+                for (int64_t k = issued; k <= last; ++k) group_end[k] = last;
+                issued = last + 1;
+            } else if (freed < issued && cudaEventQuery(io->events[group_end[freed] % ring]) == cudaSuccess) {
+                freed = group_end[freed] + 1;
+                released.store(freed, std::memory_order_release);
             } else {
                 MGB_CPU_RELAX();
             }
