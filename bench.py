@@ -349,7 +349,9 @@ def run_b200(args) -> dict:
             everyone = [None] * world
             dist.all_gather_object(everyone, mine)
             sharing = sum(1 for other in everyone if other and other[0] == mine[0])
-            os.environ["MGB_HOST_THREADS"] = str(max(4, min(32, len(mine) // max(1, sharing))))
+            # ... and all ranks share the container's CPU quota (usable_cores): leave the main threads their share
+            budget = min(len(mine) // max(1, sharing), usable_cores() // world - 3)
+            os.environ["MGB_HOST_THREADS"] = str(max(4, min(16, budget)))
 
     port = oracle()  # synthetic-input recipes + the cpu_baseline leg only
     import matchering_b200 as mg

@@ -251,8 +251,8 @@ int mgb_process_host(const mgb_plan* plan, const mgb_track_layout* layout, const
  * widened on the device and DMA'd straight into pinned memory from mgb_host_alloc (one copy, no host
  * pass), or as float32 chunks through the same ring, widened by the workers, into any other memory.
  * `*_width` = bytes per sample of the host arrays: 4 (float32) or 8 (float64).
- * threads / chunk_samples / ring <= 0 pick defaults (half the hardware threads the process may run on, at
- * most 32; 64 Ki samples; 16 chunks -- a 4 MB ring that stays in cache between the workers and the DMA engine).  One transfer at a time per mgb_host_io. */
+ * threads / chunk_samples / ring <= 0 pick defaults (16 workers, fewer under a smaller affinity mask or cgroup
+ * CPU quota; 64 Ki samples; 16 chunks -- a 4 MB ring that stays in cache between the workers and the DMA engine).  One transfer at a time per mgb_host_io. */
 typedef struct mgb_host_io mgb_host_io;
 int mgb_host_io_create(int32_t threads, int64_t chunk_samples, int32_t ring, mgb_host_io** out);
 int mgb_host_io_destroy(mgb_host_io* io);

@@ -16,6 +16,7 @@
 // atomics inside one).  Nothing here touches sample VALUES except the float64 <-> float32 conversion
 // the reference's caller would otherwise pay for on the device.
 #include <sched.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -354,14 +355,31 @@ extern "C" {
 int mgb_host_io_create(int32_t threads, int64_t chunk_samples, int32_t ring, mgb_host_io** out) {
     MGB_REQUIRE(out != nullptr, MGB_ERR_INVALID, "host_io: NULL argument");
     if (threads <= 0) {
-        // half of the hardware threads this process may run on, at most 32: on the 128-thread B200 host the
-        // float64 -> float32 upload goes from 42 GB/s with 8 workers to 69 GB/s with 32 and flattens after that
+        // Sixteen workers keep up with the link (each narrows 8-10 GB/s of source, the link takes 108 GB/s of
+        // it; 32 were no faster on the 128-thread B200 host) -- fewer when the process may not use that many cores:
+        // the affinity mask, and the cgroup's CPU quota (the B200 boxes grant 16 cores per GPU; workers that
+        // spin past the quota get the whole process throttled).
         int usable = (int)std::thread::hardware_concurrency();
-#if defined(__linux__) && !defined(MGB_EMULATE)
+#if defined(__linux__)
         cpu_set_t set;
         if (sched_getaffinity(0, sizeof(set), &set) == 0) usable = CPU_COUNT(&set);
+        long long quota = 0, period = 0;
+        if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {  // cgroup v2: "<quota|max> <period>"
+            if (fscanf(f, "%lld %lld", &quota, &period) != 2) quota = period = 0;
+            fclose(f);
+        } else if (FILE* q = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r")) {  // cgroup v1
+            FILE* p = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r");
+            if (fscanf(q, "%lld", &quota) != 1) quota = 0;
+            if (!p || fscanf(p, "%lld", &period) != 1) period = 0;
+            fclose(q);
+            if (p) fclose(p);
+        }
+        if (quota > 0 && period > 0) {
+            const int cores = (int)(quota / period);
+            if (cores >= 1 && cores < usable) usable = cores;
+        }
 #endif
-        threads = usable >= 64 ? 32 : (usable >= 4 ? usable / 2 : 1);
+        threads = usable >= 20 ? 16 : (usable > 5 ? usable - 4 : (usable > 1 ? usable - 1 : 1));
     }
     // A ring of 16 chunks of 256 KB: small enough to stay in the cores' caches between the workers' stores and the
     // DMA engine's reads.  Measured with four ranks on one socket (tools/gpu_n4_sweep.sh): 7.8 ms per

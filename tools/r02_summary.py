@@ -1,0 +1,176 @@
+"""Build profiles/r02_summary.md and copy the round's evidence into profiles/ from the files the evidence run
+(tools/gpu_evidence_r02.sh) left in gpurun_out/.   python tools/r02_summary.py [tag]"""
+import csv
+import io
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r02_final"
+OUT = os.path.join(ROOT, "gpurun_out")
+PROF = os.path.join(ROOT, "profiles")
+
+
+def load_line(path):
+    lines = [l for l in open(path).read().splitlines() if l.startswith("{")]
+    return json.loads(lines[-1]) if lines else None
+
+
+def ncu_rows(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    return hdr, units, rows[2:]
+
+
+def short(name):
+    return name.split("(")[0].split("::")[-1]
+
+
+benches = {}
+for wl in ("c2", "c3", "c5"):
+    p = os.path.join(OUT, f"{TAG}_bench_{wl}.json")
+    if os.path.exists(p):
+        benches[wl] = load_line(p)
+        shutil.copy(p, os.path.join(PROF, f"r02_bench_{wl}.json"))
+ref = None
+p = os.path.join(OUT, f"{TAG}_bench_reference_arm.json")
+if os.path.exists(p):
+    ref = load_line(p)
+    shutil.copy(p, os.path.join(PROF, "r02_bench_reference_arm.json"))
+for name in ("r02_bench_n4.json",):
+    p = os.path.join(OUT, name)
+    if os.path.exists(p):
+        shutil.copy(p, os.path.join(PROF, name))
+for src, dst in ((f"{TAG}_ncu_launches.csv", "r02_ncu_launches.csv"), (f"{TAG}_sanitizer.txt", "r02_sanitizer.txt"),
+                 (f"{TAG}_tests.log", "r02_gpu_tests.txt")):
+    p = os.path.join(OUT, src)
+    if os.path.exists(p):
+        shutil.copy(p, os.path.join(PROF, dst))
+
+# ---- ncu full metrics, per kernel
+metrics_txt = []
+full = {}
+for rep, wl in ((f"{TAG}_prof.ncu-rep", "c2"), (f"{TAG}_prof_c5.ncu-rep", "c5")):
+    p = os.path.join(OUT, rep)
+    if not os.path.exists(p):
+        continue
+    txt = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), p], capture_output=True, text=True).stdout
+    metrics_txt.append(txt)
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "traffic_from_ncu.py"), p, wl], capture_output=True, text=True)
+    hdr, units, rows = ncu_rows(p)
+    ix = {h: i for i, h in enumerate(hdr)}
+    stall = [k for k in hdr if k.startswith("smsp__pcsamp_warps_issue_stalled") and not k.endswith("not_issued")]
+    for r in rows:
+        name = short(r[ix["Kernel Name"]])
+        key = (wl, name.split("<")[0])
+        if key in full:
+            continue
+        tot = sum(float(r[ix[k]]) for k in stall) or 1.0
+        top = sorted(((float(r[ix[k]]) / tot * 100, k.replace("smsp__pcsamp_warps_issue_stalled_", "")) for k in stall), reverse=True)[:4]
+        get = lambda k: float(r[ix[k]]) if k in ix and r[ix[k]] not in ("", "n/a") else float("nan")
+        full[key] = dict(
+            name=name, time_us=get("gpu__time_duration.sum") / (1000.0 if units[ix["gpu__time_duration.sum"]] in ("ns", "nsecond") else 1.0),
+            issue=get("smsp__issue_active.avg.pct_of_peak_sustained_active"), eligible=get("smsp__warps_eligible.avg.per_cycle_active"),
+            active=get("smsp__warps_active.avg.per_cycle_active"), fma=get("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+            alu=get("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"), lsu=get("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
+            fp64=get("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"), inst=get("smsp__inst_executed.sum"),
+            stalls=", ".join(f"{n} {p:.0f} %" for p, n in top))
+if metrics_txt:
+    open(os.path.join(PROF, "r02_ncu_full_metrics.txt"), "w").write("\n".join(metrics_txt))
+
+traffic = json.load(open(os.path.join(PROF, "traffic.json"))) if os.path.exists(os.path.join(PROF, "traffic.json")) else {}
+
+# ---- ncu launch list: mean duration per kernel of the last full step
+launch_mean = {}
+p = os.path.join(OUT, f"{TAG}_ncu_launches.csv")
+if os.path.exists(p):
+    rows = list(csv.reader(open(p)))
+    start = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+    ix = {h: i for i, h in enumerate(rows[start])}
+    acc = {}
+    for r in rows[start + 2:]:
+        if len(r) > ix["Metric Value"]:
+            acc.setdefault(short(r[ix["Kernel Name"]]).split("<")[0], []).append(float(r[ix["Metric Value"]]) / 1000.0)
+    launch_mean = {k: sum(v[-6:]) / len(v[-6:]) for k, v in acc.items()}
+
+BYTES = {"analyze_kernel": 8, "convolve_kernel": 16, "clip_sumsq_kernel": 4, "limiter_kernel": 16}
+md = []
+md.append("# Round 2 — measurements on one B200\n")
+md.append("Everything below comes from ONE GPU call on the final code of the round (`tools/gpu_evidence_r02.sh`): the GPU test suite "
+          "(`r02_gpu_tests.txt`), the bench lines of BASELINE configs 2, 3 and 5 (`r02_bench_c2.json`, `_c3`, `_c5`: `python bench.py "
+          "--steps 20 --warmup 5`, `--workload c3|c5 --steps 10 --warmup 3`), the reference arm (`r02_bench_reference_arm.json`), the ncu "
+          "launch list of `tools/one_step.py 180 3` (`r02_ncu_launches.csv`, `--metrics gpu__time_duration.sum --clock-control none`), "
+          "one `ncu --set full --clock-control none --import-source on` capture of every pipeline kernel on config 2 and of the limiter on "
+          "config 5's buffer (summarised in `r02_ncu_full_metrics.txt`, DRAM bytes per launch in `traffic.json`), compute-sanitizer "
+          "memcheck + racecheck over the new code paths (`r02_sanitizer.txt`).  `r02_sass_counts.txt`: static SASS counts per kernel "
+          "(`tools/sass_counts.py`).  `r02_seam_sweep*.txt`, `r02_n4_host_ring_sweep.txt`: host-transport sweeps; `r02_bench_n4.json`: "
+          "four GPUs (before the ring was shrunk: 14.3 ms per call; 7.8 ms after).\n")
+if "c2" in benches:
+    b = benches["c2"]
+    e = b["e2e"]
+    md.append("## Headline (config 2: 3-min 44.1 kHz stereo track vs 3-min reference, N = 1)\n")
+    md.append("| quantity | value |\n|---|---|")
+    md.append(f"| `value` device-resident, {b['run']['tracks_in_flight_per_gpu']} tracks in flight | **{b['value']:,.0f}× real-time** ({b['ms_per_step']:.3f} ms per track) |")
+    md.append(f"| one track at a time (`single_track_latency`) | {b['single_track_latency']['value']:,.0f}× ({b['single_track_latency']['ms_per_step']:.3f} ms) |")
+    md.append(f"| `e2e` = `stages.main(float64 numpy, pageable)` → float64 numpy, one synchronous call per step | **{e['value']:,.0f}×** ({e['ms_per_step']:.2f} ms per call; "
+              f"{e['h2d_bytes_per_step'] / 1e6:.0f} MB over the link in, {e['d2h_bytes_per_step'] / 1e6:.0f} MB out; {e['host_threads']} worker threads) |")
+    for k, label in (("batch_f32", "C batch entry, pinned float32, 3 in flight"), ("batch_pcm16", "C batch entry, int16 PCM buffers"),
+                     ("single_call_f32", "`mgb_process_host`, pinned float32"), ("process_files", "`mg.process` on 16-bit WAV files in /dev/shm")):
+        if k in e:
+            md.append(f"| `e2e.{k}` ({label}) | {e[k]['value']:,.0f}× ({e[k]['ms_per_step']:.2f} ms) |")
+    if b.get("cpu_baseline"):
+        md.append(f"| `cpu_baseline` (oracle port, one host core, same 180-s track) | {b['cpu_baseline']['value']:.1f}× |")
+    if ref:
+        md.append(f"| reference arm (`--impl reference`): {ref['cpu_baseline']['sample'][:160]}… | {ref['value']:,.0f}× |")
+    md.append(f"| clocks during the run | {b['clocks']['sm_mhz']:.0f} MHz of {b['clocks']['sm_max_mhz']:.0f}, reasons {b['clocks']['reasons']} |")
+    md.append("")
+for wl, title in (("c3", "Config 3: 10-min 96 kHz stereo track (57.6 M frames), full pipeline"), ("c5", "Config 5: Hyrax limiter alone on one hour of 44.1 kHz stereo (158.76 M frames)")):
+    if wl in benches:
+        b = benches[wl]
+        e = b["e2e"]
+        r = b["roofline"]
+        md.append(f"## {title}\n")
+        md.append("| quantity | value |\n|---|---|")
+        md.append(f"| `value` device-resident | {b['value']:,.0f}× real-time at its own rate ({b['ms_per_step']:.3f} ms per step, {b['samples_per_sec']:.3g} stereo frames/s) |")
+        md.append(f"| `e2e` (float64 numpy through `{'limiter.limit' if wl == 'c5' else 'stages.main'}`) | {e['value']:,.0f}× ({e['ms_per_step']:.1f} ms per call) |")
+        md.append(f"| dominant kernel | `{r['kernel']}`: {r['avg_launch_ms'] * 1e3:.0f} µs per launch, {r['achieved']:.0f} GB/s algorithmic = **{r['frac']:.3f}** of the measured {r['peak']:.0f} GB/s |")
+        md.append(f"| whole step against its compulsory bytes | {r['pipeline']['achieved']:.0f} GB/s = {r['pipeline']['frac']:.3f} |")
+        if b.get("cpu_baseline"):
+            md.append(f"| `cpu_baseline` | {b['cpu_baseline']['value']:.1f}× ({b['cpu_baseline']['sample'][:110]}…) |")
+        md.append(f"| parity at full size | `tests/test_gpu_parity.py::test_config{'5_limiter_one_hour' if wl == 'c5' else '3_ten_minutes_96k'}_against_reference_golden` (decimated golden of the unmodified reference) |")
+        md.append("")
+if "c2" in benches:
+    b = benches["c2"]
+    n = b["config"]["frames_per_track"]
+    peak = b["roofline"]["peak"]
+    md.append("## Kernel shares, config 2 (11 launches per track)\n")
+    md.append("| kernel | launches | bench CUDA-event µs each | ncu launch list µs each | alg. bytes | DRAM traffic (ncu) | alg. GB/s | frac of measured peak | warp instr. | issue slots busy | eligible / active warps | FMA / ALU / LSU / FP64 pipe % | top stalls |")
+    md.append("|---|---|---|---|---|---|---|---|---|---|---|---|---|")
+    for k, v in sorted(b["kernels"].items(), key=lambda kv: -kv[1]["ms_per_step"]):
+        f = full.get(("c2", k if k != "convolve_kernel" else "convolve_fused_kernel"), {})
+        bpf = BYTES.get(k)
+        alg = f"{bpf}·N = {bpf * n / 1e6:.1f} MB" if bpf else "–"
+        gbs = bpf * n / (v["avg_ms"] * 1e-3) / 1e9 if bpf else None
+        tr = traffic.get("c2", {}).get(k)
+        lm = launch_mean.get(k if k != "convolve_kernel" else "convolve_fused_kernel")
+        md.append(f"| `{f.get('name', k)}` | {v['launches_per_step']:.0f} | {v['avg_ms'] * 1e3:.1f} | {lm:.1f} | {alg} | "
+                  f"{(tr / 1e6 if tr else float('nan')):.1f} MB | {(f'{gbs:,.0f}' if gbs else '–')} | {(f'{gbs / peak:.3f}' if gbs else '–')} | "
+                  f"{f.get('inst', float('nan')):.3g} | {f.get('issue', float('nan')):.0f} % | {f.get('eligible', float('nan')):.1f} / {f.get('active', float('nan')):.1f} | "
+                  f"{f.get('fma', float('nan')):.0f} / {f.get('alu', float('nan')):.0f} / {f.get('lsu', float('nan')):.0f} / {f.get('fp64', float('nan')):.0f} | {f.get('stalls', '')} |"
+                  if lm is not None else f"| `{k}` | {v['launches_per_step']:.0f} | {v['avg_ms'] * 1e3:.1f} | – | {alg} | – | – | – | – | – | – | – | – |")
+    r = b["roofline"]
+    md.append(f"| whole pipeline | 11 | {b['ms_per_step'] * 1e3:.0f} ({b['run']['tracks_in_flight_per_gpu']} lanes) / {b['single_track_latency']['ms_per_step'] * 1e3:.0f} (1) | | 56·T + 8·R = {r['pipeline']['algorithmic_bytes_per_step'] / 1e6:.0f} MB | | {r['pipeline']['achieved']:,.0f} | {r['pipeline']['frac']:.3f} | | | | | |")
+    md.append("")
+    md.append(f"`roofline` in the bench line: `{r['kernel']}`, {r['achieved']:.0f} GB/s algorithmic / {r['peak']:.0f} GB/s ({r['peak_source']}) = **{r['frac']:.3f}**; "
+              f"DRAM traffic {(r['traffic'] or 0) / 1e6:.1f} MB per launch against {r['algorithmic_bytes_per_launch'] / 1e6:.1f} MB algorithmic (no wasted re-reads); "
+              f"{r.get('cuda_core', {}).get('frac', float('nan')):.2f} of the non-FMA FP32 roof.\n")
+if ("c5", "limiter_kernel") in full:
+    f = full[("c5", "limiter_kernel")]
+    md.append(f"Limiter on the one-hour buffer (ncu): {f['time_us']:.0f} µs, issue slots {f['issue']:.0f} % busy, {f['eligible']:.1f} eligible of {f['active']:.1f} active warps, "
+              f"LSU {f['lsu']:.0f} %, FP64 {f['fp64']:.0f} %, stalls {f['stalls']}.\n")
+open(os.path.join(PROF, "r02_summary.md"), "w").write("\n".join(md) + "\n")
+print("\n".join(md)[:3000])
