@@ -315,7 +315,7 @@ ALGORITHMIC_BYTES_PER_FRAME = {
     "limiter_kernel": 16,     # read result, write final
 }
 # real FP32 operations per stereo frame of the two FFT kernels, for the CUDA-core roof
-FP32_OPS_PER_FRAME = {"convolve_kernel": 290.0, "analyze_kernel": 75.0}
+FP32_OPS_PER_FRAME = {"convolve_kernel": 217.0, "analyze_kernel": 75.0}  # (convolution: 4F-point frames, 3F outputs; 290 with 2F frames)
 
 
 def run_b200(args) -> dict:

@@ -73,7 +73,8 @@ for rep, wl in ((f"{TAG}_prof.ncu-rep", "c2"), (f"{TAG}_prof_c5.ncu-rep", "c5"))
         top = sorted(((float(r[ix[k]]) / tot * 100, k.replace("smsp__pcsamp_warps_issue_stalled_", "")) for k in stall), reverse=True)[:4]
         get = lambda k: float(r[ix[k]]) if k in ix and r[ix[k]] not in ("", "n/a") else float("nan")
         full[key] = dict(
-            name=name, time_us=get("gpu__time_duration.sum") / (1000.0 if units[ix["gpu__time_duration.sum"]] in ("ns", "nsecond") else 1.0),
+            name=name, time_us=get("gpu__time_duration.sum") * {"ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3,
+                                                                "msecond": 1e3, "s": 1e6, "second": 1e6}.get(units[ix["gpu__time_duration.sum"]], 1.0),
             issue=get("smsp__issue_active.avg.pct_of_peak_sustained_active"), eligible=get("smsp__warps_eligible.avg.per_cycle_active"),
             active=get("smsp__warps_active.avg.per_cycle_active"), fma=get("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
             alu=get("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"), lsu=get("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
@@ -172,5 +173,21 @@ if ("c5", "limiter_kernel") in full:
     f = full[("c5", "limiter_kernel")]
     md.append(f"Limiter on the one-hour buffer (ncu): {f['time_us']:.0f} µs, issue slots {f['issue']:.0f} % busy, {f['eligible']:.1f} eligible of {f['active']:.1f} active warps, "
               f"LSU {f['lsu']:.0f} %, FP64 {f['fp64']:.0f} %, stalls {f['stalls']}.\n")
+md.append("""## What moved this round (B200, config 2 unless stated)
+
+| change | before | after |
+|---|---|---|
+| convolution: overlap-save frames of 4 FIR lengths (4F-point transform pair, 3F outputs) | 124.4 µs, 8.8e7 warp instr. | 112-113 µs, 6.27e7 warp instr. (-29 %); one 1024-thread CTA per SM stalls as a whole at its barriers (issue slots 60 % against 70 %) and 646 frames are 4.4 waves that cost 5 |
+| smoothing operator kept as row bands | 33.6 MB read, 21-25 µs | 5.1 MB, 8-12 µs |
+| level statistics / correction coefficients per warp, per-piece sums folded by the whole block, selected-item lists | spectrum mean 24.6 µs (ncu) | 17.9 µs (ncu; its barriers now wait for one warp's statistics) |
+| limiter: chunks by block index instead of an atomic ticket, input loads issued before anything else | 99.4 µs / 1691 µs (1 h) | 96.8 µs / 1655 µs: 0.197 / 0.234 of the HBM roof |
+| design kernel: one in-place forward float64 FFT for its three transforms | 34.7 µs (ncu), 32 % of stalls "no instruction" | 36 µs: no gain -- the kernel is 8 CTAs of dependent latencies |
+| `stages.main` on the reference's own pageable float64 arrays (worker threads narrowing into a pinned ring, pooled pinned results) | no number; float64 over the link both ways from pageable memory | 7.3-8.4 ms per call = 21 000-25 000x real-time; the link carries 127 MB each way at 54 GB/s = 4.7 ms of it |
+| the same with four ranks on one socket | 14.3 ms per call (12 MB ring through DRAM) | 7.8 ms (4 MB ring, cache-resident): 3.65x of one rank |
+| `mg.process` on 16-bit WAV files | 93 ms | 19 ms (payloads straight through pooled pinned buffers, parallel reads) |
+| tracks in flight for `value` | 3: 625 000x | 6: 637 000-642 000x |
+
+Not built, with the reason: RMS correction as one persistent kernel (a cooperative launch needs every SM at once and would serialise against the other tracks in flight, which is where `value` comes from; 3 x 13 µs of a 388 µs single track); `fft_size` 16384 (a 2F-point float32 frame and the float64 design FFT are 262 KB each, one SM has 227 KB); hold / release orders above 2 (scipy's own transfer-function arithmetic is off by 5e-5 ... unstable there, DESIGN.md section 4).
+""")
 open(os.path.join(PROF, "r02_summary.md"), "w").write("\n".join(md) + "\n")
 print("\n".join(md)[:3000])
