@@ -313,6 +313,7 @@ int mgb_set_option(const char* name, int value) {
         g_design_direct = value ? 1 : 0;
         return MGB_OK;
     }
+    if (host_set_option(name, value)) return MGB_OK;
     set_error("unknown option '%s'", name);
     return MGB_ERR_INVALID;
 }

@@ -119,6 +119,7 @@ int twiddle_count(int n);
 int inverse_twiddle_count(int n);
 
 extern int g_use_tma;
+bool host_set_option(const char* name, int value);  // hostio.cu: the host transport's tuning switches
 extern int g_limiter_ticket;      // limiter chunks by atomic ticket (1) or by block index (0, default)
 extern int g_lookback_inclusive;  // limiter chunks publish their inclusive state (1, default) or aggregates only (0, tests)
 extern int g_clip_ctas_per_sm;  // grid of the correction passes, in CTAs per SM (tuning switch)
