@@ -165,10 +165,7 @@ inline void widen_plain(const float* __restrict__ src, double* __restrict__ dst,
 // construction for the ring (slices start on 16-sample boundaries of a pinned allocation).
 // MGB_HOST_NT: 0 = plain stores, 1 = 256-bit streaming stores, 2 = 512-bit where the CPU has them (default).
 // MGB_HOST_PREFETCH: software prefetch distance in bytes (0 = none).
-static const int g_prefetch = [] {
-    const char* e = getenv("MGB_HOST_PREFETCH");
-    return e ? atoi(e) : 0;
-}();
+static int g_prefetch = getenv("MGB_HOST_PREFETCH") ? atoi(getenv("MGB_HOST_PREFETCH")) : 0;
 __attribute__((target("avx2"))) inline void narrow_stream(const double* __restrict__ src, float* __restrict__ dst, int64_t n) {
     int64_t i = 0;
     if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
@@ -188,9 +185,14 @@ __attribute__((target("avx512f"))) inline void narrow_stream512(const double* __
     if ((reinterpret_cast<uintptr_t>(dst) & 63) == 0) {
         const int pf = g_prefetch;
         for (; i + 16 <= n; i += 16) {  // one destination line per iteration, two source lines
-            if (pf) {
-                _mm_prefetch((const char*)(src + i) + pf, _MM_HINT_NTA);
-                _mm_prefetch((const char*)(src + i) + pf + 64, _MM_HINT_NTA);
+            // the hardware's stream prefetcher stops at every 4 KB page of the source: touch the head of a page
+            // further on once per page, so that its translation and first lines are there when the stream arrives
+            if (pf && (i & 511) == 0) {
+                const char* ahead = (const char*)(src + i) + pf;
+                _mm_prefetch(ahead, _MM_HINT_T0);
+                _mm_prefetch(ahead + 64, _MM_HINT_T0);
+                _mm_prefetch(ahead + 128, _MM_HINT_T0);
+                _mm_prefetch(ahead + 192, _MM_HINT_T0);
             }
             const __m256 lo = _mm512_cvtpd_ps(_mm512_loadu_pd(src + i));
             const __m256 hi = _mm512_cvtpd_ps(_mm512_loadu_pd(src + i + 8));
@@ -516,6 +518,7 @@ bool mgb::host_set_option(const char* name, int value) {
     else if (!strcmp(name, "host_split_chunks")) g_host_split_chunks = value;
 #if defined(__x86_64__)
     else if (!strcmp(name, "host_streaming_stores")) g_stream_stores = clamp_stream_stores(value);
+    else if (!strcmp(name, "host_prefetch")) g_prefetch = value;
 #endif
     else return false;
     return true;

@@ -64,6 +64,35 @@ def test_repeated_transfers_reuse_the_ring(lib, io):
         assert np.array_equal(dev[:len(src)], src.astype(np.float32))
 
 
+@pytest.mark.parametrize("stores", [0, 1, 2])
+@pytest.mark.parametrize("whole_chunks", [0, 1])
+@pytest.mark.parametrize("download_ring", [0, 1])
+def test_transport_switches_do_not_change_the_bytes(lib, io, stores, whole_chunks, download_ring):
+    """Streaming stores (256 / 512 bit), whole chunks per worker, the ring route for pinned float64 results:
+    tuning switches of the transport (mgb_set_option), every combination moves the same bytes."""
+    switches = (("host_streaming_stores", stores, 2), ("host_split_chunks", whole_chunks, 0),
+                ("host_download_ring", download_ring, 0), ("host_prefetch", 4096 * whole_chunks, 0))
+    try:
+        for name, value, _ in switches:
+            _native.check(lib, lib.mgb_set_option(name.encode(), value))
+        rng = np.random.default_rng(7)
+        for samples in (5, 1024, 40011):
+            a, b = rng.standard_normal(samples), rng.standard_normal(samples + 3)
+            dev_a, dev_b = aligned((samples,), np.float32), aligned((samples + 3,), np.float32)
+            _native.check(lib, lib.mgb_host_upload(io, a.ctypes.data, 8, ptr(dev_a), samples, None))
+            _native.check(lib, lib.mgb_host_upload(io, b[1:].ctypes.data, 8, ptr(dev_b), samples + 2, None))  # odd alignment
+            assert np.array_equal(dev_a, a.astype(np.float32))
+            assert np.array_equal(dev_b[:samples + 2], b[1:].astype(np.float32))
+            wide = aligned((samples,), np.float64)
+            pinned, p = _pinned(lib, (samples + 1,), np.float64)
+            _native.check(lib, lib.mgb_host_download(io, ptr(dev_a), p + 8, 8, samples, ptr(wide), None))  # 8-byte aligned only
+            assert np.array_equal(pinned[1:], a.astype(np.float32).astype(np.float64))
+            lib.mgb_host_free(p)
+    finally:
+        for name, _, default in switches:
+            lib.mgb_set_option(name.encode(), default)
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_stages_main_host_matches_staged_calls(lib, io, dtype):
     cfg = port.OracleConfig(fft_size=1024, max_piece_size=0.3)

@@ -33,34 +33,33 @@ out = HostIO.get().pool.array((n, 2), np.float64)
 stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 state = _native.TrackState()
 
-# (label, threads, chunk samples, ring, streaming stores, download through the ring, whole chunks per worker)
+# (label, threads, chunk samples, ring, streaming stores, download through the ring, whole chunks per worker, prefetch bytes)
 CONFIGS = [
-    ("t12 64K x16 plain  dma ", 12, 1 << 16, 16, 0, 0, 0),
-    ("t12 64K x16 nt512  dma ", 12, 1 << 16, 16, 2, 0, 0),
-    ("t12 256K x8 nt512  dma ", 12, 1 << 18, 8, 2, 0, 0),
-    ("t12 256K x8 nt256  dma ", 12, 1 << 18, 8, 1, 0, 0),
-    ("t12 256K x8 nt512  ring", 12, 1 << 18, 8, 2, 1, 0),
-    ("t12 1M x6   nt512  dma ", 12, 1 << 20, 6, 2, 0, 0),
-    ("t12 1M x6   nt512  ring", 12, 1 << 20, 6, 2, 1, 0),
-    ("t12 512K x8 nt512  ring", 12, 1 << 19, 8, 2, 1, 0),
-    ("t12 256K x16 nt512 whole-chunks ring", 12, 1 << 18, 16, 2, 1, 1),
-    ("t13 256K x8 nt512  ring", 13, 1 << 18, 8, 2, 1, 0),
-    ("t14 256K x8 nt512  ring", 14, 1 << 18, 8, 2, 1, 0),
-    ("t10 256K x8 nt512  ring", 10, 1 << 18, 8, 2, 1, 0),
-    ("t8  256K x8 nt512  ring", 8, 1 << 18, 8, 2, 1, 0),
+    ("t12 64K x16 plain  dma ", 12, 1 << 16, 16, 0, 0, 0, 0),
+    ("t12 256K x8 nt512  dma ", 12, 1 << 18, 8, 2, 0, 0, 0),
+    ("t12 512K x8 nt512  dma ", 12, 1 << 19, 8, 2, 0, 0, 0),
+    ("t12 512K x8 nt512  ring", 12, 1 << 19, 8, 2, 1, 0, 0),
+    ("t12 512K x8 nt512  ring pf4k", 12, 1 << 19, 8, 2, 1, 0, 4096),
+    ("t12 512K x8 nt512  ring pf8k", 12, 1 << 19, 8, 2, 1, 0, 8192),
+    ("t12 512K x8 nt256  ring", 12, 1 << 19, 8, 1, 1, 0, 0),
+    ("t12 1M x6   nt512  ring", 12, 1 << 20, 6, 2, 1, 0, 0),
+    ("t12 512K x8 nt512  whole-chunks ring", 12, 1 << 19, 16, 2, 1, 1, 0),
+    ("t13 512K x8 nt512  ring", 13, 1 << 19, 8, 2, 1, 0, 0),
+    ("t14 512K x8 nt512  ring", 14, 1 << 19, 8, 2, 1, 0, 0),
+    ("t10 512K x8 nt512  ring", 10, 1 << 19, 8, 2, 1, 0, 0),
 ]
 if len(sys.argv) > 2:
     CONFIGS = [c for c in CONFIGS if any(key in c[0] for key in sys.argv[2:])]
 handles = []
-for label, threads, chunk, ring, nt, dring, whole in CONFIGS:
+for label, threads, chunk, ring, nt, dring, whole, pf in CONFIGS:
     h = C.c_void_p()
     _native.check(lib, lib.mgb_host_io_create(threads, chunk, ring, C.byref(h)))
     handles.append(h)
 
 
 def call(i, k):
-    label, threads, chunk, ring, nt, dring, whole = CONFIGS[i]
-    for name, value in (("host_streaming_stores", nt), ("host_download_ring", dring), ("host_split_chunks", whole)):
+    label, threads, chunk, ring, nt, dring, whole, pf = CONFIGS[i]
+    for name, value in (("host_streaming_stores", nt), ("host_download_ring", dring), ("host_split_chunks", whole), ("host_prefetch", pf)):
         _native.check(lib, lib.mgb_set_option(name.encode(), value))
     t0 = time.perf_counter()
     _native.check(lib, lib.mgb_stages_main_host(handles[i], C.byref(plan.struct), C.byref(sess.layout), ts[k % 3].ctypes.data,
