@@ -113,6 +113,102 @@ struct Dft<1, DIR, T> {
     static __device__ __forceinline__ void run(cpx<T>*) {}
 };
 
+// Where a frame lives in shared memory between passes.
+// SplitPlanes: two padded arrays (re / im), one extra word per 32 -- used by the float64 transforms.
+// PackedPlanes: one padded float2 array, one extra element per 16 -- used by the float32 kernels:
+// a point is one 8-byte access instead of two 4-byte ones, which halves the shared-memory
+// instructions of kernels that are bound by instruction issue.  Both paddings keep the stride-R
+// scatters of the early passes and the unit-stride gathers conflict-free.
+template <typename T>
+struct SplitPlanes {
+    T* re;
+    T* im;
+    static constexpr int kPadEvery = 32;  // one extra element per kPadEvery points
+    static __device__ __host__ constexpr int pad(int i) { return i + (i >> 5); }
+    __device__ __forceinline__ cpx<T> load_at(int a) const { return cpx<T>{re[a], im[a]}; }  // a = pad(i)
+    __device__ __forceinline__ void store_at(int a, cpx<T> v) const {
+        re[a] = v.x;
+        im[a] = v.y;
+    }
+    static __device__ __host__ constexpr int elems(int n) { return n + (n >> 5) + 1; }
+    static __device__ __host__ constexpr size_t bytes(int n) { return 2 * (size_t)elems(n) * sizeof(T); }
+    __device__ __forceinline__ cpx<T> load(int i) const {
+        const int a = pad(i);
+        return cpx<T>{re[a], im[a]};
+    }
+    __device__ __forceinline__ void store(int i, cpx<T> v) const {
+        const int a = pad(i);
+        re[a] = v.x;
+        im[a] = v.y;
+    }
+};
+struct PackedPlanes {
+    float2* z;
+    static constexpr int kPadEvery = 16;
+    static __device__ __host__ constexpr int pad(int i) { return i + (i >> 4); }
+    __device__ __forceinline__ cpx<float> load_at(int a) const {  // a = pad(i)
+        const float2 v = z[a];
+        return cpx<float>{v.x, v.y};
+    }
+    __device__ __forceinline__ void store_at(int a, cpx<float> v) const { z[a] = make_float2(v.x, v.y); }
+    static __device__ __host__ constexpr int elems(int n) { return n + (n >> 4) + 1; }
+    static __device__ __host__ constexpr size_t bytes(int n) { return (size_t)elems(n) * sizeof(float2); }
+    __device__ __forceinline__ cpx<float> load(int i) const {
+        const float2 v = z[pad(i)];
+        return cpx<float>{v.x, v.y};
+    }
+    __device__ __forceinline__ void store(int i, cpx<float> v) const { z[pad(i)] = make_float2(v.x, v.y); }
+};
+template <typename P>
+struct PlaneLoad {
+    P p;
+    __device__ __forceinline__ auto operator()(int i) const { return p.load(i); }
+};
+template <typename P>
+struct PlaneStore {
+    P p;
+    template <typename V>
+    __device__ __forceinline__ void operator()(int i, V v) const { p.store(i, v); }
+};
+
+// Strided accesses of a pass, with the padding taken out of the per-access arithmetic.  pad(i) = i + i/Q, and
+// for a stride D that is a multiple of Q, pad(i + r*D) = pad(i) + r*(D + D/Q) exactly (the low bits of i never
+// carry into a multiple of Q): one padded base per butterfly, the rest is an immediate offset of the LDS / STS.
+// Left to itself the compiler forms every index and pads it again: three integer instructions per access
+// (LOP3, LEA.HI, LEA), ~700 of the 16384-point convolution frame's ~3000 instructions per thread.
+// Functors that are not planes (landing buffers, accumulators) keep the plain call.
+template <typename Fn> struct PlaneOf { static constexpr int every = 0; };
+template <typename P> struct PlaneOf<PlaneLoad<P>> { static constexpr int every = P::kPadEvery; };
+template <typename P> struct PlaneOf<PlaneStore<P>> { static constexpr int every = P::kPadEvery; };
+
+// v[r] = load(i0 + r*D), r < R
+template <int R, int D, typename T, typename Load>
+__device__ __forceinline__ void strided_load(Load load, int i0, cpx<T>* v) {
+    constexpr int Q = PlaneOf<Load>::every;
+    if constexpr (Q > 0 && D % (Q > 0 ? Q : 1) == 0) {
+        const int a0 = decltype(load.p)::pad(i0);
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = load.p.load_at(a0 + r * (D + D / (Q > 0 ? Q : 1)));
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = load(i0 + r * D);
+    }
+}
+// store(i0 + q*D, v[q]), q < R.  D == 1 needs i0 to be a multiple of R (R dividing the padding period).
+template <int R, int D, typename T, typename Store>
+__device__ __forceinline__ void strided_store(Store store, int i0, const cpx<T>* v) {
+    constexpr int Q = PlaneOf<Store>::every;
+    if constexpr (Q > 0 && (D % (Q > 0 ? Q : 1) == 0 || (D == 1 && (Q > 0 ? Q : 1) % R == 0))) {
+        const int a0 = decltype(store.p)::pad(i0);
+        constexpr int step = D == 1 ? 1 : D + D / (Q > 0 ? Q : 1);
+#pragma unroll
+        for (int q = 0; q < R; ++q) store.p.store_at(a0 + q * step, v[q]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < R; ++q) store(i0 + q * D, v[q]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // one Stockham pass
 // ------------------------------------------------------------------------------------------------
@@ -171,8 +267,7 @@ __device__ __forceinline__ void fft_pass(const cpx<T>* __restrict__ tw, Load loa
 #pragma unroll
         for (int p = 0; p < PER; ++p) {
             const int j = tid + p * THREADS;
-#pragma unroll
-            for (int r = 0; r < R; ++r) v[p][r] = load(j + r * NB);
+            strided_load<R, NB>(load, j, v[p]);
         }
     }
     if (barrier_between) __syncthreads();
@@ -197,58 +292,11 @@ __device__ __forceinline__ void fft_pass(const cpx<T>* __restrict__ tw, Load loa
                 }
             }
             Dft<R, DIR, T>::run(v[p]);
-            const int j0 = (j - k) * R + k;
-#pragma unroll
-            for (int q = 0; q < R; ++q) store(j0 + q * NS, v[p][q]);
+            const int j0 = (j - k) * R + k;  // (NS == 1: k = 0, j0 = j*R)
+            strided_store<R, NS>(store, j0, v[p]);
         }
     }
 }
-
-// Where a frame lives in shared memory between passes.
-// SplitPlanes: two padded arrays (re / im), one extra word per 32 -- used by the float64 transforms.
-// PackedPlanes: one padded float2 array, one extra element per 16 -- used by the float32 kernels:
-// a point is one 8-byte access instead of two 4-byte ones, which halves the shared-memory
-// instructions of kernels that are bound by instruction issue.  Both paddings keep the stride-R
-// scatters of the early passes and the unit-stride gathers conflict-free.
-template <typename T>
-struct SplitPlanes {
-    T* re;
-    T* im;
-    static __device__ __host__ constexpr int pad(int i) { return i + (i >> 5); }
-    static __device__ __host__ constexpr int elems(int n) { return n + (n >> 5) + 1; }
-    static __device__ __host__ constexpr size_t bytes(int n) { return 2 * (size_t)elems(n) * sizeof(T); }
-    __device__ __forceinline__ cpx<T> load(int i) const {
-        const int a = pad(i);
-        return cpx<T>{re[a], im[a]};
-    }
-    __device__ __forceinline__ void store(int i, cpx<T> v) const {
-        const int a = pad(i);
-        re[a] = v.x;
-        im[a] = v.y;
-    }
-};
-struct PackedPlanes {
-    float2* z;
-    static __device__ __host__ constexpr int pad(int i) { return i + (i >> 4); }
-    static __device__ __host__ constexpr int elems(int n) { return n + (n >> 4) + 1; }
-    static __device__ __host__ constexpr size_t bytes(int n) { return (size_t)elems(n) * sizeof(float2); }
-    __device__ __forceinline__ cpx<float> load(int i) const {
-        const float2 v = z[pad(i)];
-        return cpx<float>{v.x, v.y};
-    }
-    __device__ __forceinline__ void store(int i, cpx<float> v) const { z[pad(i)] = make_float2(v.x, v.y); }
-};
-template <typename P>
-struct PlaneLoad {
-    P p;
-    __device__ __forceinline__ auto operator()(int i) const { return p.load(i); }
-};
-template <typename P>
-struct PlaneStore {
-    P p;
-    template <typename V>
-    __device__ __forceinline__ void operator()(int i, V v) const { p.store(i, v); }
-};
 
 // Radix schedule of an N-point transform.  Sizes outside this list are rejected by the C ABI.
 template <int N> struct Radices;
@@ -277,9 +325,7 @@ __device__ __forceinline__ void fft_first_pass_regs(Planes pl, cpx<T>* v, bool b
     static_assert(N / R == THREADS, "one butterfly per thread in the first pass");
     if (barrier_before_store) __syncthreads();
     Dft<R, DIR, T>::run(v);
-    const int j0 = threadIdx.x * R;  // NS = 1
-#pragma unroll
-    for (int q = 0; q < R; ++q) pl.store(j0 + q, v[q]);
+    strided_store<R, 1>(PlaneStore<Planes>{pl}, threadIdx.x * R, v);  // NS = 1
 }
 
 // Remaining passes, in place on the planes; the caller has put a barrier after the first pass.
@@ -364,8 +410,7 @@ __device__ __forceinline__ void fft_middle(Planes pl, const cpx<T>* __restrict__
 // The R inputs of butterfly j of a pass with NB = N/R butterflies.
 template <int R, int NB, typename T, typename Load>
 __device__ __forceinline__ void fft_gather(Load load, int j, cpx<T>* v) {
-#pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = load(j + r * NB);
+    strided_load<R, NB>(load, j, v);
 }
 // Twiddle (index k = j mod NS) and radix-R DFT of one gathered butterfly; outputs belong at
 // (j - k)*R + k + q*NS.
