@@ -342,16 +342,24 @@ def run_b200(args) -> dict:
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=device)
+        mine = sorted(os.sched_getaffinity(0))
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        sharing = sum(1 for other in everyone if other and other[0] == mine[0])  # ranks on this rank's socket
         if "MGB_HOST_THREADS" not in os.environ:
             # ranks whose GPUs hang off the same socket share its hardware threads: one worker per thread in all
             # (measured with four ranks on one 64-thread socket: 16 workers each 7.8 ms per call, 8 each 9.2 ms)
-            mine = sorted(os.sched_getaffinity(0))
-            everyone = [None] * world
-            dist.all_gather_object(everyone, mine)
-            sharing = sum(1 for other in everyone if other and other[0] == mine[0])
             # ... and all ranks share the container's CPU quota (usable_cores): leave the main threads their share
             budget = min(len(mine) // max(1, sharing), usable_cores() // world - 3)
             os.environ["MGB_HOST_THREADS"] = str(max(4, min(16, budget)))
+        # The transport's two modes (csrc/hostio.cu): "streaming" (staging chunks written past the caches, every
+        # staged byte crosses the socket's memory twice more; fastest for one or two ranks per socket) and "cached"
+        # (ordinary stores into a 4 MB ring that stays in the cores' caches, results by one DMA: no staging traffic
+        # in memory, what ranks that compete for one socket's memory bandwidth want).
+        mode = os.environ.get("MGB_BENCH_SHARED_SOCKET_MODE", SHARED_SOCKET_MODE if sharing >= 3 else "streaming")
+        if mode == "cached":
+            os.environ.setdefault("MGB_HOST_NT", "0")
+            os.environ.setdefault("MGB_DOWNLOAD_RING", "0")
 
     port = oracle()  # synthetic-input recipes + the cpu_baseline leg only
     import matchering_b200 as mg
@@ -658,14 +666,17 @@ def run_b200(args) -> dict:
                             "sample": f"the first {sample_s:.0f} s of one {seconds:.0f}-s {name} track, oracle/port.py "
                                       f"(numpy/scipy float64, one thread), {cpu_s:.2f} s wall; host has "
                                       f"{os.cpu_count()} hardware threads"}
+        ring_route = bool(lib.mgb_host_download_through_ring(2 * n))  # the result crosses the link as float32 / float64
         e2e = {"value": xrt(times["seam"]), "unit": UNIT, "ms_per_step": times["seam"] / args.steps,
-               "h2d_bytes_per_step": (1 if is_limiter else 2) * n * 8, "d2h_bytes_per_step": n * 16,
+               "h2d_bytes_per_step": (1 if is_limiter else 2) * n * 8, "d2h_bytes_per_step": n * (8 if ring_route else 16),
                "host_bytes_read_per_step": (1 if is_limiter else 2) * n * 16, "host_threads": io.threads,
                "api": ("matchering_b200.limiter.limit" if is_limiter else "matchering_b200.stages.main")
                       + "(float64 numpy in pageable memory) -> float64 numpy, one synchronous call per step: the library's "
                         "worker threads narrow the arrays to float32 into a pinned ring while the link copies them, the "
-                        "result is widened on the device and copied into pooled pinned memory; wall clock between device "
-                        "synchronisations"}
+                        + ("result comes back as float32 chunks through the same ring and is widened by the workers into "
+                           "pooled pinned memory" if ring_route else
+                           "result is widened on the device and copied into pooled pinned memory by one DMA")
+                        + "; wall clock between device synchronisations"}
         if "batch_f32" in times:
             e2e["batch_f32"] = {"value": xrt(times["batch_f32"]), "ms_per_step": times["batch_f32"] / args.steps,
                                 "h2d_bytes_per_step": 2 * n * 8, "d2h_bytes_per_step": n * 8,
@@ -700,6 +711,10 @@ def run_b200(args) -> dict:
         dist.barrier()
         dist.destroy_process_group()
     return result or {}
+
+
+# transport mode of ranks that share a socket with two or more other ranks (tools/gpu_n4_transport.sh decides)
+SHARED_SOCKET_MODE = "cached"
 
 
 def main():

@@ -249,10 +249,11 @@ int mgb_process_host(const mgb_plan* plan, const mgb_track_layout* layout, const
  * pool of worker threads narrows float64 -> float32 (or copies float32) into a ring of pinned chunks
  * while the calling thread issues one asynchronous copy per finished chunk; results come back either
  * widened on the device and DMA'd straight into pinned memory from mgb_host_alloc (one copy, no host
- * pass), or as float32 chunks through the same ring, widened by the workers, into any other memory.
+ * pass), or as float32 chunks through the same ring, widened by the workers (half the bytes over the link).
  * `*_width` = bytes per sample of the host arrays: 4 (float32) or 8 (float64).
  * threads / chunk_samples / ring <= 0 pick defaults (16 workers, fewer under a smaller affinity mask or cgroup
- * CPU quota; 64 Ki samples; 16 chunks -- a 4 MB ring that stays in cache between the workers and the DMA engine).  One transfer at a time per mgb_host_io. */
+ * CPU quota; six chunks of 1 Mi samples written with streaming stores -- with MGB_HOST_NT=0 sixteen chunks of
+ * 64 Ki samples, a 4 MB ring that stays in the cores' caches).  One transfer at a time per mgb_host_io. */
 typedef struct mgb_host_io mgb_host_io;
 int mgb_host_io_create(int32_t threads, int64_t chunk_samples, int32_t ring, mgb_host_io** out);
 int mgb_host_io_destroy(mgb_host_io* io);
@@ -262,11 +263,15 @@ void* mgb_host_alloc(int64_t bytes);
 void mgb_host_free(void* p);
 /* host array -> device float32; returns when the last chunk has left the staging ring */
 int mgb_host_upload(mgb_host_io* io, const void* h_src, int32_t src_width, float* d_dst, int64_t samples, void* stream);
-/* device float32 -> host array.  Pinned destinations (mgb_host_alloc) are written by ONE DMA: float32 as it is,
- * float64 after widening on the device into d_wide (`samples` doubles; NULL = no such route).  Anything else is
- * filled by the worker threads from float32 chunks that come through the ring.  Synchronises `stream`. */
+/* device float32 -> host array.  Pinned float32 destinations (mgb_host_alloc) are written by ONE DMA.  Pinned
+ * float64 destinations: up to 64 Mi samples as float32 chunks through the ring, widened by the workers; above
+ * that (or with option host_download_ring = 0) widened on the device into d_wide (`samples` doubles; NULL = no
+ * such route) and written by ONE DMA.  Anything else is filled by the workers from chunks that come through the
+ * ring.  Synchronises `stream`. */
 int mgb_host_download(mgb_host_io* io, const float* d_src, void* h_dst, int32_t dst_width, int64_t samples,
                       double* d_wide, void* stream);
+/* 1 if a pinned float64 result of `samples` samples crosses the link as float32 (ring route), 0 if as float64 */
+int mgb_host_download_through_ring(int64_t samples);
 
 /* device staging of one job, provided by the caller (PyTorch allocations on the Python side) */
 typedef struct mgb_host_buffers {

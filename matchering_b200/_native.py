@@ -148,6 +148,7 @@ PROTOTYPES = {
     "mgb_host_io_create": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.POINTER(C.c_void_p)]),
     "mgb_host_io_destroy": (C.c_int, [C.c_void_p]),
     "mgb_host_io_threads": (C.c_int, [C.c_void_p]),
+    "mgb_host_download_through_ring": (C.c_int, [C.c_int64]),
     "mgb_host_alloc": (C.c_void_p, [C.c_int64]),
     "mgb_host_free": (None, [C.c_void_p]),
     "mgb_host_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),

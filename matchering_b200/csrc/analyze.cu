@@ -40,7 +40,7 @@ struct AnalyzeFirst {
     }
 };
 
-template <int F>
+template <int F, bool CHAIN>
 __global__ void __launch_bounds__(F / 16)
 analyze_kernel(const float2* __restrict__ x, long long frames, long long piece, int divisions, int slots,
                const cpx<float>* __restrict__ tw, float* __restrict__ spec_part, double* __restrict__ sumsq_part,
@@ -142,7 +142,7 @@ analyze_kernel(const float2* __restrict__ x, long long frames, long long piece, 
             fence_proxy_async();
             issue(f + 1);  // overlaps the remaining passes of this frame
         }
-        fft_remaining<F, +1, THREADS, float>(planes, tw, PlaneStore<PackedPlanes>{planes}, /*last_in_place=*/true);
+        fft_remaining<F, +1, THREADS, float, CHAIN>(planes, tw, PlaneStore<PackedPlanes>{planes}, /*last_in_place=*/true);
         __syncthreads();
 #pragma unroll
         for (int b = 0; b < BINS; ++b) {
@@ -203,7 +203,10 @@ analyze_kernel(const float2* __restrict__ x, long long frames, long long piece, 
 template <int F>
 int launch_analyze_t(const mgb_plan& plan, const float2* x, int64_t frames, int64_t piece, int divisions, int slots,
                      float* spec_part, double* sumsq_part, float* absmax_part, cudaStream_t stream) {
-    return launch("analyze_kernel", analyze_kernel<F>, dim3(slots, divisions), dim3(F / 16), AnalyzeSmem<F>::kBytes,
+    // option "analyze_chain": twiddle powers built in registers from two table reads per radix-16 butterfly
+    // instead of fifteen reads (what the convolution's transforms do)
+    auto kernel = g_analyze_chain ? analyze_kernel<F, true> : analyze_kernel<F, false>;
+    return launch("analyze_kernel", kernel, dim3(slots, divisions), dim3(F / 16), AnalyzeSmem<F>::kBytes,
                   stream, x, (long long)frames, (long long)piece, divisions, slots,
                   (const cpx<float>*)plan.d_tw_f32_F, spec_part, sumsq_part, absmax_part, g_use_tma);
 }

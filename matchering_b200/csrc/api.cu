@@ -13,6 +13,8 @@ namespace mgb {
 
 int g_use_tma = 1;
 int g_twiddle_chain = 1;
+int g_analyze_chain = 0;
+int g_conv_persistent = 0;
 int g_conv_fused = 1;
 int g_conv_ovs = 4;
 int g_clip_ctas_per_sm = 3;
@@ -299,6 +301,14 @@ int mgb_set_option(const char* name, int value) {
     }
     if (strcmp(name, "twiddle_chain") == 0) {
         g_twiddle_chain = value ? 1 : 0;
+        return MGB_OK;
+    }
+    if (strcmp(name, "conv_persistent") == 0) {
+        g_conv_persistent = value ? 1 : 0;
+        return MGB_OK;
+    }
+    if (strcmp(name, "analyze_chain") == 0) {
+        g_analyze_chain = value ? 1 : 0;
         return MGB_OK;
     }
     if (strcmp(name, "lookback_inclusive") == 0) {

@@ -51,39 +51,68 @@ struct ConvBalance {
     bool mid_silent, side_silent, any_silent;
 };
 
+// The part of a frame's N input samples that lies inside the signal, and how the bulk copy brings it in.
+struct ConvSpan {
+    long long lo, hi;   // [lo, hi) absolute sample indices
+    long long count;    // samples the bulk copy moves (even: 16-byte granules)
+    int fix_index;      // buffer index of the odd last sample that comes through a plain load, or -1
+};
+template <int N>
+__device__ __forceinline__ ConvSpan conv_span(long long frames, long long origin) {
+    ConvSpan sp;
+    sp.lo = origin < 0 ? 0 : origin;
+    sp.hi = (origin + N < frames) ? origin + N : frames;  // exclusive
+    // lo - origin is 0 or F/2 (multiple of 2): source and destination stay 16-byte aligned
+    sp.count = sp.hi - sp.lo;
+    sp.fix_index = -1;
+    if (sp.count & 1) {  // odd tail: the last sample comes through a plain load
+        sp.fix_index = (int)(sp.hi - 1 - origin);
+        sp.count -= 1;
+    }
+    return sp;
+}
+// (one thread) start the bulk copy of the frame at `origin` into the landing buffer
+template <int N>
+__device__ __forceinline__ void conv_issue_frame(const float2* __restrict__ x, long long frames, long long origin, float2* raw,
+                                                 TmaBarrier* bar) {
+    const ConvSpan sp = conv_span<N>(frames, origin);
+    tma_load_1d(raw + (sp.lo - origin), x + sp.lo, (uint32_t)(sp.count * 8), bar);
+}
+
 // Loads the frame's N input samples (clipped to the signal) into the landing buffer, hands every thread
 // its 16 points z[r] = mid + i*g*side of index tid + r*THREADS.  On return every thread is past a
 // barrier that follows its last read of the landing buffer.
+// `prefetched_phase` >= 0: the bulk copy was issued earlier (conv_issue_frame) on a barrier that is in that
+// phase, and red_u is already zero; the function only waits.
 template <int N, int PTS = 16>
 __device__ __forceinline__ ConvBalance conv_load_frame(const float2* __restrict__ x, long long frames, long long origin,
                                                        float2* raw, TmaBarrier* bar, unsigned* red_u, int use_tma,
-                                                       cpx<float>* z) {
+                                                       cpx<float>* z, int prefetched_phase = -1) {
     constexpr int THREADS = N / PTS;
     const int tid = threadIdx.x;
-    const long long lo = origin < 0 ? 0 : origin;
-    const long long hi = (origin + N < frames) ? origin + N : frames;  // exclusive
+    const ConvSpan span = conv_span<N>(frames, origin);
+    const long long lo = span.lo, hi = span.hi;
     ConvFirst first;
     first.raw = raw;
     first.lo = (int)(lo - origin);
     first.hi = (int)(hi - origin);
-    first.fixup = nullptr;
-    first.fix_index = -1;
-    if (tid == 0) red_u[0] = red_u[1] = 0u;
-    if (use_tma) {
-        if (tid == 0) tma_barrier_init(bar);
-        __syncthreads();
-        // lo - origin is 0 or F/2 (multiple of 2): source and destination stay 16-byte aligned
-        long long count = hi - lo;
-        if (count & 1) {  // odd tail: the last sample comes through a plain load
-            first.fix_index = (int)(hi - 1 - origin);
-            first.fixup = x + (hi - 1);
-            count -= 1;
-        }
-        if (tid == 0) tma_load_1d(raw + (lo - origin), x + lo, (uint32_t)(count * 8), bar);
-        tma_barrier_wait(bar, 0);
+    first.fixup = span.fix_index >= 0 ? x + (hi - 1) : nullptr;
+    first.fix_index = span.fix_index;
+    if (prefetched_phase >= 0) {
+        tma_barrier_wait(bar, (uint32_t)prefetched_phase);
     } else {
-        for (long long n = lo + tid; n < hi; n += THREADS) raw[n - origin] = x[n];
-        __syncthreads();
+        if (tid == 0) red_u[0] = red_u[1] = 0u;
+        if (use_tma) {
+            if (tid == 0) tma_barrier_init(bar);
+            __syncthreads();
+            if (tid == 0) tma_load_1d(raw + (lo - origin), x + lo, (uint32_t)(span.count * 8), bar);
+            tma_barrier_wait(bar, 0);
+        } else {
+            first.fixup = nullptr;
+            first.fix_index = -1;
+            for (long long n = lo + tid; n < hi; n += THREADS) raw[n - origin] = x[n];
+            __syncthreads();
+        }
     }
     float max_mid = 0.0f, max_side = 0.0f;
     // each channel from L and R directly, one rounding each: (L-R)/2 is the reference's mid - R, and
@@ -296,12 +325,17 @@ convolve_kernel(const float2* __restrict__ x, long long frames, long long piece,
 // on F outputs; OVS = 4 spends a 4F-point pair on 3F outputs: 5*4F*log2(4F)*2 / 3F = 187 flop per output
 // frame for F = 4096 against 260 (-28 %), at one 139 KB CTA of 1024 threads per SM instead of two
 // 70 KB CTAs of 512.
-template <int F, int OVS, bool CHAIN>
+//
+// PERSIST (option "conv_persistent"): one CTA per SM walks the frames blockIdx.x, blockIdx.x + gridDim.x, ...; as
+// soon as every thread has gathered its inputs of the last inverse pass the frame buffer is free, and the bulk copy
+// of the CTA's NEXT frame is issued into it -- it lands while the last butterflies, the epilogue's stores and the
+// block reduction run, instead of being waited for with the whole SM idle at the top of the frame.
+template <int F, int OVS, bool CHAIN, bool PERSIST>
 __global__ void __launch_bounds__(OVS * F / 16, (OVS * F <= 8192 ? 2 : 1))
 convolve_fused_kernel(const float2* __restrict__ x, long long frames, long long piece, int divisions,
                       const cpx<float>* __restrict__ tw, const float2* __restrict__ h_mid,
                       const float2* __restrict__ h_side, float2* __restrict__ result, float* __restrict__ mid_plane,
-                      double* __restrict__ piece_sums, mgb_track_state* __restrict__ state, int use_tma) {
+                      double* __restrict__ piece_sums, mgb_track_state* __restrict__ state, int use_tma, int nframes) {
     constexpr int N = OVS * F;
     constexpr int OUT = N - F;  // outputs per frame
     constexpr int THREADS = N / 16;
@@ -318,12 +352,23 @@ convolve_fused_kernel(const float2* __restrict__ x, long long frames, long long 
     const PackedPlanes planes = sp.planes;
     const PlaneLoad<PackedPlanes> sl{planes};
     const int tid = threadIdx.x;
-    const long long n0 = (long long)blockIdx.x * OUT;
+    if constexpr (PERSIST) {
+        if (tid == 0) {
+            tma_barrier_init(sp.bar);
+            sp.red_u[0] = sp.red_u[1] = 0u;
+        }
+        __syncthreads();
+        if (tid == 0 && (int)blockIdx.x < nframes) conv_issue_frame<N>(x, frames, (long long)blockIdx.x * OUT - F / 2, sp.raw, sp.bar);
+    }
+    const int frame_end = PERSIST ? nframes : (int)blockIdx.x + 1;
+    int phase = 0;
+    for (int frame = blockIdx.x; frame < frame_end; frame += gridDim.x, ++phase) {
+    const long long n0 = (long long)frame * OUT;
 
     ConvBalance bal;
     {
         cpx<float> z[N / THREADS];
-        bal = conv_load_frame<N>(x, frames, n0 - F / 2, sp.raw, sp.bar, sp.red_u, use_tma, z);
+        bal = conv_load_frame<N>(x, frames, n0 - F / 2, sp.raw, sp.bar, sp.red_u, use_tma, z, PERSIST ? phase : -1);
         fft_first_pass_regs<N, +1, THREADS, float>(planes, z, /*barrier_before_store=*/false);
     }
     __syncthreads();
@@ -375,6 +420,16 @@ convolve_fused_kernel(const float2* __restrict__ x, long long frames, long long 
         const int j = tid + p * THREADS;
         cpx<float> v[8];
         fft_gather<8, NB8>(sl, j, v);
+        if constexpr (PERSIST) {
+            if (p == 1) {  // the frame buffer has been read for the last time: the next frame may land in it
+                if (tid == 0) sp.red_u[0] = sp.red_u[1] = 0u;
+                __syncthreads();
+                if (tid == 0 && frame + (int)gridDim.x < nframes) {
+                    fence_proxy_async();
+                    conv_issue_frame<N>(x, frames, (long long)(frame + gridDim.x) * OUT - F / 2, sp.raw, sp.bar);
+                }
+            }
+        }
         fft_butterfly<8, NB8, -1, CHAIN>(tw_last, j, v);  // v[q] = y[j + q*NB8]
         if (ep.full) {
 #pragma unroll
@@ -388,6 +443,7 @@ convolve_fused_kernel(const float2* __restrict__ x, long long frames, long long 
         }
     }
     ep.finish(sp.red_a, sp.red_b, sp.red_f, piece_sums, state);
+    }  // frames of this CTA
 }
 
 template <int F>
@@ -402,21 +458,35 @@ int launch_convolve_t(const mgb_plan& plan, const mgb_track_layout& layout, cons
                       (const float2*)ws.h_mid, (const float2*)ws.h_side, result, ws.mid_plane, ws.piece_sums, state,
                       g_use_tma);
     };
+    auto args2 = [&](auto kernel, int out, int threads, size_t smem) {  // (the fused kernel also takes the frame count)
+        const unsigned nframes = (unsigned)((T + out - 1) / out);
+        return launch("convolve_kernel", kernel, dim3(nframes), dim3(threads), smem, stream, target, T,
+                      (long long)layout.target_piece, layout.target_divisions, (const cpx<float>*)plan.d_tw_f32_2F,
+                      (const float2*)ws.h_mid, (const float2*)ws.h_side, result, ws.mid_plane, ws.piece_sums, state,
+                      g_use_tma, (int)nframes);
+    };
     if constexpr (InverseRadices<4 * F>::fused) {
         if (ovs == 4) {
             // twiddles of the 4F transform live behind the 2F tables (mgb_plan_twiddle_bytes)
             const cpx<float>* tw4 = (const cpx<float>*)plan.d_tw_f32_2F + twiddle_count(2 * F) + inverse_twiddle_count(2 * F);
             const unsigned nframes = (unsigned)((T + 3 * F - 1) / (3 * F));
-            auto kernel = g_twiddle_chain ? convolve_fused_kernel<F, 4, true> : convolve_fused_kernel<F, 4, false>;
+            if (g_conv_persistent && g_use_tma && 4 * F > 8192) {  // (one CTA per SM: the 16384-point frames)
+                const unsigned grid = nframes < (unsigned)num_sms() ? nframes : (unsigned)num_sms();
+                auto kernel = g_twiddle_chain ? convolve_fused_kernel<F, 4, true, true> : convolve_fused_kernel<F, 4, false, true>;
+                return launch("convolve_kernel", kernel, dim3(grid), dim3(4 * F / 16), ConvSmem<4 * F>::kBytes, stream, target, T,
+                              (long long)layout.target_piece, layout.target_divisions, tw4, (const float2*)ws.h_mid,
+                              (const float2*)ws.h_side, result, ws.mid_plane, ws.piece_sums, state, g_use_tma, (int)nframes);
+            }
+            auto kernel = g_twiddle_chain ? convolve_fused_kernel<F, 4, true, false> : convolve_fused_kernel<F, 4, false, false>;
             return launch("convolve_kernel", kernel, dim3(nframes), dim3(4 * F / 16), ConvSmem<4 * F>::kBytes, stream, target, T,
                           (long long)layout.target_piece, layout.target_divisions, tw4, (const float2*)ws.h_mid,
-                          (const float2*)ws.h_side, result, ws.mid_plane, ws.piece_sums, state, g_use_tma);
+                          (const float2*)ws.h_side, result, ws.mid_plane, ws.piece_sums, state, g_use_tma, (int)nframes);
         }
     }
     if constexpr (InverseRadices<2 * F>::fused) {
         if (g_conv_fused)
-            return args(g_twiddle_chain ? convolve_fused_kernel<F, 2, true> : convolve_fused_kernel<F, 2, false>, F, F / 8,
-                        ConvSmem<2 * F>::kBytes);
+            return args2(g_twiddle_chain ? convolve_fused_kernel<F, 2, true, false> : convolve_fused_kernel<F, 2, false, false>, F, F / 8,
+                         ConvSmem<2 * F>::kBytes);
     }
     return args(g_twiddle_chain ? convolve_kernel<F, true> : convolve_kernel<F, false>, F, F / 8, ConvSmem<2 * F>::kBytes);
 }

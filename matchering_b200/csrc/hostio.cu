@@ -78,7 +78,10 @@ namespace {
 
 // tuning switches (mgb_set_option "host_download_ring" / "host_split_chunks" / "host_streaming_stores"; the
 // environment gives their initial values)
-int g_host_download_ring = getenv("MGB_DOWNLOAD_RING") ? atoi(getenv("MGB_DOWNLOAD_RING")) : 0;
+// host_download_ring: 0 = pinned float64 results always by one DMA of device-widened data, 1 = through the ring up to
+// kRingDownloadMaxSamples (default), 2 = always through the ring
+int g_host_download_ring = getenv("MGB_DOWNLOAD_RING") ? atoi(getenv("MGB_DOWNLOAD_RING")) : 1;
+constexpr int64_t kRingDownloadMaxSamples = 64LL << 20;  // 256 MB of float32: what has been measured to win
 int g_host_split_chunks = getenv("MGB_HOST_SPLIT") && !strcmp(getenv("MGB_HOST_SPLIT"), "chunk");
 
 class WorkerPool {
@@ -165,7 +168,7 @@ inline void widen_plain(const float* __restrict__ src, double* __restrict__ dst,
 // construction for the ring (slices start on 16-sample boundaries of a pinned allocation).
 // MGB_HOST_NT: 0 = plain stores, 1 = 256-bit streaming stores, 2 = 512-bit where the CPU has them (default).
 // MGB_HOST_PREFETCH: software prefetch distance in bytes (0 = none).
-static int g_prefetch = getenv("MGB_HOST_PREFETCH") ? atoi(getenv("MGB_HOST_PREFETCH")) : 0;
+static int g_prefetch = getenv("MGB_HOST_PREFETCH") ? atoi(getenv("MGB_HOST_PREFETCH")) : 8192;
 __attribute__((target("avx2"))) inline void narrow_stream(const double* __restrict__ src, float* __restrict__ dst, int64_t n) {
     int64_t i = 0;
     if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
@@ -412,12 +415,13 @@ int download(mgb_host_io* io, const float* d_src, void* h_dst, int dst_width, in
              cudaStream_t st) {
     MGB_REQUIRE(dst_width == 4 || dst_width == 8, MGB_ERR_INVALID, "host array must be float32 or float64");
     if (samples == 0) return MGB_OK;
-    // float64 results into pinned memory: widened on the device and copied by ONE DMA (2.4 ms for a 3-minute
-    // track at 54 GB/s).  Float32 chunks through the ring, widened by the workers, move half the bytes over the
-    // link and measured 1.5-1.8 ms for that track when the host was otherwise idle -- but 50 % SLOWER on the
-    // one-hour limiter buffer (2.5 GB: the widening competes with itself for the socket's memory bandwidth), so
-    // the DMA route, which does not depend on host threads at all, is the default; MGB_DOWNLOAD_RING=1 switches.
-    const bool prefer_ring = g_host_download_ring != 0;
+    // float64 results into pinned memory, two routes.  (a) Widened on the device and copied by ONE DMA: twice the
+    // bytes over the link (2.4 ms for a 3-minute track at 54 GB/s), no host thread involved.  (b) Float32 chunks
+    // through the ring, widened by the workers with streaming stores: 1.7 ms for that track (tools/seam_ab.py,
+    // profiles/r02_seam_ab2.txt: 4.90 against 5.74 ms per stages.main call) -- but 50 % SLOWER than (a) on the
+    // one-hour limiter buffer (2.5 GB: the widening competes with itself for the socket's memory bandwidth).
+    // So (b) up to 256 MB of float32 and (a) beyond; option host_download_ring = 0 / 2 forces (a) / (b).
+    const bool prefer_ring = mgb_host_download_through_ring(samples) != 0;
     const bool direct = is_pinned(h_dst) && (dst_width == 4 || (d_wide && !prefer_ring));
     if (direct) {
         const void* src = d_src;
@@ -556,16 +560,18 @@ int mgb_host_io_create(int32_t threads, int64_t chunk_samples, int32_t ring, mgb
 #endif
         threads = usable >= 19 ? 16 : (usable > 4 ? usable - 3 : (usable > 1 ? usable - 1 : 1));
     }
-    // A ring of eight 2 MB chunks, written with streaming stores.  Measured on the B200 host, one process
-    // (tools/seam_ab.py, alternating calls; profiles/r02_seam_ab.txt): with ordinary stores the DMA engine has to
-    // pull every line out of the writing core's cache and the ring drains at 13 GB/s, whatever its size (7.1 ms
-    // per stages.main call); with streaming stores the chunks sit in memory, the ring drains at link speed and
-    // larger chunks mean fewer copy launches (5.9 ms, 5.4 ms with the result widened by the workers too).
+    // A ring of six 4 MB chunks, written with streaming stores.  Measured on the B200 host (Xeon 8562Y+, 16 cores
+    // of quota per GPU), one process (tools/seam_ab.py, alternating calls; profiles/r02_seam_ab.txt, r02_seam_ab2.txt):
+    // with ordinary stores the DMA engine has to pull every line out of the writing core's cache and the ring
+    // drains at 13 GB/s, whatever its size (6.9-7.0 ms per stages.main call; demoting the lines to the last-level
+    // cache with CLDEMOTE after writing them: 5.9-6.9 ms); with streaming stores the chunks sit in memory and the
+    // ring drains at link speed (5.7 ms; 4.9 ms with the result coming back through the ring as well).  Larger chunks
+    // mean fewer copies, and a download pays ~18 us per copy: 2 MB chunks 5.20 ms, 4 MB 4.90, 8 MB 5.01.
     // With ordinary stores (MGB_HOST_NT=0) the best geometry is sixteen 256 KB chunks, which stay in the
     // cores' caches: that is what several processes sharing one socket's memory bandwidth should use
     // (tools/gpu_n4_sweep.sh: 7.8 ms per call against 14.3 ms with twelve 1 MB chunks going through memory).
-    if (chunk_samples <= 0) chunk_samples = g_stream_stores ? 1 << 19 : 1 << 16;
-    if (ring <= 0) ring = g_stream_stores ? 8 : 16;
+    if (chunk_samples <= 0) chunk_samples = g_stream_stores ? 1 << 20 : 1 << 16;
+    if (ring <= 0) ring = g_stream_stores ? 6 : 16;
     MGB_REQUIRE(threads <= 256 && ring <= 64 && chunk_samples % 16 == 0, MGB_ERR_INVALID, "host_io: bad geometry");
     mgb_host_io* io = new mgb_host_io();
     io->chunk = chunk_samples;
@@ -596,6 +602,10 @@ int mgb_host_io_destroy(mgb_host_io* io) {
 }
 
 int mgb_host_io_threads(const mgb_host_io* io) { return io && io->pool ? io->pool->size() : 0; }
+
+int mgb_host_download_through_ring(int64_t samples) {
+    return g_host_download_ring >= 2 || (g_host_download_ring == 1 && samples <= kRingDownloadMaxSamples);
+}
 
 void* mgb_host_alloc(int64_t bytes) {
     if (bytes <= 0) return nullptr;

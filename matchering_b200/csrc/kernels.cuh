@@ -125,6 +125,8 @@ extern int g_lookback_inclusive;  // limiter chunks publish their inclusive stat
 extern int g_clip_ctas_per_sm;  // grid of the correction passes, in CTAs per SM (tuning switch)
 extern int g_conv_ovs;       // convolution: FIR lengths per overlap-save frame where the long-frame kernel exists (4, default) or 2
 extern int g_conv_fused;     // convolution: ends of both transforms in registers where the schedule allows (1)
+extern int g_conv_persistent;  // convolution (16384-point frames): one CTA per SM walks its frames, next frame's bulk copy under the epilogue
+extern int g_analyze_chain;  // analysis FFT: twiddle powers built in registers (1) or all read from the table (0)
 extern int g_twiddle_chain;  // convolution FFTs: build twiddle powers in registers (1) or read them all (0)
 
 }  // namespace mgb

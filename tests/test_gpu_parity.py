@@ -579,6 +579,30 @@ def test_both_convolution_frame_lengths_against_oracle(torch_cuda, lib, fft_size
     assert lib.mgb_set_option(b"conv_frame", 3) != 0
 
 
+def test_kernel_variants_behind_switches_agree(torch_cuda, lib):
+    """The persistent convolution (one CTA per SM walks its frames, next frame's bulk copy under the epilogue) and the
+    analysis with twiddle powers built in registers: same results as the default kernels, on a track long enough
+    that every CTA of the persistent grid takes several frames."""
+    import port
+    from matchering_b200 import stages
+    cfg = _config(max_piece_size=15.0)
+    n = 44100 * 120 + 77  # 431 frames of 12288 outputs on 148 SMs: two or three per CTA
+    t, r = port.synth_target(n, 41), port.synth_reference(n - 4321, 42)
+    base = stages.main(t, r, cfg, True, True, True)
+    try:
+        for name in (b"conv_persistent", b"analyze_chain"):
+            assert lib.mgb_set_option(name, 1) == 0
+            got = stages.main(t, r, cfg, True, True, True)
+            assert lib.mgb_set_option(name, 0) == 0
+            for a, b in zip(got, base):
+                # the convolution variants are the same arithmetic in the same order (bit-identical); the chained
+                # twiddles differ in the last bits of the analysis spectra
+                assert np.abs(a - b).max() < (1e-6 if name == b"analyze_chain" else 1e-12), name
+    finally:
+        lib.mgb_set_option(b"conv_persistent", 0)
+        lib.mgb_set_option(b"analyze_chain", 0)
+
+
 def test_host_seam_results_are_owned_by_the_caller(torch_cuda):
     """stages.main(numpy) returns arrays in pooled pinned memory: two live results never share memory,
     a dropped result's block is reused, and the inputs are not touched (SURVEY.md 8b ownership)."""

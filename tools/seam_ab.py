@@ -33,20 +33,17 @@ out = HostIO.get().pool.array((n, 2), np.float64)
 stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 state = _native.TrackState()
 
-# (label, threads, chunk samples, ring, streaming stores, download through the ring, whole chunks per worker, prefetch bytes)
+# (label, threads, chunk samples, ring, streaming stores (0 plain, 1 / 2 = 256 / 512 bit), download route (0 one DMA of
+#  device-widened float64, 2 float32 chunks through the ring), whole chunks per worker, prefetch bytes)
 CONFIGS = [
-    ("t12 64K x16 plain  dma ", 12, 1 << 16, 16, 0, 0, 0, 0),
-    ("t12 256K x8 nt512  dma ", 12, 1 << 18, 8, 2, 0, 0, 0),
-    ("t12 512K x8 nt512  dma ", 12, 1 << 19, 8, 2, 0, 0, 0),
-    ("t12 512K x8 nt512  ring", 12, 1 << 19, 8, 2, 1, 0, 0),
-    ("t12 512K x8 nt512  ring pf4k", 12, 1 << 19, 8, 2, 1, 0, 4096),
-    ("t12 512K x8 nt512  ring pf8k", 12, 1 << 19, 8, 2, 1, 0, 8192),
-    ("t12 512K x8 nt256  ring", 12, 1 << 19, 8, 1, 1, 0, 0),
-    ("t12 1M x6   nt512  ring", 12, 1 << 20, 6, 2, 1, 0, 0),
-    ("t12 512K x8 nt512  whole-chunks ring", 12, 1 << 19, 16, 2, 1, 1, 0),
-    ("t13 512K x8 nt512  ring", 13, 1 << 19, 8, 2, 1, 0, 0),
-    ("t14 512K x8 nt512  ring", 14, 1 << 19, 8, 2, 1, 0, 0),
-    ("t10 512K x8 nt512  ring", 10, 1 << 19, 8, 2, 1, 0, 0),
+    ("t13 64K x16 plain  dma ", 13, 1 << 16, 16, 0, 0, 0, 0),
+    ("t13 512K x8 nt512  dma ", 13, 1 << 19, 8, 2, 0, 0, 0),
+    ("t15 512K x8 nt512  dma ", 15, 1 << 19, 8, 2, 0, 0, 0),
+    ("t13 512K x8 nt512  ring pf8k", 13, 1 << 19, 8, 2, 2, 0, 8192),
+    ("t13 1M x6   nt512  ring pf8k", 13, 1 << 20, 6, 2, 2, 0, 8192),
+    ("t13 1M x6   nt512  ring", 13, 1 << 20, 6, 2, 2, 0, 0),
+    ("t13 2M x4   nt512  ring pf8k", 13, 1 << 21, 4, 2, 2, 0, 8192),
+    ("t15 1M x6   nt512  ring pf8k", 15, 1 << 20, 6, 2, 2, 0, 8192),
 ]
 if len(sys.argv) > 2:
     CONFIGS = [c for c in CONFIGS if any(key in c[0] for key in sys.argv[2:])]
