@@ -13,8 +13,8 @@ namespace mgb {
 
 int g_use_tma = 1;
 int g_twiddle_chain = 1;
-int g_analyze_chain = 0;
-int g_conv_persistent = 0;
+int g_analyze_chain = 1;
+int g_conv_persistent = 1;
 int g_conv_fused = 1;
 int g_conv_ovs = 4;
 int g_clip_ctas_per_sm = 3;

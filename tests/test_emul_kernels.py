@@ -146,23 +146,26 @@ def test_long_frame_convolution_against_oracle(lib, fft_size, n, piece_s):
 
 
 def test_persistent_convolution_and_chained_analysis_twiddles(lib):
-    """Options conv_persistent (a CTA walks several frames; the next frame's bulk copy is issued into the frame
-    buffer once the last inverse pass has gathered from it) and analyze_chain: same results as the default kernels."""
+    """Defaults: conv_persistent (a CTA walks several frames; the next frame's bulk copy is issued into the frame
+    buffer once the last inverse pass has gathered from it) and analyze_chain (twiddle powers built in registers).
+    Switched off, the one-frame-per-CTA convolution gives the same bits and the table-read analysis the same
+    spectra to float32 rounding."""
     cfg = port.OracleConfig(max_piece_size=1.5)
     n = 12288 * 19 + 4097  # 20 frames of 3F outputs on the emulator's 8 SMs: two or three per CTA, ragged end
     t, r = port.synth_target(n, 5), port.synth_reference(n - 3001, 6)
     base, _, _, _, L = run_pipeline(cfg, t, r)
     assert L.target_piece >= 3 * 4096
+    _compare(base, port.main(t.astype(np.float64), r.astype(np.float64), cfg, True, True, True))
     try:
         for name, tol in ((b"conv_persistent", 0.0), (b"analyze_chain", 1e-6)):
-            assert lib.mgb_set_option(name, 1) == 0
-            outs, _, _, _, _ = run_pipeline(cfg, t, r)
             assert lib.mgb_set_option(name, 0) == 0
+            outs, _, _, _, _ = run_pipeline(cfg, t, r)
+            assert lib.mgb_set_option(name, 1) == 0
             for a, b in zip(outs, base):
                 assert np.abs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)).max() <= tol, name
     finally:
-        lib.mgb_set_option(b"conv_persistent", 0)
-        lib.mgb_set_option(b"analyze_chain", 0)
+        lib.mgb_set_option(b"conv_persistent", 1)
+        lib.mgb_set_option(b"analyze_chain", 1)
 
 
 @pytest.mark.parametrize("fft_size,sr", [(512, 44100), (512, 8000), (1024, 44100), (2048, 22050), (4096, 96000), (8192, 44100)])
