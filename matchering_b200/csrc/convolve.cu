@@ -484,9 +484,19 @@ int launch_convolve_t(const mgb_plan& plan, const mgb_track_layout& layout, cons
         }
     }
     if constexpr (InverseRadices<2 * F>::fused) {
-        if (g_conv_fused)
+        if (g_conv_fused) {
+            if (g_conv_persistent && g_use_tma && 2 * F > 8192) {  // (fft_size 8192: 16384-point frames, one CTA per SM)
+                const unsigned nframes = (unsigned)((T + F - 1) / F);
+                const unsigned grid = nframes < (unsigned)num_sms() ? nframes : (unsigned)num_sms();
+                auto kernel = g_twiddle_chain ? convolve_fused_kernel<F, 2, true, true> : convolve_fused_kernel<F, 2, false, true>;
+                return launch("convolve_kernel", kernel, dim3(grid), dim3(F / 8), ConvSmem<2 * F>::kBytes, stream, target, T,
+                              (long long)layout.target_piece, layout.target_divisions, (const cpx<float>*)plan.d_tw_f32_2F,
+                              (const float2*)ws.h_mid, (const float2*)ws.h_side, result, ws.mid_plane, ws.piece_sums, state,
+                              g_use_tma, (int)nframes);
+            }
             return args2(g_twiddle_chain ? convolve_fused_kernel<F, 2, true, false> : convolve_fused_kernel<F, 2, false, false>, F, F / 8,
                          ConvSmem<2 * F>::kBytes);
+        }
     }
     return args(g_twiddle_chain ? convolve_kernel<F, true> : convolve_kernel<F, false>, F, F / 8, ConvSmem<2 * F>::kBytes);
 }

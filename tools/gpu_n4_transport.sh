@@ -5,7 +5,7 @@ python -m matchering_b200.build > gpurun_out/r02_n4_build.log 2>&1
 : > gpurun_out/r02_n4_transport.log
 run() {
   tag=$1; shift
-  env "$@" python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 4 --steps 12 --warmup 4 --no-files --no-cpu-baseline 2> gpurun_out/r02_n4_$tag.err | grep '^{' > gpurun_out/r02_n4_$tag.json
+  env "$@" python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 4 --steps 10 --warmup 3 --no-files --no-cpu-baseline 2> gpurun_out/r02_n4_$tag.err | grep '^{' > gpurun_out/r02_n4_$tag.json
   python - "$tag" >> gpurun_out/r02_n4_transport.log <<'PY'
 import sys, json
 tag = sys.argv[1]
@@ -17,6 +17,5 @@ except Exception as ex:
 PY
 }
 run streaming_ring MGB_BENCH_SHARED_SOCKET_MODE=streaming
-run streaming_dma MGB_BENCH_SHARED_SOCKET_MODE=streaming MGB_DOWNLOAD_RING=0
 run cached_dma MGB_BENCH_SHARED_SOCKET_MODE=cached
 cat gpurun_out/r02_n4_transport.log
