@@ -55,10 +55,6 @@ static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cu
 static inline cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
-enum { cudaStreamNonBlocking = 1 };
-static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, int) { *s = nullptr; return cudaSuccess; }
-static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
-static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, int) { return cudaSuccess; }
 static std::mutex g_pinned_mutex;
 static std::map<const unsigned char*, size_t> g_pinned_blocks;  // what mgb_host_alloc / the ring handed out
 static inline cudaError_t cudaHostAlloc(void** p, size_t n, int) {
@@ -87,9 +83,6 @@ namespace {
 int g_host_download_ring = getenv("MGB_DOWNLOAD_RING") ? atoi(getenv("MGB_DOWNLOAD_RING")) : 1;
 constexpr int64_t kRingDownloadMaxSamples = 64LL << 20;  // 256 MB of float32: what has been measured to win
 int g_host_split_chunks = getenv("MGB_HOST_SPLIT") && !strcmp(getenv("MGB_HOST_SPLIT"), "chunk");
-// host_copy_streams: 1 = the chunk copies of a ring download follow each other on the caller's stream, 2 = they
-// alternate between it and a second stream of the transport, so that one copy's completion overlaps the next one's start
-int g_host_copy_streams = getenv("MGB_HOST_COPY_STREAMS") ? atoi(getenv("MGB_HOST_COPY_STREAMS")) : 1;
 
 class WorkerPool {
 public:
@@ -265,9 +258,6 @@ struct mgb_host_io {
     int ring = 0;
     float* staging = nullptr;  // pinned, ring * chunk floats
     std::vector<cudaEvent_t> events;
-    cudaStream_t aux = nullptr;    // second copy stream of ring downloads (option host_copy_streams = 2)
-    cudaEvent_t aux_gate = 0;      // "the caller's stream has produced the data" for that stream
-    bool has_aux = false;
 };
 
 using namespace mgb;
@@ -478,11 +468,6 @@ int download(mgb_host_io* io, const float* d_src, void* h_dst, int dst_width, in
         }
     };
     int rc = MGB_OK;
-    const bool two_streams = g_host_copy_streams >= 2 && io->has_aux;
-    if (two_streams) {  // the second stream may read d_src once the caller's stream has got this far
-        if (cudaEventRecord(io->aux_gate, st) != cudaSuccess || cudaStreamWaitEvent(io->aux, io->aux_gate, 0) != cudaSuccess)
-            return cuda_status("D2H second stream");
-    }
     auto lead = [&]() {
         int64_t issued = 0, landed = 0;
         const double lead_t0 = stats ? now_us() : 0.0;
@@ -498,9 +483,8 @@ int download(mgb_host_io* io, const float* d_src, void* h_dst, int dst_width, in
                 const int64_t len = (samples - base < chunk) ? samples - base : chunk;
                 const int slot = (int)(issued % ring);
                 const double c0 = stats ? now_us() : 0.0;
-                const cudaStream_t cs = (two_streams && (issued & 1)) ? io->aux : st;
-                if (cudaMemcpyAsync(io->staging + slot * chunk, d_src + base, (size_t)len * 4, cudaMemcpyDeviceToHost, cs) != cudaSuccess ||
-                    cudaEventRecord(io->events[slot], cs) != cudaSuccess) {
+                if (cudaMemcpyAsync(io->staging + slot * chunk, d_src + base, (size_t)len * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                    cudaEventRecord(io->events[slot], st) != cudaSuccess) {
                     rc = cuda_status("D2H chunk");
                     failed.store(1);
                     return;
@@ -536,7 +520,6 @@ int download(mgb_host_io* io, const float* d_src, void* h_dst, int dst_width, in
 bool mgb::host_set_option(const char* name, int value) {
     if (!strcmp(name, "host_download_ring")) g_host_download_ring = value;
     else if (!strcmp(name, "host_split_chunks")) g_host_split_chunks = value;
-    else if (!strcmp(name, "host_copy_streams")) g_host_copy_streams = value;
 #if defined(__x86_64__)
     else if (!strcmp(name, "host_streaming_stores")) g_stream_stores = clamp_stream_stores(value);
     else if (!strcmp(name, "host_prefetch")) g_prefetch = value;
@@ -603,8 +586,6 @@ int mgb_host_io_create(int32_t threads, int64_t chunk_samples, int32_t ring, mgb
             mgb_host_io_destroy(io);
             return cuda_status("host_io: events");
         }
-    io->has_aux = cudaStreamCreateWithFlags(&io->aux, cudaStreamNonBlocking) == cudaSuccess &&
-                  cudaEventCreateWithFlags(&io->aux_gate, cudaEventDisableTiming) == cudaSuccess;
     io->pool = new WorkerPool(threads);
     *out = io;
     return MGB_OK;
@@ -616,10 +597,6 @@ int mgb_host_io_destroy(mgb_host_io* io) {
     for (auto e : io->events)
         if (e) cudaEventDestroy(e);
     if (io->staging) cudaFreeHost(io->staging);
-    if (io->has_aux) {
-        cudaEventDestroy(io->aux_gate);
-        cudaStreamDestroy(io->aux);
-    }
     delete io;
     return MGB_OK;
 }

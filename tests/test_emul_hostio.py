@@ -71,8 +71,7 @@ def test_transport_switches_do_not_change_the_bytes(lib, io, stores, whole_chunk
     """Streaming stores (256 / 512 bit), whole chunks per worker, the ring route for pinned float64 results:
     tuning switches of the transport (mgb_set_option), every combination moves the same bytes."""
     switches = (("host_streaming_stores", stores, 2), ("host_split_chunks", whole_chunks, 0),
-                ("host_download_ring", download_ring, 1), ("host_prefetch", 4096 * whole_chunks, 8192),
-                ("host_copy_streams", 1 + whole_chunks, 1))
+                ("host_download_ring", download_ring, 1), ("host_prefetch", 4096 * whole_chunks, 8192))
     try:
         for name, value, _ in switches:
             _native.check(lib, lib.mgb_set_option(name.encode(), value))

@@ -9,7 +9,7 @@ python -m matchering_b200.build > gpurun_out/${TAG}_build.log 2>&1
 timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_c2.json 2> gpurun_out/${TAG}_bench_c2.err
 timeout 900 python bench.py --workload c3 --steps 10 --warmup 3 > gpurun_out/${TAG}_bench_c3.json 2> gpurun_out/${TAG}_bench_c3.err
 timeout 900 python bench.py --workload c5 --steps 10 --warmup 3 > gpurun_out/${TAG}_bench_c5.json 2> gpurun_out/${TAG}_bench_c5.err
-timeout 900 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_reference_arm.json 2> gpurun_out/${TAG}_bench_reference_arm.err
+timeout 900 python bench.py --impl reference --steps 4 --warmup 1 > gpurun_out/${TAG}_bench_reference_arm.json 2> gpurun_out/${TAG}_bench_reference_arm.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
   --log-file gpurun_out/${TAG}_ncu_launches.csv python tools/one_step.py 180 3 > gpurun_out/${TAG}_ncu_launch.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on \
@@ -18,7 +18,7 @@ timeout 900 ncu --set full --clock-control none --import-source on \
 timeout 600 ncu --set full --clock-control none -k "regex:limiter_kernel" --launch-count 1 -f -o gpurun_out/${TAG}_prof_c5 \
   python bench.py --workload c5 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_c5.log 2>&1
 (timeout 900 compute-sanitizer --tool memcheck python -m pytest tests -m gpu -q -x \
-  -k "second_order or resampl or lowess or frame_lengths or host_seam or golden" 2>&1 | tail -6) > gpurun_out/${TAG}_sanitizer.txt
+  -k "second_order or resampl or lowess or frame_lengths or host_seam or kernel_variants or pipeline_matches_golden" 2>&1 | tail -6) > gpurun_out/${TAG}_sanitizer.txt
 (timeout 900 compute-sanitizer --tool racecheck python -m pytest tests -m gpu -q -x \
-  -k "second_order or pipeline_matches_golden" 2>&1 | tail -6) >> gpurun_out/${TAG}_sanitizer.txt
+  -k "second_order or pipeline_matches_golden or kernel_variants" 2>&1 | tail -6) >> gpurun_out/${TAG}_sanitizer.txt
 tail -3 gpurun_out/${TAG}_tests.log; tail -c 300 gpurun_out/${TAG}_bench_c2.json; echo; cat gpurun_out/${TAG}_sanitizer.txt

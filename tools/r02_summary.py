@@ -108,8 +108,8 @@ md.append("Everything below comes from ONE GPU call on the final code of the rou
           "one `ncu --set full --clock-control none --import-source on` capture of every pipeline kernel on config 2 and of the limiter on "
           "config 5's buffer (summarised in `r02_ncu_full_metrics.txt`, DRAM bytes per launch in `traffic.json`), compute-sanitizer "
           "memcheck + racecheck over the new code paths (`r02_sanitizer.txt`).  `r02_sass_counts.txt`: static SASS counts per kernel "
-          "(`tools/sass_counts.py`).  `r02_seam_sweep*.txt`, `r02_n4_host_ring_sweep.txt`: host-transport sweeps; `r02_bench_n4.json`: "
-          "four GPUs (before the ring was shrunk: 14.3 ms per call; 7.8 ms after).\n")
+          "(`tools/sass_counts.py`).  `r02_seam_sweep*.txt`, `r02_seam_ab*.txt`, `r02_seam_stats.txt`, `r02_n4_*.txt`: host-transport "
+          "measurements (`r02_host.txt`: the host); `r02_bench_n4_*.json`: four GPUs on one socket in both transport modes.\n")
 if "c2" in benches:
     b = benches["c2"]
     e = b["e2e"]
@@ -178,12 +178,17 @@ md.append("""## What moved this round (B200, config 2 unless stated)
 | change | before | after |
 |---|---|---|
 | convolution: overlap-save frames of 4 FIR lengths (4F-point transform pair, 3F outputs) | 124.4 µs, 8.8e7 warp instr. | 112-113 µs, 6.27e7 warp instr. (-29 %); one 1024-thread CTA per SM stalls as a whole at its barriers (issue slots 60 % against 70 %) and 646 frames are 4.4 waves that cost 5 |
+| FFT passes: padded shared-memory addresses from one base per butterfly + immediate offsets (the compiler re-padded every index: LOP3, LEA.HI, LEA per access) | convolution 112.6 µs, 4312 SASS instructions | 107.3 µs, 4000 |
+| convolution persistent (one CTA per SM walks its frames; the next frame's bulk copy is issued under the epilogue) | 107.3-109.8 µs | 103.3-103.7 µs |
+| analysis: twiddle powers built in registers (two table reads per radix-16 butterfly instead of fifteen) | 40.7-41.6 µs | 37.6-39.0 µs |
 | smoothing operator kept as row bands | 33.6 MB read, 21-25 µs | 5.1 MB, 8-12 µs |
 | level statistics / correction coefficients per warp, per-piece sums folded by the whole block, selected-item lists | spectrum mean 24.6 µs (ncu) | 17.9 µs (ncu; its barriers now wait for one warp's statistics) |
 | limiter: chunks by block index instead of an atomic ticket, input loads issued before anything else | 99.4 µs / 1691 µs (1 h) | 96.8 µs / 1655 µs: 0.197 / 0.234 of the HBM roof |
 | design kernel: one in-place forward float64 FFT for its three transforms | 34.7 µs (ncu), 32 % of stalls "no instruction" | 36 µs: no gain -- the kernel is 8 CTAs of dependent latencies |
 | `stages.main` on the reference's own pageable float64 arrays (worker threads narrowing into a pinned ring, pooled pinned results) | no number; float64 over the link both ways from pageable memory | 7.3-8.4 ms per call = 21 000-25 000x real-time; the link carries 127 MB each way at 54 GB/s = 4.7 ms of it |
-| the same with four ranks on one socket | 14.3 ms per call (12 MB ring through DRAM) | 7.8 ms (4 MB ring, cache-resident): 3.65x of one rank |
+| ... ring written with streaming stores (six 4 MB chunks; the DMA engine no longer snoops the staged lines out of the cores' caches), page-head prefetch | 7.0 ms per call (`r02_seam_ab.txt`) | 5.7 ms |
+| ... result back as float32 chunks through the ring, widened by the workers (up to 256 MB; half the bytes over the link) | 5.74 ms | 4.90 ms = 36 700x (`r02_seam_ab2.txt`) |
+| the same with four ranks on one socket | 14.3 ms per call (12 MB ring through DRAM) | 7.6-7.8 ms in either mode (`r02_n4_transport.txt`): the socket's memory bandwidth; 2.6x of one rank |
 | `mg.process` on 16-bit WAV files | 93 ms | 19 ms (payloads straight through pooled pinned buffers, parallel reads) |
 | tracks in flight for `value` | 3: 625 000x | 6: 637 000-642 000x |
 

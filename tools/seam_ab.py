@@ -34,31 +34,29 @@ stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 state = _native.TrackState()
 
 # (label, threads, chunk samples, ring, streaming stores (0 plain, 1 / 2 = 256 / 512 bit), download route (0 one DMA of
-#  device-widened float64, 2 float32 chunks through the ring), whole chunks per worker, prefetch bytes, copy streams of a
-#  ring download)
+#  device-widened float64, 2 float32 chunks through the ring), whole chunks per worker, prefetch bytes)
 CONFIGS = [
-    ("t13 64K x16 plain  dma ", 13, 1 << 16, 16, 0, 0, 0, 0, 1),
-    ("t13 512K x8 nt512  dma ", 13, 1 << 19, 8, 2, 0, 0, 0, 1),
-    ("t13 512K x8 nt512  ring pf8k", 13, 1 << 19, 8, 2, 2, 0, 8192, 1),
-    ("t13 1M x6   nt512  ring pf8k", 13, 1 << 20, 6, 2, 2, 0, 8192, 1),
-    ("t13 1M x6   nt512  ring pf8k 2 streams", 13, 1 << 20, 6, 2, 2, 0, 8192, 2),
-    ("t13 512K x8 nt512  ring pf8k 2 streams", 13, 1 << 19, 8, 2, 2, 0, 8192, 2),
-    ("t13 256K x12 nt512 ring pf8k 2 streams", 13, 1 << 18, 12, 2, 2, 0, 8192, 2),
-    ("t15 1M x6   nt512  ring pf8k 2 streams", 15, 1 << 20, 6, 2, 2, 0, 8192, 2),
+    ("t13 64K x16 plain  dma ", 13, 1 << 16, 16, 0, 0, 0, 0),
+    ("t13 512K x8 nt512  dma ", 13, 1 << 19, 8, 2, 0, 0, 0),
+    ("t15 512K x8 nt512  dma ", 15, 1 << 19, 8, 2, 0, 0, 0),
+    ("t13 512K x8 nt512  ring pf8k", 13, 1 << 19, 8, 2, 2, 0, 8192),
+    ("t13 1M x6   nt512  ring pf8k", 13, 1 << 20, 6, 2, 2, 0, 8192),
+    ("t13 1M x6   nt512  ring", 13, 1 << 20, 6, 2, 2, 0, 0),
+    ("t13 2M x4   nt512  ring pf8k", 13, 1 << 21, 4, 2, 2, 0, 8192),
+    ("t15 1M x6   nt512  ring pf8k", 15, 1 << 20, 6, 2, 2, 0, 8192),
 ]
 if len(sys.argv) > 2:
     CONFIGS = [c for c in CONFIGS if any(key in c[0] for key in sys.argv[2:])]
 handles = []
-for label, threads, chunk, ring, nt, dring, whole, pf, streams in CONFIGS:
+for label, threads, chunk, ring, nt, dring, whole, pf in CONFIGS:
     h = C.c_void_p()
     _native.check(lib, lib.mgb_host_io_create(threads, chunk, ring, C.byref(h)))
     handles.append(h)
 
 
 def call(i, k):
-    label, threads, chunk, ring, nt, dring, whole, pf, streams = CONFIGS[i]
-    for name, value in (("host_streaming_stores", nt), ("host_download_ring", dring), ("host_split_chunks", whole), ("host_prefetch", pf),
-                        ("host_copy_streams", streams)):
+    label, threads, chunk, ring, nt, dring, whole, pf = CONFIGS[i]
+    for name, value in (("host_streaming_stores", nt), ("host_download_ring", dring), ("host_split_chunks", whole), ("host_prefetch", pf)):
         _native.check(lib, lib.mgb_set_option(name.encode(), value))
     t0 = time.perf_counter()
     _native.check(lib, lib.mgb_stages_main_host(handles[i], C.byref(plan.struct), C.byref(sess.layout), ts[k % 3].ctypes.data,
