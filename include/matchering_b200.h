@@ -64,7 +64,7 @@ typedef struct mgb_limiter_params {
  * n_log = (fft_size/2)*lin_log_oversampling+1. */
 typedef struct mgb_plan {
     int32_t sample_rate;
-    int32_t fft_size;          /* F: 1024, 2048, 4096 or 8192 */
+    int32_t fft_size;          /* F: 512, 1024, 2048, 4096, 8192 or 16384 */
     int32_t n_lin, n_log;
     int32_t rms_correction_steps;
     int32_t lowess_k;          /* neighbourhood size int(frac*n_log + 1e-10) */
@@ -157,7 +157,9 @@ const char* mgb_last_error_string(void);
  * fft_size 4096 and 8192) or sends every pass through shared memory (0).  "conv_frame": overlap-save
  * frame of the convolution in FIR lengths, 4 (default: a 4F-point transform pair yields 3F outputs; fft_size
  * 2048 and 4096 with pieces of at least 3F samples) or 2 (2F-point pair, F outputs).  "clip_ctas_per_sm": grid of
- * the RMS-correction passes in CTAs per SM (1..16, default 3).  "design_direct": mgb_test_design_fir runs the
+ * the RMS-correction passes in CTAs per SM (1..16, default 3).  "conv_persistent": the 16384-point convolution frames are
+ * walked by one CTA per SM with the next frame's bulk copy under the epilogue (1, default) or take one CTA each (0).
+ * "analyze_chain": the analysis FFT builds twiddle powers in registers (1, default) or reads them all (0).  "design_direct": mgb_test_design_fir runs the
  * spline/LOWESS chain directly even when the plan has a smoothing operator.  "lookback_inclusive":
  * 0 makes limiter chunks publish aggregates only, so every look-back walks to its cut-off.  "limiter_ticket":
  * 1 hands the limiter's chunks out by an atomic ticket instead of the block index (0, default).

@@ -22,9 +22,13 @@ namespace mgb {
 
 namespace {
 
+// fft_size 16384: frame and landing buffer do not fit one SM together (131 + 139 KB), so the frame's samples are
+// read straight from global memory while they are gathered for the first pass (no bulk copy, no overlap of the next
+// frame's load: a rare Config, correct first).
 template <int F>
 struct AnalyzeSmem {
-    static constexpr int kRawBytes = ((F + 2) * 8 + 15) / 16 * 16;
+    static constexpr bool kDirect = F > 8192;
+    static constexpr int kRawBytes = kDirect ? 0 : ((F + 2) * 8 + 15) / 16 * 16;
     static constexpr int kPlaneBytes = (int)((PackedPlanes::bytes(F) + 15) / 16 * 16);
     static constexpr int kBytes = kRawBytes + kPlaneBytes + 16 /*barrier*/ + 32 * 8 + 96 * 4 + 32;
 };
@@ -73,6 +77,7 @@ analyze_kernel(const float2* __restrict__ x, long long frames, long long piece, 
 #pragma unroll
     for (int b = 0; b < BINS; ++b) acc_mid[b] = acc_side[b] = 0.0f;
 
+    if constexpr (L::kDirect) use_tma = 0;
     if (use_tma && tid == 0) tma_barrier_init(bar);
     if (tid == 0) red_u[0] = red_u[1] = red_u[2] = red_u[3] = 0u;
     __syncthreads();
@@ -103,11 +108,11 @@ analyze_kernel(const float2* __restrict__ x, long long frames, long long piece, 
                 first.fixup = x + start + (F - 1);
             }
             tma_barrier_wait(bar, (uint32_t)(f - f_lo));
-        } else {
+        } else if constexpr (!L::kDirect) {
             for (int i = tid; i < F; i += THREADS) raw[i] = x[start + i];
             __syncthreads();
         }
-        first.raw = raw + off;
+        first.raw = L::kDirect ? x + start : raw + off;
         // the thread's 16 input points: mid / side, sum(mid^2) in float64, the peak, and the frame's
         // channel balance before the two channels share a transform (see balance_factor)
         cpx<float> z[F / THREADS];
@@ -221,6 +226,7 @@ int launch_analyze(const mgb_plan& plan, const float2* x, int64_t frames, int64_
         case 2048: return launch_analyze_t<2048>(plan, x, frames, piece, divisions, slots, spec_part, sumsq_part, absmax_part, stream);
         case 4096: return launch_analyze_t<4096>(plan, x, frames, piece, divisions, slots, spec_part, sumsq_part, absmax_part, stream);
         case 8192: return launch_analyze_t<8192>(plan, x, frames, piece, divisions, slots, spec_part, sumsq_part, absmax_part, stream);
+        case 16384: return launch_analyze_t<16384>(plan, x, frames, piece, divisions, slots, spec_part, sumsq_part, absmax_part, stream);
         default: break;
     }
     set_error("analyze: fft_size %d has no kernel", plan.fft_size);

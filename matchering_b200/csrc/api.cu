@@ -105,6 +105,7 @@ Workspace carve_workspace(const mgb_plan& plan, const mgb_track_layout& L, void*
     w.h_mid = (float2*)take((2 * F + 1) * 8);           // FIR spectrum bins 0..N/2 of the N = 2F or 4F grid
     w.h_side = (float2*)take((2 * F + 1) * 8);
     w.mid_plane = (float*)take(L.target_frames * 4);
+    w.conv_scratch = (float2*)take(conv_global_scratch_bytes(plan.fft_size, L.target_frames));
     w.zero_begin = base ? base + off : nullptr;
     w.piece_sums = (double*)take((int64_t)MGB_MAX_CORRECTION_STEPS * L.target_divisions * 8);
     w.zero_end = base ? base + off : nullptr;
@@ -121,8 +122,8 @@ Workspace carve_workspace(const mgb_plan& plan, const mgb_track_layout& L, void*
 static int check_plan(const mgb_plan* plan) {
     MGB_REQUIRE(plan != nullptr, MGB_ERR_INVALID, "plan is NULL");
     const int F = plan->fft_size;
-    MGB_REQUIRE(F == 512 || F == 1024 || F == 2048 || F == 4096 || F == 8192, MGB_ERR_UNSUPPORTED,
-                "fft_size %d: kernels exist for 512, 1024, 2048, 4096, 8192", F);
+    MGB_REQUIRE(F == 512 || F == 1024 || F == 2048 || F == 4096 || F == 8192 || F == 16384, MGB_ERR_UNSUPPORTED,
+                "fft_size %d: kernels exist for 512, 1024, 2048, 4096, 8192, 16384", F);
     MGB_REQUIRE(plan->n_lin == F / 2 + 1 && plan->n_log >= 4, MGB_ERR_INVALID, "plan grid sizes inconsistent");
     MGB_REQUIRE(plan->rms_correction_steps >= 0 && plan->rms_correction_steps <= MGB_MAX_CORRECTION_STEPS,
                 MGB_ERR_UNSUPPORTED, "rms_correction_steps %d > %d", plan->rms_correction_steps, MGB_MAX_CORRECTION_STEPS);
@@ -207,6 +208,7 @@ static bool radix_schedule(int n, int* npass, int r[4]) {
         case 4096: radices_of<4096>(npass, r); return true;
         case 8192: radices_of<8192>(npass, r); return true;
         case 16384: radices_of<16384>(npass, r); return true;
+        case 32768: radices_of<32768>(npass, r); return true;
         default: return false;
     }
 }

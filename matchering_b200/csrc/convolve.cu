@@ -446,10 +446,89 @@ convolve_fused_kernel(const float2* __restrict__ x, long long frames, long long 
     }  // frames of this CTA
 }
 
+// ---- fft_size 16384: the frame lives in global memory ------------------------------------------------
+// A 2F = 32768-point float frame is 262 KB, more than one SM's shared memory.  This kernel keeps each CTA's frame
+// in a scratch region of the workspace (L2-resident) and runs the same passes on it through generic pointers:
+// every pass costs a trip through L2 instead of shared memory -- a rare Config, correct first.  A CTA walks the
+// frames blockIdx.x, blockIdx.x + gridDim.x, ...; the input is read twice from global memory (once for the
+// channel balance, once while it is gathered for the first pass).
+constexpr int kConvGlobalThreads = 512;
+template <int F, bool CHAIN>
+__global__ void __launch_bounds__(kConvGlobalThreads)
+convolve_global_kernel(const float2* __restrict__ x, long long frames, long long piece, int divisions,
+                       const cpx<float>* __restrict__ tw, const float2* __restrict__ h_mid,
+                       const float2* __restrict__ h_side, float2* __restrict__ result, float* __restrict__ mid_plane,
+                       double* __restrict__ piece_sums, mgb_track_state* __restrict__ state, float2* scratch, int nframes) {
+    constexpr int N = 2 * F;
+    constexpr int THREADS = kConvGlobalThreads;
+    __shared__ double red_a[32], red_b[32];
+    __shared__ float red_f[32];
+    __shared__ unsigned red_u[2];
+    const PackedPlanes planes{scratch + (long long)blockIdx.x * PackedPlanes::elems(N)};
+    const int tid = threadIdx.x;
+    for (int frame = blockIdx.x; frame < nframes; frame += gridDim.x) {
+        const long long n0 = (long long)frame * F;
+        const long long origin = n0 - F / 2;
+        const ConvSpan span = conv_span<N>(frames, origin);
+        ConvFirst first;
+        first.raw = x + origin;  // (only indices inside [lo, hi) are dereferenced)
+        first.lo = (int)(span.lo - origin);
+        first.hi = (int)(span.hi - origin);
+        first.fixup = nullptr;
+        first.fix_index = -1;
+        float max_mid = 0.0f, max_side = 0.0f;
+        for (int i = tid; i < N; i += THREADS) {
+            const float2 v = first.sample(i);
+            max_mid = fmaxf(max_mid, fabsf((v.x + v.y) * 0.5f));
+            max_side = fmaxf(max_side, fabsf((v.x - v.y) * 0.5f));
+        }
+        if (tid == 0) red_u[0] = red_u[1] = 0u;
+        __syncthreads();
+        block_max2(max_mid, max_side, red_u);
+        const float g_side = balance_factor(max_mid, max_side);
+        ConvBalance bal;
+        bal.inv_g = 1.0f / g_side;
+        bal.mid_silent = max_mid == 0.0f;
+        bal.side_silent = max_side == 0.0f;
+        bal.any_silent = bal.mid_silent || bal.side_silent;
+        // forward transform of z = mid + i*g*side, formed while the first pass gathers its inputs
+        auto z_of = [&](int i) {
+            const float2 v = first.sample(i);
+            return cpx<float>{(v.x + v.y) * 0.5f, (v.x - v.y) * 0.5f * g_side};
+        };
+        fft_run<N, +1, THREADS, float, CHAIN>(planes, tw, z_of, PlaneStore<PackedPlanes>{planes}, /*first_in_place=*/false,
+                                              /*last_in_place=*/true);
+        __syncthreads();
+        for (int k = tid; k <= F; k += THREADS) {
+            const int kn = (N - k) & (N - 1);
+            cpx<float> zk = planes.load(k), zn = planes.load(kn);
+            conv_apply_pair(zk, zn, k, h_mid, h_side, bal);
+            planes.store(k, zk);
+            if (kn != k) planes.store(kn, zn);
+        }
+        __syncthreads();
+        fft_run<N, -1, THREADS, float, CHAIN>(planes, tw, PlaneLoad<PackedPlanes>{planes}, PlaneStore<PackedPlanes>{planes},
+                                              /*first_in_place=*/true, /*last_in_place=*/true);
+        __syncthreads();
+        ConvEpilogue<F> ep(result, mid_plane, n0, frames, piece, divisions, bal);
+        for (int o = tid; o < ep.valid; o += THREADS) ep.emit(o, planes.load(F - 1 + o));
+        ep.finish(red_a, red_b, red_f, piece_sums, state);
+        __syncthreads();  // the frame buffer and the reduction slots serve the CTA's next frame
+    }
+}
+
 template <int F>
 int launch_convolve_t(const mgb_plan& plan, const mgb_track_layout& layout, const float2* target, float2* result,
                       const Workspace& ws, mgb_track_state* state, cudaStream_t stream) {
     const long long T = layout.target_frames;
+    if constexpr (F > 8192) {
+        const int nframes = (int)((T + F - 1) / F);
+        auto kernel = g_twiddle_chain ? convolve_global_kernel<F, true> : convolve_global_kernel<F, false>;
+        return launch("convolve_kernel", kernel, dim3(conv_global_ctas(F, T)), dim3(kConvGlobalThreads), 0, stream, target, T,
+                      (long long)layout.target_piece, layout.target_divisions, (const cpx<float>*)plan.d_tw_f32_2F,
+                      (const float2*)ws.h_mid, (const float2*)ws.h_side, result, ws.mid_plane, ws.piece_sums, state,
+                      ws.conv_scratch, nframes);
+    } else {
     const int ovs = conv_frame_ovs(plan.fft_size, layout.target_piece);
     auto args = [&](auto kernel, int out, int threads, size_t smem) {
         const unsigned nframes = (unsigned)((T + out - 1) / out);
@@ -499,9 +578,21 @@ int launch_convolve_t(const mgb_plan& plan, const mgb_track_layout& layout, cons
         }
     }
     return args(g_twiddle_chain ? convolve_kernel<F, true> : convolve_kernel<F, false>, F, F / 8, ConvSmem<2 * F>::kBytes);
+    }
 }
 
 }  // namespace
+
+// scratch of convolve_global_kernel: one padded 2F-point frame per CTA (carve_workspace)
+int conv_global_ctas(int fft_size, long long target_frames) {
+    if (fft_size <= 8192) return 0;
+    const long long nframes = (target_frames + fft_size - 1) / fft_size;
+    const long long cap = 2LL * num_sms();
+    return (int)(nframes < cap ? nframes : cap);
+}
+int64_t conv_global_scratch_bytes(int fft_size, long long target_frames) {
+    return (int64_t)conv_global_ctas(fft_size, target_frames) * (int64_t)PackedPlanes::bytes(2 * fft_size);
+}
 
 // Overlap-save frame length, in FIR lengths, of the convolution (and therefore the grid the design kernel
 // must put the FIR spectra on): 4 where the 4F-point fused kernel exists, is switched on and every output
@@ -523,6 +614,7 @@ int launch_convolve(const mgb_plan& plan, const mgb_track_layout& layout, const 
         case 2048: return launch_convolve_t<2048>(plan, layout, target, result, ws, state, stream);
         case 4096: return launch_convolve_t<4096>(plan, layout, target, result, ws, state, stream);
         case 8192: return launch_convolve_t<8192>(plan, layout, target, result, ws, state, stream);
+        case 16384: return launch_convolve_t<16384>(plan, layout, target, result, ws, state, stream);
         default: break;
     }
     set_error("convolve: fft_size %d has no kernel", plan.fft_size);

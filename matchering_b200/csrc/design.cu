@@ -494,10 +494,13 @@ spectrum_mean_kernel(DesignArgs a, int n_lin, int fft_size, double eps, Prefetch
     }
 }
 
+// fft_size 16384: the float64 planes (2 x 132 KB) do not fit one SM; they live in the CTA's scratch block in
+// global memory instead (L2-resident; the passes and their barriers are the same code on generic pointers).
 template <int F>
 struct DesignSmem {
+    static constexpr bool kGlobalPlanes = F > 8192;
     static constexpr int kPlane = fft_padded_size(F);
-    static constexpr int kBytes = 2 * kPlane * 8 + 64;
+    static constexpr int kBytes = kGlobalPlanes ? 64 : 2 * kPlane * 8 + 64;
 };
 
 // The one float64 transform of the design kernel: forward, in place on the planes (barriers inside and between
@@ -513,12 +516,15 @@ __global__ void __launch_bounds__(kDesignThreads)
 design_kernel(mgb_plan plan, DesignArgs a) {
     constexpr int HB = F / 2 + 1;
     MGB_DYN_SMEM(smem);
-    double* re = reinterpret_cast<double*>(smem);
-    double* im = re + DesignSmem<F>::kPlane;
-    const SplitPlanes<double> planes{re, im};
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int ch = blockIdx.x / a.ovs;
     const int parity = blockIdx.x % a.ovs;  // which residue class of the FIR spectrum's bins this CTA produces (step G)
+    // (global planes: behind the design vectors of this CTA's scratch block, see design_doubles_per_channel)
+    double* re = DesignSmem<F>::kGlobalPlanes
+                     ? a.scratch + ((long long)(kDesignBlocks * ch) + parity) * a.stride + (a.stride - 2 * DesignSmem<F>::kPlane)
+                     : reinterpret_cast<double*>(smem);
+    double* im = re + DesignSmem<F>::kPlane;
+    const SplitPlanes<double> planes{re, im};
     const int NL = plan.n_log;
     const cpx<double>* tw = (const cpx<double>*)plan.d_tw_f64_F;
 
@@ -702,7 +708,10 @@ int launch_design_t(const mgb_plan& plan, const DesignArgs& a, cudaStream_t stre
 }  // namespace
 
 int64_t design_doubles_per_channel(const mgb_plan& plan) {
-    return 3LL * plan.n_lin + 4LL * plan.n_log + plan.fft_size + 16;
+    int64_t n = 3LL * plan.n_lin + 4LL * plan.n_log + plan.fft_size + 16;
+    n = (n + 31) / 32 * 32;
+    if (plan.fft_size > 8192) n += 2LL * fft_padded_size(plan.fft_size) + 32;  // the design FFT's planes (DesignSmem::kGlobalPlanes)
+    return n;
 }
 
 int g_design_direct = 0;
@@ -810,6 +819,7 @@ int launch_design(const mgb_plan& plan, const mgb_track_layout& layout, const Wo
         case 2048: return launch_design_t<2048>(plan, a, stream);
         case 4096: return launch_design_t<4096>(plan, a, stream);
         case 8192: return launch_design_t<8192>(plan, a, stream);
+        case 16384: return launch_design_t<16384>(plan, a, stream);
         default: break;
     }
     set_error("design: fft_size %d has no kernel", plan.fft_size);

@@ -307,6 +307,7 @@ template <> struct Radices<2048>  { static constexpr int n = 3; static constexpr
 template <> struct Radices<4096>  { static constexpr int n = 3; static constexpr int r[4] = {16, 16, 16, 1}; };
 template <> struct Radices<8192>  { static constexpr int n = 4; static constexpr int r[4] = {16, 8, 8, 8}; };
 template <> struct Radices<16384> { static constexpr int n = 4; static constexpr int r[4] = {16, 16, 8, 8}; };
+template <> struct Radices<32768> { static constexpr int n = 4; static constexpr int r[4] = {16, 16, 16, 8}; };  // fft_size 16384's convolution frame (planes in global memory)
 
 
 // First pass of the transform: `first` supplies the input points (logical index -> value), results

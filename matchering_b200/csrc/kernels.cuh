@@ -18,6 +18,7 @@ struct Workspace {
     float2* h_mid;          // [2F+1] spectrum of the mid FIR on the convolution's N = 2F or 4F grid (bins 0..N/2), c0/N folded in
     float2* h_side;         // [2F+1]
     float* mid_plane;       // [T] mid channel of the convolution result
+    float2* conv_scratch;   // fft_size 16384 only: one padded 2F-point frame per CTA of convolve_global_kernel
     // ---- zeroed at the start of every job (one memset) ----
     unsigned char* zero_begin;
     double* piece_sums;     // [MGB_MAX_CORRECTION_STEPS][Dt] sums of clip(mid*gain)^2
@@ -118,6 +119,8 @@ int fill_twiddles(int n, int is_f64, void* table, cudaStream_t stream);
 int twiddle_count(int n);
 int inverse_twiddle_count(int n);
 
+int conv_global_ctas(int fft_size, long long target_frames);  // convolve.cu: CTAs / scratch of the fft_size 16384 convolution
+int64_t conv_global_scratch_bytes(int fft_size, long long target_frames);
 extern int g_use_tma;
 bool host_set_option(const char* name, int value);  // hostio.cu: the host transport's tuning switches
 extern int g_limiter_ticket;      // limiter chunks by atomic ticket (1) or by block index (0, default)

@@ -55,7 +55,7 @@ class DevicePlan:
         self.struct = s
         with torch.cuda.device(device):
             _native.check(self.lib, self.lib.mgb_plan_fill_twiddles(C.byref(s), _stream_ptr(device)))
-            if t.lowess_it > 0:
+            if t.lowess_it > 0 or t.fft_size > _plan.OPERATOR_MAX_FFT_SIZE:
                 return  # robustness iterations make the smoothing non-linear in the data: direct chain per track
             # the smoothing chain as one Config-only matrix, built on the device from the direct kernels
             ws_bytes = int(self.lib.mgb_plan_operator_workspace_bytes(C.byref(s)))

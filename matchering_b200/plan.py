@@ -23,7 +23,8 @@ from dataclasses import dataclass, field
 import numpy as np
 from scipy import signal as _signal
 
-SUPPORTED_FFT_SIZES = (512, 1024, 2048, 4096, 8192)
+SUPPORTED_FFT_SIZES = (512, 1024, 2048, 4096, 8192, 16384)
+OPERATOR_MAX_FFT_SIZE = 8192  # above: no Config-only smoothing matrix (its row bands would be 80 MB), direct chain per track
 
 
 class UnsupportedConfig(NotImplementedError):

@@ -179,6 +179,19 @@ def test_pipeline_other_configs(lib, fft_size, sr):
     assert st.steps_done == 2
 
 
+def test_pipeline_fft_size_16384(lib):
+    """fft_size 16384: the analysis reads its frames straight from global memory, the design FFT's float64 planes and
+    the convolution's 32768-point frames live in global memory (convolve_global_kernel: a CTA walks several frames,
+    ragged last frame, pieces of two and a bit frames)."""
+    cfg = port.OracleConfig(fft_size=16384, max_piece_size=1.0)
+    n = 16384 * 20 + 777  # 21 frames on 16 CTAs: some walk two
+    t, r = port.synth_target(n, 8), port.synth_reference(n - 5003, 9)
+    outs, st, fir, _, L = run_pipeline(cfg, t, r)
+    want = port.main(t.astype(np.float64), r.astype(np.float64), cfg, True, True, True)
+    _compare(outs, want)
+    assert st.steps_done == 4 and L.target_piece >= 16384
+
+
 def _limit(lib, x, cfg):
     params = limiter_params(plan_mod.limiter_constants(cfg))
     n = len(x)
@@ -270,7 +283,7 @@ def test_limiter_rejects_too_short_input(lib):
 
 
 def test_unsupported_configs_fail_loudly():
-    for fft_size in (256, 16384):
+    for fft_size in (256, 32768):
         with pytest.raises(plan_mod.UnsupportedConfig):
             plan_mod.build_tables(port.OracleConfig(fft_size=fft_size))
     with pytest.raises(plan_mod.UnsupportedConfig):

@@ -127,6 +127,19 @@ def test_pipeline_other_configs_against_oracle(torch_cuda, fft_size, sr, seconds
     _compare(got, want)
 
 
+def test_pipeline_fft_size_16384_against_oracle(torch_cuda):
+    """fft_size 16384 (frames and design planes in global memory): two minutes, so that every CTA of the
+    global-memory convolution walks several frames; pieces of a few frames with ragged tails."""
+    import port
+    from matchering_b200 import stages
+    cfg = _config(fft_size=16384, max_piece_size=2.0)
+    n = 44100 * 120 + 311  # 323 frames of 16384 outputs on 296 CTAs
+    t, r = port.synth_target(n, 15), port.synth_reference(n - 7001, 16)
+    got = stages.main(t, r, cfg, True, True, True)
+    want = port.main(t.astype(np.float64), r.astype(np.float64), cfg, True, True, True)
+    _compare(got, want)
+
+
 @pytest.mark.parametrize("fft_size", [4096, 8192])
 def test_generic_convolution_kernel_against_oracle(torch_cuda, lib, fft_size):
     """These sizes normally take the fused convolution kernel; the all-shared-memory one must agree too."""
@@ -363,7 +376,7 @@ def test_unsupported_configs_fail_loudly(torch_cuda):
     from matchering_b200.plan import UnsupportedConfig
     import matchering_b200 as mg
     x = np.zeros((20000, 2), dtype=np.float32)
-    for cfg in (_config(fft_size=256), _config(fft_size=16384), _config(limiter=mg.LimiterConfig(release_filter_order=3)),
+    for cfg in (_config(fft_size=256), _config(fft_size=32768), _config(limiter=mg.LimiterConfig(release_filter_order=3)),
                 _config(fft_size=4096, max_piece_size=0.1)):
         with pytest.raises(UnsupportedConfig):
             stages.main(x[:5000], x[:5000], cfg)

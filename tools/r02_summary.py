@@ -46,7 +46,7 @@ for name in ("r02_bench_n4.json",):
     if os.path.exists(p):
         shutil.copy(p, os.path.join(PROF, name))
 for src, dst in ((f"{TAG}_ncu_launches.csv", "r02_ncu_launches.csv"), (f"{TAG}_sanitizer.txt", "r02_sanitizer.txt"),
-                 (f"{TAG}_tests.log", "r02_gpu_tests.txt")):
+                 (f"{TAG}_tests.log", "r02_gpu_tests.txt"), (f"{TAG}_hot_lines.txt", "r02_hot_lines.txt")):
     p = os.path.join(OUT, src)
     if os.path.exists(p):
         shutil.copy(p, os.path.join(PROF, dst))
