@@ -24,6 +24,7 @@ timeout 600 ncu --set full --clock-control none -k "regex:limiter_kernel" --laun
   -k "second_order or resampl or lowess or frame_lengths or kernel_variants or pipeline_matches_golden or fft_size_16384" 2>&1 | tail -6) > gpurun_out/${TAG}_sanitizer.txt
 (timeout 600 compute-sanitizer --tool racecheck python -m pytest tests -m gpu -q -x \
   -k "second_order or pipeline_matches_golden or kernel_variants" 2>&1 | tail -6) >> gpurun_out/${TAG}_sanitizer.txt
+(timeout 300 compute-sanitizer --tool memcheck python -m pytest tests -m gpu -q -x -k "host_seam_results" 2>&1 | tail -60) > gpurun_out/${TAG}_sanitizer_host_seam.txt
 # ---- summaries on the box
 (
   for k in limiter_kernel convolve analyze_kernel spectrum_mean design_kernel; do
