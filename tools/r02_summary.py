@@ -187,12 +187,13 @@ md.append("""## What moved this round (B200, config 2 unless stated)
 | design kernel: one in-place forward float64 FFT for its three transforms | 34.7 µs (ncu), 32 % of stalls "no instruction" | 36 µs: no gain -- the kernel is 8 CTAs of dependent latencies |
 | `stages.main` on the reference's own pageable float64 arrays (worker threads narrowing into a pinned ring, pooled pinned results) | no number; float64 over the link both ways from pageable memory | 7.3-8.4 ms per call = 21 000-25 000x real-time; the link carries 127 MB each way at 54 GB/s = 4.7 ms of it |
 | ... ring written with streaming stores (six 4 MB chunks; the DMA engine no longer snoops the staged lines out of the cores' caches), page-head prefetch | 7.0 ms per call (`r02_seam_ab.txt`) | 5.7 ms |
-| ... result back as float32 chunks through the ring, widened by the workers (up to 256 MB; half the bytes over the link) | 5.74 ms | 4.90 ms = 36 700x (`r02_seam_ab2.txt`) |
+| ... result back as float32 chunks through the ring, widened by the workers (up to 256 MB; half the bytes over the link) | 5.74 ms | 4.90 ms = 36 700x (`r02_seam_ab2.txt`; 4.89-5.08 ms on four boxes, 5.56 ms = 32 400x on the box of this evidence run) |
 | the same with four ranks on one socket | 14.3 ms per call (12 MB ring through DRAM) | 7.6-7.8 ms in either mode (`r02_n4_transport.txt`): the socket's memory bandwidth; 2.6x of one rank |
 | `mg.process` on 16-bit WAV files | 93 ms | 19 ms (payloads straight through pooled pinned buffers, parallel reads) |
-| tracks in flight for `value` | 3: 625 000x | 6: 637 000-642 000x |
+| tracks in flight for `value` | 3: 625 000x | 6: 637 000-642 000x (with the round's final kernels: 4: 698 000x, 6: 710 000x, 8: 679 000x, 12: 682 000x on one box; 683 000x on the box of this evidence run) |
+| `fft_size` 16384 | rejected | supported (frames and design planes in global memory; parity tests, emulator and GPU) |
 
-Not built, with the reason: RMS correction as one persistent kernel (a cooperative launch needs every SM at once and would serialise against the other tracks in flight, which is where `value` comes from; 3 x 13 µs of a 388 µs single track); `fft_size` 16384 (a 2F-point float32 frame and the float64 design FFT are 262 KB each, one SM has 227 KB); hold / release orders above 2 (scipy's own transfer-function arithmetic is off by 5e-5 ... unstable there, DESIGN.md section 4).
+Not built, with the reason: RMS correction as one persistent kernel (a cooperative launch needs every SM at once and would serialise against the other tracks in flight, which is where `value` comes from; 3 x 13 µs of a 388 µs single track); hold / release orders above 2 (scipy's own transfer-function arithmetic is off by 5e-5 ... unstable there, DESIGN.md section 4).
 """)
 open(os.path.join(PROF, "r02_summary.md"), "w").write("\n".join(md) + "\n")
 print("\n".join(md)[:3000])
