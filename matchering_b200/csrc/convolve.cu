@@ -363,86 +363,86 @@ convolve_fused_kernel(const float2* __restrict__ x, long long frames, long long 
     const int frame_end = PERSIST ? nframes : (int)blockIdx.x + 1;
     int phase = 0;
     for (int frame = blockIdx.x; frame < frame_end; frame += gridDim.x, ++phase) {
-    const long long n0 = (long long)frame * OUT;
+        const long long n0 = (long long)frame * OUT;
 
-    ConvBalance bal;
-    {
-        cpx<float> z[N / THREADS];
-        bal = conv_load_frame<N>(x, frames, n0 - F / 2, sp.raw, sp.bar, sp.red_u, use_tma, z, PERSIST ? phase : -1);
-        fft_first_pass_regs<N, +1, THREADS, float>(planes, z, /*barrier_before_store=*/false);
-    }
-    __syncthreads();
-    fft_middle<N, +1, THREADS, float, CHAIN, Fwd>(planes, tw);
-
-    // ---- last forward pass, FIR spectra, first inverse pass ----------------------------------------
-    {
-        const int ja = tid, jb = tid == 0 ? NB8 / 2 : NB8 - tid;
-        cpx<float> a[8], b[8];
-        fft_gather<8, NB8>(sl, ja, a);
-        fft_gather<8, NB8>(sl, jb, b);
-        __syncthreads();  // in place: everybody has gathered before anybody scatters
-        const cpx<float>* tw_last = tw + fft_last_pass_twiddles<Fwd>();
-        fft_butterfly<8, NB8, +1, CHAIN>(tw_last, ja, a);  // a[q] = Z[ja + q*NB8]
-        fft_butterfly<8, NB8, +1, CHAIN>(tw_last, jb, b);  // b[q] = Z[jb + q*NB8]
-        if (tid != 0) {
-            // N - (ja + q*NB8) = jb + (7-q)*NB8
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                conv_apply_pair(a[q], b[7 - q], ja + q * NB8, h_mid, h_side, bal);
-                conv_apply_pair(b[q], a[7 - q], jb + q * NB8, h_mid, h_side, bal);
-            }
-        } else {
-            // butterflies 0 and N/16 pair with themselves: a[q] <-> a[8-q], b[q] <-> b[7-q]
-            cpx<float> t = a[0];
-            conv_apply_pair(a[0], t, 0, h_mid, h_side, bal);
-            t = a[4];
-            conv_apply_pair(a[4], t, N / 2, h_mid, h_side, bal);
-#pragma unroll
-            for (int q = 1; q < 4; ++q) conv_apply_pair(a[q], a[8 - q], q * NB8, h_mid, h_side, bal);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) conv_apply_pair(b[q], b[7 - q], NB8 / 2 + q * NB8, h_mid, h_side, bal);
+        ConvBalance bal;
+        {
+            cpx<float> z[N / THREADS];
+            bal = conv_load_frame<N>(x, frames, n0 - F / 2, sp.raw, sp.bar, sp.red_u, use_tma, z, PERSIST ? phase : -1);
+            fft_first_pass_regs<N, +1, THREADS, float>(planes, z, /*barrier_before_store=*/false);
         }
-        Dft<8, -1, float>::run(a);
-        Dft<8, -1, float>::run(b);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) planes.store(ja * 8 + q, a[q]);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) planes.store(jb * 8 + q, b[q]);
-    }
-    __syncthreads();
-    fft_middle<N, -1, THREADS, float, CHAIN, Inv>(planes, tw_inv);
+        __syncthreads();
+        fft_middle<N, +1, THREADS, float, CHAIN, Fwd>(planes, tw);
 
-    // ---- last inverse pass straight into the epilogue ------------------------------------------------
-    ConvEpilogue<OUT> ep(result, mid_plane, n0, frames, piece, divisions, bal);
-    const cpx<float>* tw_last = tw_inv + fft_last_pass_twiddles<Inv>();
-#pragma unroll
-    for (int p = 0; p < 2; ++p) {
-        const int j = tid + p * THREADS;
-        cpx<float> v[8];
-        fft_gather<8, NB8>(sl, j, v);
-        if constexpr (PERSIST) {
-            if (p == 1) {  // the frame buffer has been read for the last time: the next frame may land in it
-                if (tid == 0) sp.red_u[0] = sp.red_u[1] = 0u;
-                __syncthreads();
-                if (tid == 0 && frame + (int)gridDim.x < nframes) {
-                    fence_proxy_async();
-                    conv_issue_frame<N>(x, frames, (long long)(frame + gridDim.x) * OUT - F / 2, sp.raw, sp.bar);
+        // ---- last forward pass, FIR spectra, first inverse pass ----------------------------------------
+        {
+            const int ja = tid, jb = tid == 0 ? NB8 / 2 : NB8 - tid;
+            cpx<float> a[8], b[8];
+            fft_gather<8, NB8>(sl, ja, a);
+            fft_gather<8, NB8>(sl, jb, b);
+            __syncthreads();  // in place: everybody has gathered before anybody scatters
+            const cpx<float>* tw_last = tw + fft_last_pass_twiddles<Fwd>();
+            fft_butterfly<8, NB8, +1, CHAIN>(tw_last, ja, a);  // a[q] = Z[ja + q*NB8]
+            fft_butterfly<8, NB8, +1, CHAIN>(tw_last, jb, b);  // b[q] = Z[jb + q*NB8]
+            if (tid != 0) {
+                // N - (ja + q*NB8) = jb + (7-q)*NB8
+    #pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    conv_apply_pair(a[q], b[7 - q], ja + q * NB8, h_mid, h_side, bal);
+                    conv_apply_pair(b[q], a[7 - q], jb + q * NB8, h_mid, h_side, bal);
+                }
+            } else {
+                // butterflies 0 and N/16 pair with themselves: a[q] <-> a[8-q], b[q] <-> b[7-q]
+                cpx<float> t = a[0];
+                conv_apply_pair(a[0], t, 0, h_mid, h_side, bal);
+                t = a[4];
+                conv_apply_pair(a[4], t, N / 2, h_mid, h_side, bal);
+    #pragma unroll
+                for (int q = 1; q < 4; ++q) conv_apply_pair(a[q], a[8 - q], q * NB8, h_mid, h_side, bal);
+    #pragma unroll
+                for (int q = 0; q < 4; ++q) conv_apply_pair(b[q], b[7 - q], NB8 / 2 + q * NB8, h_mid, h_side, bal);
+            }
+            Dft<8, -1, float>::run(a);
+            Dft<8, -1, float>::run(b);
+    #pragma unroll
+            for (int q = 0; q < 8; ++q) planes.store(ja * 8 + q, a[q]);
+    #pragma unroll
+            for (int q = 0; q < 8; ++q) planes.store(jb * 8 + q, b[q]);
+        }
+        __syncthreads();
+        fft_middle<N, -1, THREADS, float, CHAIN, Inv>(planes, tw_inv);
+
+        // ---- last inverse pass straight into the epilogue ------------------------------------------------
+        ConvEpilogue<OUT> ep(result, mid_plane, n0, frames, piece, divisions, bal);
+        const cpx<float>* tw_last = tw_inv + fft_last_pass_twiddles<Inv>();
+    #pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const int j = tid + p * THREADS;
+            cpx<float> v[8];
+            fft_gather<8, NB8>(sl, j, v);
+            if constexpr (PERSIST) {
+                if (p == 1) {  // the frame buffer has been read for the last time: the next frame may land in it
+                    if (tid == 0) sp.red_u[0] = sp.red_u[1] = 0u;
+                    __syncthreads();
+                    if (tid == 0 && frame + (int)gridDim.x < nframes) {
+                        fence_proxy_async();
+                        conv_issue_frame<N>(x, frames, (long long)(frame + gridDim.x) * OUT - F / 2, sp.raw, sp.bar);
+                    }
                 }
             }
+            fft_butterfly<8, NB8, -1, CHAIN>(tw_last, j, v);  // v[q] = y[j + q*NB8]
+            if (ep.full) {
+    #pragma unroll
+                for (int q = Q0; q < 7; ++q) ep.emit_full(j + 1 + (q - Q0) * NB8, v[q]);
+                if (j != NB8 - 1) ep.emit_full(j + 1 + (7 - Q0) * NB8, v[7]);  // (o = OUT for j = NB8-1: not an output)
+                else ep.emit_full(0, v[Q0 - 1]);
+            } else {
+    #pragma unroll
+                for (int q = Q0; q < 8; ++q) ep.emit(j + 1 + (q - Q0) * NB8, v[q]);  // (o = OUT for j = NB8-1, q = 7: not valid)
+                if (j == NB8 - 1) ep.emit(0, v[Q0 - 1]);
+            }
         }
-        fft_butterfly<8, NB8, -1, CHAIN>(tw_last, j, v);  // v[q] = y[j + q*NB8]
-        if (ep.full) {
-#pragma unroll
-            for (int q = Q0; q < 7; ++q) ep.emit_full(j + 1 + (q - Q0) * NB8, v[q]);
-            if (j != NB8 - 1) ep.emit_full(j + 1 + (7 - Q0) * NB8, v[7]);  // (o = OUT for j = NB8-1: not an output)
-            else ep.emit_full(0, v[Q0 - 1]);
-        } else {
-#pragma unroll
-            for (int q = Q0; q < 8; ++q) ep.emit(j + 1 + (q - Q0) * NB8, v[q]);  // (o = OUT for j = NB8-1, q = 7: not valid)
-            if (j == NB8 - 1) ep.emit(0, v[Q0 - 1]);
-        }
-    }
-    ep.finish(sp.red_a, sp.red_b, sp.red_f, piece_sums, state);
+        ep.finish(sp.red_a, sp.red_b, sp.red_f, piece_sums, state);
     }  // frames of this CTA
 }
 
@@ -529,55 +529,55 @@ int launch_convolve_t(const mgb_plan& plan, const mgb_track_layout& layout, cons
                       (const float2*)ws.h_mid, (const float2*)ws.h_side, result, ws.mid_plane, ws.piece_sums, state,
                       ws.conv_scratch, nframes);
     } else {
-    const int ovs = conv_frame_ovs(plan.fft_size, layout.target_piece);
-    auto args = [&](auto kernel, int out, int threads, size_t smem) {
-        const unsigned nframes = (unsigned)((T + out - 1) / out);
-        return launch("convolve_kernel", kernel, dim3(nframes), dim3(threads), smem, stream, target, T,
-                      (long long)layout.target_piece, layout.target_divisions, (const cpx<float>*)plan.d_tw_f32_2F,
-                      (const float2*)ws.h_mid, (const float2*)ws.h_side, result, ws.mid_plane, ws.piece_sums, state,
-                      g_use_tma);
-    };
-    auto args2 = [&](auto kernel, int out, int threads, size_t smem) {  // (the fused kernel also takes the frame count)
-        const unsigned nframes = (unsigned)((T + out - 1) / out);
-        return launch("convolve_kernel", kernel, dim3(nframes), dim3(threads), smem, stream, target, T,
-                      (long long)layout.target_piece, layout.target_divisions, (const cpx<float>*)plan.d_tw_f32_2F,
-                      (const float2*)ws.h_mid, (const float2*)ws.h_side, result, ws.mid_plane, ws.piece_sums, state,
-                      g_use_tma, (int)nframes);
-    };
-    if constexpr (InverseRadices<4 * F>::fused) {
-        if (ovs == 4) {
-            // twiddles of the 4F transform live behind the 2F tables (mgb_plan_twiddle_bytes)
-            const cpx<float>* tw4 = (const cpx<float>*)plan.d_tw_f32_2F + twiddle_count(2 * F) + inverse_twiddle_count(2 * F);
-            const unsigned nframes = (unsigned)((T + 3 * F - 1) / (3 * F));
-            if (g_conv_persistent && g_use_tma && 4 * F > 8192) {  // (one CTA per SM: the 16384-point frames)
-                const unsigned grid = nframes < (unsigned)num_sms() ? nframes : (unsigned)num_sms();
-                auto kernel = g_twiddle_chain ? convolve_fused_kernel<F, 4, true, true> : convolve_fused_kernel<F, 4, false, true>;
-                return launch("convolve_kernel", kernel, dim3(grid), dim3(4 * F / 16), ConvSmem<4 * F>::kBytes, stream, target, T,
+        const int ovs = conv_frame_ovs(plan.fft_size, layout.target_piece);
+        auto args = [&](auto kernel, int out, int threads, size_t smem) {
+            const unsigned nframes = (unsigned)((T + out - 1) / out);
+            return launch("convolve_kernel", kernel, dim3(nframes), dim3(threads), smem, stream, target, T,
+                          (long long)layout.target_piece, layout.target_divisions, (const cpx<float>*)plan.d_tw_f32_2F,
+                          (const float2*)ws.h_mid, (const float2*)ws.h_side, result, ws.mid_plane, ws.piece_sums, state,
+                          g_use_tma);
+        };
+        auto args2 = [&](auto kernel, int out, int threads, size_t smem) {  // (the fused kernel also takes the frame count)
+            const unsigned nframes = (unsigned)((T + out - 1) / out);
+            return launch("convolve_kernel", kernel, dim3(nframes), dim3(threads), smem, stream, target, T,
+                          (long long)layout.target_piece, layout.target_divisions, (const cpx<float>*)plan.d_tw_f32_2F,
+                          (const float2*)ws.h_mid, (const float2*)ws.h_side, result, ws.mid_plane, ws.piece_sums, state,
+                          g_use_tma, (int)nframes);
+        };
+        if constexpr (InverseRadices<4 * F>::fused) {
+            if (ovs == 4) {
+                // twiddles of the 4F transform live behind the 2F tables (mgb_plan_twiddle_bytes)
+                const cpx<float>* tw4 = (const cpx<float>*)plan.d_tw_f32_2F + twiddle_count(2 * F) + inverse_twiddle_count(2 * F);
+                const unsigned nframes = (unsigned)((T + 3 * F - 1) / (3 * F));
+                if (g_conv_persistent && g_use_tma && 4 * F > 8192) {  // (one CTA per SM: the 16384-point frames)
+                    const unsigned grid = nframes < (unsigned)num_sms() ? nframes : (unsigned)num_sms();
+                    auto kernel = g_twiddle_chain ? convolve_fused_kernel<F, 4, true, true> : convolve_fused_kernel<F, 4, false, true>;
+                    return launch("convolve_kernel", kernel, dim3(grid), dim3(4 * F / 16), ConvSmem<4 * F>::kBytes, stream, target, T,
+                                  (long long)layout.target_piece, layout.target_divisions, tw4, (const float2*)ws.h_mid,
+                                  (const float2*)ws.h_side, result, ws.mid_plane, ws.piece_sums, state, g_use_tma, (int)nframes);
+                }
+                auto kernel = g_twiddle_chain ? convolve_fused_kernel<F, 4, true, false> : convolve_fused_kernel<F, 4, false, false>;
+                return launch("convolve_kernel", kernel, dim3(nframes), dim3(4 * F / 16), ConvSmem<4 * F>::kBytes, stream, target, T,
                               (long long)layout.target_piece, layout.target_divisions, tw4, (const float2*)ws.h_mid,
                               (const float2*)ws.h_side, result, ws.mid_plane, ws.piece_sums, state, g_use_tma, (int)nframes);
             }
-            auto kernel = g_twiddle_chain ? convolve_fused_kernel<F, 4, true, false> : convolve_fused_kernel<F, 4, false, false>;
-            return launch("convolve_kernel", kernel, dim3(nframes), dim3(4 * F / 16), ConvSmem<4 * F>::kBytes, stream, target, T,
-                          (long long)layout.target_piece, layout.target_divisions, tw4, (const float2*)ws.h_mid,
-                          (const float2*)ws.h_side, result, ws.mid_plane, ws.piece_sums, state, g_use_tma, (int)nframes);
         }
-    }
-    if constexpr (InverseRadices<2 * F>::fused) {
-        if (g_conv_fused) {
-            if (g_conv_persistent && g_use_tma && 2 * F > 8192) {  // (fft_size 8192: 16384-point frames, one CTA per SM)
-                const unsigned nframes = (unsigned)((T + F - 1) / F);
-                const unsigned grid = nframes < (unsigned)num_sms() ? nframes : (unsigned)num_sms();
-                auto kernel = g_twiddle_chain ? convolve_fused_kernel<F, 2, true, true> : convolve_fused_kernel<F, 2, false, true>;
-                return launch("convolve_kernel", kernel, dim3(grid), dim3(F / 8), ConvSmem<2 * F>::kBytes, stream, target, T,
-                              (long long)layout.target_piece, layout.target_divisions, (const cpx<float>*)plan.d_tw_f32_2F,
-                              (const float2*)ws.h_mid, (const float2*)ws.h_side, result, ws.mid_plane, ws.piece_sums, state,
-                              g_use_tma, (int)nframes);
+        if constexpr (InverseRadices<2 * F>::fused) {
+            if (g_conv_fused) {
+                if (g_conv_persistent && g_use_tma && 2 * F > 8192) {  // (fft_size 8192: 16384-point frames, one CTA per SM)
+                    const unsigned nframes = (unsigned)((T + F - 1) / F);
+                    const unsigned grid = nframes < (unsigned)num_sms() ? nframes : (unsigned)num_sms();
+                    auto kernel = g_twiddle_chain ? convolve_fused_kernel<F, 2, true, true> : convolve_fused_kernel<F, 2, false, true>;
+                    return launch("convolve_kernel", kernel, dim3(grid), dim3(F / 8), ConvSmem<2 * F>::kBytes, stream, target, T,
+                                  (long long)layout.target_piece, layout.target_divisions, (const cpx<float>*)plan.d_tw_f32_2F,
+                                  (const float2*)ws.h_mid, (const float2*)ws.h_side, result, ws.mid_plane, ws.piece_sums, state,
+                                  g_use_tma, (int)nframes);
+                }
+                return args2(g_twiddle_chain ? convolve_fused_kernel<F, 2, true, false> : convolve_fused_kernel<F, 2, false, false>, F, F / 8,
+                             ConvSmem<2 * F>::kBytes);
             }
-            return args2(g_twiddle_chain ? convolve_fused_kernel<F, 2, true, false> : convolve_fused_kernel<F, 2, false, false>, F, F / 8,
-                         ConvSmem<2 * F>::kBytes);
         }
-    }
-    return args(g_twiddle_chain ? convolve_kernel<F, true> : convolve_kernel<F, false>, F, F / 8, ConvSmem<2 * F>::kBytes);
+        return args(g_twiddle_chain ? convolve_kernel<F, true> : convolve_kernel<F, false>, F, F / 8, ConvSmem<2 * F>::kBytes);
     }
 }
 
