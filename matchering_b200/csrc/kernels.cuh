@@ -41,7 +41,7 @@ struct alignas(16) LookbackWord {
 
 // powers of a pole for a blocked scan with `ept` elements per thread (limiter.cu)
 struct ScanPow {
-    double pe[19];  // p^k, k = 0..18
+    double pe[27];  // p^k, k = 0..kLimiterSpanEptMax + 1 (an odd count keeps sizeof a multiple of 16: SectionTab follows it in the table)
     double ql[33];  // q^k, q = p^ept
     double qw[17];  // Q^k, Q = q^32
     double pc[33];  // P^k, P = p^kLimiterCore: weight of a chunk k chunks back (look-back)
@@ -64,7 +64,7 @@ struct SectionTab {
 constexpr int kLimiterThreads = 512;
 constexpr int kLimiterCoreEpt = 9;                                   // core samples per thread
 constexpr int kLimiterCore = kLimiterThreads * kLimiterCoreEpt;      // 4608 samples per chunk
-constexpr int kLimiterSpanEptMax = 17;                               // span samples per thread (odd)
+constexpr int kLimiterSpanEptMax = 25;                               // span samples per thread (odd): up to 8192 samples of halo (215 KB of shared memory)
 
 Workspace carve_workspace(const mgb_plan& plan, const mgb_track_layout& layout, void* base);
 int64_t limiter_lookback_bytes(const mgb_limiter_params& lp, int64_t frames);

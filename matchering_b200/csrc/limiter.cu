@@ -352,7 +352,8 @@ __global__ void limiter_tables_kernel(mgb_limiter_params lp, int span_ept, unsig
 // GAINS (tests only, mgb_test_limiter_gains): instead of the limited samples, write the two float64-scan results
 // per frame: (g_att, the attack filter's gain; max(hold_out, release_out), the release gain).
 template <int EPT, int NO, bool GAINS = false>
-__global__ void __launch_bounds__(NT, NO == 1 ? 2 : 1)
+// (two CTAs per SM where the span leaves room for them: up to 17 samples per thread at order capacity 1)
+__global__ void __launch_bounds__(NT, (NO == 1 && EPT <= 17) ? 2 : 1)
 limiter_kernel(mgb_limiter_params lp, LimiterGeom gm, const float2* __restrict__ in, float2* __restrict__ out,
                long long frames, const double* __restrict__ pre_gain, const double* __restrict__ post_gain,
                const int* __restrict__ engaged, int* __restrict__ ticket, LookbackWord* __restrict__ slots,
@@ -971,6 +972,10 @@ int launch_limiter(const mgb_limiter_params& lp, const float2* in, float2* out, 
         MGB_LIMITER_CASE(13)
         MGB_LIMITER_CASE(15)
         MGB_LIMITER_CASE(17)
+        MGB_LIMITER_CASE(19)  // slow attacks / high sample rates (the default limiter at 176.4 and 192 kHz): one CTA per SM
+        MGB_LIMITER_CASE(21)
+        MGB_LIMITER_CASE(23)
+        MGB_LIMITER_CASE(25)
         default: break;
     }
 #undef MGB_LIMITER_CASE

@@ -212,7 +212,7 @@ class LimiterConstants:
 
 
 MAX_FILTER_ORDER = 2   # MGB_MAX_FILTER_ORDER
-MAX_LIMITER_HALO = 4096  # left + right halo the limiter kernel's shared-memory span can hold
+MAX_LIMITER_HALO = 8192  # left + right halo the limiter kernel's shared-memory span can hold (kLimiterSpanEptMax = 25)
 
 
 def limiter_constants(config) -> LimiterConstants:

@@ -238,6 +238,21 @@ def test_limiter_narrow_and_wide_windows(lib, sr, attack):
     assert engaged == 1 and np.abs(out - want).max() < 3e-7
 
 
+@pytest.mark.parametrize("sr,attack,hold_order", [(192000, 1.0, 1), (176400, 1.0, 2), (96000, 2.0, 1), (96000, 3.0, 1), (192000, 2.0, 1),
+                                                  (192000, 2.0, 2)])
+def test_limiter_wide_halos(lib, sr, attack, hold_order):
+    """The default limiter at 176.4 / 192 kHz and slow attacks: the attack filter's warm-up needs 4200 ... 8130 samples
+    of halo around a 4608-sample chunk (19 ... 25 span samples per thread, one CTA per SM)."""
+    lim = port.OracleLimiterConfig(attack=attack, hold_filter_order=hold_order)
+    cfg = port.OracleConfig(internal_sample_rate=sr, limiter=lim)
+    lc = plan_mod.limiter_constants(cfg)
+    assert (2 * lc.warmup + lc.hold + 2 * lc.reach + 64 > 4096) == (sr * attack > 180000)  # (176.4 kHz fits the old span)
+    x = port.synth_limiter_input(30011, seed=sr // 100 + int(10 * attack))
+    out, engaged = _limit(lib, x, cfg)
+    want = port.limit(x.astype(np.float64), cfg)
+    assert engaged == 1 and np.abs(out - want).max() < 3e-7
+
+
 @pytest.mark.parametrize("hold_order,release_order,sr", [(2, 1, 44100), (1, 2, 44100), (2, 2, 44100), (2, 2, 96000),
                                                          (2, 2, 8000)])
 def test_limiter_higher_filter_orders(lib, hold_order, release_order, sr):
