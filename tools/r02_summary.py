@@ -193,7 +193,7 @@ md.append("""## What moved this round (B200, config 2 unless stated)
 | tracks in flight for `value` | 3: 625 000x | 6: 637 000-642 000x (with the round's final kernels: 4: 698 000x, 6: 710 000x, 8: 679 000x, 12: 682 000x on one box; 683 000x on the box of this evidence run) |
 | `fft_size` 16384 | rejected | supported (frames and design planes in global memory; parity tests, emulator and GPU) |
 
-Not built, with the reason: RMS correction as one persistent kernel (a cooperative launch needs every SM at once and would serialise against the other tracks in flight, which is where `value` comes from; 3 x 13 µs of a 388 µs single track); hold / release orders above 2 (scipy's own transfer-function arithmetic is off by 5e-5 ... unstable there, DESIGN.md section 4).
+Not built, with the reason: RMS correction as one persistent kernel (a cooperative launch needs every SM at once and would serialise against the other tracks in flight, which is where `value` comes from; 3 x 13 µs of a 363 µs single track); hold / release orders above 2 (scipy's own transfer-function arithmetic is off by 5e-5 ... unstable there, DESIGN.md section 4).
 """)
 open(os.path.join(PROF, "r02_summary.md"), "w").write("\n".join(md) + "\n")
 print("\n".join(md)[:3000])
